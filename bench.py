@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json configs[1]: `pdr` + `lpmd` over synthetic 30x WGBS of a chr19-sized contig.
+
+One "step" = one full pass of the hot path over the whole read set (11.7 M reads, ~31 M CpG calls): ingest
+(validation + site marking + LPMD), site dictionary, PDR counters, row emission.
+
+  value : reads/s with the SoA batch already resident in HBM (device pointers handed to mth_submit, rows left in HBM)
+  e2e   : reads/s through the same C-ABI calls with HOST (pinned) buffers: H2D of the batch and D2H of the rows inside
+          the timed region
+  roofline : the slowest kernel of the step, algorithmic bytes / its CUDA-event time, vs MEASURED_PEAKS.json
+  cpu_baseline : the CPU oracle (C++ restatement of metheor 0.1.9, NOT the Rust binary) on a bounded sample, 1 core
+
+N > 1 (torchrun): every rank processes its own chr19-sized contig (weak scaling, genomic sharding needs no data-path
+collective); LPMD's four int64 counters are all-reduced over NCCL each step.
+`--impl reference` times the CPU oracle alone (rank 0 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 20260101
+CONTIG_LEN = 58_617_616
+COVERAGE = 30.0
+WORKLOAD = "pdr+lpmd, synthetic 30x WGBS, chr19-sized contig (58.6 Mb, ~1.1 M CpG sites, 150-bp SE reads, both strands)"
+MEASURES = ("pdr", "lpmd")
+CPU_SAMPLE_READS = 12_000_000  # the whole chr19-sized read set: a full pass takes the oracle only a few seconds
+
+
+def make_workload(rank, coverage=COVERAGE, length=CONTIG_LEN):
+    from metheor_b200 import synth
+    b, sites = synth.chr19_like(seed=SEED + 1000 * rank, coverage=coverage, length=length)
+    return b, sites
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def oracle_time(b, n_sample, steps=1):
+    """CPU oracle (pdr + lpmd, reference defaults) on the first n_sample reads. -> (reads/s, seconds per pass)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from metheor_b200 import batch as B
+    from oracle_lib import Oracle
+    sub = B.slice_reads(b, 0, min(n_sample, b["n_reads"]))
+    o = Oracle.from_soa(**B.to_oracle_soa([sub]))
+    best = None
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        o.pdr(10, 4, 10)
+        o.lpmd(2, 16, 10)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return sub["n_reads"] / best, best, sub["n_reads"]
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    b, _ = make_workload(0)
+    n = CPU_SAMPLE_READS
+    times = []
+    for _ in range(args.warmup):
+        oracle_time(b, n // 8)
+    t_all0 = time.perf_counter()
+    rps = []
+    for _ in range(args.steps):
+        r, dt, nn = oracle_time(b, n)
+        rps.append(r); times.append(dt)
+    v = float(np.mean(rps))
+    line = {"impl": "reference", "metric": "reads_per_sec", "value": v, "unit": "reads/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u32/u64 integer + f32 finalisation", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "measures": list(MEASURES)},
+            "cpu_baseline": {"value": v, "unit": "reads/s", "cores": 1, "kind": "port",
+                             "sample": f"first {n} reads of the workload; C++ restatement of metheor 0.1.9 (single-threaded "
+                                       f"like the reference), not the Rust binary"},
+            "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "host": {"nproc": os.cpu_count()}, "wall_s": time.perf_counter() - t_all0}
+    print(json.dumps(line))
+
+
+class _DevI64:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 2}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--coverage", type=float, default=COVERAGE)
+    ap.add_argument("--length", type=int, default=CONTIG_LEN)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from metheor_b200 import engine
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the engine has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    b, sites = make_workload(rank, args.coverage, args.length)
+    R, I = b["n_reads"], b["n_cpg"]
+    view = {np.dtype("uint32"): np.int32, np.dtype("uint16"): np.int16, np.dtype("uint64"): np.int64}
+    host, devb = dict(b), dict(b)
+    for k in ("start", "end", "meta", "cpg_off", "cpg_pos", "cpg_rel", "meth"):
+        t = torch.from_numpy(b[k].view(view.get(b[k].dtype, b[k].dtype)))
+        host[k] = t.pin_memory()
+        devb[k] = t.to(dev)
+    stream = torch.cuda.current_stream()
+
+    def make_ctx(flags):
+        c = engine.Context(engine.default_params(MEASURES, flags=flags), [args.length], device=local_rank)
+        c.set_stream(stream.cuda_stream)
+        return c
+
+    def allreduce_lpmd(ctx):
+        if world > 1:
+            t = torch.as_tensor(_DevI64(ctx.lpmd_counters_device_ptr(), 4), device=dev)
+            dist.all_reduce(t)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(steps):
+            step()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        ms = torch.tensor([e0.elapsed_time(e1), wall * 1e3], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(ms[0]), float(ms[1])
+
+    # ---------------- resident (value) ----------------
+    ctx = make_ctx(engine.FLAG_KEEP_ON_DEVICE)
+    rows = {}
+
+    def step_resident():
+        ctx.reset()
+        ctx.submit(devb)
+        rows.update(ctx.finish())
+        allreduce_lpmd(ctx)
+
+    for _ in range(args.warmup):
+        step_resident()
+    launches0 = ctx.stats()["kernel_launches"]
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_dev, ms_wall = timed(step_resident, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    st = ctx.stats()
+    n_sites = st["n_sites"]
+    n_rows = rows["pdr"]["n"]
+    ms_step = ms_dev / args.steps
+    total_reads = R * world
+    value = total_reads / (ms_step * 1e-3)
+
+    # ---------------- per-kernel times (profile flag: CUDA events around every kernel) ----------------
+    pctx = make_ctx(engine.FLAG_KEEP_ON_DEVICE | engine.FLAG_PROFILE)
+    PSTEPS = 5
+    for _ in range(3):
+        pctx.reset(); pctx.submit(devb); pctx.finish()
+    # stats are reset by reset(): collect from the LAST step only, repeated PSTEPS times for an average
+    acc = {}
+    for _ in range(PSTEPS):
+        pctx.reset(); pctx.submit(devb); pctx.finish()
+        for k, v in pctx.stats()["kernels"].items():
+            a = acc.setdefault(k, [0, 0.0])
+            a[0] += v["launches"]; a[1] += v["ms"]
+    kern = {k: {"launches_per_step": a[0] / PSTEPS, "ms_per_step": a[1] / PSTEPS} for k, a in acc.items()}
+    pctx.close()
+    C = n_sites
+    alg = {  # algorithmic bytes per launch, DESIGN.md §5
+        "k_ingest": 16 * R + 6 * I + 32,          # LPMD: meta+cpg_off+meth per read, cpg_pos+cpg_rel per CpG call, 4 counters
+        "k_pdr_scatter": 16 * R + 4 * I + 8 * C,  # PDR: meta+cpg_off+meth per read, cpg_pos per call, 2 u32 counters per site
+        "k_pdr_gather": 16 * R + 4 * I + 8 * C,
+        "k_sites_count": C * 4, "k_sites_emit": C * 4, "pdr_rows_count": C * 12, "k_pdr_emit": C * 8 + n_rows * 20,
+    }
+    hot = max((k for k in kern if k in ("k_ingest", "k_pdr_scatter", "k_pdr_gather")), key=lambda k: kern[k]["ms_per_step"])
+    peak, peak_src = peaks()
+    ach = alg[hot] / (kern[hot]["ms_per_step"] * 1e-3) / 1e9
+    step_alg = (16 * R + 4 * I + 12 * C) + (16 * R + 6 * I + 16)  # PDR + LPMD
+    kern_ms_total = sum(v["ms_per_step"] for v in kern.values())
+    roofline = {"bound": "hbm", "kernel": hot, "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                "frac": ach / peak, "traffic": None, "algorithmic_bytes_per_launch": alg[hot],
+                "ms_per_launch": kern[hot]["ms_per_step"]}
+    roofline_step = {"algorithmic_bytes": step_alg, "kernel_ms_sum": kern_ms_total,
+                     "achieved": step_alg / (kern_ms_total * 1e-3) / 1e9, "unit": "GB/s",
+                     "frac": step_alg / (kern_ms_total * 1e-3) / 1e9 / peak}
+
+    # ---------------- end to end through host buffers ----------------
+    ectx = make_ctx(0)
+    eres = {}
+
+    def step_e2e():
+        ectx.reset()
+        ectx.submit(host)
+        eres.update(ectx.finish())
+        allreduce_lpmd(ectx)
+        if world > 1:
+            eres["lpmd"] = ectx.lpmd_refresh()
+
+    for _ in range(args.warmup):
+        step_e2e()
+    e_steps = max(3, min(args.steps, 10))
+    _, e_wall = timed(step_e2e, e_steps)
+    est = ectx.stats()
+    e2e_value = total_reads / (e_wall / e_steps * 1e-3)
+    assert eres["pdr"]["n"] == n_rows
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rps, dt, nn = oracle_time(b, CPU_SAMPLE_READS, steps=3)
+        cpu = {"value": rps, "unit": "reads/s", "cores": 1, "kind": "port", "seconds": dt,
+               "sample": f"first {nn} reads of the workload (pdr+lpmd, defaults); C++ restatement of metheor 0.1.9, "
+                         f"single-threaded like the reference; host has {os.cpu_count()} cores"}
+
+    if rank == 0:
+        line = {"metric": "reads_per_sec", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u32/u64 integer + f32 finalisation", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "measures": list(MEASURES), "reads_per_gpu": R, "cpg_calls_per_gpu": I,
+                           "cpg_sites_per_gpu": int(C), "pdr_rows_per_gpu": int(n_rows), "seed": SEED,
+                           "l2": "inputs (%.0f MB per step) larger than L2" % ((16 * R + 6 * I + 8 * R) / 1e6),
+                           "parallelism": f"genomic sharding x{world}, NCCL all-reduce of 4 LPMD counters"},
+                "cpgs_per_sec": C * world / (ms_step * 1e-3), "wall_ms_per_step": ms_wall / args.steps,
+                "e2e": {"value": e2e_value, "unit": "reads/s", "ms_per_step": e_wall / e_steps,
+                        "h2d_bytes_per_step": int(est["h2d_bytes"]), "d2h_bytes_per_step": int(est["d2h_bytes"]), "steps": e_steps},
+                "gpu_launches": int((st["kernel_launches"] - 0) * args.steps),
+                "launches_per_step": int(st["kernel_launches"]),
+                "roofline": roofline, "roofline_step": roofline_step, "kernels": kern, "cpu_baseline": cpu,
+                "clocks": clocks, "pdr_path": {1: "scatter", 2: "gather"}.get(st["pdr_path"]), "lpmd": float(rows["lpmd"]["lpmd"])}
+        print(json.dumps(line))
+    ctx.close(); ectx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

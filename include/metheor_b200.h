@@ -1,0 +1,193 @@
+/* metheor_b200.h — C ABI of the B200-native methylation-heterogeneity engine (libmetheor_b200.so).
+ *
+ * The reference (dohlee/metheor v0.1.9) has no FFI of its own: its seam for this path is the per-measure
+ *   compute_helper(input, <thresholds>, cpg_set) -> map      src/pdr.rs:119  src/lpmd.rs:154  src/mhl.rs:135
+ *                                                            src/pm.rs:85    src/me.rs:90      src/fdrp.rs:176
+ *                                                            src/qfdrp.rs:188
+ * fed by BismarkRead accessors (src/readutil.rs:55-95).  This header is the boundary a host (the C++ host in
+ * metheor_b200/host, or a Rust host binding these symbols) calls instead of the body of those
+ * loops: the host decodes BAM records + XM tags into structure-of-arrays batches (what BismarkRead::new,
+ * src/readutil.rs:24-53,323-345, produces, AFTER the optional --cpg-set filter of src/readutil.rs:87-95) and the
+ * engine does every per-read / per-CpG / per-quartet / per-read-pair computation on the GPU.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types; every function returns MTH_OK (0) or a negative
+ * mth_status and never aborts; mth_last_error() gives the message.  One caller thread per context; one context
+ * per GPU.  The library refuses to run without a CUDA device (no CPU fallback).
+ */
+#ifndef METHEOR_B200_H
+#define METHEOR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MTH_ABI_VERSION 1
+
+typedef enum {
+    MTH_OK = 0,
+    MTH_ERR_INVALID = -1,      /* bad argument / malformed batch */
+    MTH_ERR_CUDA = -2,         /* CUDA runtime error (no device, out of memory, launch failure) */
+    MTH_ERR_UNSORTED = -3,     /* reads not sorted by (tid, start): the engine requires coordinate-sorted input */
+    MTH_ERR_UNSUPPORTED = -4,  /* input outside the engine's documented limits (see DESIGN.md "Limits") */
+    MTH_ERR_STATE = -5         /* call sequence error (e.g. submit after finish without reset) */
+} mth_status;
+
+/* measure bitmask */
+#define MTH_PDR   (1u << 0)
+#define MTH_LPMD  (1u << 1)
+#define MTH_MHL   (1u << 2)
+#define MTH_PM    (1u << 3)
+#define MTH_ME    (1u << 4)
+#define MTH_FDRP  (1u << 5)
+#define MTH_QFDRP (1u << 6)
+#define MTH_ALL   0x7Fu
+
+/* context flags */
+#define MTH_FLAG_KEEP_ON_DEVICE (1u << 0) /* finish() leaves rows in HBM only (mth_results_device); host pointers NULL */
+#define MTH_FLAG_PROFILE        (1u << 1) /* bracket every kernel with CUDA events; mth_get_stats reports per-kernel ms */
+#define MTH_FLAG_QUARTET_COUNTS (1u << 2) /* also return the 16 pattern counts per PM/ME row */
+#define MTH_FLAG_FORCE_GATHER   (1u << 3) /* PDR: always use the segment-exact gather kernel (testing) */
+
+/* thresholds: one block per reference subcommand, same names/defaults as src/lib.rs:24-231 */
+typedef struct { uint32_t min_depth, min_cpgs, min_qual; } mth_pdr_params;                     /* lib.rs:28-52  (10,4,10) */
+typedef struct { int32_t min_distance, max_distance; uint32_t min_qual, want_pairs; } mth_lpmd_params; /* lib.rs:198-231 (2,16,10) */
+typedef struct { uint32_t min_depth, min_cpgs, min_qual; } mth_mhl_params;                     /* lib.rs:166-192 (10,4,10) */
+typedef struct { uint32_t min_depth, min_qual; } mth_quartet_params;                           /* lib.rs:55-98  (10,10) */
+typedef struct { uint32_t min_qual, min_depth, max_depth; int32_t min_overlap; } mth_fdrp_params; /* lib.rs:101-163 (10,10,40,35) */
+
+typedef struct {
+    uint32_t abi_version; /* MTH_ABI_VERSION */
+    uint32_t measures;    /* MTH_* bitmask */
+    uint32_t flags;       /* MTH_FLAG_* */
+    uint32_t reserved;
+    mth_pdr_params pdr;
+    mth_lpmd_params lpmd;
+    mth_mhl_params mhl;
+    mth_quartet_params pm, me;
+    mth_fdrp_params fdrp, qfdrp;
+    uint64_t seed;        /* reservoir sampling once a pile exceeds max_depth (reference: unseeded, fdrp.rs:90) */
+} mth_params;
+
+void mth_params_default(mth_params* p); /* reference defaults, measures = 0 */
+
+/* One batch of decoded reads of ONE contig, in file order (start ascending).  Replaces the per-record
+ * BismarkRead of src/readutil.rs:15-21.  Arrays are caller-owned and must stay valid until the next
+ * mth_finish()/mth_sync() returns (copies are asynchronous).  mem_kind: 0 = host memory (pinned preferred,
+ * see mth_host_alloc), 1 = device memory on the context's GPU.
+ *   start/end : first / last aligned reference position of the read (readutil.rs:25-33)
+ *   meta      : bits 0-7 mapq (pdr.rs:150), bit 8 = forward strand (informational)
+ *   cpg_off   : n_reads+1 prefix offsets into cpg_pos / cpg_rel, cpg_off[0] == 0
+ *   cpg_pos   : strand-adjusted CpG positions (readutil.rs:332-339), strictly increasing within a read
+ *   cpg_rel   : query index of each CpG (readutil.rs:335); only read when MTH_LPMD is set, may be NULL otherwise
+ *   meth      : packed methylation calls, bit k of a read's word(s) = its k-th CpG is 'Z' (readutil.rs:258)
+ *   meth_off  : n_reads+1 word offsets into meth, or NULL meaning exactly one word per read (needs <= 64 CpGs/read)
+ */
+typedef struct {
+    int32_t tid;
+    int32_t mem_kind;
+    int64_t n_reads;
+    int64_t n_cpg;
+    int64_t n_meth_words; /* length of meth[] in 64-bit words (= n_reads when meth_off is NULL) */
+    const int32_t* start;
+    const int32_t* end;
+    const uint32_t* meta;
+    const uint32_t* cpg_off;
+    const int32_t* cpg_pos;
+    const uint16_t* cpg_rel;
+    const uint64_t* meth;
+    const uint32_t* meth_off;
+} mth_batch;
+
+/* Result rows.  Arrays are owned by the context and valid until the next mth_finish / mth_reset / mth_ctx_destroy. */
+typedef struct {          /* pdr.rs:102-116, mhl.rs:122-131, fdrp.rs:169-172, qfdrp.rs:181-184: sorted by (tid,pos) */
+    int64_t n;
+    const int32_t* tid;
+    const int32_t* pos;
+    const float* value;
+    const uint32_t* n_conc; /* PDR only, else NULL */
+    const uint32_t* n_disc; /* PDR only, else NULL */
+} mth_site_rows;
+
+typedef struct {          /* pm.rs:53-60, me.rs:57-65; sorted by (tid,p1,p2,p3,p4) (reference order is unspecified) */
+    int64_t n;
+    const int32_t* tid;
+    const int32_t* p1;
+    const int32_t* p2;
+    const int32_t* p3;
+    const int32_t* p4;
+    const float* value;
+    const uint32_t* counts; /* n*16 when MTH_FLAG_QUARTET_COUNTS, else NULL */
+} mth_quartet_rows;
+
+typedef struct {          /* lpmd.rs:7-15,51-55 (reference counters are i32; these are int64) */
+    int64_t n_read, n_valid_read, n_conc, n_disc;
+    float lpmd;
+} mth_lpmd_result;
+
+typedef struct {          /* lpmd.rs:89-122 (--pairs), sorted by (tid,pos1,pos2) */
+    int64_t n;
+    const int32_t* tid;
+    const int32_t* pos1;
+    const int32_t* pos2;
+    const float* lpmd;
+    const int32_t* n_conc;
+    const int32_t* n_disc;
+} mth_pair_rows;
+
+typedef struct {
+    mth_site_rows pdr, mhl, fdrp, qfdrp;
+    mth_quartet_rows pm, me;
+    mth_lpmd_result lpmd;
+    mth_pair_rows lpmd_pairs;
+} mth_results;
+
+#define MTH_MAX_KERNEL_STATS 48
+typedef struct {
+    int64_t n_reads, n_cpg, n_sites, n_regions;
+    int64_t kernel_launches;      /* engine kernels launched since create/reset */
+    int64_t h2d_bytes, d2h_bytes; /* bytes copied since create/reset */
+    int32_t max_ref_span;         /* longest end-start+1 seen */
+    int32_t pdr_path;             /* 0 none, 1 scatter (no segment hazard possible), 2 gather */
+    int32_t n_kernel_stats;
+    struct { char name[32]; int64_t launches; double ms; } kernel[MTH_MAX_KERNEL_STATS]; /* MTH_FLAG_PROFILE */
+} mth_stats;
+
+typedef struct mth_ctx mth_ctx;
+
+/* n_ref / ref_len: the BAM reference list (bamutil.rs:13-25), needed to lay contigs out in the device coordinate. */
+int mth_ctx_create(mth_ctx** out, int device, const mth_params* params, int32_t n_ref, const int64_t* ref_len);
+int mth_ctx_destroy(mth_ctx* ctx);
+/* Use `cuda_stream` (a cudaStream_t) for all kernels instead of the context's own stream; NULL restores it. */
+int mth_set_stream(mth_ctx* ctx, void* cuda_stream);
+/* Asynchronous: enqueues the host->device copy on the copy stream and the ingest kernels behind it. */
+int mth_submit(mth_ctx* ctx, const mth_batch* batch);
+/* Host reads that carried no CpG call were dropped before submit: only LPMD's n_read counts them (lpmd.rs:176). */
+int mth_add_skipped_reads(mth_ctx* ctx, int64_t n_reads, int64_t n_reads_mapq_ok);
+/* Closes the input, runs the measure kernels, brings the rows back (unless KEEP_ON_DEVICE) and synchronises. */
+int mth_finish(mth_ctx* ctx, mth_results* out);
+/* Device-resident view of the last results (same struct, device pointers). */
+int mth_results_device(mth_ctx* ctx, mth_results* out);
+/* int64[4] on the device: n_read, n_valid_read, n_conc, n_disc — what a multi-GPU host all-reduces (NCCL sum). */
+int mth_lpmd_counters_device(mth_ctx* ctx, void** dev_ptr);
+/* Recompute the LPMD scalar of the last results from (all-reduced) device counters. */
+int mth_lpmd_refresh(mth_ctx* ctx, mth_lpmd_result* out);
+int mth_reset(mth_ctx* ctx);        /* forget all input and results, keep allocations */
+int mth_sync(mth_ctx* ctx);         /* wait for everything enqueued so far */
+int mth_get_stats(mth_ctx* ctx, mth_stats* out);
+const char* mth_last_error(mth_ctx* ctx); /* ctx may be NULL: last create error */
+
+void* mth_host_alloc(size_t bytes); /* pinned host memory (cudaHostAlloc) or NULL */
+void mth_host_free(void* p);
+int mth_device_count(void);
+const char* mth_version(void);
+
+/* Seeded replacement draw used for reservoir sampling: returns j in 1..=total (documented in DESIGN.md). */
+uint32_t mth_reservoir_draw(uint64_t seed, int32_t tid, int32_t pos, uint32_t total);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* METHEOR_B200_H */

@@ -1,0 +1,130 @@
+"""ctypes binding of libmetheor_b200.so (include/metheor_b200.h).  The library is the product: if it is missing or
+cannot be loaded this module raises — there is no Python/CPU fallback."""
+import ctypes as C
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libmetheor_b200.so")
+
+MTH_PDR, MTH_LPMD, MTH_MHL, MTH_PM, MTH_ME, MTH_FDRP, MTH_QFDRP = (1 << i for i in range(7))
+MTH_ALL = 0x7F
+MEASURE_BITS = dict(pdr=MTH_PDR, lpmd=MTH_LPMD, mhl=MTH_MHL, pm=MTH_PM, me=MTH_ME, fdrp=MTH_FDRP, qfdrp=MTH_QFDRP)
+FLAG_KEEP_ON_DEVICE, FLAG_PROFILE, FLAG_QUARTET_COUNTS, FLAG_FORCE_GATHER = 1, 2, 4, 8
+MTH_OK, ERR_INVALID, ERR_CUDA, ERR_UNSORTED, ERR_UNSUPPORTED, ERR_STATE = 0, -1, -2, -3, -4, -5
+ABI_VERSION = 1
+
+u32, i32, i64, u64, vp = C.c_uint32, C.c_int32, C.c_int64, C.c_uint64, C.c_void_p
+
+
+class PdrParams(C.Structure):
+    _fields_ = [("min_depth", u32), ("min_cpgs", u32), ("min_qual", u32)]
+
+
+class LpmdParams(C.Structure):
+    _fields_ = [("min_distance", i32), ("max_distance", i32), ("min_qual", u32), ("want_pairs", u32)]
+
+
+class MhlParams(C.Structure):
+    _fields_ = [("min_depth", u32), ("min_cpgs", u32), ("min_qual", u32)]
+
+
+class QuartetParams(C.Structure):
+    _fields_ = [("min_depth", u32), ("min_qual", u32)]
+
+
+class FdrpParams(C.Structure):
+    _fields_ = [("min_qual", u32), ("min_depth", u32), ("max_depth", u32), ("min_overlap", i32)]
+
+
+class Params(C.Structure):
+    _fields_ = [("abi_version", u32), ("measures", u32), ("flags", u32), ("reserved", u32), ("pdr", PdrParams),
+                ("lpmd", LpmdParams), ("mhl", MhlParams), ("pm", QuartetParams), ("me", QuartetParams),
+                ("fdrp", FdrpParams), ("qfdrp", FdrpParams), ("seed", u64)]
+
+
+class Batch(C.Structure):
+    _fields_ = [("tid", i32), ("mem_kind", i32), ("n_reads", i64), ("n_cpg", i64), ("n_meth_words", i64),
+                ("start", vp), ("end", vp), ("meta", vp), ("cpg_off", vp), ("cpg_pos", vp), ("cpg_rel", vp),
+                ("meth", vp), ("meth_off", vp)]
+
+
+class SiteRows(C.Structure):
+    _fields_ = [("n", i64), ("tid", vp), ("pos", vp), ("value", vp), ("n_conc", vp), ("n_disc", vp)]
+
+
+class QuartetRows(C.Structure):
+    _fields_ = [("n", i64), ("tid", vp), ("p1", vp), ("p2", vp), ("p3", vp), ("p4", vp), ("value", vp), ("counts", vp)]
+
+
+class LpmdResult(C.Structure):
+    _fields_ = [("n_read", i64), ("n_valid_read", i64), ("n_conc", i64), ("n_disc", i64), ("lpmd", C.c_float)]
+
+
+class PairRows(C.Structure):
+    _fields_ = [("n", i64), ("tid", vp), ("pos1", vp), ("pos2", vp), ("lpmd", vp), ("n_conc", vp), ("n_disc", vp)]
+
+
+class Results(C.Structure):
+    _fields_ = [("pdr", SiteRows), ("mhl", SiteRows), ("fdrp", SiteRows), ("qfdrp", SiteRows), ("pm", QuartetRows),
+                ("me", QuartetRows), ("lpmd", LpmdResult), ("lpmd_pairs", PairRows)]
+
+
+class KernelStat(C.Structure):
+    _fields_ = [("name", C.c_char * 32), ("launches", i64), ("ms", C.c_double)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("n_reads", i64), ("n_cpg", i64), ("n_sites", i64), ("n_regions", i64), ("kernel_launches", i64),
+                ("h2d_bytes", i64), ("d2h_bytes", i64), ("max_ref_span", i32), ("pdr_path", i32),
+                ("n_kernel_stats", i32), ("kernel", KernelStat * 48)]
+
+
+EXPORTS = ["mth_params_default", "mth_ctx_create", "mth_ctx_destroy", "mth_set_stream", "mth_submit",
+           "mth_add_skipped_reads", "mth_finish", "mth_results_device", "mth_lpmd_counters_device", "mth_lpmd_refresh",
+           "mth_reset", "mth_sync", "mth_get_stats", "mth_last_error", "mth_host_alloc", "mth_host_free",
+           "mth_device_count", "mth_version", "mth_reservoir_draw"]
+
+
+def build(force=False):
+    """Compile the CUDA library in-tree (nvcc cross-compiles sm_100a without a GPU)."""
+    if force:
+        subprocess.check_call(["make", "-C", CSRC, "clean"], stdout=subprocess.DEVNULL)
+    subprocess.check_call(["make", "-C", CSRC, "-j8"], stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: build it with `make -C {CSRC}` (python -c 'import __graft_entry__ as g; "
+                           "g.build()'); metheor_b200 has no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    P = C.POINTER
+    L.mth_params_default.argtypes = [P(Params)]; L.mth_params_default.restype = None
+    L.mth_ctx_create.argtypes = [P(vp), C.c_int, P(Params), i32, P(i64)]; L.mth_ctx_create.restype = C.c_int
+    L.mth_ctx_destroy.argtypes = [vp]; L.mth_ctx_destroy.restype = C.c_int
+    L.mth_set_stream.argtypes = [vp, vp]; L.mth_set_stream.restype = C.c_int
+    L.mth_submit.argtypes = [vp, P(Batch)]; L.mth_submit.restype = C.c_int
+    L.mth_add_skipped_reads.argtypes = [vp, i64, i64]; L.mth_add_skipped_reads.restype = C.c_int
+    L.mth_finish.argtypes = [vp, P(Results)]; L.mth_finish.restype = C.c_int
+    L.mth_results_device.argtypes = [vp, P(Results)]; L.mth_results_device.restype = C.c_int
+    L.mth_lpmd_counters_device.argtypes = [vp, P(vp)]; L.mth_lpmd_counters_device.restype = C.c_int
+    L.mth_lpmd_refresh.argtypes = [vp, P(LpmdResult)]; L.mth_lpmd_refresh.restype = C.c_int
+    L.mth_reset.argtypes = [vp]; L.mth_reset.restype = C.c_int
+    L.mth_sync.argtypes = [vp]; L.mth_sync.restype = C.c_int
+    L.mth_get_stats.argtypes = [vp, P(Stats)]; L.mth_get_stats.restype = C.c_int
+    L.mth_last_error.argtypes = [vp]; L.mth_last_error.restype = C.c_char_p
+    L.mth_host_alloc.argtypes = [C.c_size_t]; L.mth_host_alloc.restype = vp
+    L.mth_host_free.argtypes = [vp]; L.mth_host_free.restype = None
+    L.mth_device_count.argtypes = []; L.mth_device_count.restype = C.c_int
+    L.mth_version.argtypes = []; L.mth_version.restype = C.c_char_p
+    L.mth_reservoir_draw.argtypes = [u64, i32, i32, u32]; L.mth_reservoir_draw.restype = u32
+    _lib = L
+    return L

@@ -1,0 +1,74 @@
+"""Helpers around the SoA read batch (the layout of `mth_batch` in include/metheor_b200.h), numpy side."""
+import numpy as np
+
+FIELDS = ("start", "end", "meta", "cpg_off", "cpg_pos", "cpg_rel", "meth", "meth_off")
+
+
+def meth_word_offsets(b):
+    if b.get("meth_off") is not None:
+        return np.asarray(b["meth_off"], np.int64)
+    return np.arange(b["n_reads"] + 1, dtype=np.int64)
+
+
+def unpack_meth(b):
+    """-> uint8[n_cpg] methylation flag per CpG incidence."""
+    off = np.asarray(b["cpg_off"], np.int64)
+    cnt = np.diff(off)
+    ridx = np.repeat(np.arange(b["n_reads"], dtype=np.int64), cnt)
+    k = np.arange(int(off[-1]), dtype=np.int64) - off[ridx]
+    moff = meth_word_offsets(b)
+    w = np.asarray(b["meth"], np.uint64)[moff[ridx] + k // 64]
+    return ((w >> (k % 64).astype(np.uint64)) & np.uint64(1)).astype(np.uint8)
+
+
+def pack_meth(cpg_off, flags):
+    off = np.asarray(cpg_off, np.int64)
+    cnt = np.diff(off)
+    R = len(cnt)
+    words = np.maximum(1, (cnt + 63) // 64)
+    moff = np.zeros(R + 1, np.int64)
+    np.cumsum(words, out=moff[1:])
+    ridx = np.repeat(np.arange(R, dtype=np.int64), cnt)
+    k = np.arange(int(off[-1]), dtype=np.int64) - off[ridx]
+    meth = np.zeros(int(moff[-1]), np.uint64)
+    np.bitwise_or.at(meth, moff[ridx] + k // 64, np.asarray(flags, np.uint64) << (k % 64).astype(np.uint64))
+    return meth, (None if int(words.max(initial=1)) == 1 else moff.astype(np.uint32))
+
+
+def select_reads(b, mask):
+    """Sub-batch keeping reads where mask is True (file order preserved)."""
+    mask = np.asarray(mask, bool)
+    off = np.asarray(b["cpg_off"], np.int64)
+    cnt = np.diff(off)
+    keep_inc = np.repeat(mask, cnt)
+    flags = unpack_meth(b)[keep_inc]
+    new_off = np.zeros(int(mask.sum()) + 1, np.int64)
+    np.cumsum(cnt[mask], out=new_off[1:])
+    meth, moff = pack_meth(new_off, flags)
+    return dict(tid=b["tid"], n_reads=int(mask.sum()), n_cpg=int(new_off[-1]), start=b["start"][mask], end=b["end"][mask],
+                meta=b["meta"][mask], cpg_off=new_off.astype(np.uint32), cpg_pos=b["cpg_pos"][keep_inc],
+                cpg_rel=None if b.get("cpg_rel") is None else b["cpg_rel"][keep_inc], meth=meth, meth_off=moff)
+
+
+def slice_reads(b, lo, hi):
+    m = np.zeros(b["n_reads"], bool)
+    m[lo:hi] = True
+    return select_reads(b, m)
+
+
+def to_oracle_soa(batches):
+    """Concatenate batches (in file order) into the argument dict of tests/oracle_lib.Oracle.from_soa."""
+    tid, start, end, mapq, pos, rel, meth, offs = [], [], [], [], [], [], [], [np.zeros(1, np.int64)]
+    base = 0
+    for b in batches:
+        tid.append(np.full(b["n_reads"], b["tid"], np.int32))
+        start.append(b["start"]); end.append(b["end"]); mapq.append((b["meta"] & 0xFF).astype(np.uint8))
+        pos.append(b["cpg_pos"]); meth.append(unpack_meth(b))
+        rel.append(np.asarray(b["cpg_rel"], np.int32) if b.get("cpg_rel") is not None
+                   else (np.arange(b["n_cpg"], dtype=np.int64) - np.repeat(np.asarray(b["cpg_off"], np.int64)[:-1],
+                                                                            np.diff(np.asarray(b["cpg_off"], np.int64)))).astype(np.int32))
+        offs.append(np.asarray(b["cpg_off"], np.int64)[1:] + base)
+        base += b["n_cpg"]
+    cat = np.concatenate
+    return dict(tid=cat(tid), start=cat(start), end=cat(end), mapq=cat(mapq), cpg_off=cat(offs), cpg_pos=cat(pos),
+                cpg_rel=cat(rel), cpg_meth=cat(meth))

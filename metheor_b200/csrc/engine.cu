@@ -1,0 +1,906 @@
+// engine.cu — host side of libmetheor_b200.so: the C ABI of include/metheor_b200.h, device memory management,
+// stream plumbing and the launch sequence.  No measure arithmetic happens on the host (the one exception is the
+// table of p*log2f(p) values built once per context so that ME matches the host libm bit for bit, see k_quartet.cu).
+//
+// Data flow:
+//   mth_submit : H2D copy of the SoA batch on the copy stream  ->  [offset / coordinate fix-ups]  ->  k_ingest
+//                (validation, site bitmap, LPMD) on the compute stream, ordered by an event.
+//   region close (contig set full, or mth_finish): bitmap -> site dictionary -> one kernel family per measure ->
+//                row counts -> exclusive scan -> row emission into device row buffers.
+//   mth_finish : D2H of the rows into pinned buffers owned by the context.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+
+using namespace mth;
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+struct HostBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct SiteRowsBuf {
+    DevBuf tid, pos, value, nc, nd;
+    HostBuf h_tid, h_pos, h_value, h_nc, h_nd;
+    int64_t n = 0;
+};
+struct QuartetRowsBuf {
+    DevBuf tid, p1, p2, p3, p4, value, counts;
+    HostBuf h_tid, h_p1, h_p2, h_p3, h_p4, h_value, h_counts;
+    int64_t n = 0;
+};
+
+struct ProfSpan {
+    const char* name;
+    cudaEvent_t e0, e1;
+    int launches;
+};
+
+enum { M_PDR = 0, M_MHL, M_FDRP, M_QFDRP, M_PM, M_ME, M_COUNT };
+
+}  // namespace
+
+struct mth_ctx {
+    int device = 0;
+    mth_params prm;
+    std::vector<int64_t> ref_len;
+    cudaStream_t own_compute = nullptr, copy = nullptr, compute = nullptr;
+    cudaEvent_t ev_copy = nullptr, ev_compute = nullptr;
+    std::string err;
+    int finished = 0;
+
+    // region state
+    bool region_active = false;
+    int32_t last_tid = -1;
+    int32_t cur_lin_off = 0;
+    int64_t R = 0, I = 0, W = 0;
+    bool borrowed = false;
+    mth_batch bview;  // borrowed device pointers
+    bool has_meth_off = false;
+    std::vector<int32_t> reg_lin_off, reg_tid;
+
+    // arena
+    DevBuf a_start, a_end, a_meta, a_off, a_pos, a_rel, a_meth, a_moff;
+    DevBuf bitmap, word_prefix, block_sums, site_pos, scalars, totals, ct_lin, ct_tid;
+    DevBuf cnt2, scan_scratch, fdrp_scratch, me_lut, lpmd_total;
+    DevBuf rowcnt[M_COUNT], value[M_COUNT];
+    size_t bitmap_words_valid = 0;
+    HostBuf h_scalars, h_totals;
+
+    SiteRowsBuf rows_pdr, rows_mhl, rows_fdrp, rows_qfdrp;
+    QuartetRowsBuf rows_pm, rows_me;
+    int64_t lpmd_total_host[4] = {0, 0, 0, 0};
+    int me_lut_max = 0;
+
+    mth_stats stats;
+    std::vector<ProfSpan> spans;
+    std::vector<cudaEvent_t> ev_pool;
+};
+
+static std::string g_create_err;
+
+#define CUDA_TRY(ctx, call)                                                                             \
+    do {                                                                                                \
+        cudaError_t _e = (call);                                                                        \
+        if (_e != cudaSuccess) {                                                                        \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(_e);                            \
+            return MTH_ERR_CUDA;                                                                        \
+        }                                                                                               \
+    } while (0)
+
+#define TRY(expr)                      \
+    do {                               \
+        int _rc = (expr);              \
+        if (_rc != MTH_OK) return _rc; \
+    } while (0)
+
+static int fail(mth_ctx* c, int code, const std::string& msg) {
+    c->err = msg;
+    return code;
+}
+
+// ---- memory helpers ----------------------------------------------------------------------------
+static int dev_reserve(mth_ctx* c, DevBuf& b, size_t bytes, size_t keep_bytes) {
+    if (bytes <= b.cap) return MTH_OK;
+    size_t ncap = bytes + bytes / 2 + 256;
+    void* np = nullptr;
+    // pending async work may still touch the old allocation
+    CUDA_TRY(c, cudaStreamSynchronize(c->copy));
+    CUDA_TRY(c, cudaStreamSynchronize(c->compute));
+    cudaError_t e = cudaMalloc(&np, ncap);
+    if (e != cudaSuccess) {
+        ncap = bytes;
+        CUDA_TRY(c, cudaMalloc(&np, ncap));
+    }
+    if (b.p && keep_bytes) CUDA_TRY(c, cudaMemcpy(np, b.p, keep_bytes, cudaMemcpyDeviceToDevice));
+    if (b.p) CUDA_TRY(c, cudaFree(b.p));
+    b.p = np;
+    b.cap = ncap;
+    return MTH_OK;
+}
+static int host_reserve(mth_ctx* c, HostBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return MTH_OK;
+    if (b.p) CUDA_TRY(c, cudaFreeHost(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    size_t ncap = bytes + bytes / 4 + 256;
+    CUDA_TRY(c, cudaHostAlloc(&b.p, ncap, cudaHostAllocDefault));
+    b.cap = ncap;
+    return MTH_OK;
+}
+static void dev_free(DevBuf& b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+static void host_free(HostBuf& b) {
+    if (b.p) cudaFreeHost(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+// ---- profiling -----------------------------------------------------------------------------------
+static cudaEvent_t get_event(mth_ctx* c) {
+    if (!c->ev_pool.empty()) {
+        cudaEvent_t e = c->ev_pool.back();
+        c->ev_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+struct ProfScope {
+    mth_ctx* c;
+    ProfSpan sp;
+    bool on;
+    ProfScope(mth_ctx* ctx, const char* name) : c(ctx) {
+        on = (c->prm.flags & MTH_FLAG_PROFILE) != 0;
+        sp.name = name;
+        sp.launches = 0;
+        if (on) {
+            sp.e0 = get_event(c);
+            sp.e1 = get_event(c);
+            cudaEventRecord(sp.e0, c->compute);
+        }
+    }
+    void add(int n) {
+        sp.launches += n;
+        c->stats.kernel_launches += n;
+    }
+    ~ProfScope() {
+        if (on) {
+            cudaEventRecord(sp.e1, c->compute);
+            c->spans.push_back(sp);
+        }
+    }
+};
+static void resolve_spans(mth_ctx* c) {
+    for (auto& sp : c->spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, sp.e0, sp.e1) != cudaSuccess) ms = 0.f;
+        int k = -1;
+        for (int i = 0; i < c->stats.n_kernel_stats; i++)
+            if (!strcmp(c->stats.kernel[i].name, sp.name)) k = i;
+        if (k < 0 && c->stats.n_kernel_stats < MTH_MAX_KERNEL_STATS) {
+            k = c->stats.n_kernel_stats++;
+            strncpy(c->stats.kernel[k].name, sp.name, sizeof(c->stats.kernel[k].name) - 1);
+            c->stats.kernel[k].launches = 0;
+            c->stats.kernel[k].ms = 0;
+        }
+        if (k >= 0) {
+            c->stats.kernel[k].launches += sp.launches;
+            c->stats.kernel[k].ms += ms;
+        }
+        c->ev_pool.push_back(sp.e0);
+        c->ev_pool.push_back(sp.e1);
+    }
+    c->spans.clear();
+}
+
+// ---- region management ---------------------------------------------------------------------------
+static ReadsView make_view(mth_ctx* c) {
+    ReadsView v;
+    if (c->borrowed) {
+        v.start = c->bview.start; v.end = c->bview.end; v.meta = c->bview.meta; v.cpg_off = c->bview.cpg_off;
+        v.cpg_pos = c->bview.cpg_pos; v.meth = c->bview.meth; v.meth_off = c->bview.meth_off;
+    } else {
+        v.start = (const int32_t*)c->a_start.p; v.end = (const int32_t*)c->a_end.p; v.meta = (const uint32_t*)c->a_meta.p;
+        v.cpg_off = (const uint32_t*)c->a_off.p; v.cpg_pos = (const int32_t*)c->a_pos.p;
+        v.meth = (const uint64_t*)c->a_meth.p; v.meth_off = c->has_meth_off ? (const uint32_t*)c->a_moff.p : nullptr;
+    }
+    v.R = c->R;
+    v.I = c->I;
+    return v;
+}
+
+static int add_contig(mth_ctx* c, int32_t tid, int32_t lin_off) {
+    c->reg_lin_off.push_back(lin_off);
+    c->reg_tid.push_back(tid);
+    c->cur_lin_off = lin_off;
+    c->last_tid = tid;
+    // bits (p+1) for p in [lin_off-1, lin_off+len): words covering [lin_off, lin_off+len+1]
+    size_t w0 = (size_t)lin_off >> 6;
+    size_t w1 = (((size_t)lin_off + (size_t)c->ref_len[tid] + 2) >> 6) + 1;
+    TRY(dev_reserve(c, c->bitmap, w1 * 8, c->bitmap_words_valid * 8));
+    CUDA_TRY(c, cudaMemsetAsync((char*)c->bitmap.p + w0 * 8, 0, (w1 - w0) * 8, c->compute));
+    c->bitmap_words_valid = w1;
+    return MTH_OK;
+}
+
+static int begin_region(mth_ctx* c, int32_t tid) {
+    c->region_active = true;
+    c->R = c->I = c->W = 0;
+    c->borrowed = false;
+    c->has_meth_off = false;
+    c->reg_lin_off.clear();
+    c->reg_tid.clear();
+    c->bitmap_words_valid = 0;
+    TRY(dev_reserve(c, c->scalars, sizeof(RegionScalars), 0));
+    RegionScalars init;
+    memset(&init, 0, sizeof(init));
+    TRY(host_reserve(c, c->h_scalars, 2 * sizeof(RegionScalars)));
+    memcpy((char*)c->h_scalars.p + sizeof(RegionScalars), &init, sizeof(init));
+    CUDA_TRY(c, cudaMemcpyAsync(c->scalars.p, (char*)c->h_scalars.p + sizeof(RegionScalars), sizeof(init),
+                                cudaMemcpyHostToDevice, c->compute));
+    return add_contig(c, tid, 0);
+}
+
+static int ensure_arena(mth_ctx* c, int64_t R, int64_t I, int64_t W, bool need_rel, bool need_moff) {
+    TRY(dev_reserve(c, c->a_start, (size_t)R * 4, (size_t)c->R * 4));
+    TRY(dev_reserve(c, c->a_end, (size_t)R * 4, (size_t)c->R * 4));
+    TRY(dev_reserve(c, c->a_meta, (size_t)R * 4, (size_t)c->R * 4));
+    TRY(dev_reserve(c, c->a_off, (size_t)(R + 1) * 4, (size_t)(c->R + 1) * 4));
+    TRY(dev_reserve(c, c->a_pos, (size_t)I * 4 + 4, (size_t)c->I * 4));
+    TRY(dev_reserve(c, c->a_meth, (size_t)W * 8 + 8, (size_t)c->W * 8));
+    if (need_rel) TRY(dev_reserve(c, c->a_rel, (size_t)I * 2 + 2, (size_t)c->I * 2));
+    if (need_moff) TRY(dev_reserve(c, c->a_moff, (size_t)(R + 1) * 4, (size_t)(c->R + 1) * 4));
+    return MTH_OK;
+}
+
+static int64_t batch_words(const mth_batch* b) { return b->meth_off ? b->n_meth_words : b->n_reads; }
+
+// copy a borrowed single-batch region into the arena so that more batches can be appended
+static int materialize(mth_ctx* c) {
+    if (!c->borrowed) return MTH_OK;
+    const mth_batch& b = c->bview;
+    bool lp = (c->prm.measures & MTH_LPMD) != 0;
+    c->borrowed = false;
+    int64_t R = c->R, I = c->I, W = c->W;
+    c->R = c->I = c->W = 0;  // nothing to preserve
+    TRY(ensure_arena(c, R, I, W, lp, c->has_meth_off));
+    c->R = R; c->I = I; c->W = W;
+    cudaStream_t s = c->compute;
+    CUDA_TRY(c, cudaMemcpyAsync(c->a_start.p, b.start, (size_t)R * 4, cudaMemcpyDeviceToDevice, s));
+    CUDA_TRY(c, cudaMemcpyAsync(c->a_end.p, b.end, (size_t)R * 4, cudaMemcpyDeviceToDevice, s));
+    CUDA_TRY(c, cudaMemcpyAsync(c->a_meta.p, b.meta, (size_t)R * 4, cudaMemcpyDeviceToDevice, s));
+    CUDA_TRY(c, cudaMemcpyAsync(c->a_off.p, b.cpg_off, (size_t)(R + 1) * 4, cudaMemcpyDeviceToDevice, s));
+    CUDA_TRY(c, cudaMemcpyAsync(c->a_pos.p, b.cpg_pos, (size_t)I * 4, cudaMemcpyDeviceToDevice, s));
+    CUDA_TRY(c, cudaMemcpyAsync(c->a_meth.p, b.meth, (size_t)W * 8, cudaMemcpyDeviceToDevice, s));
+    if (c->has_meth_off)
+        CUDA_TRY(c, cudaMemcpyAsync(c->a_moff.p, b.meth_off, (size_t)(R + 1) * 4, cudaMemcpyDeviceToDevice, s));
+    return MTH_OK;
+}
+
+static int process_region(mth_ctx* c);
+
+static int check_scalars_err(mth_ctx* c, uint32_t e) {
+    if (!e) return MTH_OK;
+    if (e & ERRBIT_UNSORTED) return fail(c, MTH_ERR_UNSORTED, "reads are not sorted by start position within a contig");
+    if (e & ERRBIT_BAD_OFFSETS) return fail(c, MTH_ERR_INVALID, "cpg_off / meth_off are not monotone prefix offsets");
+    if (e & ERRBIT_TOO_MANY_CPGS)
+        return fail(c, MTH_ERR_UNSUPPORTED, "a read carries more CpG calls than supported (64 without meth_off, 256 with)");
+    if (e & ERRBIT_CPG_ORDER) return fail(c, MTH_ERR_INVALID, "cpg_pos not strictly increasing within a read");
+    if (e & ERRBIT_SPAN) return fail(c, MTH_ERR_UNSUPPORTED, "read reference span < 1 or > 65024 bp");
+    if (e & ERRBIT_POS_RANGE)
+        return fail(c, MTH_ERR_INVALID, "read or CpG position outside its contig / CpG outside [start-1, end]");
+    if (e & ERRBIT_PILE_OVERFLOW) return fail(c, MTH_ERR_UNSUPPORTED, "FDRP pile scratch overflow");
+    return fail(c, MTH_ERR_INVALID, "device-side validation failed");
+}
+
+// ---- C ABI -----------------------------------------------------------------------------------------
+extern "C" {
+
+void mth_params_default(mth_params* p) {
+    memset(p, 0, sizeof(*p));
+    p->abi_version = MTH_ABI_VERSION;
+    p->pdr = {10, 4, 10};
+    p->lpmd = {2, 16, 10, 0};
+    p->mhl = {10, 4, 10};
+    p->pm = {10, 10};
+    p->me = {10, 10};
+    p->fdrp = {10, 10, 40, 35};
+    p->qfdrp = {10, 10, 40, 35};
+    p->seed = 0;
+}
+
+const char* mth_version(void) { return "metheor_b200 0.1.0 (sm_100a)"; }
+
+int mth_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+void* mth_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void mth_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+uint32_t mth_reservoir_draw(uint64_t seed, int32_t tid, int32_t pos, uint32_t total) {
+    return reservoir_draw(seed, tid, pos, total);
+}
+
+const char* mth_last_error(mth_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int mth_ctx_create(mth_ctx** out, int device, const mth_params* params, int32_t n_ref, const int64_t* ref_len) {
+    if (!out || !params || n_ref < 0 || (n_ref > 0 && !ref_len)) { g_create_err = "null argument"; return MTH_ERR_INVALID; }
+    *out = nullptr;
+    if (params->abi_version != MTH_ABI_VERSION) { g_create_err = "mth_params.abi_version mismatch"; return MTH_ERR_INVALID; }
+    if (params->measures & ~MTH_ALL) { g_create_err = "unknown measure bits"; return MTH_ERR_INVALID; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_err = std::string("no CUDA device available (the engine has no CPU fallback): ") + cudaGetErrorString(e);
+        return MTH_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) { g_create_err = "device index out of range"; return MTH_ERR_INVALID; }
+    for (int32_t i = 0; i < n_ref; i++)
+        if (ref_len[i] < 0 || ref_len[i] > (int64_t)INT32_MAX - 4 * CONTIG_GAP) {
+            g_create_err = "contig length outside the supported range (< 2^31 - 2^18)";
+            return MTH_ERR_UNSUPPORTED;
+        }
+    if ((params->measures & (MTH_FDRP)) && params->fdrp.max_depth == 0) { g_create_err = "fdrp.max_depth must be >= 1"; return MTH_ERR_INVALID; }
+    if ((params->measures & (MTH_QFDRP)) && params->qfdrp.max_depth == 0) { g_create_err = "qfdrp.max_depth must be >= 1"; return MTH_ERR_INVALID; }
+    mth_ctx* c = new mth_ctx();
+    c->device = device;
+    c->prm = *params;
+    c->ref_len.assign(ref_len, ref_len + n_ref);
+    memset(&c->stats, 0, sizeof(c->stats));
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->own_compute, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_compute, cudaEventDisableTiming) != cudaSuccess) {
+        g_create_err = std::string("CUDA initialisation failed: ") + cudaGetErrorString(cudaGetLastError());
+        delete c;
+        return MTH_ERR_CUDA;
+    }
+    c->compute = c->own_compute;
+    *out = c;
+    return MTH_OK;
+}
+
+int mth_ctx_destroy(mth_ctx* c) {
+    if (!c) return MTH_OK;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    DevBuf* devs[] = {&c->a_start, &c->a_end, &c->a_meta, &c->a_off, &c->a_pos, &c->a_rel, &c->a_meth, &c->a_moff, &c->bitmap,
+                      &c->word_prefix, &c->block_sums, &c->site_pos, &c->scalars, &c->totals, &c->ct_lin, &c->ct_tid, &c->cnt2,
+                      &c->scan_scratch, &c->fdrp_scratch, &c->me_lut, &c->lpmd_total};
+    for (DevBuf* b : devs) dev_free(*b);
+    for (int m = 0; m < M_COUNT; m++) { dev_free(c->rowcnt[m]); dev_free(c->value[m]); }
+    for (SiteRowsBuf* r : {&c->rows_pdr, &c->rows_mhl, &c->rows_fdrp, &c->rows_qfdrp}) {
+        dev_free(r->tid); dev_free(r->pos); dev_free(r->value); dev_free(r->nc); dev_free(r->nd);
+        host_free(r->h_tid); host_free(r->h_pos); host_free(r->h_value); host_free(r->h_nc); host_free(r->h_nd);
+    }
+    for (QuartetRowsBuf* r : {&c->rows_pm, &c->rows_me}) {
+        dev_free(r->tid); dev_free(r->p1); dev_free(r->p2); dev_free(r->p3); dev_free(r->p4); dev_free(r->value); dev_free(r->counts);
+        host_free(r->h_tid); host_free(r->h_p1); host_free(r->h_p2); host_free(r->h_p3); host_free(r->h_p4);
+        host_free(r->h_value); host_free(r->h_counts);
+    }
+    host_free(c->h_scalars);
+    host_free(c->h_totals);
+    for (auto& sp : c->spans) { cudaEventDestroy(sp.e0); cudaEventDestroy(sp.e1); }
+    for (auto e : c->ev_pool) cudaEventDestroy(e);
+    if (c->ev_copy) cudaEventDestroy(c->ev_copy);
+    if (c->ev_compute) cudaEventDestroy(c->ev_compute);
+    if (c->own_compute) cudaStreamDestroy(c->own_compute);
+    if (c->copy) cudaStreamDestroy(c->copy);
+    delete c;
+    return MTH_OK;
+}
+
+int mth_set_stream(mth_ctx* c, void* cuda_stream) {
+    if (!c) return MTH_ERR_INVALID;
+    CUDA_TRY(c, cudaStreamSynchronize(c->compute));
+    c->compute = cuda_stream ? (cudaStream_t)cuda_stream : c->own_compute;
+    return MTH_OK;
+}
+
+int mth_sync(mth_ctx* c) {
+    if (!c) return MTH_ERR_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, cudaStreamSynchronize(c->copy));
+    CUDA_TRY(c, cudaStreamSynchronize(c->compute));
+    return MTH_OK;
+}
+
+int mth_reset(mth_ctx* c) {
+    if (!c) return MTH_ERR_INVALID;
+    TRY(mth_sync(c));
+    c->region_active = false;
+    c->finished = 0;
+    c->R = c->I = c->W = 0;
+    c->borrowed = false;
+    c->last_tid = -1;
+    c->rows_pdr.n = c->rows_mhl.n = c->rows_fdrp.n = c->rows_qfdrp.n = 0;
+    c->rows_pm.n = c->rows_me.n = 0;
+    memset(c->lpmd_total_host, 0, sizeof(c->lpmd_total_host));
+    resolve_spans(c);
+    memset(&c->stats, 0, sizeof(c->stats));
+    c->err.clear();
+    return MTH_OK;
+}
+
+int mth_add_skipped_reads(mth_ctx* c, int64_t n_reads, int64_t n_reads_mapq_ok) {
+    if (!c || n_reads < 0 || n_reads_mapq_ok < 0) return MTH_ERR_INVALID;
+    c->lpmd_total_host[0] += n_reads;
+    c->lpmd_total_host[1] += n_reads_mapq_ok;
+    return MTH_OK;
+}
+
+int mth_submit(mth_ctx* c, const mth_batch* b) {
+    if (!c || !b) return MTH_ERR_INVALID;
+    if (c->finished) return fail(c, MTH_ERR_STATE, "mth_submit after mth_finish (call mth_reset first)");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (b->n_reads < 0 || b->n_cpg < 0) return fail(c, MTH_ERR_INVALID, "negative batch size");
+    if (b->n_reads == 0) return MTH_OK;
+    if (b->tid < 0 || (size_t)b->tid >= c->ref_len.size()) return fail(c, MTH_ERR_INVALID, "batch tid outside the reference list");
+    if (!b->start || !b->end || !b->meta || !b->cpg_off || (b->n_cpg && !b->cpg_pos) || !b->meth)
+        return fail(c, MTH_ERR_INVALID, "null array in batch");
+    bool lp = (c->prm.measures & MTH_LPMD) != 0;
+    if (lp && b->n_cpg && !b->cpg_rel) return fail(c, MTH_ERR_INVALID, "cpg_rel is required when MTH_LPMD is requested");
+    if (b->mem_kind != 0 && b->mem_kind != 1) return fail(c, MTH_ERR_INVALID, "mem_kind must be 0 (host) or 1 (device)");
+    if (b->n_reads > (int64_t)INT32_MAX - 64 || b->n_cpg > (int64_t)UINT32_MAX - 64)
+        return fail(c, MTH_ERR_UNSUPPORTED, "batch too large (reads < 2^31, CpG calls < 2^32)");
+    int64_t bw = batch_words(b);
+    if (bw < b->n_reads && b->meth_off == nullptr) return fail(c, MTH_ERR_INVALID, "n_meth_words inconsistent");
+
+    if (c->region_active) {
+        if (b->tid < c->last_tid) return fail(c, MTH_ERR_UNSORTED, "contigs must arrive in ascending tid order (coordinate-sorted input)");
+        if (b->tid != c->last_tid) {
+            int64_t noff = (((int64_t)c->cur_lin_off + c->ref_len[c->last_tid] + CONTIG_GAP) + 63) & ~63ll;
+            bool fits = noff + c->ref_len[b->tid] + 64 < (int64_t)INT32_MAX && c->I + b->n_cpg < (int64_t)UINT32_MAX - 64 &&
+                        c->R + b->n_reads < (int64_t)INT32_MAX - 64 && c->W + bw < (int64_t)UINT32_MAX - 64;
+            if (fits) {
+                TRY(materialize(c));
+                TRY(add_contig(c, b->tid, (int32_t)noff));
+            } else {
+                TRY(process_region(c));
+            }
+        } else if (c->I + b->n_cpg >= (int64_t)UINT32_MAX - 64 || c->R + b->n_reads >= (int64_t)INT32_MAX - 64) {
+            return fail(c, MTH_ERR_UNSUPPORTED, "a single contig holds more than 2^32 CpG calls / 2^31 reads");
+        }
+    }
+    if (!c->region_active) TRY(begin_region(c, b->tid));
+
+    const int32_t lin_off = c->cur_lin_off;
+    const int64_t r0 = c->R, i0 = c->I, w0 = c->W;
+    const bool can_borrow = b->mem_kind == 1 && r0 == 0 && lin_off == 0;
+    const uint16_t* rel_dev = nullptr;
+    if (can_borrow) {
+        c->borrowed = true;
+        c->bview = *b;
+        c->has_meth_off = b->meth_off != nullptr;
+        rel_dev = b->cpg_rel;
+    } else {
+        TRY(materialize(c));
+        bool need_moff = c->has_meth_off || b->meth_off != nullptr;
+        TRY(ensure_arena(c, r0 + b->n_reads, i0 + b->n_cpg, w0 + bw, lp, need_moff));
+        cudaStream_t cs = c->copy;
+        // Batch k+1 only writes arena slots that no in-flight kernel of batch k reads: the shared terminal offset
+        // a_off[r0] (== i0 after fix-up) is NOT rewritten — the copy skips the batch's own leading 0.
+        if (b->mem_kind == 0 && (b->cpg_off[0] != 0 || (b->meth_off && b->meth_off[0] != 0)))
+            return fail(c, MTH_ERR_INVALID, "cpg_off[0] / meth_off[0] must be 0");
+        cudaMemcpyKind kind = b->mem_kind == 0 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+        size_t nR = (size_t)b->n_reads, nI = (size_t)b->n_cpg;
+        size_t skip = r0 ? 1 : 0;
+        CUDA_TRY(c, cudaMemcpyAsync((int32_t*)c->a_start.p + r0, b->start, nR * 4, kind, cs));
+        CUDA_TRY(c, cudaMemcpyAsync((int32_t*)c->a_end.p + r0, b->end, nR * 4, kind, cs));
+        CUDA_TRY(c, cudaMemcpyAsync((uint32_t*)c->a_meta.p + r0, b->meta, nR * 4, kind, cs));
+        CUDA_TRY(c, cudaMemcpyAsync((uint32_t*)c->a_off.p + r0 + skip, b->cpg_off + skip, (nR + 1 - skip) * 4, kind, cs));
+        if (nI) CUDA_TRY(c, cudaMemcpyAsync((int32_t*)c->a_pos.p + i0, b->cpg_pos, nI * 4, kind, cs));
+        CUDA_TRY(c, cudaMemcpyAsync((uint64_t*)c->a_meth.p + w0, b->meth, (size_t)bw * 8, kind, cs));
+        if (lp && nI) CUDA_TRY(c, cudaMemcpyAsync((uint16_t*)c->a_rel.p + i0, b->cpg_rel, nI * 2, kind, cs));
+        if (b->meth_off)
+            CUDA_TRY(c, cudaMemcpyAsync((uint32_t*)c->a_moff.p + r0 + skip, b->meth_off + skip, (nR + 1 - skip) * 4, kind, cs));
+        if (b->mem_kind == 0)
+            c->stats.h2d_bytes += (int64_t)(nR * 16 + 4 + nI * (lp ? 6 : 4) + (size_t)bw * 8 + (b->meth_off ? (nR + 1) * 4 : 0));
+        CUDA_TRY(c, cudaEventRecord(c->ev_copy, cs));
+        CUDA_TRY(c, cudaStreamWaitEvent(c->compute, c->ev_copy, 0));
+        {
+            ProfScope ps(c, "fixup");
+            if (i0) ps.add(launch_add_u32((uint32_t*)c->a_off.p + r0 + 1, b->n_reads, (uint32_t)i0, c->compute));
+            if (need_moff) {
+                // reads ingested before the first batch that carried meth_off had one word each
+                if (!c->has_meth_off && r0) ps.add(launch_iota_u32((uint32_t*)c->a_moff.p, r0 + 1, 0, c->compute));
+                if (b->meth_off) {
+                    if (w0) ps.add(launch_add_u32((uint32_t*)c->a_moff.p + r0 + skip, b->n_reads + 1 - (int64_t)skip, (uint32_t)w0, c->compute));
+                } else {
+                    ps.add(launch_iota_u32((uint32_t*)c->a_moff.p + r0 + skip, b->n_reads + 1 - (int64_t)skip, (uint32_t)(w0 + skip), c->compute));
+                }
+                c->has_meth_off = true;
+            }
+            if (lin_off) {
+                ps.add(launch_add_i32((int32_t*)c->a_start.p + r0, b->n_reads, lin_off, c->compute));
+                ps.add(launch_add_i32((int32_t*)c->a_end.p + r0, b->n_reads, lin_off, c->compute));
+                ps.add(launch_add_i32((int32_t*)c->a_pos.p + i0, b->n_cpg, lin_off, c->compute));
+            }
+        }
+        rel_dev = lp ? (const uint16_t*)c->a_rel.p + i0 : nullptr;
+    }
+    c->R = r0 + b->n_reads;
+    c->I = i0 + b->n_cpg;
+    c->W = w0 + bw;
+
+    IngestArgs ia;
+    ia.rv = make_view(c);
+    ia.r0 = r0;
+    ia.n = b->n_reads;
+    ia.i0 = i0;
+    ia.cpg_rel = rel_dev;
+    ia.bitmap = (unsigned long long*)c->bitmap.p;
+    ia.lin_lo = lin_off;
+    ia.lin_hi = lin_off + (int32_t)c->ref_len[b->tid];
+    ia.do_lpmd = lp ? 1 : 0;
+    ia.lpmd = c->prm.lpmd;
+    ia.sc = (RegionScalars*)c->scalars.p;
+    {
+        ProfScope ps(c, "k_ingest");
+        ps.add(launch_ingest(ia, c->compute));
+    }
+    CUDA_TRY(c, cudaGetLastError());
+    c->stats.n_reads += b->n_reads;
+    c->stats.n_cpg += b->n_cpg;
+    return MTH_OK;
+}
+
+}  // extern "C"
+
+// ---- per-region processing -------------------------------------------------------------------------
+static int reserve_site_rows(mth_ctx* c, SiteRowsBuf& r, int64_t n, bool counts) {
+    TRY(dev_reserve(c, r.tid, (size_t)n * 4 + 4, (size_t)r.n * 4));
+    TRY(dev_reserve(c, r.pos, (size_t)n * 4 + 4, (size_t)r.n * 4));
+    TRY(dev_reserve(c, r.value, (size_t)n * 4 + 4, (size_t)r.n * 4));
+    if (counts) {
+        TRY(dev_reserve(c, r.nc, (size_t)n * 4 + 4, (size_t)r.n * 4));
+        TRY(dev_reserve(c, r.nd, (size_t)n * 4 + 4, (size_t)r.n * 4));
+    }
+    return MTH_OK;
+}
+static int reserve_quartet_rows(mth_ctx* c, QuartetRowsBuf& r, int64_t n, bool counts) {
+    for (DevBuf* b : {&r.tid, &r.p1, &r.p2, &r.p3, &r.p4, &r.value}) TRY(dev_reserve(c, *b, (size_t)n * 4 + 4, (size_t)r.n * 4));
+    if (counts) TRY(dev_reserve(c, r.counts, (size_t)n * 64 + 64, (size_t)r.n * 64));
+    return MTH_OK;
+}
+static SiteRowsDev site_rows_dev(SiteRowsBuf& r) {
+    return SiteRowsDev{(int32_t*)r.tid.p, (int32_t*)r.pos.p, (float*)r.value.p, (uint32_t*)r.nc.p, (uint32_t*)r.nd.p};
+}
+static QuartetRowsDev quartet_rows_dev(QuartetRowsBuf& r) {
+    return QuartetRowsDev{(int32_t*)r.tid.p, (int32_t*)r.p1.p, (int32_t*)r.p2.p, (int32_t*)r.p3.p, (int32_t*)r.p4.p,
+                          (float*)r.value.p, (uint32_t*)r.counts.p};
+}
+
+static int build_me_lut(mth_ctx* c) {
+    if (c->me_lut.p) return MTH_OK;
+    // lut[t*(t+1)/2 + k] = p * log2f(p), p = k as f32 / t as f32 (me.rs:47-50), from the HOST libm so that the
+    // device result equals what the reference binary prints on this machine; totals > LUT_MAX use k_quartet's own log2.
+    const int LUT_MAX = 1024;
+    size_t n = (size_t)(LUT_MAX + 1) * (LUT_MAX + 2) / 2;
+    std::vector<float> lut(n, 0.f);
+    for (int t = 1; t <= LUT_MAX; t++)
+        for (int k = 1; k <= t; k++) {
+            volatile float p = (float)k / (float)t;
+            volatile float lg = log2f(p);
+            volatile float v = p * lg;
+            lut[(size_t)t * (t + 1) / 2 + k] = v;
+        }
+    TRY(dev_reserve(c, c->me_lut, n * 4, 0));
+    CUDA_TRY(c, cudaMemcpy(c->me_lut.p, lut.data(), n * 4, cudaMemcpyHostToDevice));
+    c->me_lut_max = LUT_MAX;
+    return MTH_OK;
+}
+
+static int process_region(mth_ctx* c) {
+    if (!c->region_active) return MTH_OK;
+    cudaStream_t s = c->compute;
+    const uint32_t M = c->prm.measures;
+    ReadsView rv = make_view(c);
+    RegionScalars* d_sc = (RegionScalars*)c->scalars.p;
+    const bool need_sites = (M & (MTH_PDR | MTH_MHL | MTH_PM | MTH_ME | MTH_FDRP | MTH_QFDRP)) != 0;
+
+    int64_t n_words = (int64_t)c->bitmap_words_valid;
+    int64_t nb = (n_words + 1023) / 1024 + 1;
+    if (need_sites) {
+        TRY(dev_reserve(c, c->block_sums, (size_t)nb * 4, 0));
+        TRY(dev_reserve(c, c->word_prefix, (size_t)n_words * 4 + 4, 0));
+        ProfScope ps(c, "k_sites_count");
+        ps.add(launch_sites_count((const unsigned long long*)c->bitmap.p, n_words, (uint32_t*)c->block_sums.p, d_sc, s));
+    }
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_scalars.p, d_sc, sizeof(RegionScalars), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(c, cudaStreamSynchronize(s));
+    RegionScalars sc = *(RegionScalars*)c->h_scalars.p;
+    TRY(check_scalars_err(c, sc.err));
+    for (int k = 0; k < 4; k++) c->lpmd_total_host[k] += (int64_t)sc.lpmd[k];
+    if (sc.lmax > c->stats.max_ref_span) c->stats.max_ref_span = sc.lmax;
+    const int64_t C = need_sites ? (int64_t)sc.n_sites : 0;
+    c->stats.n_sites += C;
+    c->stats.n_regions += 1;
+
+    if (C > 0) {
+        TRY(dev_reserve(c, c->site_pos, (size_t)C * 4, 0));
+        {
+            ProfScope ps(c, "k_sites_emit");
+            ps.add(launch_sites_emit((const unsigned long long*)c->bitmap.p, n_words, (const uint32_t*)c->block_sums.p,
+                                     (uint32_t*)c->word_prefix.p, (int32_t*)c->site_pos.p, s));
+        }
+        // contig table
+        size_t nct = c->reg_tid.size();
+        TRY(dev_reserve(c, c->ct_lin, nct * 4, 0));
+        TRY(dev_reserve(c, c->ct_tid, nct * 4, 0));
+        CUDA_TRY(c, cudaMemcpyAsync(c->ct_lin.p, c->reg_lin_off.data(), nct * 4, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(c, cudaMemcpyAsync(c->ct_tid.p, c->reg_tid.data(), nct * 4, cudaMemcpyHostToDevice, s));
+        ContigTable ct{(int32_t)nct, (const int32_t*)c->ct_lin.p, (const int32_t*)c->ct_tid.p};
+        const int32_t* site_pos = (const int32_t*)c->site_pos.p;
+
+        TRY(dev_reserve(c, c->totals, 8 * M_COUNT, 0));
+        TRY(host_reserve(c, c->h_totals, 8 * M_COUNT));
+        CUDA_TRY(c, cudaMemsetAsync(c->totals.p, 0, 8 * M_COUNT, s));
+        unsigned long long* d_tot = (unsigned long long*)c->totals.p;
+        TRY(dev_reserve(c, c->scan_scratch, (size_t)((C + 2047) / 2048 + 2) * 4, 0));
+        uint32_t* scratch = (uint32_t*)c->scan_scratch.p;
+        for (int m = 0; m < M_COUNT; m++) {
+            static const uint32_t bit[M_COUNT] = {MTH_PDR, MTH_MHL, MTH_FDRP, MTH_QFDRP, MTH_PM, MTH_ME};
+            if (M & bit[m]) TRY(dev_reserve(c, c->rowcnt[m], (size_t)C * 4 + 4, 0));
+            if ((M & bit[m]) && (m == M_MHL || m == M_FDRP || m == M_QFDRP)) TRY(dev_reserve(c, c->value[m], (size_t)C * 4 + 4, 0));
+        }
+
+        // ---------------- phase A: measure kernels + row counts + scans ----------------
+        if (M & MTH_PDR) {
+            TRY(dev_reserve(c, c->cnt2, (size_t)C * 8 + 8, 0));
+            bool gather = (c->prm.flags & MTH_FLAG_FORCE_GATHER) || sc.lmax > 150;
+            c->stats.pdr_path = gather ? 2 : 1;
+            if (gather) {
+                ProfScope ps(c, "k_pdr_gather");
+                ps.add(launch_pdr_gather(rv, site_pos, C, d_sc, (uint32_t*)c->cnt2.p, c->prm.pdr, s));
+            } else {
+                CUDA_TRY(c, cudaMemsetAsync(c->cnt2.p, 0, (size_t)C * 8, s));
+                ProfScope ps(c, "k_pdr_scatter");
+                ps.add(launch_pdr_scatter(rv, (const unsigned long long*)c->bitmap.p, (const uint32_t*)c->word_prefix.p,
+                                          (uint32_t*)c->cnt2.p, c->prm.pdr, s));
+            }
+            ProfScope ps(c, "pdr_rows_count");
+            ps.add(launch_pdr_rowcnt((const uint32_t*)c->cnt2.p, C, c->prm.pdr.min_depth, (uint32_t*)c->rowcnt[M_PDR].p, s));
+            ps.add(launch_exclusive_scan_u32((uint32_t*)c->rowcnt[M_PDR].p, C, scratch, d_tot + M_PDR, s));
+        }
+        if (M & MTH_MHL) {
+            {
+                ProfScope ps(c, "k_mhl");
+                ps.add(launch_mhl(rv, site_pos, C, d_sc, c->prm.mhl, (float*)c->value[M_MHL].p, (uint32_t*)c->rowcnt[M_MHL].p,
+                                  &d_sc->err, s));
+            }
+            ProfScope ps(c, "mhl_rows_count");
+            ps.add(launch_exclusive_scan_u32((uint32_t*)c->rowcnt[M_MHL].p, C, scratch, d_tot + M_MHL, s));
+        }
+        for (int q = 0; q < 2; q++) {
+            uint32_t bit = q ? MTH_QFDRP : MTH_FDRP;
+            int m = q ? M_QFDRP : M_FDRP;
+            if (!(M & bit)) continue;
+            mth_fdrp_params fp = q ? c->prm.qfdrp : c->prm.fdrp;
+            size_t sb = fdrp_scratch_bytes(fp, q);
+            TRY(dev_reserve(c, c->fdrp_scratch, sb, 0));
+            {
+                ProfScope ps(c, q ? "k_qfdrp" : "k_fdrp");
+                ps.add(launch_fdrp(rv, site_pos, C, d_sc, fp, q, c->prm.seed, ct, c->fdrp_scratch.p, sb, (float*)c->value[m].p,
+                                   (uint32_t*)c->rowcnt[m].p, &d_sc->err, s));
+            }
+            ProfScope ps(c, q ? "qfdrp_rows_count" : "fdrp_rows_count");
+            ps.add(launch_exclusive_scan_u32((uint32_t*)c->rowcnt[m].p, C, scratch, d_tot + m, s));
+        }
+        for (int q = 0; q < 2; q++) {
+            uint32_t bit = q ? MTH_ME : MTH_PM;
+            int m = q ? M_ME : M_PM;
+            if (!(M & bit)) continue;
+            mth_quartet_params qp = q ? c->prm.me : c->prm.pm;
+            // PM and ME with identical thresholds share the count pass
+            if (q == 1 && (M & MTH_PM) && c->prm.pm.min_depth == qp.min_depth && c->prm.pm.min_qual == qp.min_qual) {
+                CUDA_TRY(c, cudaMemcpyAsync(c->rowcnt[M_ME].p, c->rowcnt[M_PM].p, (size_t)C * 4, cudaMemcpyDeviceToDevice, s));
+                CUDA_TRY(c, cudaMemcpyAsync(d_tot + M_ME, d_tot + M_PM, 8, cudaMemcpyDeviceToDevice, s));
+                continue;
+            }
+            {
+                ProfScope ps(c, q ? "k_me_count" : "k_pm_count");
+                ps.add(launch_quartet_count(rv, site_pos, C, d_sc, qp, (uint32_t*)c->rowcnt[m].p, s));
+            }
+            ProfScope ps(c, q ? "me_rows_count" : "pm_rows_count");
+            ps.add(launch_exclusive_scan_u32((uint32_t*)c->rowcnt[m].p, C, scratch, d_tot + m, s));
+        }
+        if (M & MTH_ME) TRY(build_me_lut(c));
+
+        CUDA_TRY(c, cudaMemcpyAsync(c->h_totals.p, d_tot, 8 * M_COUNT, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(c, cudaMemcpyAsync(c->h_scalars.p, d_sc, sizeof(RegionScalars), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(c, cudaStreamSynchronize(s));
+        TRY(check_scalars_err(c, ((RegionScalars*)c->h_scalars.p)->err));
+        const unsigned long long* tot = (const unsigned long long*)c->h_totals.p;
+
+        // ---------------- phase B: row emission ----------------
+        if (M & MTH_PDR) {
+            TRY(reserve_site_rows(c, c->rows_pdr, c->rows_pdr.n + (int64_t)tot[M_PDR], true));
+            ProfScope ps(c, "k_pdr_emit");
+            ps.add(launch_pdr_emit((const uint32_t*)c->cnt2.p, (const uint32_t*)c->rowcnt[M_PDR].p, site_pos, C, c->prm.pdr.min_depth,
+                                   ct, site_rows_dev(c->rows_pdr), c->rows_pdr.n, s));
+            c->rows_pdr.n += (int64_t)tot[M_PDR];
+        }
+        struct { uint32_t bit; int m; SiteRowsBuf* r; const char* name; } simple[3] = {
+            {MTH_MHL, M_MHL, &c->rows_mhl, "k_mhl_emit"}, {MTH_FDRP, M_FDRP, &c->rows_fdrp, "k_fdrp_emit"},
+            {MTH_QFDRP, M_QFDRP, &c->rows_qfdrp, "k_qfdrp_emit"}};
+        for (auto& e : simple) {
+            if (!(M & e.bit)) continue;
+            TRY(reserve_site_rows(c, *e.r, e.r->n + (int64_t)tot[e.m], false));
+            ProfScope ps(c, e.name);
+            ps.add(launch_site_emit((const float*)c->value[e.m].p, (const uint32_t*)c->rowcnt[e.m].p, tot[e.m], site_pos, C, ct,
+                                    site_rows_dev(*e.r), e.r->n, s));
+            e.r->n += (int64_t)tot[e.m];
+        }
+        for (int q = 0; q < 2; q++) {
+            uint32_t bit = q ? MTH_ME : MTH_PM;
+            int m = q ? M_ME : M_PM;
+            if (!(M & bit)) continue;
+            QuartetRowsBuf& r = q ? c->rows_me : c->rows_pm;
+            bool counts = (c->prm.flags & MTH_FLAG_QUARTET_COUNTS) != 0;
+            TRY(reserve_quartet_rows(c, r, r.n + (int64_t)tot[m], counts));
+            QuartetRowsDev rd = quartet_rows_dev(r);
+            if (!counts) rd.counts = nullptr;
+            ProfScope ps(c, q ? "k_me_emit" : "k_pm_emit");
+            ps.add(launch_quartet_emit(rv, site_pos, C, d_sc, q ? c->prm.me : c->prm.pm, q, (const uint32_t*)c->rowcnt[m].p,
+                                       (const float*)c->me_lut.p, c->me_lut_max, ct, rd, r.n, s));
+            r.n += (int64_t)tot[m];
+        }
+        CUDA_TRY(c, cudaGetLastError());
+    }
+    c->region_active = false;
+    c->borrowed = false;
+    c->R = c->I = c->W = 0;
+    return MTH_OK;
+}
+
+static int fetch_site_rows(mth_ctx* c, SiteRowsBuf& r, bool counts, bool to_host, mth_site_rows* out) {
+    memset(out, 0, sizeof(*out));
+    out->n = r.n;
+    if (!to_host || r.n == 0) return MTH_OK;
+    size_t nb = (size_t)r.n * 4;
+    TRY(host_reserve(c, r.h_tid, nb)); TRY(host_reserve(c, r.h_pos, nb)); TRY(host_reserve(c, r.h_value, nb));
+    cudaStream_t s = c->compute;
+    CUDA_TRY(c, cudaMemcpyAsync(r.h_tid.p, r.tid.p, nb, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(c, cudaMemcpyAsync(r.h_pos.p, r.pos.p, nb, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(c, cudaMemcpyAsync(r.h_value.p, r.value.p, nb, cudaMemcpyDeviceToHost, s));
+    c->stats.d2h_bytes += (int64_t)nb * 3;
+    out->tid = (const int32_t*)r.h_tid.p; out->pos = (const int32_t*)r.h_pos.p; out->value = (const float*)r.h_value.p;
+    if (counts) {
+        TRY(host_reserve(c, r.h_nc, nb)); TRY(host_reserve(c, r.h_nd, nb));
+        CUDA_TRY(c, cudaMemcpyAsync(r.h_nc.p, r.nc.p, nb, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(c, cudaMemcpyAsync(r.h_nd.p, r.nd.p, nb, cudaMemcpyDeviceToHost, s));
+        c->stats.d2h_bytes += (int64_t)nb * 2;
+        out->n_conc = (const uint32_t*)r.h_nc.p; out->n_disc = (const uint32_t*)r.h_nd.p;
+    }
+    return MTH_OK;
+}
+static int fetch_quartet_rows(mth_ctx* c, QuartetRowsBuf& r, bool counts, bool to_host, mth_quartet_rows* out) {
+    memset(out, 0, sizeof(*out));
+    out->n = r.n;
+    if (!to_host || r.n == 0) return MTH_OK;
+    size_t nb = (size_t)r.n * 4;
+    cudaStream_t s = c->compute;
+    DevBuf* d[6] = {&r.tid, &r.p1, &r.p2, &r.p3, &r.p4, &r.value};
+    HostBuf* h[6] = {&r.h_tid, &r.h_p1, &r.h_p2, &r.h_p3, &r.h_p4, &r.h_value};
+    for (int i = 0; i < 6; i++) {
+        TRY(host_reserve(c, *h[i], nb));
+        CUDA_TRY(c, cudaMemcpyAsync(h[i]->p, d[i]->p, nb, cudaMemcpyDeviceToHost, s));
+    }
+    c->stats.d2h_bytes += (int64_t)nb * 6;
+    out->tid = (const int32_t*)r.h_tid.p; out->p1 = (const int32_t*)r.h_p1.p; out->p2 = (const int32_t*)r.h_p2.p;
+    out->p3 = (const int32_t*)r.h_p3.p; out->p4 = (const int32_t*)r.h_p4.p; out->value = (const float*)r.h_value.p;
+    if (counts) {
+        TRY(host_reserve(c, r.h_counts, nb * 16));
+        CUDA_TRY(c, cudaMemcpyAsync(r.h_counts.p, r.counts.p, nb * 16, cudaMemcpyDeviceToHost, s));
+        c->stats.d2h_bytes += (int64_t)nb * 16;
+        out->counts = (const uint32_t*)r.h_counts.p;
+    }
+    return MTH_OK;
+}
+
+static void lpmd_from_totals(const int64_t* t, mth_lpmd_result* out) {
+    out->n_read = t[0]; out->n_valid_read = t[1]; out->n_conc = t[2]; out->n_disc = t[3];
+    // lpmd.rs:51-55: n_discordant as f32 / (n_concordant + n_discordant) as f32
+    volatile float num = (float)t[3];
+    volatile float den = (float)(t[2] + t[3]);
+    out->lpmd = num / den;
+}
+
+extern "C" {
+
+int mth_finish(mth_ctx* c, mth_results* out) {
+    if (!c || !out) return MTH_ERR_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (!c->finished) {
+        TRY(process_region(c));
+        c->finished = 1;
+    }
+    memset(out, 0, sizeof(*out));
+    const bool to_host = !(c->prm.flags & MTH_FLAG_KEEP_ON_DEVICE);
+    const bool qc = (c->prm.flags & MTH_FLAG_QUARTET_COUNTS) != 0;
+    TRY(fetch_site_rows(c, c->rows_pdr, true, to_host, &out->pdr));
+    TRY(fetch_site_rows(c, c->rows_mhl, false, to_host, &out->mhl));
+    TRY(fetch_site_rows(c, c->rows_fdrp, false, to_host, &out->fdrp));
+    TRY(fetch_site_rows(c, c->rows_qfdrp, false, to_host, &out->qfdrp));
+    TRY(fetch_quartet_rows(c, c->rows_pm, qc, to_host, &out->pm));
+    TRY(fetch_quartet_rows(c, c->rows_me, qc, to_host, &out->me));
+    lpmd_from_totals(c->lpmd_total_host, &out->lpmd);
+    TRY(dev_reserve(c, c->lpmd_total, 32, 0));
+    CUDA_TRY(c, cudaMemcpyAsync(c->lpmd_total.p, c->lpmd_total_host, 32, cudaMemcpyHostToDevice, c->compute));
+    CUDA_TRY(c, cudaStreamSynchronize(c->copy));
+    CUDA_TRY(c, cudaStreamSynchronize(c->compute));
+    resolve_spans(c);
+    return MTH_OK;
+}
+
+int mth_results_device(mth_ctx* c, mth_results* out) {
+    if (!c || !out) return MTH_ERR_INVALID;
+    if (!c->finished) return fail(c, MTH_ERR_STATE, "mth_results_device before mth_finish");
+    memset(out, 0, sizeof(*out));
+    auto site = [](SiteRowsBuf& r, bool counts, mth_site_rows* o) {
+        o->n = r.n; o->tid = (const int32_t*)r.tid.p; o->pos = (const int32_t*)r.pos.p; o->value = (const float*)r.value.p;
+        o->n_conc = counts ? (const uint32_t*)r.nc.p : nullptr; o->n_disc = counts ? (const uint32_t*)r.nd.p : nullptr;
+    };
+    auto quart = [](QuartetRowsBuf& r, bool counts, mth_quartet_rows* o) {
+        o->n = r.n; o->tid = (const int32_t*)r.tid.p; o->p1 = (const int32_t*)r.p1.p; o->p2 = (const int32_t*)r.p2.p;
+        o->p3 = (const int32_t*)r.p3.p; o->p4 = (const int32_t*)r.p4.p; o->value = (const float*)r.value.p;
+        o->counts = counts ? (const uint32_t*)r.counts.p : nullptr;
+    };
+    const bool qc = (c->prm.flags & MTH_FLAG_QUARTET_COUNTS) != 0;
+    site(c->rows_pdr, true, &out->pdr); site(c->rows_mhl, false, &out->mhl);
+    site(c->rows_fdrp, false, &out->fdrp); site(c->rows_qfdrp, false, &out->qfdrp);
+    quart(c->rows_pm, qc, &out->pm); quart(c->rows_me, qc, &out->me);
+    lpmd_from_totals(c->lpmd_total_host, &out->lpmd);
+    return MTH_OK;
+}
+
+int mth_lpmd_counters_device(mth_ctx* c, void** dev_ptr) {
+    if (!c || !dev_ptr) return MTH_ERR_INVALID;
+    if (!c->finished) return fail(c, MTH_ERR_STATE, "mth_lpmd_counters_device before mth_finish");
+    *dev_ptr = c->lpmd_total.p;
+    return MTH_OK;
+}
+
+int mth_lpmd_refresh(mth_ctx* c, mth_lpmd_result* out) {
+    if (!c || !out) return MTH_ERR_INVALID;
+    if (!c->finished) return fail(c, MTH_ERR_STATE, "mth_lpmd_refresh before mth_finish");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    int64_t t[4];
+    CUDA_TRY(c, cudaMemcpy(t, c->lpmd_total.p, 32, cudaMemcpyDeviceToHost));
+    lpmd_from_totals(t, out);
+    return MTH_OK;
+}
+
+int mth_get_stats(mth_ctx* c, mth_stats* out) {
+    if (!c || !out) return MTH_ERR_INVALID;
+    *out = c->stats;
+    return MTH_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,258 @@
+// k_quartet.cu — PM (epipolymorphism, pm.rs:85-128 + :42-51) and ME (methylation entropy, me.rs:90-132 + :42-55):
+// 16-pattern histograms of 4 read-consecutive CpGs (readutil.rs:97-132).
+//
+// A quartet is keyed by its four positions; the warp that owns site p handles every quartet whose FIRST CpG is p.
+// All reads calling p lie in p's window (gather.cuh); a read whose k-th CpG is p contributes key (pos[k+1],
+// pos[k+2], pos[k+3]) and pattern 8*m[k]+4*m[k+1]+2*m[k+2]+m[k+3] when k+3 < n.  Reads that miss a call give a
+// different key for the same p, so a site can own several quartets: the common single-key case is resolved in one
+// pass over the window (count for the first key seen while checking that no other key occurs); otherwise keys are
+// enumerated in ascending order, one counting pass each — exact for any number of keys and it yields the rows
+// already sorted by (p1,p2,p3,p4) (the reference prints HashMap order, pm.rs:76).
+// No flushing exists for PM/ME (whole-input maps), so there are no segments here.
+// Two kernels from one template: COUNT (rows per site, for the output offsets) and EMIT (rows).
+#include "gather.cuh"
+#include "kernels.h"
+
+namespace mth {
+
+struct QKey {
+    int32_t a, b, c;
+};
+__device__ __forceinline__ bool key_less(const QKey& x, const QKey& y) {
+    if (x.a != y.a) return x.a < y.a;
+    if (x.b != y.b) return x.b < y.b;
+    return x.c < y.c;
+}
+__device__ __forceinline__ bool key_eq(const QKey& x, const QKey& y) { return x.a == y.a && x.b == y.b && x.c == y.c; }
+
+// warp-wide lexicographic minimum of the keys of the lanes in `mask` (mask != 0)
+__device__ __forceinline__ QKey warp_min_key(uint32_t mask, QKey k) {
+    const int32_t BIG = INT32_MAX;
+    bool in = (mask >> lane_id()) & 1u;
+    int32_t a = in ? k.a : BIG;
+    int32_t ma = __reduce_min_sync(FULL, a);
+    bool ina = in && k.a == ma;
+    int32_t b = ina ? k.b : BIG;
+    int32_t mb = __reduce_min_sync(FULL, b);
+    bool inb = ina && k.b == mb;
+    int32_t cc = inb ? k.c : BIG;
+    int32_t mc = __reduce_min_sync(FULL, cc);
+    return QKey{ma, mb, mc};
+}
+
+// glibc / ARM optimized-routines log2f (sysdeps/ieee754/flt-32/e_log2f.c, LOG2F_TABLE_BITS = 4, N = 16), evaluated
+// in double without contraction.  Only used for quartet depths beyond the host-libm table (see engine.cu
+// build_me_lut); PARITY UNPINNED there (table constants restated from the published algorithm).
+__device__ const double LOG2F_INVC[16] = {0x1.661ec79f8f3bep+0, 0x1.571ed4aaf883dp+0, 0x1.49539f0f010bp+0,  0x1.3c995b0b80385p+0,
+                                          0x1.30d190c8864a5p+0, 0x1.25e227b0b8eap+0,  0x1.1bb4a4a1a343fp+0, 0x1.12358f08ae5bap+0,
+                                          0x1.0953f419900a7p+0, 0x1p+0,               0x1.e608cfd9a47acp-1, 0x1.ca4b31f026aap-1,
+                                          0x1.b2036576afce6p-1, 0x1.9c2d163a1aa2dp-1, 0x1.886e6037841edp-1, 0x1.767dcf5534862p-1};
+__device__ const double LOG2F_LOGC[16] = {-0x1.efec65b963019p-2, -0x1.b0b6832d4fca4p-2, -0x1.7418b0a1fb77bp-2, -0x1.39de91a6dcf7bp-2,
+                                          -0x1.01d9bf3f2b631p-2, -0x1.97c1d1b3b7afp-3,  -0x1.2f9e393af3c9fp-3, -0x1.960cbbf788d5cp-4,
+                                          -0x1.a6f9db6475fcep-5, 0x0p+0,                0x1.338ca9f24f53dp-4,  0x1.476a9543891bap-3,
+                                          0x1.e840b4ac4e4d2p-3,  0x1.40645f0c6651cp-2,  0x1.88e9c2c1b9ff8p-2,  0x1.ce0a44eb17bccp-2};
+__device__ __forceinline__ float dev_log2f(float x) {
+    const double* invc = LOG2F_INVC;
+    const double* logc = LOG2F_LOGC;
+    const double A0 = -0x1.712b6f70a7e4dp-2, A1 = 0x1.ecabf496832ep-2, A2 = -0x1.715479ffae3dep-1, A3 = 0x1.715475f35c8b8p0;
+    uint32_t ix = __float_as_uint(x);
+    if (ix == 0x3f800000u) return 0.f;
+    uint32_t tmp = ix - 0x3f330000u;
+    int i = (tmp >> 19) & 15;
+    uint32_t top = tmp & 0xff800000u;
+    uint32_t iz = ix - top;
+    int k = (int32_t)tmp >> 23;
+    double z = (double)__uint_as_float(iz);
+    double r = __dadd_rn(__dmul_rn(z, invc[i]), -1.0);
+    double y0 = __dadd_rn(logc[i], (double)k);
+    double r2 = __dmul_rn(r, r);
+    double y = __dadd_rn(__dmul_rn(A1, r), A2);
+    y = __dadd_rn(__dmul_rn(A0, r2), y);
+    double pp = __dadd_rn(__dmul_rn(A3, r), y0);
+    y = __dadd_rn(__dmul_rn(y, r2), pp);
+    return (float)y;
+}
+
+__device__ __forceinline__ float pm_value(const uint32_t* cnt, uint32_t total) {  // pm.rs:42-51
+    float pm = 1.0f;
+    float ft = (float)total;
+    for (int k = 0; k < 16; k++) {
+        float q = __fdiv_rn((float)cnt[k], ft);
+        pm = __fsub_rn(pm, __fmul_rn(q, q));
+    }
+    return pm;
+}
+__device__ __forceinline__ float me_value(const uint32_t* cnt, uint32_t total, const float* __restrict__ lut, int lut_max) {
+    float me = 0.0f;  // me.rs:42-55
+    float ft = (float)total;
+    for (int k = 0; k < 16; k++) {
+        uint32_t ck = cnt[k];
+        if (ck == 0) continue;
+        float t;
+        if ((int)total <= lut_max) {
+            t = lut[(size_t)total * (total + 1) / 2 + ck];
+        } else {
+            float p = __fdiv_rn((float)ck, ft);
+            t = __fmul_rn(p, dev_log2f(p));
+        }
+        me = __fadd_rn(me, t);
+    }
+    return __fmul_rn(me, -0.25f);
+}
+
+struct QuartetArgs {
+    ReadsView rv;
+    const int32_t* site_pos;
+    int64_t C;
+    const RegionScalars* sc;
+    mth_quartet_params prm;
+    int kind;                 // 0 PM, 1 ME (EMIT only)
+    uint32_t* rowcnt;         // COUNT: out
+    const uint32_t* rowoff;   // EMIT: in
+    const float* me_lut;
+    int me_lut_max;
+    ContigTable ct;
+    QuartetRowsDev rows;
+    int64_t row_base;
+};
+
+template <bool EMIT>
+__global__ void __launch_bounds__(GATHER_BLOCK) k_quartet(QuartetArgs a) {
+    __shared__ uint32_t s_cnt[GATHER_BLOCK / 32][16];
+    uint32_t* cnt = s_cnt[threadIdx.x >> 5];
+    const ReadsView& rv = a.rv;
+    const int lane = lane_id();
+    const uint32_t min_qual = a.prm.min_qual, min_depth = a.prm.min_depth;
+
+    for_each_site(rv, a.site_pos, a.C, a.sc->lmax, [&](int64_t s, int32_t p, int64_t lo, int32_t target) {
+        uint32_t n_rows = 0;
+        const int64_t out0 = EMIT ? (a.row_base + a.rowoff[s]) : 0;
+
+        auto lane_quartet = [&](const LaneRead& lr, QKey* key, uint32_t* pat) -> bool {
+            // pm.rs:111 / me.rs:115 mapq filter; readutil.rs:101-105 needs 4 CpGs from the site onwards
+            if (lr.idx < 0 || lr.mapq < min_qual || (uint32_t)lr.idx + 3 >= lr.n) return false;
+            const int32_t* cp = rv.cpg_pos + lr.o0 + lr.idx;
+            key->a = cp[1]; key->b = cp[2]; key->c = cp[3];
+            uint32_t k = (uint32_t)lr.idx;
+            *pat = (meth_bit(rv, lr.j, k) << 3) | (meth_bit(rv, lr.j, k + 1) << 2) | (meth_bit(rv, lr.j, k + 2) << 1) |
+                   meth_bit(rv, lr.j, k + 3);
+            return true;
+        };
+        auto finish_key = [&](const QKey& key) {
+            __syncwarp();
+            uint32_t c = lane < 16 ? cnt[lane] : 0u;
+            uint32_t total = __reduce_add_sync(FULL, c);
+            if (total > 0 && total >= min_depth) {  // pm.rs:77 / me.rs:82
+                if (EMIT && lane == 0) {
+                    int64_t r = out0 + n_rows;
+                    int32_t tid, pos;
+                    delinearize(a.ct, p, &tid, &pos);
+                    int32_t off = p - pos;  // linear offset of the contig
+                    a.rows.tid[r] = tid;
+                    a.rows.p1[r] = pos;
+                    a.rows.p2[r] = key.a - off;
+                    a.rows.p3[r] = key.b - off;
+                    a.rows.p4[r] = key.c - off;
+                    a.rows.value[r] = a.kind == 0 ? pm_value(cnt, total) : me_value(cnt, total, a.me_lut, a.me_lut_max);
+                    if (a.rows.counts)
+                        for (int k = 0; k < 16; k++) a.rows.counts[(size_t)r * 16 + k] = cnt[k];
+                }
+                n_rows++;
+            }
+            __syncwarp();
+            if (lane < 16) cnt[lane] = 0;
+            __syncwarp();
+        };
+        auto count_chunk = [&](bool match, uint32_t pat) {
+            uint32_t mm = __ballot_sync(FULL, match);
+            if (match) {
+                uint32_t peers = __match_any_sync(mm, pat);
+                if (lane == __ffs(peers) - 1) cnt[pat] += __popc(peers);  // one leader per pattern: no conflicts
+            }
+            __syncwarp();
+        };
+
+        if (lane < 16) cnt[lane] = 0;
+        __syncwarp();
+
+        // ---- pass 0: optimistic single-key pass ----
+        bool have_guess = false, mixed = false;
+        QKey guess{0, 0, 0};
+        scan_window(rv, lo, p, target, [&](const LaneRead& lr) {
+            QKey key{0, 0, 0};
+            uint32_t pat = 0;
+            bool valid = lane_quartet(lr, &key, &pat);
+            uint32_t vm = __ballot_sync(FULL, valid);
+            if (!vm) return;
+            if (!have_guess) {
+                int src = __ffs(vm) - 1;
+                guess.a = __shfl_sync(FULL, key.a, src);
+                guess.b = __shfl_sync(FULL, key.b, src);
+                guess.c = __shfl_sync(FULL, key.c, src);
+                have_guess = true;
+            }
+            bool match = valid && key_eq(key, guess);
+            if (__ballot_sync(FULL, match) != vm) mixed = true;
+            count_chunk(match, pat);
+        });
+        if (have_guess && !mixed) {
+            finish_key(guess);
+        } else if (have_guess) {
+            // ---- general path: enumerate keys in ascending order ----
+            if (lane < 16) cnt[lane] = 0;
+            __syncwarp();
+            QKey last{INT32_MIN, INT32_MIN, INT32_MIN};
+            bool first_round = true;
+            while (true) {
+                bool found = false;
+                QKey best{INT32_MAX, INT32_MAX, INT32_MAX};
+                scan_window(rv, lo, p, target, [&](const LaneRead& lr) {
+                    QKey key{0, 0, 0};
+                    uint32_t pat = 0;
+                    bool valid = lane_quartet(lr, &key, &pat);
+                    bool cand = valid && (first_round || key_less(last, key));
+                    uint32_t cmask = __ballot_sync(FULL, cand);
+                    if (!cmask) return;
+                    QKey m = warp_min_key(cmask, key);
+                    if (!found || key_less(m, best)) best = m;
+                    found = true;
+                });
+                if (!found) break;
+                scan_window(rv, lo, p, target, [&](const LaneRead& lr) {
+                    QKey key{0, 0, 0};
+                    uint32_t pat = 0;
+                    bool valid = lane_quartet(lr, &key, &pat);
+                    count_chunk(valid && key_eq(key, best), pat);
+                });
+                finish_key(best);
+                last = best;
+                first_round = false;
+            }
+        }
+        if (!EMIT && lane == 0) a.rowcnt[s] = n_rows;
+    });
+}
+
+int launch_quartet_count(const ReadsView& rv, const int32_t* site_pos, int64_t C, const RegionScalars* sc,
+                         mth_quartet_params prm, uint32_t* rowcnt, cudaStream_t s) {
+    if (C <= 0) return 0;
+    QuartetArgs a;
+    memset(&a, 0, sizeof(a));
+    a.rv = rv; a.site_pos = site_pos; a.C = C; a.sc = sc; a.prm = prm; a.rowcnt = rowcnt;
+    k_quartet<false><<<gather_grid(C), GATHER_BLOCK, 0, s>>>(a);
+    return 1;
+}
+
+int launch_quartet_emit(const ReadsView& rv, const int32_t* site_pos, int64_t C, const RegionScalars* sc,
+                        mth_quartet_params prm, int kind, const uint32_t* rowoff, const float* me_lut, int me_lut_max,
+                        ContigTable ct, QuartetRowsDev rows, int64_t row_base, cudaStream_t s) {
+    if (C <= 0) return 0;
+    QuartetArgs a;
+    memset(&a, 0, sizeof(a));
+    a.rv = rv; a.site_pos = site_pos; a.C = C; a.sc = sc; a.prm = prm; a.kind = kind; a.rowoff = rowoff;
+    a.me_lut = me_lut; a.me_lut_max = me_lut_max; a.ct = ct; a.rows = rows; a.row_base = row_base;
+    k_quartet<true><<<gather_grid(C), GATHER_BLOCK, 0, s>>>(a);
+    return 1;
+}
+
+}  // namespace mth

@@ -1,0 +1,73 @@
+// kernels.h — host-callable launchers of the sm_100a kernels (definitions in k_*.cu).
+#pragma once
+#include "common.cuh"
+#include "../../include/metheor_b200.h"
+
+namespace mth {
+
+// Every launcher returns the number of kernels it launched (for mth_stats.kernel_launches).
+
+// ---- ingest (k_ingest.cu) -------------------------------------------------------------------
+int launch_add_u32(uint32_t* a, int64_t n, uint32_t add, cudaStream_t s);
+int launch_iota_u32(uint32_t* a, int64_t n, uint32_t base, cudaStream_t s);
+int launch_add_i32(int32_t* a, int64_t n, int32_t add, cudaStream_t s);
+struct IngestArgs {
+    ReadsView rv;             // region-wide view (already contains the batch)
+    int64_t r0, n;            // reads [r0, r0+n) are the new batch
+    int64_t i0;               // first incidence of the batch (cpg_rel is batch-local)
+    const uint16_t* cpg_rel;  // device, batch-local, or nullptr
+    unsigned long long* bitmap;  // bit (p+1) set for every CpG position p seen
+    int32_t lin_lo, lin_hi;   // valid position range of this contig in device coordinates: [lin_lo-1, lin_hi)
+    int do_lpmd;
+    mth_lpmd_params lpmd;
+    RegionScalars* sc;
+};
+int launch_ingest(const IngestArgs& a, cudaStream_t s);
+
+// ---- site dictionary + scans (k_sites.cu) ---------------------------------------------------
+// phase 1: popcount per 1024-word block -> block_sums, scanned in place; total -> sc->n_sites
+int launch_sites_count(const unsigned long long* bitmap, int64_t n_words, uint32_t* block_sums, RegionScalars* sc,
+                       cudaStream_t s);
+// phase 2: word_prefix[w] = #sites before word w; site_pos[rank] = position
+int launch_sites_emit(const unsigned long long* bitmap, int64_t n_words, const uint32_t* block_sums,
+                      uint32_t* word_prefix, int32_t* site_pos, cudaStream_t s);
+// in-place exclusive scan of a[0..n) (u32); total written to *total (device, u64). scratch >= ceil(n/2048)+1 u32
+int launch_exclusive_scan_u32(uint32_t* a, int64_t n, uint32_t* scratch, unsigned long long* total, cudaStream_t s);
+
+// ---- PDR (k_pdr.cu) -------------------------------------------------------------------------
+int launch_pdr_scatter(const ReadsView& rv, const unsigned long long* bitmap, const uint32_t* word_prefix,
+                       uint32_t* cnt2, mth_pdr_params prm, cudaStream_t s);
+int launch_pdr_gather(const ReadsView& rv, const int32_t* site_pos, int64_t C, const RegionScalars* sc,
+                      uint32_t* cnt2, mth_pdr_params prm, cudaStream_t s);
+// rowcnt[s] = 1 iff site s yields a row
+int launch_pdr_rowcnt(const uint32_t* cnt2, int64_t C, uint32_t min_depth, uint32_t* rowcnt, cudaStream_t s);
+struct SiteRowsDev { int32_t* tid; int32_t* pos; float* value; uint32_t* n_conc; uint32_t* n_disc; };
+int launch_pdr_emit(const uint32_t* cnt2, const uint32_t* rowoff, const int32_t* site_pos, int64_t C, uint32_t min_depth,
+                    ContigTable ct, SiteRowsDev rows, int64_t row_base, cudaStream_t s);
+
+// ---- MHL (k_mhl.cu) -------------------------------------------------------------------------
+// value[s], rowcnt[s] in {0,1}
+int launch_mhl(const ReadsView& rv, const int32_t* site_pos, int64_t C, const RegionScalars* sc, mth_mhl_params prm,
+               float* value, uint32_t* rowcnt, uint32_t* err, cudaStream_t s);
+// generic: rows for sites with rowcnt (pre-scan value kept in `flag`), value from dense array
+int launch_site_emit(const float* value, const uint32_t* rowoff, uint64_t n_rows_region, const int32_t* site_pos,
+                     int64_t C, ContigTable ct, SiteRowsDev rows, int64_t row_base, cudaStream_t s);
+int gather_grid(int64_t C);  // grid size for the warp-per-site kernels
+
+// ---- PM / ME (k_quartet.cu) -----------------------------------------------------------------
+struct QuartetRowsDev { int32_t* tid; int32_t* p1; int32_t* p2; int32_t* p3; int32_t* p4; float* value; uint32_t* counts; };
+// pass 1: rowcnt[s] = number of quartets starting at site s whose depth >= min_depth
+int launch_quartet_count(const ReadsView& rv, const int32_t* site_pos, int64_t C, const RegionScalars* sc,
+                         mth_quartet_params prm, uint32_t* rowcnt, cudaStream_t s);
+// pass 2: write the rows (sorted by key within a site) at rowoff[s]; kind 0 = PM, 1 = ME
+int launch_quartet_emit(const ReadsView& rv, const int32_t* site_pos, int64_t C, const RegionScalars* sc,
+                        mth_quartet_params prm, int kind, const uint32_t* rowoff, const float* me_lut, int me_lut_max,
+                        ContigTable ct, QuartetRowsDev rows, int64_t row_base, cudaStream_t s);
+
+// ---- FDRP / qFDRP (k_fdrp.cu) ---------------------------------------------------------------
+int launch_fdrp(const ReadsView& rv, const int32_t* site_pos, int64_t C, const RegionScalars* sc, mth_fdrp_params prm,
+                int quantitative, uint64_t seed, ContigTable ct, void* scratch, size_t scratch_bytes, float* value,
+                uint32_t* rowcnt, uint32_t* err, cudaStream_t s);
+size_t fdrp_scratch_bytes(mth_fdrp_params prm, int quantitative);
+
+}  // namespace mth

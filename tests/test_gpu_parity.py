@@ -1,0 +1,185 @@
+"""GPU parity: the CUDA engine (through the C ABI) against the CPU oracle, bit-exact, on the reference's fixtures
+and on seeded synthetic reads that exercise what the fixtures do not (both strands, deletions, no-calls, low mapq,
+segment hazards, several batches / contigs / regions, deep piles)."""
+import numpy as np
+import pytest
+
+import parity
+from metheor_b200 import batch as B
+from metheor_b200 import engine, synth
+
+pytestmark = pytest.mark.gpu
+
+ALL = ("pdr", "lpmd", "mhl", "pm", "me", "fdrp", "qfdrp")
+CHR1 = [248956422]
+
+
+def test_reference_fixture_pins(golden, pins):
+    """The values the reference's unit tests assert (tests/golden/reference_pins.json), now from the GPU."""
+    f32 = np.float32
+    for c in pins["pdr"]["cases"]:
+        b = parity.records_to_batch(golden[c["input"]]["reads"])
+        res, _ = engine.run_batches([b], CHR1, ["pdr"], pdr=dict(min_depth=0, min_cpgs=c["min_cpgs"], min_qual=10))
+        assert res["pdr"]["n"] == c["n_rows"]
+        if c["n_rows"]:
+            assert (res["pdr"]["value"] == f32(c["pdr"])).all() and (res["pdr"]["n_conc"] == c["n_conc"]).all() \
+                and (res["pdr"]["n_disc"] == c["n_disc"]).all()
+    for c in pins["lpmd"]["cases"]:
+        b = parity.records_to_batch(golden[c["input"]]["reads"])
+        v = engine.run_batches([b], CHR1, ["lpmd"])[0]["lpmd"]["lpmd"]
+        assert np.isnan(v) if c["lpmd"] == "NaN" else v == f32(c["lpmd"])
+    for c in pins["mhl"]["cases"]:
+        b = parity.records_to_batch(golden[c["input"]]["reads"])
+        r = engine.run_batches([b], CHR1, ["mhl"], mhl=dict(min_depth=0, min_cpgs=0, min_qual=10))[0]["mhl"]
+        assert r["n"] == c["n_rows"] and (r["value"] == f32(c.get("mhl", 0))).all()
+    for name in ("pm", "me"):
+        for c in pins[name]["cases"]:
+            b = parity.records_to_batch(golden[c["input"]]["reads"])
+            r = engine.run_batches([b], CHR1, [name], **{name: dict(min_depth=0, min_qual=10)})[0][name]
+            assert r["n"] == c["n_quartets"] and (r["value"] == f32(c.get(name, 0))).all(), (name, c, r["value"])
+    for name in ("fdrp", "qfdrp"):
+        a = pins[name]["args"]
+        for c in pins[name]["cases"]:
+            b = parity.records_to_batch(golden[c["input"]]["reads"])
+            r = engine.run_batches([b], CHR1, [name], **{name: dict(min_qual=c["min_qual"], min_depth=a["min_depth"],
+                                                                    max_depth=a["max_depth"], min_overlap=a["min_overlap"])})[0][name]
+            assert list(r["pos"]) == c["positions"]
+            if c["positions"]:
+                if name + "_f32_of" in c:
+                    x, y = c[name + "_f32_of"].split("/")
+                    want = f32(x) / f32(y)
+                else:
+                    want = f32(c[name])
+                if c["exact"]:
+                    assert (r["value"] == want).all(), (name, c, r["value"])
+                else:
+                    assert (np.abs(r["value"] - want) < c["tol"]).all()
+
+
+@pytest.mark.parametrize("name", ["test1", "test2", "test3", "test4", "test5", "test6"])
+def test_fixtures_default_flags_vs_oracle(golden, name):
+    b = parity.records_to_batch(golden[name]["reads"])
+    parity.check_all([b], CHR1, ALL)
+    parity.check_all([b], CHR1, ALL, pdr=dict(min_depth=1, min_cpgs=1), mhl=dict(min_depth=1, min_cpgs=1),
+                     pm=dict(min_depth=1), me=dict(min_depth=1), fdrp=dict(min_depth=1, min_overlap=1, max_depth=100),
+                     qfdrp=dict(min_depth=1, min_overlap=1, max_depth=100))
+
+
+def test_chr19_real_reads(golden):
+    """1000 real Bismark reads (both strands, 24-29 bp) of the reference's tag fixture."""
+    fx = golden["chr19_1000"]
+    b = parity.records_to_batch(fx["reads"])
+    ref_len = [l for _, l in fx["refs"]]
+    parity.check_all([b], ref_len, ALL, pdr=dict(min_depth=2, min_cpgs=1), mhl=dict(min_depth=2, min_cpgs=1),
+                     pm=dict(min_depth=1), me=dict(min_depth=1), fdrp=dict(min_depth=2, min_overlap=5),
+                     qfdrp=dict(min_depth=2, min_overlap=5))
+
+
+def _synth(seed, length=200_000, cov=30.0, **kw):
+    sites = synth.make_sites(seed, length)
+    return synth.make_reads(seed + 1, sites, length, cov, **kw)
+
+
+@pytest.mark.parametrize("seed", [11, 12])
+def test_synthetic_default_flags(seed):
+    b = _synth(seed)
+    res, st = parity.check_all([b], [200_000], ALL)
+    assert st["pdr_path"] == 1  # 150-bp reads: the scatter path is provably exact
+    assert res["pdr"]["n"] > 1000 and res["mhl"]["n"] > 100 and res["pm"]["n"] > 100 and res["fdrp"]["n"] > 1000
+
+
+def test_synthetic_forced_gather_equals_scatter():
+    b = _synth(13)
+    parity.check_all([b], [200_000], ("pdr",), flags=engine.FLAG_FORCE_GATHER)
+
+
+def test_synthetic_long_spans_segment_hazards():
+    """Deletions stretch reads to > 150 reference bases: PDR must take the gather path and replay flush segments."""
+    b = _synth(14, read_len=140, del_frac=0.5, del_max=60, nocall=0.05, lowq=0.15)
+    res, st = parity.check_all([b], [200_000], ALL, pdr=dict(min_depth=3, min_cpgs=2), mhl=dict(min_depth=3, min_cpgs=2),
+                               fdrp=dict(min_depth=3), qfdrp=dict(min_depth=3), pm=dict(min_depth=3), me=dict(min_depth=3))
+    assert st["pdr_path"] == 2 and st["max_ref_span"] > 150
+
+
+def test_synthetic_dense_islands_many_cpgs_per_read():
+    sites = synth.make_sites(15, 60_000, mean_gap=6.0)
+    b = synth.make_reads(16, sites, 60_000, 20.0)
+    n = np.diff(b["cpg_off"].astype(np.int64)).max()
+    assert n > 16
+    parity.check_all([b], [60_000], ALL, pdr=dict(min_depth=5), mhl=dict(min_depth=5))
+
+
+def test_more_than_64_cpgs_per_read_uses_meth_off():
+    sites = np.arange(10, 20_000, 2, dtype=np.int32)  # a CpG every 2 bp: 75 calls per 150-bp read
+    b = synth.make_reads(17, sites, 20_000, 12.0, nocall=0.02)
+    assert b["meth_off"] is not None and np.diff(b["cpg_off"].astype(np.int64)).max() > 64
+    parity.check_all([b], [20_000], ALL, pdr=dict(min_depth=4), mhl=dict(min_depth=4), fdrp=dict(min_depth=4),
+                     qfdrp=dict(min_depth=4), pm=dict(min_depth=4), me=dict(min_depth=4))
+
+
+def test_batches_contigs_and_zero_cpg_reads():
+    """Several batches per contig and several contigs in one region: identical to one oracle pass over all reads."""
+    lens = [150_000, 80_000, 120_000]
+    batches = []
+    for tid, L in enumerate(lens):
+        b = _synth(20 + tid, length=L, cov=25.0, tid=tid)
+        b["tid"] = tid
+        cuts = [0, b["n_reads"] // 3, b["n_reads"] // 3 + 1, (2 * b["n_reads"]) // 3, b["n_reads"]]
+        for lo, hi in zip(cuts[:-1], cuts[1:]):
+            batches.append(B.slice_reads(b, lo, hi))
+    res, st = parity.check_all(batches, lens, ALL)
+    assert st["n_regions"] == 1 and set(np.unique(res["pdr"]["tid"])) == {0, 1, 2}
+
+
+def test_region_split_when_contigs_do_not_fit():
+    lens = [1_400_000_000, 1_300_000_000, 900_000]
+    batches = []
+    for tid, off in ((0, 1_399_000_000), (1, 5_000), (2, 100)):
+        b = _synth(30 + tid, length=100_000, cov=15.0)
+        b["tid"] = tid
+        for k in ("start", "end", "cpg_pos"):
+            b[k] = (b[k].astype(np.int64) + off).astype(np.int32)
+        batches.append(b)
+    res, st = parity.check_all(batches, lens, ("pdr", "lpmd", "mhl", "pm"))
+    assert st["n_regions"] == 2
+
+
+def test_deep_piles_reservoir_sampling_matches_seeded_oracle():
+    b = _synth(40, length=30_000, cov=90.0)
+    parity.check_all([b], [30_000], ("fdrp", "qfdrp"), seed=1234)
+    parity.check_all([b], [30_000], ("fdrp", "qfdrp"), seed=99, fdrp=dict(max_depth=4096), qfdrp=dict(max_depth=4096))
+
+
+def test_device_resident_batch_is_borrowed_zero_copy():
+    torch = pytest.importorskip("torch")
+    b = _synth(50)
+    d = dict(b)
+    for k in ("start", "end", "meta", "cpg_off", "cpg_pos", "cpg_rel", "meth"):
+        a = b[k]
+        view = {np.dtype("uint32"): np.int32, np.dtype("uint16"): np.int16, np.dtype("uint64"): np.int64}.get(a.dtype, a.dtype)
+        d[k] = torch.from_numpy(a.view(view)).cuda()
+    want, _ = engine.run_batches([b], [200_000], ALL)
+    got, st = engine.run_batches([d], [200_000], ALL)
+    assert st["h2d_bytes"] == 0
+    for m in want:
+        for k in want[m]:
+            assert np.array_equal(np.asarray(want[m][k]), np.asarray(got[m][k]), equal_nan=True), (m, k)
+
+
+def test_error_paths():
+    b = _synth(60, length=50_000, cov=5.0)
+    bad = dict(b)
+    bad["start"] = b["start"][::-1].copy()
+    with pytest.raises(engine.EngineError) as e:
+        engine.run_batches([bad], [50_000], ("pdr",))
+    assert e.value.code in (engine._lib.ERR_UNSORTED, engine._lib.ERR_INVALID)
+    b2 = dict(b); b2["tid"] = 1
+    b1 = dict(b); b1["tid"] = 0
+    with pytest.raises(engine.EngineError) as e:
+        engine.run_batches([b2, b1], [50_000, 50_000], ("pdr",))
+    assert e.value.code == engine._lib.ERR_UNSORTED
+    with pytest.raises(engine.EngineError):
+        engine.run_batches([dict(b, cpg_rel=None)], [50_000], ("lpmd",))  # LPMD needs the query indices
+    empty = B.slice_reads(b, 0, 0)
+    res, _ = engine.run_batches([empty], [50_000], ALL)
+    assert res["pdr"]["n"] == 0 and np.isnan(res["lpmd"]["lpmd"])
