@@ -6,7 +6,8 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libmetheor_b200.so")
+# METHEOR_B200_LIB selects another build of the same library (kernel-variant experiments); never a fallback
+LIB_PATH = os.environ.get("METHEOR_B200_LIB") or os.path.join(CSRC, "libmetheor_b200.so")
 
 MTH_PDR, MTH_LPMD, MTH_MHL, MTH_PM, MTH_ME, MTH_FDRP, MTH_QFDRP = (1 << i for i in range(7))
 MTH_ALL = 0x7F

@@ -491,7 +491,9 @@ int mth_submit(mth_ctx* c, const mth_batch* b) {
 
     const int32_t lin_off = c->cur_lin_off;
     const int64_t r0 = c->R, i0 = c->I, w0 = c->W;
-    const bool can_borrow = b->mem_kind == 1 && r0 == 0 && lin_off == 0;
+    // borrowed arrays are read in place; the TMA bulk copies of k_ingest need 16-byte aligned bases
+    auto al16 = [](const void* p) { return ((uintptr_t)p & 15u) == 0; };
+    const bool can_borrow = b->mem_kind == 1 && r0 == 0 && lin_off == 0 && al16(b->cpg_pos) && al16(b->cpg_rel);
     const uint16_t* rel_dev = nullptr;
     if (can_borrow) {
         c->borrowed = true;
@@ -542,7 +544,7 @@ int mth_submit(mth_ctx* c, const mth_batch* b) {
                 ps.add(launch_add_i32((int32_t*)c->a_pos.p + i0, b->n_cpg, lin_off, c->compute));
             }
         }
-        rel_dev = lp ? (const uint16_t*)c->a_rel.p + i0 : nullptr;
+        rel_dev = lp ? (const uint16_t*)c->a_rel.p : nullptr;
     }
     c->R = r0 + b->n_reads;
     c->I = i0 + b->n_cpg;

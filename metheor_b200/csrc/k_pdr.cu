@@ -16,21 +16,80 @@ __device__ __forceinline__ bool pdr_read_ok(const mth_pdr_params& prm, uint32_t 
     return n >= prm.min_cpgs && mapq >= prm.min_qual && n > 0;
 }
 
-__global__ void __launch_bounds__(256) k_pdr_scatter(ReadsView rv, const unsigned long long* __restrict__ bitmap,
-                                                     const uint32_t* __restrict__ word_prefix,
-                                                     uint32_t* __restrict__ cnt2, mth_pdr_params prm) {
-    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= rv.R) return;
-    uint32_t o0 = rv.cpg_off[j], n = rv.cpg_off[j + 1] - o0;
-    if (n == 0) return;
-    uint32_t mapq = rv.meta[j] & 0xFFu;
-    if (!pdr_read_ok(prm, mapq, n)) return;
-    uint32_t disc = read_discordant(rv, j, n) ? 1u : 0u;
-    for (uint32_t k = 0; k < n; k++) {
-        uint32_t bit = (uint32_t)(rv.cpg_pos[o0 + k] + 1);
+// One CTA = one tile of PDS_TILE consecutive reads (their CpG calls are one contiguous slice of cpg_pos).
+//   phase 1, one thread per read : filters + concordance state -> code {0 skip, 1 concordant, 2 discordant} and the
+//            owner table (call -> read of the tile) in shared memory;
+//   phase 2, one thread per call : coalesced cpg_pos load, site rank from the dictionary, shared-memory atomics into a
+//            window of PDS_WIN site ranks starting at the first site the tile can touch (reads are sorted, a 30x tile
+//            of 256 reads covers ~1.3 kb = a few dozen sites), direct global atomics for ranks outside the window;
+//   phase 3: non-zero window counters are flushed with one global atomic each.
+// Global atomics drop from one per CpG call to one per (tile, site, state).
+constexpr int PDS_TILE = 256;
+constexpr int PDS_CAP = 4096;   // calls per tile with an owner entry; beyond that the per-read fallback runs
+constexpr int PDS_WIN = 1024;   // site ranks aggregated in shared memory
+
+__device__ __forceinline__ uint32_t site_rank(const unsigned long long* __restrict__ bitmap,
+                                              const uint32_t* __restrict__ word_prefix, int32_t pos) {
+    uint32_t bit = (uint32_t)(pos + 1);
+    uint32_t w = bit >> 6;
+    return __ldg(word_prefix + w) + (uint32_t)__popcll(__ldg(bitmap + w) & ((1ull << (bit & 63)) - 1ull));
+}
+
+__global__ void __launch_bounds__(PDS_TILE) k_pdr_scatter(ReadsView rv, const unsigned long long* __restrict__ bitmap,
+                                                          const uint32_t* __restrict__ word_prefix,
+                                                          uint32_t* __restrict__ cnt2, mth_pdr_params prm) {
+    __shared__ uint32_t s_cnt[2 * PDS_WIN];
+    __shared__ uint8_t s_owner[PDS_CAP];
+    __shared__ uint8_t s_code[PDS_TILE];
+    __shared__ uint32_t s_lo, s_hi, s_rank0;
+
+    const int tid = threadIdx.x;
+    const int64_t tile0 = (int64_t)blockIdx.x * PDS_TILE;
+    const int64_t tile1 = min(rv.R, tile0 + PDS_TILE);
+    if (tid == 0) {
+        s_lo = rv.cpg_off[tile0];
+        s_hi = rv.cpg_off[tile1];
+        // every call of the tile lies at or after start[tile0] - 1 (reads sorted by start, calls in [start-1, end])
+        int32_t pmin = rv.start[tile0] - 1;
+        uint32_t bit = (uint32_t)(pmin + 1);
         uint32_t w = bit >> 6;
-        uint32_t rank = word_prefix[w] + (uint32_t)__popcll(bitmap[w] & ((1ull << (bit & 63)) - 1ull));
-        atomicAdd(&cnt2[2 * (size_t)rank + disc], 1u);
+        s_rank0 = word_prefix[w] + (uint32_t)__popcll(bitmap[w] & ((1ull << (bit & 63)) - 1ull));
+    }
+    for (int k = tid; k < 2 * PDS_WIN; k += PDS_TILE) s_cnt[k] = 0;
+
+    const int64_t j = tile0 + tid;
+    uint32_t o0 = 0, n = 0, code = 0;
+    if (j < tile1) {
+        o0 = rv.cpg_off[j];
+        n = rv.cpg_off[j + 1] - o0;
+        uint32_t mapq = rv.meta[j] & 0xFFu;
+        if (n > 0 && pdr_read_ok(prm, mapq, n)) code = read_discordant(rv, j, n) ? 2u : 1u;
+    }
+    s_code[tid] = (uint8_t)code;
+    __syncthreads();
+    const uint32_t lo = s_lo, hi = s_hi, rank0 = s_rank0;
+    const bool tabled = hi - lo <= (uint32_t)PDS_CAP;
+    if (tabled) {
+        for (uint32_t k = 0; k < n; k++) s_owner[o0 - lo + k] = (uint8_t)tid;
+        __syncthreads();
+        for (uint32_t x = lo + tid; x < hi; x += PDS_TILE) {
+            uint32_t cd = s_code[s_owner[x - lo]];
+            if (!cd) continue;
+            uint32_t r = site_rank(bitmap, word_prefix, rv.cpg_pos[x]);
+            uint32_t rel = r - rank0;
+            if (rel < (uint32_t)PDS_WIN) atomicAdd(&s_cnt[2 * rel + (cd - 1)], 1u);
+            else atomicAdd(&cnt2[2 * (size_t)r + (cd - 1)], 1u);
+        }
+    } else if (code) {  // dense tile: one thread per read, straight to global memory
+        for (uint32_t k = 0; k < n; k++) {
+            uint32_t r = site_rank(bitmap, word_prefix, rv.cpg_pos[o0 + k]);
+            atomicAdd(&cnt2[2 * (size_t)r + (code - 1)], 1u);
+        }
+    }
+    __syncthreads();
+    for (int k = tid; k < 2 * PDS_WIN; k += PDS_TILE) {
+        uint32_t v = s_cnt[k];
+        if (v) atomicAdd(&cnt2[2 * (size_t)rank0 + k], v);
     }
 }
 
@@ -98,7 +157,7 @@ static inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + b
 int launch_pdr_scatter(const ReadsView& rv, const unsigned long long* bitmap, const uint32_t* word_prefix,
                        uint32_t* cnt2, mth_pdr_params prm, cudaStream_t s) {
     if (rv.R <= 0) return 0;
-    k_pdr_scatter<<<grid_for(rv.R, 256), 256, 0, s>>>(rv, bitmap, word_prefix, cnt2, prm);
+    k_pdr_scatter<<<grid_for(rv.R, PDS_TILE), PDS_TILE, 0, s>>>(rv, bitmap, word_prefix, cnt2, prm);
     return 1;
 }
 

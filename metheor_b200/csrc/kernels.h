@@ -14,8 +14,8 @@ int launch_add_i32(int32_t* a, int64_t n, int32_t add, cudaStream_t s);
 struct IngestArgs {
     ReadsView rv;             // region-wide view (already contains the batch)
     int64_t r0, n;            // reads [r0, r0+n) are the new batch
-    int64_t i0;               // first incidence of the batch (cpg_rel is batch-local)
-    const uint16_t* cpg_rel;  // device, batch-local, or nullptr
+    int64_t i0;               // first CpG call of the batch
+    const uint16_t* cpg_rel;  // device, REGION-wide like rv.cpg_pos (same indices), or nullptr; 16-byte aligned base
     unsigned long long* bitmap;  // bit (p+1) set for every CpG position p seen
     int32_t lin_lo, lin_hi;   // valid position range of this contig in device coordinates: [lin_lo-1, lin_hi)
     int do_lpmd;
