@@ -75,7 +75,7 @@ void mth_params_default(mth_params* p); /* reference defaults, measures = 0 */
 
 /* One batch of decoded reads of ONE contig, in file order (start ascending).  Replaces the per-record
  * BismarkRead of src/readutil.rs:15-21.  Arrays are caller-owned and must stay valid until the next
- * mth_finish()/mth_sync() returns (copies are asynchronous).  mem_kind: 0 = host memory (pinned preferred,
+ * mth_finish()/mth_sync()/mth_sync_copies() returns (copies are asynchronous).  mem_kind: 0 = host memory (pinned preferred,
  * see mth_host_alloc), 1 = device memory on the context's GPU.
  *   start/end : first / last aligned reference position of the read (readutil.rs:25-33)
  *   meta      : bits 0-7 mapq (pdr.rs:150), bit 8 = forward strand (informational)
@@ -176,6 +176,9 @@ int mth_lpmd_counters_device(mth_ctx* ctx, void** dev_ptr);
 int mth_lpmd_refresh(mth_ctx* ctx, mth_lpmd_result* out);
 int mth_reset(mth_ctx* ctx);        /* forget all input and results, keep allocations */
 int mth_sync(mth_ctx* ctx);         /* wait for everything enqueued so far */
+/* Wait only for the host->device copies of the batches submitted so far: after it returns their host arrays may be
+ * reused (a streaming host keeps a small ring of pinned batches), while the ingest kernels keep running. */
+int mth_sync_copies(mth_ctx* ctx);
 int mth_get_stats(mth_ctx* ctx, mth_stats* out);
 const char* mth_last_error(mth_ctx* ctx); /* ctx may be NULL: last create error */
 

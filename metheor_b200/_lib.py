@@ -84,7 +84,7 @@ class Stats(C.Structure):
 
 EXPORTS = ["mth_params_default", "mth_ctx_create", "mth_ctx_destroy", "mth_set_stream", "mth_submit",
            "mth_add_skipped_reads", "mth_finish", "mth_results_device", "mth_lpmd_counters_device", "mth_lpmd_refresh",
-           "mth_reset", "mth_sync", "mth_get_stats", "mth_last_error", "mth_host_alloc", "mth_host_free",
+           "mth_reset", "mth_sync", "mth_sync_copies", "mth_get_stats", "mth_last_error", "mth_host_alloc", "mth_host_free",
            "mth_device_count", "mth_version", "mth_reservoir_draw"]
 
 
@@ -120,6 +120,7 @@ def lib():
     L.mth_lpmd_refresh.argtypes = [vp, P(LpmdResult)]; L.mth_lpmd_refresh.restype = C.c_int
     L.mth_reset.argtypes = [vp]; L.mth_reset.restype = C.c_int
     L.mth_sync.argtypes = [vp]; L.mth_sync.restype = C.c_int
+    L.mth_sync_copies.argtypes = [vp]; L.mth_sync_copies.restype = C.c_int
     L.mth_get_stats.argtypes = [vp, P(Stats)]; L.mth_get_stats.restype = C.c_int
     L.mth_last_error.argtypes = [vp]; L.mth_last_error.restype = C.c_char_p
     L.mth_host_alloc.argtypes = [C.c_size_t]; L.mth_host_alloc.restype = vp

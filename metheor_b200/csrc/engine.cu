@@ -430,6 +430,13 @@ int mth_sync(mth_ctx* c) {
     return MTH_OK;
 }
 
+int mth_sync_copies(mth_ctx* c) {
+    if (!c) return MTH_ERR_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, cudaStreamSynchronize(c->copy));
+    return MTH_OK;
+}
+
 int mth_reset(mth_ctx* c) {
     if (!c) return MTH_ERR_INVALID;
     TRY(mth_sync(c));

@@ -1,0 +1,271 @@
+// input.cpp — see input.hpp.  BGZF/BAM layout per the SAM specification.
+#include "input.hpp"
+
+#include <errno.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <zlib.h>
+
+#include <algorithm>
+
+namespace mthh {
+
+int Header::tid_of(const std::string& n) const {
+    for (size_t i = 0; i < names.size(); i++)
+        if (names[i] == n) return (int)i;
+    return -1;
+}
+
+static HostError open_error(const std::string& what) { return HostError{101, "Error opening BAM file. " + what}; }
+
+MappedFile::~MappedFile() {
+    if (data_ && size_) munmap((void*)data_, size_);
+    if (fd_ >= 0) close(fd_);
+}
+
+void MappedFile::open(const std::string& path) {
+    fd_ = ::open(path.c_str(), O_RDONLY);
+    if (fd_ < 0) {
+        // rust-htslib: Error::FileNotFound { path } => "file not found: {path}" (tests/pdr-cli.rs:19-33 checks both parts)
+        if (errno == ENOENT) throw open_error("file not found: " + path);
+        throw open_error("unable to open " + path + ": " + strerror(errno));
+    }
+    struct stat st;
+    if (fstat(fd_, &st) != 0 || !S_ISREG(st.st_mode)) throw open_error("not a regular file: " + path);
+    size_ = (size_t)st.st_size;
+    if (size_ == 0) throw open_error("invalid (empty) file: " + path);
+    void* p = mmap(nullptr, size_, PROT_READ, MAP_PRIVATE, fd_, 0);
+    if (p == MAP_FAILED) throw open_error("mmap failed for " + path + ": " + strerror(errno));
+    madvise(p, size_, MADV_SEQUENTIAL);
+    data_ = (const uint8_t*)p;
+}
+
+namespace {
+
+struct Inflater {
+    z_stream zs;
+    bool ready = false;
+    ~Inflater() {
+        if (ready) inflateEnd(&zs);
+    }
+    // raw DEFLATE payload of one BGZF member -> exactly usize bytes; CRC32 checked like htslib's bgzf reader does
+    bool run(const uint8_t* in, size_t clen, uint8_t* out, uint32_t usize, uint32_t crc_expected) {
+        if (!ready) {
+            memset(&zs, 0, sizeof(zs));
+            if (inflateInit2(&zs, -15) != Z_OK) return false;
+            ready = true;
+        } else if (inflateReset(&zs) != Z_OK) {
+            return false;
+        }
+        zs.next_in = (Bytef*)in;
+        zs.avail_in = (uInt)clen;
+        zs.next_out = out;
+        zs.avail_out = usize;
+        int rc = inflate(&zs, Z_FINISH);
+        if (rc != Z_STREAM_END || zs.avail_out != 0) return false;
+        return (uint32_t)crc32(crc32(0L, Z_NULL, 0), out, usize) == crc_expected;
+    }
+};
+
+// Parses one BGZF member header at `o`; returns the member size or 0 if it is not a valid BGZF member.
+size_t bgzf_member(const uint8_t* d, size_t size, size_t o, size_t* cdata, size_t* clen, uint32_t* usize, uint32_t* crc) {
+    if (o + 18 > size) return 0;
+    if (d[o] != 31 || d[o + 1] != 139 || d[o + 2] != 8 || !(d[o + 3] & 4)) return 0;
+    uint16_t xlen = le16(d + o + 10);
+    size_t x = o + 12, xend = x + xlen;
+    if (xend > size) return 0;
+    int bsize = -1;
+    while (x + 4 <= xend) {
+        uint16_t slen = le16(d + x + 2);
+        if (d[x] == 'B' && d[x + 1] == 'C' && slen == 2 && x + 6 <= xend) bsize = le16(d + x + 4);
+        x += 4 + (size_t)slen;
+    }
+    if (bsize < 0) return 0;
+    size_t total = (size_t)bsize + 1;
+    if (total < (size_t)xlen + 20 || o + total > size) return 0;
+    *cdata = o + 12 + xlen;
+    *clen = total - xlen - 12 - 8;
+    *crc = (uint32_t)le32(d + o + total - 8);
+    *usize = (uint32_t)le32(d + o + total - 4);
+    return total;
+}
+
+}  // namespace
+
+RecordStream::RecordStream(const std::string& path, ThreadPool& pool, size_t window_bytes)
+    : path_(path), pool_(pool), window_bytes_(window_bytes) {
+    file_.open(path);
+    const uint8_t* d = file_.data();
+    if (file_.size() >= 2 && d[0] == 31 && d[1] == 139) {
+        format_ = Format::BAM;
+        parse_bam_header();
+    } else if (d[0] == '@') {
+        format_ = Format::SAM;
+        parse_sam_header();
+    } else {
+        // htslib also accepts header-less SAM; require at least one plausible alignment line (11 tab-separated fields)
+        size_t e = 0, tabs = 0;
+        while (e < file_.size() && d[e] != '\n' && e < 65536) tabs += d[e++] == '\t';
+        if (tabs < 10) throw open_error("unrecognised format (neither BGZF/BAM nor SAM): " + path);
+        format_ = Format::SAM;
+    }
+}
+
+bool RecordStream::fill_bam_window() {
+    const uint8_t* d = file_.data();
+    size_t carry = buf_len_ - buf_pos_;
+    blocks_.clear();
+    size_t utotal = 0;
+    while (coff_ < file_.size() && utotal < window_bytes_) {
+        Block b;
+        uint32_t crc;
+        size_t total = bgzf_member(d, file_.size(), coff_, &b.cdata, &b.clen, &b.usize, &crc);
+        if (!total) throw open_error("corrupt or truncated BGZF block at offset " + std::to_string(coff_) + ": " + path_);
+        b.uoff = utotal;
+        utotal += b.usize;
+        if (b.usize) blocks_.push_back(b);
+        coff_ += total;
+    }
+    if (blocks_.empty()) {
+        eof_ = true;
+        return false;
+    }
+    std::vector<uint8_t> nb(carry + utotal);
+    if (carry) memcpy(nb.data(), buf_.data() + buf_pos_, carry);
+    double t0 = now_s();
+    std::vector<Inflater> infl((size_t)pool_.size());
+    std::atomic<int> bad{0};
+    uint8_t* out = nb.data() + carry;
+    pool_.run((int64_t)blocks_.size(), [&](int64_t i, int w) {
+        const Block& b = blocks_[(size_t)i];
+        uint32_t crc = (uint32_t)le32(d + b.cdata + b.clen);
+        if (!infl[(size_t)w].run(d + b.cdata, b.clen, out + b.uoff, b.usize, crc)) bad.store(1);
+    });
+    if (bad.load()) throw open_error("BGZF inflate / CRC failure: " + path_);
+    seconds_inflate += now_s() - t0;
+    bytes_uncompressed += utotal;
+    buf_.swap(nb);
+    buf_len_ = carry + utotal;
+    buf_pos_ = 0;
+    return true;
+}
+
+void RecordStream::parse_bam_header() {
+    // the header may span several windows: keep appending until it is complete
+    for (;;) {
+        size_t before = buf_len_;
+        buf_pos_ = 0;
+        bool more = fill_bam_window();
+        const uint8_t* b = buf_.data();
+        size_t n = buf_len_;
+        if (n < 12 || memcmp(b, "BAM\1", 4) != 0) throw open_error("not a BAM file (bad magic): " + path_);
+        bool ok = false;
+        size_t o = 4;
+        do {
+            int32_t l_text = le32(b + o);
+            if (l_text < 0) throw open_error("corrupt BAM header: " + path_);
+            o += 4 + (size_t)l_text;
+            if (o + 4 > n) break;
+            int32_t n_ref = le32(b + o);
+            o += 4;
+            Header h;
+            bool complete = true;
+            for (int32_t i = 0; i < n_ref; i++) {
+                if (o + 4 > n) { complete = false; break; }
+                int32_t l_name = le32(b + o);
+                o += 4;
+                if (l_name < 1 || o + (size_t)l_name + 4 > n) { complete = false; break; }
+                h.names.emplace_back((const char*)b + o, (size_t)l_name - 1);
+                o += (size_t)l_name;
+                h.lengths.push_back((int64_t)(uint32_t)le32(b + o));
+                o += 4;
+            }
+            if (!complete) break;
+            header_ = std::move(h);
+            ok = true;
+        } while (false);
+        if (ok) {
+            buf_pos_ = o;
+            return;
+        }
+        if (!more || buf_len_ == before) throw open_error("truncated BAM header: " + path_);
+    }
+}
+
+void RecordStream::parse_sam_header() {
+    const uint8_t* d = file_.data();
+    size_t n = file_.size(), o = 0;
+    while (o < n && d[o] == '@') {
+        size_t e = o;
+        while (e < n && d[e] != '\n') e++;
+        if (e - o >= 3 && d[o + 1] == 'S' && d[o + 2] == 'Q') {
+            std::string sn;
+            int64_t ln = 0;
+            size_t f = o;
+            while (f < e) {
+                size_t g = f;
+                while (g < e && d[g] != '\t') g++;
+                if (g - f > 3 && d[f + 2] == ':') {
+                    if (d[f] == 'S' && d[f + 1] == 'N') sn.assign((const char*)d + f + 3, g - f - 3);
+                    if (d[f] == 'L' && d[f + 1] == 'N') ln = atoll(std::string((const char*)d + f + 3, g - f - 3).c_str());
+                }
+                f = g + 1;
+            }
+            if (!sn.empty() && sn.back() == '\r') sn.pop_back();
+            header_.names.push_back(sn);
+            header_.lengths.push_back(ln);
+        }
+        o = e + 1;
+    }
+    coff_ = o;
+}
+
+bool RecordStream::next(std::vector<RecordRef>* recs) {
+    recs->clear();
+    if (format_ == Format::SAM) {
+        const uint8_t* d = file_.data();
+        size_t n = file_.size();
+        if (coff_ >= n) return false;
+        double t0 = now_s();
+        size_t stop = std::min(n, coff_ + window_bytes_);
+        size_t o = coff_;
+        while (o < n && (o < stop)) {
+            const uint8_t* nl = (const uint8_t*)memchr(d + o, '\n', n - o);
+            size_t e = nl ? (size_t)(nl - d) : n;
+            size_t len = e - o;
+            if (len && d[e - 1] == '\r') len--;
+            if (len && d[o] != '@') recs->push_back(RecordRef{d + o, (uint32_t)len});
+            o = e + 1;
+        }
+        bytes_uncompressed += o - coff_;
+        coff_ = o;
+        seconds_walk += now_s() - t0;
+        return true;
+    }
+    for (;;) {
+        if (buf_pos_ + 4 > buf_len_ || (size_t)le32(buf_.data() + buf_pos_) + 4 + buf_pos_ > buf_len_) {
+            if (!fill_bam_window()) {
+                if (buf_pos_ != buf_len_) throw open_error("truncated BAM record at end of file: " + path_);
+                return false;
+            }
+        }
+        double t0 = now_s();
+        const uint8_t* b = buf_.data();
+        size_t o = buf_pos_;
+        while (o + 4 <= buf_len_) {
+            int32_t bs = le32(b + o);
+            if (bs < 32) throw open_error("corrupt BAM record (block_size < 32): " + path_);
+            if (o + 4 + (size_t)bs > buf_len_) break;
+            recs->push_back(RecordRef{b + o + 4, (uint32_t)bs});
+            o += 4 + (size_t)bs;
+        }
+        buf_pos_ = o;
+        seconds_walk += now_s() - t0;
+        if (!recs->empty()) return true;
+        // a single record larger than what is buffered: pull more blocks behind it
+    }
+}
+
+}  // namespace mthh

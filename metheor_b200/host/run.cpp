@@ -1,0 +1,506 @@
+// run.cpp — one reference subcommand end to end: decode windows of the alignment file on all host cores into pinned
+// SoA batches, stream them to the GPU engine(s) through the C ABI of include/metheor_b200.h, fetch the rows and write
+// the reference's TSV formats (pdr.rs:102-116, mhl.rs:122-131, fdrp.rs:169-172, qfdrp.rs:181-184, pm.rs:53-60,
+// me.rs:57-65, lpmd.rs:89-122,145-147).
+//
+// Pipeline per window (~64 MiB of uncompressed records):
+//   inflate BGZF blocks (all cores) -> walk record boundaries -> cut at contig changes -> decode records (all cores,
+//   one SoaChunk per task) -> gather the chunks into one pinned batch (all cores) -> mth_submit (asynchronous H2D on
+//   the engine's copy stream + ingest kernels) -> next window while the GPU works.
+// Multi-GPU (--gpus N): contigs are assigned to N engine contexts (longest-first balancing on the header lengths);
+// a contig's reads all go to one GPU, so every per-CpG / per-quartet row is final on its GPU and only LPMD's four
+// counters are summed across contexts.
+#include <algorithm>
+#include <charconv>
+#include <cmath>
+#include <cstdio>
+#include <memory>
+
+#include "../../include/metheor_b200.h"
+#include "../../include/metheor_host.h"
+#include "decode.hpp"
+#include "input.hpp"
+
+namespace mthh {
+
+int format_f32(float v, char* buf, int cap) {
+    // Rust `{}` for f32: shortest digits that round-trip, positional notation, "NaN", "inf", "-0"
+    if (std::isnan(v)) return snprintf(buf, (size_t)cap, "NaN");
+    if (std::isinf(v)) return snprintf(buf, (size_t)cap, v < 0 ? "-inf" : "inf");
+    auto r = std::to_chars(buf, buf + cap - 1, v, std::chars_format::fixed);
+    *r.ptr = 0;
+    return (int)(r.ptr - buf);
+}
+
+namespace {
+
+const size_t WINDOW_BYTES = 64u << 20;
+const size_t TASK_RECORDS = 4096;
+const int RING = 3;
+
+struct PinnedBatch {
+    enum { START, END, META, OFF, POS, REL, METH, MOFF, NARR };
+    void* p[NARR] = {nullptr};
+    size_t cap[NARR] = {0};
+    ~PinnedBatch() {
+        for (void* x : p) mth_host_free(x);
+    }
+    void reserve(int k, size_t bytes) {
+        if (bytes <= cap[k]) return;
+        mth_host_free(p[k]);
+        size_t ncap = bytes + bytes / 4 + 4096;
+        p[k] = mth_host_alloc(ncap);
+        if (!p[k]) throw HostError{1, "cannot allocate pinned host memory"};
+        cap[k] = ncap;
+    }
+};
+
+struct Gpu {
+    mth_ctx* ctx = nullptr;
+    PinnedBatch ring[RING];
+    int next_slot = 0;
+    int64_t submitted = 0;
+    mth_results res;
+    mth_stats stats;
+    int rc = 0;
+    std::string err;
+};
+
+[[noreturn]] void engine_fail(mth_ctx* ctx, int rc, const char* what) {
+    std::string m = std::string("metheor_b200 engine: ") + what + " failed (" + std::to_string(rc) + "): " + mth_last_error(ctx);
+    if (rc == MTH_ERR_UNSORTED) m += "\nThe GPU engine needs coordinate-sorted input (samtools sort).";
+    throw HostError{1, m};
+}
+
+uint32_t measure_bit(int m) {
+    static const uint32_t bits[] = {MTH_PDR, MTH_LPMD, MTH_MHL, MTH_PM, MTH_ME, MTH_FDRP, MTH_QFDRP};
+    return bits[m];
+}
+
+// Gathers the decoded chunks [c0, c1) (all of one contig) into the pinned arrays of `pb` and fills `b`.
+void assemble(ThreadPool& pool, std::vector<SoaChunk>& chunks, size_t c0, size_t c1, int32_t tid, bool want_rel, int max_cpgs,
+              PinnedBatch& pb, mth_batch* b) {
+    const size_t nc = c1 - c0;
+    std::vector<size_t> r_off(nc + 1, 0), i_off(nc + 1, 0), w_off(nc + 1, 0);
+    const bool multiword = max_cpgs > 64;
+    for (size_t k = 0; k < nc; k++) {
+        const SoaChunk& ch = chunks[c0 + k];
+        r_off[k + 1] = r_off[k] + ch.start.size();
+        i_off[k + 1] = i_off[k] + ch.cpg_pos.size();
+        size_t w = ch.start.size();
+        if (multiword) {
+            w = 0;
+            for (uint32_t n : ch.n_cpg) w += std::max<size_t>(1, (n + 63) / 64);
+        }
+        w_off[k + 1] = w_off[k] + w;
+    }
+    const size_t R = r_off[nc], I = i_off[nc], W = w_off[nc];
+    if (I >= 0xFFFFFFF0ull) throw HostError{1, "more than 2^32 CpG calls in one window"};
+    pb.reserve(PinnedBatch::START, R * 4); pb.reserve(PinnedBatch::END, R * 4); pb.reserve(PinnedBatch::META, R * 4);
+    pb.reserve(PinnedBatch::OFF, (R + 1) * 4); pb.reserve(PinnedBatch::POS, I * 4 + 64); pb.reserve(PinnedBatch::METH, W * 8 + 8);
+    if (want_rel) pb.reserve(PinnedBatch::REL, I * 2 + 64);
+    if (multiword) pb.reserve(PinnedBatch::MOFF, (R + 1) * 4);
+    int32_t* start = (int32_t*)pb.p[PinnedBatch::START];
+    int32_t* end = (int32_t*)pb.p[PinnedBatch::END];
+    uint32_t* meta = (uint32_t*)pb.p[PinnedBatch::META];
+    uint32_t* off = (uint32_t*)pb.p[PinnedBatch::OFF];
+    int32_t* pos = (int32_t*)pb.p[PinnedBatch::POS];
+    uint16_t* rel = (uint16_t*)pb.p[PinnedBatch::REL];
+    uint64_t* meth = (uint64_t*)pb.p[PinnedBatch::METH];
+    uint32_t* moff = (uint32_t*)pb.p[PinnedBatch::MOFF];
+    pool.run((int64_t)nc, [&](int64_t k, int) {
+        const SoaChunk& ch = chunks[c0 + (size_t)k];
+        const size_t r0 = r_off[(size_t)k], i0 = i_off[(size_t)k], n = ch.start.size();
+        if (!n) return;
+        memcpy(start + r0, ch.start.data(), n * 4);
+        memcpy(end + r0, ch.end.data(), n * 4);
+        memcpy(meta + r0, ch.meta.data(), n * 4);
+        memcpy(pos + i0, ch.cpg_pos.data(), ch.cpg_pos.size() * 4);
+        if (want_rel) memcpy(rel + i0, ch.cpg_rel.data(), ch.cpg_rel.size() * 2);
+        size_t io = i0, wo = w_off[(size_t)k];
+        const uint8_t* m = ch.cpg_meth.data();
+        for (size_t r = 0; r < n; r++) {
+            const uint32_t nr = ch.n_cpg[r];
+            off[r0 + r] = (uint32_t)io;
+            if (multiword) moff[r0 + r] = (uint32_t)wo;
+            const size_t nw = multiword ? std::max<size_t>(1, (nr + 63) / 64) : 1;
+            for (size_t w = 0; w < nw; w++) {
+                uint64_t bits = 0;
+                const uint32_t lo = (uint32_t)w * 64, hi = std::min(nr, lo + 64);
+                for (uint32_t x = lo; x < hi; x++) bits |= (uint64_t)m[x] << (x - lo);
+                meth[wo + w] = bits;
+            }
+            m += nr;
+            io += nr;
+            wo += nw;
+        }
+    });
+    off[R] = (uint32_t)I;
+    if (multiword) moff[R] = (uint32_t)W;
+    memset(b, 0, sizeof(*b));
+    b->tid = tid;
+    b->mem_kind = 0;
+    b->n_reads = (int64_t)R;
+    b->n_cpg = (int64_t)I;
+    b->n_meth_words = (int64_t)W;
+    b->start = start; b->end = end; b->meta = meta; b->cpg_off = off; b->cpg_pos = pos;
+    b->cpg_rel = want_rel ? rel : nullptr;
+    b->meth = meth;
+    b->meth_off = multiword ? moff : nullptr;
+}
+
+// ---- TSV ----------------------------------------------------------------------------------------------------
+struct OutFile {
+    FILE* f = nullptr;
+    explicit OutFile(const char* path) {
+        // pdr.rs:95-101: create + truncate; .unwrap() panics when the path cannot be opened
+        f = fopen(path, "w");
+        if (!f) throw HostError{101, std::string("called `Result::unwrap()` on an `Err` value: cannot open output file ") + path + ": " + strerror(errno)};
+        setvbuf(f, nullptr, _IOFBF, 1 << 20);
+    }
+    ~OutFile() {
+        if (f) fclose(f);
+    }
+    void write(const std::string& s) {
+        if (fwrite(s.data(), 1, s.size(), f) != s.size()) throw HostError{101, "Error writing to output file."};
+    }
+};
+
+inline void put_i32(std::string& s, int64_t v) {
+    char b[24];
+    auto r = std::to_chars(b, b + sizeof(b), v);
+    s.append(b, (size_t)(r.ptr - b));
+}
+inline void put_f32(std::string& s, float v) {
+    char b[128];
+    s.append(b, (size_t)format_f32(v, b, sizeof(b)));
+}
+
+// rows [0,n) formatted by `row(i, string&)` on all cores, written in order
+template <class RowFn>
+void write_rows(ThreadPool& pool, OutFile& out, int64_t n, RowFn&& row) {
+    const int64_t CH = 1 << 16;
+    const int64_t nch = (n + CH - 1) / CH;
+    const int64_t GROUP = (int64_t)pool.size() * 4;
+    std::vector<std::string> bufs((size_t)std::min<int64_t>(nch, GROUP));
+    for (int64_t g0 = 0; g0 < nch; g0 += GROUP) {
+        const int64_t g1 = std::min(nch, g0 + GROUP);
+        pool.run(g1 - g0, [&](int64_t k, int) {
+            std::string& s = bufs[(size_t)k];
+            s.clear();
+            const int64_t a = (g0 + k) * CH, b = std::min(n, a + CH);
+            for (int64_t i = a; i < b; i++) row(i, s);
+        });
+        for (int64_t k = 0; k < g1 - g0; k++) out.write(bufs[(size_t)k]);
+    }
+}
+
+// Row sources of several GPUs merged by contig: each contig lives on exactly one GPU and rows are sorted by
+// (tid, pos) within a GPU, so the global order is "for tid ascending: that GPU's run of rows with this tid".
+struct Run { int gpu; int64_t lo, hi; };
+template <class TidOf>
+std::vector<Run> merge_runs(int n_gpus, const std::vector<int64_t>& n_rows, TidOf&& tid_of) {
+    struct Item { int32_t tid; Run r; };
+    std::vector<Item> items;
+    for (int g = 0; g < n_gpus; g++) {
+        int64_t i = 0, n = n_rows[(size_t)g];
+        while (i < n) {
+            const int32_t t = tid_of(g, i);
+            int64_t lo = i, a = i, b = n;  // first index with tid > t
+            while (a < b) {
+                int64_t m = (a + b) / 2;
+                if (tid_of(g, m) <= t) a = m + 1; else b = m;
+            }
+            items.push_back(Item{t, Run{g, lo, a}});
+            i = a;
+        }
+    }
+    std::stable_sort(items.begin(), items.end(), [](const Item& x, const Item& y) { return x.tid < y.tid; });
+    std::vector<Run> runs;
+    for (auto& it : items) runs.push_back(it.r);
+    return runs;
+}
+
+void json_escape(FILE* f, const char* s) {
+    for (; *s; s++) {
+        if (*s == '"' || *s == '\\') fputc('\\', f);
+        fputc(*s, f);
+    }
+}
+
+}  // namespace
+
+void run(const mthh_options& o) {
+    const double t_begin = now_s();
+    if (!o.input || !o.output) throw HostError{2, "error: the following required arguments were not provided:\n  --input <INPUT>\n  --output <OUTPUT>"};
+    if (o.measure < 0 || o.measure > MTHH_QFDRP) throw HostError{2, "error: unknown measure"};
+    int n_threads = o.threads > 0 ? o.threads : (int)std::thread::hardware_concurrency();
+    if (n_threads < 1) n_threads = 1;
+    ThreadPool pool(n_threads);
+
+    // bamutil.rs:4-11: the input is opened first; a missing / non-BAM file panics with "Error opening BAM file. ..."
+    RecordStream in(o.input, pool, WINDOW_BYTES);
+    const Header& hdr = in.header();
+    CpgSet cpg_set;
+    if (o.cpg_set) cpg_set.load(o.cpg_set, hdr);  // readutil.rs:347-374
+
+    const int n_dev = mth_device_count();
+    if (n_dev <= 0) throw HostError{1, "metheor_b200: no CUDA device found (this engine has no CPU path)"};
+    const int n_gpus = std::max(1, o.n_gpus);
+    if (o.device < 0 || o.device + n_gpus > n_dev)
+        throw HostError{1, "metheor_b200: --device/--gpus outside the " + std::to_string(n_dev) + " visible CUDA device(s)"};
+
+    mth_params prm;
+    mth_params_default(&prm);
+    prm.measures = measure_bit(o.measure);
+    prm.seed = o.seed;
+    if (o.stats_json) prm.flags |= MTH_FLAG_PROFILE;
+    prm.pdr = {o.min_depth, o.min_cpgs, o.min_qual};
+    prm.mhl = {o.min_depth, o.min_cpgs, o.min_qual};
+    prm.pm = {o.min_depth, o.min_qual};
+    prm.me = {o.min_depth, o.min_qual};
+    prm.fdrp = {o.min_qual, o.min_depth, o.max_depth, o.min_overlap};
+    prm.qfdrp = prm.fdrp;
+    prm.lpmd = {o.min_distance, o.max_distance, o.min_qual, o.pairs ? 1u : 0u};
+    if ((o.measure == MTHH_FDRP || o.measure == MTHH_QFDRP) && o.max_depth == 0)
+        throw HostError{1, "metheor_b200: --max-depth must be at least 1"};
+
+    std::vector<int64_t> ref_len = hdr.lengths;
+    std::vector<std::unique_ptr<Gpu>> gpus;
+    for (int g = 0; g < n_gpus; g++) {
+        gpus.emplace_back(new Gpu());
+        int rc = mth_ctx_create(&gpus.back()->ctx, o.device + g, &prm, (int32_t)ref_len.size(), ref_len.data());
+        if (rc != MTH_OK) throw HostError{1, std::string("metheor_b200 engine: ") + mth_last_error(nullptr)};
+    }
+    struct CtxGuard {
+        std::vector<std::unique_ptr<Gpu>>& g;
+        ~CtxGuard() {
+            for (auto& x : g) mth_ctx_destroy(x->ctx);
+        }
+    } guard{gpus};
+
+    // contig -> GPU: longest-first onto the least loaded GPU
+    std::vector<int> gpu_of(ref_len.size(), 0);
+    if (n_gpus > 1) {
+        std::vector<size_t> order(ref_len.size());
+        for (size_t i = 0; i < order.size(); i++) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return ref_len[a] > ref_len[b]; });
+        std::vector<int64_t> load((size_t)n_gpus, 0);
+        for (size_t t : order) {
+            int g = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+            gpu_of[t] = g;
+            load[(size_t)g] += ref_len[t];
+        }
+    }
+
+    DecodeOptions dopt;
+    dopt.cpg_set = o.cpg_set ? &cpg_set : nullptr;
+    dopt.min_qual = o.min_qual;
+    dopt.lpmd_order = o.measure == MTHH_LPMD;
+    const bool want_rel = o.measure == MTHH_LPMD;
+
+    std::vector<RecordRef> recs;
+    std::vector<SoaChunk> chunks;
+    std::vector<DecodeCounters> task_cnt;
+    DecodeCounters total;
+    double s_decode = 0, s_assemble = 0, s_submit = 0;
+    int64_t n_batches = 0, n_shipped_reads = 0, n_shipped_cpg = 0;
+    const Format fmt = in.format();
+
+    while (in.next(&recs)) {
+        // cut the window at contig changes (a batch carries one tid)
+        size_t seg0 = 0;
+        while (seg0 < recs.size()) {
+            const int32_t tid = record_tid(fmt, hdr, recs[seg0]);
+            size_t seg1 = seg0 + 1;
+            if (record_tid(fmt, hdr, recs.back()) == tid) {
+                seg1 = recs.size();
+            } else {
+                size_t a = seg0, b = recs.size();  // reads are grouped by contig: first record with another tid
+                while (b - a > 1) {
+                    size_t m = (a + b) / 2;
+                    if (record_tid(fmt, hdr, recs[m]) == tid) a = m; else b = m;
+                }
+                seg1 = b;
+            }
+            const size_t n_tasks = (seg1 - seg0 + TASK_RECORDS - 1) / TASK_RECORDS;
+            if (chunks.size() < n_tasks) chunks.resize(n_tasks);
+            task_cnt.assign(n_tasks, DecodeCounters());
+            double t0 = now_s();
+            std::atomic<int> failed{0};
+            HostError first_err{0, ""};
+            std::mutex err_m;
+            pool.run((int64_t)n_tasks, [&](int64_t k, int) {
+                SoaChunk& ch = chunks[(size_t)k];
+                ch.clear();
+                if (failed.load()) return;
+                const size_t a = seg0 + (size_t)k * TASK_RECORDS, b = std::min(seg1, a + TASK_RECORDS);
+                try {
+                    decode_records(fmt, hdr, recs.data(), a, b, dopt, &ch, &task_cnt[(size_t)k]);
+                } catch (const HostError& e) {
+                    std::lock_guard<std::mutex> g(err_m);
+                    if (!failed.exchange(1)) first_err = e;
+                }
+            });
+            if (failed.load()) throw first_err;
+            for (size_t k = 0; k < n_tasks; k++)  // the cut above assumed reads grouped by contig
+                for (int32_t t : chunks[k].tid)
+                    if (t != tid) throw HostError{1, "metheor_b200: input is not coordinate-sorted (contigs interleave); sort it with samtools sort"};
+            DecodeCounters seg;
+            for (auto& c : task_cnt) seg.add(c);
+            total.add(seg);
+            s_decode += now_s() - t0;
+
+            size_t kept = 0;
+            for (size_t k = 0; k < n_tasks; k++) kept += chunks[k].start.size();
+            if (kept && tid >= 0 && (size_t)tid < ref_len.size()) {
+                Gpu& G = *gpus[(size_t)gpu_of[(size_t)tid]];
+                t0 = now_s();
+                // the slot was last used RING submits ago: its copy has long been issued, wait for it to have completed
+                if (G.submitted >= RING) {
+                    int rc = mth_sync_copies(G.ctx);
+                    if (rc != MTH_OK) engine_fail(G.ctx, rc, "mth_sync_copies");
+                }
+                PinnedBatch& pb = G.ring[G.next_slot];
+                G.next_slot = (G.next_slot + 1) % RING;
+                mth_batch b;
+                assemble(pool, chunks, 0, n_tasks, tid, want_rel, seg.max_cpgs, pb, &b);
+                s_assemble += now_s() - t0;
+                t0 = now_s();
+                int rc = mth_submit(G.ctx, &b);
+                if (rc != MTH_OK) engine_fail(G.ctx, rc, "mth_submit");
+                G.submitted++;
+                s_submit += now_s() - t0;
+                n_batches++;
+                n_shipped_reads += b.n_reads;
+                n_shipped_cpg += b.n_cpg;
+            }
+            seg0 = seg1;
+        }
+    }
+    const double t_decoded = now_s();
+
+    // reads that carried no CpG call never reach the GPU; LPMD still counts them (lpmd.rs:176, :189)
+    mth_add_skipped_reads(gpus[0]->ctx, total.n_dropped, total.n_dropped_mapq_ok);
+
+    // finish every GPU (concurrently: mth_finish blocks on its device)
+    {
+        std::vector<std::thread> th;
+        for (auto& gp : gpus) th.emplace_back([&gp] {
+            Gpu& G = *gp;
+            G.rc = mth_finish(G.ctx, &G.res);
+            if (G.rc != MTH_OK) G.err = mth_last_error(G.ctx);
+            mth_get_stats(G.ctx, &G.stats);
+        });
+        for (auto& t : th) t.join();
+        for (auto& gp : gpus)
+            if (gp->rc != MTH_OK) engine_fail(gp->ctx, gp->rc, "mth_finish");
+    }
+    const double t_finished = now_s();
+
+    // ---- output ----
+    OutFile out(o.output);
+    auto chrom = [&](int32_t tid) -> const std::string& { return hdr.names[(size_t)tid]; };
+    int64_t n_rows_total = 0;
+    if (o.measure == MTHH_LPMD) {
+        int64_t t[4] = {0, 0, 0, 0};
+        for (auto& gp : gpus) {
+            t[0] += gp->res.lpmd.n_read; t[1] += gp->res.lpmd.n_valid_read; t[2] += gp->res.lpmd.n_conc; t[3] += gp->res.lpmd.n_disc;
+        }
+        // lpmd.rs:51-55: n_discordant as f32 / (n_concordant + n_discordant) as f32
+        volatile float num = (float)t[3], den = (float)(t[2] + t[3]);
+        float lpmd = num / den;
+        std::string s = "name\tlpmd\n";  // lpmd.rs:145-147
+        s += o.input;
+        s += '\t';
+        put_f32(s, lpmd);
+        s += '\n';
+        out.write(s);
+        if (o.pairs) {
+            OutFile pf(o.pairs);
+            pf.write("chrom\tcpg1\tcpg2\tlpmd\tn_concordant\tn_discordant\n");  // lpmd.rs:104
+            std::vector<int64_t> nr;
+            for (auto& gp : gpus) nr.push_back(gp->res.lpmd_pairs.n);
+            auto runs = merge_runs(n_gpus, nr, [&](int g, int64_t i) { return gpus[(size_t)g]->res.lpmd_pairs.tid[i]; });
+            for (const Run& r : runs) {
+                const mth_pair_rows& R = gpus[(size_t)r.gpu]->res.lpmd_pairs;
+                write_rows(pool, pf, r.hi - r.lo, [&](int64_t k, std::string& s2) {
+                    const int64_t i = r.lo + k;
+                    s2 += chrom(R.tid[i]); s2 += '\t'; put_i32(s2, R.pos1[i]); s2 += '\t'; put_i32(s2, R.pos2[i]); s2 += '\t';
+                    put_f32(s2, R.lpmd[i]); s2 += '\t'; put_i32(s2, R.n_conc[i]); s2 += '\t'; put_i32(s2, R.n_disc[i]); s2 += '\n';
+                });
+                n_rows_total += r.hi - r.lo;
+            }
+        }
+    } else if (o.measure == MTHH_PM || o.measure == MTHH_ME) {
+        auto rows_of = [&](Gpu& G) -> const mth_quartet_rows& { return o.measure == MTHH_PM ? G.res.pm : G.res.me; };
+        std::vector<int64_t> nr;
+        for (auto& gp : gpus) nr.push_back(rows_of(*gp).n);
+        auto runs = merge_runs(n_gpus, nr, [&](int g, int64_t i) { return rows_of(*gpus[(size_t)g]).tid[i]; });
+        for (const Run& r : runs) {
+            const mth_quartet_rows& R = rows_of(*gpus[(size_t)r.gpu]);
+            write_rows(pool, out, r.hi - r.lo, [&](int64_t k, std::string& s) {  // pm.rs:56-59, me.rs:61-64
+                const int64_t i = r.lo + k;
+                s += chrom(R.tid[i]); s += '\t'; put_i32(s, R.p1[i]); s += '\t'; put_i32(s, R.p2[i]); s += '\t';
+                put_i32(s, R.p3[i]); s += '\t'; put_i32(s, R.p4[i]); s += '\t'; put_f32(s, R.value[i]); s += '\n';
+            });
+            n_rows_total += r.hi - r.lo;
+        }
+    } else {
+        auto rows_of = [&](Gpu& G) -> const mth_site_rows& {
+            switch (o.measure) {
+                case MTHH_PDR: return G.res.pdr;
+                case MTHH_MHL: return G.res.mhl;
+                case MTHH_FDRP: return G.res.fdrp;
+                default: return G.res.qfdrp;
+            }
+        };
+        const bool counts = o.measure == MTHH_PDR;
+        std::vector<int64_t> nr;
+        for (auto& gp : gpus) nr.push_back(rows_of(*gp).n);
+        auto runs = merge_runs(n_gpus, nr, [&](int g, int64_t i) { return rows_of(*gpus[(size_t)g]).tid[i]; });
+        for (const Run& r : runs) {
+            const mth_site_rows& R = rows_of(*gpus[(size_t)r.gpu]);
+            write_rows(pool, out, r.hi - r.lo, [&](int64_t k, std::string& s) {  // pdr.rs:105-114, mhl.rs:123-130, fdrp.rs:171
+                const int64_t i = r.lo + k;
+                s += chrom(R.tid[i]); s += '\t'; put_i32(s, R.pos[i]); s += '\t'; put_i32(s, (int64_t)R.pos[i] + 2); s += '\t';
+                put_f32(s, R.value[i]);
+                if (counts) { s += '\t'; put_i32(s, R.n_conc[i]); s += '\t'; put_i32(s, R.n_disc[i]); }
+                s += '\n';
+            });
+            n_rows_total += r.hi - r.lo;
+        }
+    }
+    const double t_end = now_s();
+
+    if (o.stats_json) {
+        FILE* f = fopen(o.stats_json, "w");
+        if (f) {
+            const double wall = t_end - t_begin;
+            fprintf(f, "{\"input\": \""); json_escape(f, o.input);
+            fprintf(f, "\", \"format\": \"%s\", \"threads\": %d, \"gpus\": %d, \"records\": %lld, \"reads_shipped\": %lld, "
+                       "\"cpg_calls_shipped\": %lld, \"batches\": %lld, \"rows\": %lld, \"bytes_uncompressed\": %llu, "
+                       "\"seconds\": {\"total\": %.6f, \"stream\": %.6f, \"inflate\": %.6f, \"walk\": %.6f, \"decode\": %.6f, "
+                       "\"assemble\": %.6f, \"submit\": %.6f, \"finish\": %.6f, \"write\": %.6f}, \"reads_per_sec\": %.1f, \"gpu\": [",
+                    fmt == Format::BAM ? "bam" : "sam", n_threads, n_gpus, (long long)total.n_records, (long long)n_shipped_reads,
+                    (long long)n_shipped_cpg, (long long)n_batches, (long long)n_rows_total, (unsigned long long)in.bytes_uncompressed,
+                    wall, t_decoded - t_begin, in.seconds_inflate, in.seconds_walk, s_decode, s_assemble, s_submit,
+                    t_finished - t_decoded, t_end - t_finished, (double)total.n_records / wall);
+            for (size_t g = 0; g < gpus.size(); g++) {
+                const mth_stats& st = gpus[g]->stats;
+                fprintf(f, "%s{\"reads\": %lld, \"cpg_calls\": %lld, \"sites\": %lld, \"regions\": %lld, \"kernel_launches\": %lld, "
+                           "\"h2d_bytes\": %lld, \"d2h_bytes\": %lld, \"kernels\": {",
+                        g ? ", " : "", (long long)st.n_reads, (long long)st.n_cpg, (long long)st.n_sites, (long long)st.n_regions,
+                        (long long)st.kernel_launches, (long long)st.h2d_bytes, (long long)st.d2h_bytes);
+                for (int k = 0; k < st.n_kernel_stats; k++)
+                    fprintf(f, "%s\"%s\": {\"launches\": %lld, \"ms\": %.4f}", k ? ", " : "", st.kernel[k].name,
+                            (long long)st.kernel[k].launches, st.kernel[k].ms);
+                fprintf(f, "}}");
+            }
+            fprintf(f, "]}\n");
+            fclose(f);
+        }
+    }
+}
+
+}  // namespace mthh

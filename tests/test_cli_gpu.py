@@ -1,0 +1,114 @@
+"""GPU: the `metheor` binary (C++ host + CUDA engine) against the oracle's CLI — TSV files byte for byte — on the
+reference's fixture BAMs, on random records (indels, clips, both strands, three contigs) and on synthetic WGBS reads."""
+import filecmp
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import bamio
+import oracle_lib
+import recgen
+from metheor_b200 import host, synth
+
+pytestmark = pytest.mark.gpu
+
+MEASURES = ("pdr", "lpmd", "mhl", "pm", "me", "fdrp", "qfdrp")
+REFS = [("chr1", 200_000), ("chr2", 90_000), ("chrM", 16_569)]
+
+
+def _oracle_cli(*args):
+    oracle_lib.build()
+    return subprocess.run([oracle_lib.CLI_PATH, *map(str, args)], capture_output=True, text=True)
+
+
+def _both(tmp_path, measure, bam, *flags, expect_rows=None):
+    a, b = str(tmp_path / f"{measure}.engine.tsv"), str(tmp_path / f"{measure}.oracle.tsv")
+    r = host.cli(measure, "-i", bam, "-o", a, *flags)
+    assert r.returncode == 0, r.stderr
+    o = _oracle_cli(measure, "-i", bam, "-o", b, *flags)
+    assert o.returncode == 0, o.stderr
+    ta, tb = open(a).read(), open(b).read()
+    assert ta == tb, f"{measure} {flags}: TSV differs\n--- engine\n{ta[:400]}\n--- oracle\n{tb[:400]}"
+    if expect_rows is not None:
+        assert ta.count("\n") == expect_rows, (measure, ta.count("\n"))
+    return ta
+
+
+@pytest.mark.parametrize("name", ["test1", "test2", "test3", "test4", "test5", "test6"])
+def test_fixture_bams_default_flags(fixture_bams, tmp_path, name):
+    for m in MEASURES:
+        _both(tmp_path, m, fixture_bams[name])
+
+
+def test_fixture_expected_rows_from_survey_appendix_b(fixture_bams, tmp_path):
+    """SURVEY.md Appendix B (derived from the reference's unit-test pins)."""
+    t = _both(tmp_path, "pdr", fixture_bams["test1"], expect_rows=4)
+    assert t.splitlines()[0] == "chr1\t0\t2\t0.875\t2\t14"
+    assert _both(tmp_path, "pm", fixture_bams["test1"]) == "chr1\t0\t2\t4\t6\t0.9375\n"
+    assert _both(tmp_path, "me", fixture_bams["test1"]) == "chr1\t0\t2\t4\t6\t1\n"
+    assert _both(tmp_path, "mhl", fixture_bams["test4"], expect_rows=8).splitlines()[4] == "chr1\t13\t15\t0.1625"
+    assert _both(tmp_path, "lpmd", fixture_bams["test5"]).splitlines()[1].endswith("\tNaN")
+    # tests/output_validation.rs:304-405 flags
+    t = _both(tmp_path, "qfdrp", fixture_bams["test1"], "-d", 1, "-D", 100, "-l", 1, "-q", 10, expect_rows=4)
+    assert t.splitlines()[0] == "chr1\t0\t2\t0.53333336"
+    t = _both(tmp_path, "fdrp", fixture_bams["test1"], "-d", 1, "-D", 100, "-l", 1, "-q", 10, expect_rows=4)
+    assert t.splitlines()[0] == "chr1\t0\t2\t1"
+    assert _both(tmp_path, "pdr", fixture_bams["test3"]) == ""  # the output file exists and is empty (pdr.rs:95-101)
+
+
+def test_random_records_three_contigs(tmp_path):
+    reads = recgen.random_records(21, REFS, 6000, max_len=80)
+    bam = str(tmp_path / "r.bam")
+    bamio.write_bam(bam, REFS, reads, block=3000)
+    for m, flags in (("pdr", ("-d", 2, "-p", 2)), ("mhl", ("-d", 2, "-p", 2)), ("pm", ("-d", 1)), ("me", ("-d", 2)),
+                     ("fdrp", ("-d", 2, "-l", 5)), ("qfdrp", ("-d", 2, "-l", 5, "-D", 8, "--seed", 5)), ("lpmd", ("-m", 1, "-M", 30))):
+        t = _both(tmp_path, m, bam, *flags)
+        assert t.count("\n") > (1 if m == "lpmd" else 20)
+    sam = str(tmp_path / "r.sam")
+    bamio.write_sam(sam, REFS, reads)
+    _both(tmp_path, "pdr", sam, "-d", 2, "-p", 2)
+
+
+def test_synthetic_wgbs_default_flags_and_cpg_set(tmp_path):
+    length = 120_000
+    sites = synth.make_sites(71, length)
+    b = synth.make_reads(72, sites, length, 30.0)
+    refs = [("chr19", length)]
+    bam = str(tmp_path / "s.bam")
+    bamio.write_bam(bam, refs, recgen.batch_to_records(b))
+    for m in MEASURES:
+        t = _both(tmp_path, m, bam)
+        assert t.count("\n") > (1 if m == "lpmd" else 100), m
+    bed = str(tmp_path / "set.bed")
+    with open(bed, "w") as f:
+        for x in sites[::2]:
+            f.write(f"chr19\t{x}\t{x + 2}\n")
+    for m in MEASURES:
+        _both(tmp_path, m, bam, "-c", bed, "-d", 5)
+    stats = str(tmp_path / "stats.json")
+    r = host.cli("pdr", "-i", bam, "-o", str(tmp_path / "x.tsv"), "--stats", stats, "--threads", 4)
+    assert r.returncode == 0, r.stderr
+    st = json.load(open(stats))
+    assert st["records"] == b["n_reads"] and st["gpu"][0]["kernel_launches"] > 0 and st["seconds"]["total"] > 0
+
+
+def test_missing_xm_aborts_like_the_reference(tmp_path):
+    reads = recgen.random_records(31, REFS, 300)
+    reads[50]["xm"] = None
+    reads[50]["mapq"] = 0
+    bam = str(tmp_path / "noxm.bam")
+    bamio.write_bam(bam, REFS, reads)
+    r = host.cli("pdr", "-i", bam, "-o", str(tmp_path / "o.tsv"))
+    assert r.returncode == 101 and "Error reading XM tag in BAM record" in r.stderr
+    # LPMD tests mapq first (lpmd.rs:177): the low-mapq record without XM is skipped
+    r = host.cli("lpmd", "-i", bam, "-o", str(tmp_path / "o.tsv"))
+    assert r.returncode == 0, r.stderr
+    r = host.cli("pdr", "-i", bam.replace("noxm", "nodir/none"), "-o", str(tmp_path / "o.tsv"))
+    assert r.returncode == 101
+    ok = str(tmp_path / "ok.bam")
+    bamio.write_bam(ok, REFS, recgen.random_records(32, REFS, 300))
+    r = host.cli("pdr", "-i", ok, "-o", "/nonexistent_directory/readonly_output.tsv")
+    assert r.returncode != 0
