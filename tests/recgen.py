@@ -9,7 +9,7 @@ def random_records(seed, refs, n, max_len=60, p_simple=0.6, xm_missing=False):
     pos_by_tid = {}
     for tid, (_, ln) in enumerate(refs):
         k = n // len(refs)
-        pos_by_tid[tid] = np.sort(rng.integers(0, max(1, ln - 4 * max_len), k))
+        pos_by_tid[tid] = np.sort(rng.integers(0, max(1, ln - 6000), k))  # N ops can stretch a read by a few kb
     flags = [0, 16, 99, 147, 83, 163, 1024, 256, 0, 16]
     for tid in sorted(pos_by_tid):
         for pos in pos_by_tid[tid]:
