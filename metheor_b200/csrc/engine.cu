@@ -41,13 +41,19 @@ struct QuartetRowsBuf {
     int64_t n = 0;
 };
 
+struct PairRowsBuf {
+    DevBuf tid, pos1, pos2, lpmd, nc, nd;
+    HostBuf h_tid, h_pos1, h_pos2, h_lpmd, h_nc, h_nd;
+    int64_t n = 0;
+};
+
 struct ProfSpan {
     const char* name;
     cudaEvent_t e0, e1;
     int launches;
 };
 
-enum { M_PDR = 0, M_MHL, M_FDRP, M_QFDRP, M_PM, M_ME, M_COUNT };
+enum { M_PDR = 0, M_MHL, M_FDRP, M_QFDRP, M_PM, M_ME, M_PAIRS, M_COUNT };
 
 }  // namespace
 
@@ -80,6 +86,7 @@ struct mth_ctx {
 
     SiteRowsBuf rows_pdr, rows_mhl, rows_fdrp, rows_qfdrp;
     QuartetRowsBuf rows_pm, rows_me;
+    PairRowsBuf rows_pairs;
     int64_t lpmd_total_host[4] = {0, 0, 0, 0};
     int me_lut_max = 0;
 
@@ -290,6 +297,7 @@ static int materialize(mth_ctx* c) {
     CUDA_TRY(c, cudaMemcpyAsync(c->a_meth.p, b.meth, (size_t)W * 8, cudaMemcpyDeviceToDevice, s));
     if (c->has_meth_off)
         CUDA_TRY(c, cudaMemcpyAsync(c->a_moff.p, b.meth_off, (size_t)(R + 1) * 4, cudaMemcpyDeviceToDevice, s));
+    if (lp && I) CUDA_TRY(c, cudaMemcpyAsync(c->a_rel.p, b.cpg_rel, (size_t)I * 2, cudaMemcpyDeviceToDevice, s));
     return MTH_OK;
 }
 
@@ -403,6 +411,11 @@ int mth_ctx_destroy(mth_ctx* c) {
         host_free(r->h_tid); host_free(r->h_p1); host_free(r->h_p2); host_free(r->h_p3); host_free(r->h_p4);
         host_free(r->h_value); host_free(r->h_counts);
     }
+    {
+        PairRowsBuf& r = c->rows_pairs;
+        for (DevBuf* b : {&r.tid, &r.pos1, &r.pos2, &r.lpmd, &r.nc, &r.nd}) dev_free(*b);
+        for (HostBuf* b : {&r.h_tid, &r.h_pos1, &r.h_pos2, &r.h_lpmd, &r.h_nc, &r.h_nd}) host_free(*b);
+    }
     host_free(c->h_scalars);
     host_free(c->h_totals);
     for (auto& sp : c->spans) { cudaEventDestroy(sp.e0); cudaEventDestroy(sp.e1); }
@@ -447,6 +460,7 @@ int mth_reset(mth_ctx* c) {
     c->last_tid = -1;
     c->rows_pdr.n = c->rows_mhl.n = c->rows_fdrp.n = c->rows_qfdrp.n = 0;
     c->rows_pm.n = c->rows_me.n = 0;
+    c->rows_pairs.n = 0;
     memset(c->lpmd_total_host, 0, sizeof(c->lpmd_total_host));
     resolve_spans(c);
     memset(&c->stats, 0, sizeof(c->stats));
@@ -631,7 +645,8 @@ static int process_region(mth_ctx* c) {
     const uint32_t M = c->prm.measures;
     ReadsView rv = make_view(c);
     RegionScalars* d_sc = (RegionScalars*)c->scalars.p;
-    const bool need_sites = (M & (MTH_PDR | MTH_MHL | MTH_PM | MTH_ME | MTH_FDRP | MTH_QFDRP)) != 0;
+    const bool want_pairs = (M & MTH_LPMD) && c->prm.lpmd.want_pairs;
+    const bool need_sites = (M & (MTH_PDR | MTH_MHL | MTH_PM | MTH_ME | MTH_FDRP | MTH_QFDRP)) != 0 || want_pairs;
 
     int64_t n_words = (int64_t)c->bitmap_words_valid;
     int64_t nb = (n_words + 1023) / 1024 + 1;
@@ -674,8 +689,8 @@ static int process_region(mth_ctx* c) {
         TRY(dev_reserve(c, c->scan_scratch, (size_t)((C + 2047) / 2048 + 2) * 4, 0));
         uint32_t* scratch = (uint32_t*)c->scan_scratch.p;
         for (int m = 0; m < M_COUNT; m++) {
-            static const uint32_t bit[M_COUNT] = {MTH_PDR, MTH_MHL, MTH_FDRP, MTH_QFDRP, MTH_PM, MTH_ME};
-            if (M & bit[m]) TRY(dev_reserve(c, c->rowcnt[m], (size_t)C * 4 + 4, 0));
+            static const uint32_t bit[M_COUNT] = {MTH_PDR, MTH_MHL, MTH_FDRP, MTH_QFDRP, MTH_PM, MTH_ME, 0};
+            if ((M & bit[m]) || (m == M_PAIRS && want_pairs)) TRY(dev_reserve(c, c->rowcnt[m], (size_t)C * 4 + 4, 0));
             if ((M & bit[m]) && (m == M_MHL || m == M_FDRP || m == M_QFDRP)) TRY(dev_reserve(c, c->value[m], (size_t)C * 4 + 4, 0));
         }
 
@@ -740,6 +755,15 @@ static int process_region(mth_ctx* c) {
             ps.add(launch_exclusive_scan_u32((uint32_t*)c->rowcnt[m].p, C, scratch, d_tot + m, s));
         }
         if (M & MTH_ME) TRY(build_me_lut(c));
+        const uint16_t* rel_all = c->borrowed ? c->bview.cpg_rel : (const uint16_t*)c->a_rel.p;
+        if (want_pairs) {
+            {
+                ProfScope ps(c, "k_lpmd_pairs_count");
+                ps.add(launch_lpmd_pairs_count(rv, rel_all, site_pos, C, d_sc, c->prm.lpmd, (uint32_t*)c->rowcnt[M_PAIRS].p, s));
+            }
+            ProfScope ps(c, "pairs_rows_count");
+            ps.add(launch_exclusive_scan_u32((uint32_t*)c->rowcnt[M_PAIRS].p, C, scratch, d_tot + M_PAIRS, s));
+        }
 
         CUDA_TRY(c, cudaMemcpyAsync(c->h_totals.p, d_tot, 8 * M_COUNT, cudaMemcpyDeviceToHost, s));
         CUDA_TRY(c, cudaMemcpyAsync(c->h_scalars.p, d_sc, sizeof(RegionScalars), cudaMemcpyDeviceToHost, s));
@@ -779,6 +803,16 @@ static int process_region(mth_ctx* c) {
             ps.add(launch_quartet_emit(rv, site_pos, C, d_sc, q ? c->prm.me : c->prm.pm, q, (const uint32_t*)c->rowcnt[m].p,
                                        (const float*)c->me_lut.p, c->me_lut_max, ct, rd, r.n, s));
             r.n += (int64_t)tot[m];
+        }
+        if (want_pairs) {
+            PairRowsBuf& r = c->rows_pairs;
+            int64_t n = r.n + (int64_t)tot[M_PAIRS];
+            for (DevBuf* b : {&r.tid, &r.pos1, &r.pos2, &r.lpmd, &r.nc, &r.nd}) TRY(dev_reserve(c, *b, (size_t)n * 4 + 4, (size_t)r.n * 4));
+            PairRowsDev rd{(int32_t*)r.tid.p, (int32_t*)r.pos1.p, (int32_t*)r.pos2.p, (float*)r.lpmd.p, (int32_t*)r.nc.p, (int32_t*)r.nd.p};
+            ProfScope ps(c, "k_lpmd_pairs_emit");
+            ps.add(launch_lpmd_pairs_emit(rv, rel_all, site_pos, C, d_sc, c->prm.lpmd, (const uint32_t*)c->rowcnt[M_PAIRS].p, ct, rd,
+                                          r.n, s));
+            r.n = n;
         }
         CUDA_TRY(c, cudaGetLastError());
     }
@@ -833,6 +867,23 @@ static int fetch_quartet_rows(mth_ctx* c, QuartetRowsBuf& r, bool counts, bool t
     return MTH_OK;
 }
 
+static int fetch_pair_rows(mth_ctx* c, PairRowsBuf& r, bool to_host, mth_pair_rows* out) {
+    memset(out, 0, sizeof(*out));
+    out->n = r.n;
+    if (!to_host || r.n == 0) return MTH_OK;
+    size_t nb = (size_t)r.n * 4;
+    DevBuf* d[6] = {&r.tid, &r.pos1, &r.pos2, &r.lpmd, &r.nc, &r.nd};
+    HostBuf* h[6] = {&r.h_tid, &r.h_pos1, &r.h_pos2, &r.h_lpmd, &r.h_nc, &r.h_nd};
+    for (int i = 0; i < 6; i++) {
+        TRY(host_reserve(c, *h[i], nb));
+        CUDA_TRY(c, cudaMemcpyAsync(h[i]->p, d[i]->p, nb, cudaMemcpyDeviceToHost, c->compute));
+    }
+    c->stats.d2h_bytes += (int64_t)nb * 6;
+    out->tid = (const int32_t*)r.h_tid.p; out->pos1 = (const int32_t*)r.h_pos1.p; out->pos2 = (const int32_t*)r.h_pos2.p;
+    out->lpmd = (const float*)r.h_lpmd.p; out->n_conc = (const int32_t*)r.h_nc.p; out->n_disc = (const int32_t*)r.h_nd.p;
+    return MTH_OK;
+}
+
 static void lpmd_from_totals(const int64_t* t, mth_lpmd_result* out) {
     out->n_read = t[0]; out->n_valid_read = t[1]; out->n_conc = t[2]; out->n_disc = t[3];
     // lpmd.rs:51-55: n_discordant as f32 / (n_concordant + n_discordant) as f32
@@ -859,6 +910,7 @@ int mth_finish(mth_ctx* c, mth_results* out) {
     TRY(fetch_site_rows(c, c->rows_qfdrp, false, to_host, &out->qfdrp));
     TRY(fetch_quartet_rows(c, c->rows_pm, qc, to_host, &out->pm));
     TRY(fetch_quartet_rows(c, c->rows_me, qc, to_host, &out->me));
+    TRY(fetch_pair_rows(c, c->rows_pairs, to_host, &out->lpmd_pairs));
     lpmd_from_totals(c->lpmd_total_host, &out->lpmd);
     TRY(dev_reserve(c, c->lpmd_total, 32, 0));
     CUDA_TRY(c, cudaMemcpyAsync(c->lpmd_total.p, c->lpmd_total_host, 32, cudaMemcpyHostToDevice, c->compute));
@@ -885,6 +937,12 @@ int mth_results_device(mth_ctx* c, mth_results* out) {
     site(c->rows_pdr, true, &out->pdr); site(c->rows_mhl, false, &out->mhl);
     site(c->rows_fdrp, false, &out->fdrp); site(c->rows_qfdrp, false, &out->qfdrp);
     quart(c->rows_pm, qc, &out->pm); quart(c->rows_me, qc, &out->me);
+    {
+        PairRowsBuf& r = c->rows_pairs;
+        out->lpmd_pairs.n = r.n; out->lpmd_pairs.tid = (const int32_t*)r.tid.p; out->lpmd_pairs.pos1 = (const int32_t*)r.pos1.p;
+        out->lpmd_pairs.pos2 = (const int32_t*)r.pos2.p; out->lpmd_pairs.lpmd = (const float*)r.lpmd.p;
+        out->lpmd_pairs.n_conc = (const int32_t*)r.nc.p; out->lpmd_pairs.n_disc = (const int32_t*)r.nd.p;
+    }
     lpmd_from_totals(c->lpmd_total_host, &out->lpmd);
     return MTH_OK;
 }

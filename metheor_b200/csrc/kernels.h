@@ -64,6 +64,14 @@ int launch_quartet_emit(const ReadsView& rv, const int32_t* site_pos, int64_t C,
                         mth_quartet_params prm, int kind, const uint32_t* rowoff, const float* me_lut, int me_lut_max,
                         ContigTable ct, QuartetRowsDev rows, int64_t row_base, cudaStream_t s);
 
+// ---- LPMD --pairs (k_pairs.cu) ----------------------------------------------------------------
+struct PairRowsDev { int32_t* tid; int32_t* pos1; int32_t* pos2; float* lpmd; int32_t* n_conc; int32_t* n_disc; };
+int launch_lpmd_pairs_count(const ReadsView& rv, const uint16_t* rel, const int32_t* site_pos, int64_t C,
+                            const RegionScalars* sc, mth_lpmd_params prm, uint32_t* rowcnt, cudaStream_t s);
+int launch_lpmd_pairs_emit(const ReadsView& rv, const uint16_t* rel, const int32_t* site_pos, int64_t C,
+                           const RegionScalars* sc, mth_lpmd_params prm, const uint32_t* rowoff, ContigTable ct,
+                           PairRowsDev rows, int64_t row_base, cudaStream_t s);
+
 // ---- FDRP / qFDRP (k_fdrp.cu) ---------------------------------------------------------------
 int launch_fdrp(const ReadsView& rv, const int32_t* site_pos, int64_t C, const RegionScalars* sc, mth_fdrp_params prm,
                 int quantitative, uint64_t seed, ContigTable ct, void* scratch, size_t scratch_bytes, float* value,

@@ -144,6 +144,11 @@ class Context:
         if M & MEASURE_BITS["lpmd"]:
             out["lpmd"] = dict(n_read=r.lpmd.n_read, n_valid_read=r.lpmd.n_valid_read, n_conc=r.lpmd.n_conc,
                                n_disc=r.lpmd.n_disc, lpmd=np.float32(r.lpmd.lpmd))
+            if self.params.lpmd.want_pairs:
+                s = r.lpmd_pairs
+                out["lpmd"]["pairs"] = dict(n=int(s.n), tid=self._np(s.tid, s.n, np.int32), pos1=self._np(s.pos1, s.n, np.int32),
+                                            pos2=self._np(s.pos2, s.n, np.int32), lpmd=self._np(s.lpmd, s.n, np.float32),
+                                            n_conc=self._np(s.n_conc, s.n, np.int32), n_disc=self._np(s.n_disc, s.n, np.int32))
         return out
 
     def results_device(self):

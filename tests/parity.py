@@ -44,7 +44,7 @@ DEFAULTS = dict(pdr=dict(min_depth=10, min_cpgs=4, min_qual=10), mhl=dict(min_de
 def check_all(batches, ref_len, measures, seed=0, flags=0, **overrides):
     """Engine vs oracle, bit-exact, for every requested measure.  Returns (engine results, stats)."""
     prm = {m: dict(DEFAULTS[m], **overrides.get(m, {})) for m in measures}
-    res, stats = engine.run_batches(batches, ref_len, measures, flags=flags, seed=seed, **prm)
+    res, stats = engine.run_batches(batches, ref_len, measures, flags=flags, seed=seed, **{k: dict(v) for k, v in prm.items()})
     orc = Oracle.from_soa(**B.to_oracle_soa(batches))
     if "pdr" in measures:
         w = orc.pdr(**prm["pdr"])
@@ -59,8 +59,15 @@ def check_all(batches, ref_len, measures, seed=0, flags=0, **overrides):
         if m in measures:
             assert_quartet_rows(res[m], orc.quartets(**prm[m]), m, m)
     if "lpmd" in measures:
-        w = orc.lpmd(**prm["lpmd"])
+        want_pairs = bool(prm["lpmd"].pop("want_pairs", 0))
+        w = orc.lpmd(pairs=want_pairs, **prm["lpmd"])
         g = res["lpmd"]
+        if want_pairs:
+            gp, wp = g["pairs"], w["pairs"]
+            assert gp["n"] == len(wp["tid"]), f"lpmd pairs: {gp['n']} rows vs oracle {len(wp['tid'])}"
+            for k in ("tid", "pos1", "pos2", "n_conc", "n_disc"):
+                assert np.array_equal(gp[k], wp[k]), f"lpmd pairs: {k}"
+            assert np.array_equal(bits(gp["lpmd"]), bits(wp["lpmd"])), "lpmd pairs: value"
         assert (g["n_read"], g["n_valid_read"], g["n_conc"], g["n_disc"]) == (w["n_read"], w["n_valid_read"], w["n_conc"], w["n_disc"]), (g, w)
         assert bits(g["lpmd"]) == bits(w["lpmd"]) or (np.isnan(g["lpmd"]) and np.isnan(w["lpmd"]))
     return res, stats

@@ -67,6 +67,10 @@ def test_random_records_three_contigs(tmp_path):
                      ("fdrp", ("-d", 2, "-l", 5)), ("qfdrp", ("-d", 2, "-l", 5, "-D", 8, "--seed", 5)), ("lpmd", ("-m", 1, "-M", 30))):
         t = _both(tmp_path, m, bam, *flags)
         assert t.count("\n") > (1 if m == "lpmd" else 20)
+    pa, pb = str(tmp_path / "pairs.engine.tsv"), str(tmp_path / "pairs.oracle.tsv")
+    assert host.cli("lpmd", "-i", bam, "-o", str(tmp_path / "l.tsv"), "-p", pa, "-m", 1, "-M", 30).returncode == 0
+    assert _oracle_cli("lpmd", "-i", bam, "-o", str(tmp_path / "l2.tsv"), "-p", pb, "-m", 1, "-M", 30).returncode == 0
+    assert open(pa).read() == open(pb).read() and open(pa).read().count("\n") > 100
     sam = str(tmp_path / "r.sam")
     bamio.write_sam(sam, REFS, reads)
     _both(tmp_path, "pdr", sam, "-d", 2, "-p", 2)

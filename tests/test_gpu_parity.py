@@ -183,3 +183,22 @@ def test_error_paths():
     empty = B.slice_reads(b, 0, 0)
     res, _ = engine.run_batches([empty], [50_000], ALL)
     assert res["pdr"]["n"] == 0 and np.isnan(res["lpmd"]["lpmd"])
+
+
+def test_lpmd_pairs_table(golden):
+    """lpmd --pairs (lpmd.rs:89-122): SURVEY Appendix B expects six rows `chr1 a b 0.5 8 8` on test1."""
+    b = parity.records_to_batch(golden["test1"]["reads"])
+    res, _ = parity.check_all([b], CHR1, ("lpmd",), lpmd=dict(want_pairs=1))
+    pr = res["lpmd"]["pairs"]
+    assert list(zip(pr["pos1"], pr["pos2"])) == [(0, 2), (0, 4), (0, 6), (2, 4), (2, 6), (4, 6)]
+    assert (pr["lpmd"] == np.float32(0.5)).all() and (pr["n_conc"] == 8).all() and (pr["n_disc"] == 8).all()
+    for seed, kw in ((81, {}), (82, dict(read_len=140, del_frac=0.5, del_max=60, nocall=0.05, lowq=0.15))):
+        s = _synth(seed, **kw)
+        res, _ = parity.check_all([s], [200_000], ("lpmd", "pdr"), lpmd=dict(want_pairs=1, min_distance=1, max_distance=40))
+        assert res["lpmd"]["pairs"]["n"] > 1000
+    lens = [150_000, 80_000]
+    batches = []
+    for tid, L in enumerate(lens):
+        x = _synth(90 + tid, length=L, cov=20.0, tid=tid)
+        batches += [B.slice_reads(x, 0, x["n_reads"] // 2), B.slice_reads(x, x["n_reads"] // 2, x["n_reads"])]
+    parity.check_all(batches, lens, ("lpmd",), lpmd=dict(want_pairs=1))
