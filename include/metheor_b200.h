@@ -78,13 +78,18 @@ void mth_params_default(mth_params* p); /* reference defaults, measures = 0 */
  * mth_finish()/mth_sync()/mth_sync_copies() returns (copies are asynchronous).  mem_kind: 0 = host memory (pinned preferred,
  * see mth_host_alloc), 1 = device memory on the context's GPU.
  *   start/end : first / last aligned reference position of the read (readutil.rs:25-33)
- *   meta      : bits 0-7 mapq (pdr.rs:150), bit 8 = forward strand (informational)
+ *   meta      : bits 0-7 mapq (pdr.rs:150), bit 8 = forward strand (informational), bit 9 = MTH_META_HALO
  *   cpg_off   : n_reads+1 prefix offsets into cpg_pos / cpg_rel, cpg_off[0] == 0
  *   cpg_pos   : strand-adjusted CpG positions (readutil.rs:332-339), strictly increasing within a read
  *   cpg_rel   : query index of each CpG (readutil.rs:335); only read when MTH_LPMD is set, may be NULL otherwise
  *   meth      : packed methylation calls, bit k of a read's word(s) = its k-th CpG is 'Z' (readutil.rs:258)
  *   meth_off  : n_reads+1 word offsets into meth, or NULL meaning exactly one word per read (needs <= 64 CpGs/read)
  */
+/* Position-bin sharding: a rank also receives the reads that start shortly before its bin (halo).
+ * They contribute to the rank's own sites like any read, but LPMD's global counters (lpmd.rs:176-191) must count each
+ * read once, on the rank that owns it: halo copies carry this bit and are skipped by the LPMD counters only. */
+#define MTH_META_HALO (1u << 9)
+
 typedef struct {
     int32_t tid;
     int32_t mem_kind;

@@ -10,6 +10,7 @@ constexpr int MAX_METH_WORDS = 4;          // <= 256 CpG calls per read (DESIGN.
 constexpr int MAX_CPGS_PER_READ = 64 * MAX_METH_WORDS;
 constexpr int CONTIG_GAP = 1 << 16;        // spacing between contigs in the device (linear) coordinate
 constexpr int MAX_REF_SPAN = CONTIG_GAP - 512;
+constexpr uint32_t META_HALO = 1u << 9;    // MTH_META_HALO
 
 // device error bits (ctx->d_err)
 enum : uint32_t {

@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(ING_TILE, ING_MINB) k_ingest(IngestArgs a) {
     // ---- phase 2: per read ----
     uint32_t err = 0;
     int32_t span = 0;
-    uint32_t lp_valid = 0, lp_c = 0, lp_d = 0;
+    uint32_t lp_read = 0, lp_valid = 0, lp_c = 0, lp_d = 0;
     if (in) {
         if (j > 0 && s < rv.start[j - 1]) err |= ERRBIT_UNSORTED;
         span = e - s + 1;
@@ -170,7 +170,8 @@ __global__ void __launch_bounds__(ING_TILE, ING_MINB) k_ingest(IngestArgs a) {
             if (p < s - 1 || p > e) err |= ERRBIT_POS_RANGE;
             prev = p;
         }
-        if (a.do_lpmd && !(err & (ERRBIT_BAD_OFFSETS | ERRBIT_TOO_MANY_CPGS))) {
+        if (a.do_lpmd && !(meta & META_HALO)) lp_read = 1;  // lpmd.rs:176 (a halo copy is counted by its owner rank)
+        if (lp_read && !(err & (ERRBIT_BAD_OFFSETS | ERRBIT_TOO_MANY_CPGS))) {
             if ((meta & 0xFFu) >= a.lpmd.min_qual) {   // lpmd.rs:177
                 lp_valid = 1;
                 uint64_t w0 = n > 1 ? meth_word(rv, j, 0) : 0;
@@ -193,21 +194,22 @@ __global__ void __launch_bounds__(ING_TILE, ING_MINB) k_ingest(IngestArgs a) {
     int32_t wmax = __reduce_max_sync(FULL, span);
     uint32_t werr = __reduce_or_sync(FULL, err);
     uint32_t wv = __reduce_add_sync(FULL, lp_valid), wc = __reduce_add_sync(FULL, lp_c), wd = __reduce_add_sync(FULL, lp_d);
+    uint32_t wr = __reduce_add_sync(FULL, lp_read);
     if (lane == 0) {
-        s_red[warp][0] = (uint32_t)wmax; s_red[warp][1] = werr; s_red[warp][2] = wv; s_red[warp][3] = wc; s_red[warp][4] = wd;
+        s_red[warp][0] = (uint32_t)wmax; s_red[warp][1] = werr; s_red[warp][2] = wv; s_red[warp][3] = wc; s_red[warp][4] = wd; s_red[warp][5] = wr;
     }
     __syncthreads();
     if (tid == 0) {
         int32_t bmax = 0;
-        uint32_t berr = 0, bv = 0, bc = 0, bd = 0;
+        uint32_t berr = 0, bv = 0, bc = 0, bd = 0, br = 0;
 #pragma unroll
         for (int w = 0; w < ING_TILE / 32; w++) {
-            bmax = max(bmax, (int32_t)s_red[w][0]); berr |= s_red[w][1]; bv += s_red[w][2]; bc += s_red[w][3]; bd += s_red[w][4];
+            bmax = max(bmax, (int32_t)s_red[w][0]); berr |= s_red[w][1]; bv += s_red[w][2]; bc += s_red[w][3]; bd += s_red[w][4]; br += s_red[w][5];
         }
         if (bmax > 0) atomicMax(&a.sc->lmax, bmax);
         if (berr) atomicOr(&a.sc->err, berr);
         if (a.do_lpmd) {
-            atomicAdd(&a.sc->lpmd[0], (unsigned long long)(tile1 - tile0));
+            if (br) atomicAdd(&a.sc->lpmd[0], (unsigned long long)br);
             if (bv) atomicAdd(&a.sc->lpmd[1], (unsigned long long)bv);
             if (bc) atomicAdd(&a.sc->lpmd[2], (unsigned long long)bc);
             if (bd) atomicAdd(&a.sc->lpmd[3], (unsigned long long)bd);

@@ -202,3 +202,39 @@ def test_lpmd_pairs_table(golden):
         x = _synth(90 + tid, length=L, cov=20.0, tid=tid)
         batches += [B.slice_reads(x, 0, x["n_reads"] // 2), B.slice_reads(x, x["n_reads"] // 2, x["n_reads"])]
     parity.check_all(batches, lens, ("lpmd",), lpmd=dict(want_pairs=1))
+
+
+def test_position_bin_sharding_with_halo_equals_one_pass():
+    """two virtual ranks (run one after the other on this GPU) each take a position bin + halo; owned
+    rows concatenated and LPMD counters summed equal a single engine pass and the oracle."""
+    from metheor_b200 import shard
+    lens = [180_000, 70_000]
+    data = []
+    for tid, L in enumerate(lens):
+        data.append(_synth(100 + tid, length=L, cov=25.0, tid=tid, read_len=140, del_frac=0.3, del_max=50, nocall=0.03, lowq=0.1))
+    ov = dict(pdr=dict(min_depth=5, min_cpgs=2), mhl=dict(min_depth=5, min_cpgs=2), fdrp=dict(min_depth=5, min_overlap=20),
+              qfdrp=dict(min_depth=5, min_overlap=20), pm=dict(min_depth=5), me=dict(min_depth=5), lpmd=dict(want_pairs=1))
+    whole, _ = parity.check_all(data, lens, ALL, **ov)
+    for world in (2, 3):
+        plan = shard.plan_bins(lens, world, weights=[b["start"] for b in data])
+        parts, lp = [], np.zeros(4, np.int64)
+        for r in range(world):
+            mine = [x for x in (shard.select_shard(b, plan[r], halo=400)[0] for b in data) if x is not None and x["n_reads"]]
+            res, _ = engine.run_batches(mine, lens, ALL, **{m: dict(parity.DEFAULTS[m], **ov.get(m, {})) for m in ALL})
+            lp += np.array([res["lpmd"][k] for k in ("n_read", "n_valid_read", "n_conc", "n_disc")], np.int64)
+            part = {m: shard.owned_rows(res[m], plan[r]) for m in ("pdr", "mhl", "fdrp", "qfdrp")}
+            part.update({m: shard.owned_rows(res[m], plan[r], pos_key="p1") for m in ("pm", "me")})
+            part["pairs"] = shard.owned_rows(res["lpmd"]["pairs"], plan[r], pos_key="pos1")
+            parts.append(part)
+        assert tuple(lp) == tuple(whole["lpmd"][k] for k in ("n_read", "n_valid_read", "n_conc", "n_disc"))
+        for m in ("pdr", "mhl", "fdrp", "qfdrp", "pm", "me", "pairs"):
+            keys = dict(pm=("tid", "p1", "p2", "p3", "p4"), me=("tid", "p1", "p2", "p3", "p4"), pairs=("tid", "pos1", "pos2")).get(m, ("tid", "pos"))
+            merged = shard.merge_rows([p[m] for p in parts], keys=keys)
+            want = whole["lpmd"]["pairs"] if m == "pairs" else whole[m]
+            assert merged["n"] == want["n"] and merged["n"] > 100, (m, world)
+            for k, v in want.items():
+                if isinstance(v, np.ndarray):
+                    a, b2 = merged[k], v
+                    if a.dtype == np.float32:
+                        a, b2 = a.view(np.uint32), b2.view(np.uint32)
+                    assert np.array_equal(a, b2), (m, k, world)
