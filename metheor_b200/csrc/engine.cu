@@ -77,7 +77,7 @@ struct mth_ctx {
     std::vector<int32_t> reg_lin_off, reg_tid;
 
     // arena
-    DevBuf a_start, a_end, a_meta, a_off, a_pos, a_rel, a_meth, a_moff;
+    DevBuf a_start, a_end, a_meta, a_off, a_pos, a_rel, a_meth, a_moff, a_flags;
     DevBuf bitmap, word_prefix, block_sums, site_pos, scalars, totals, ct_lin, ct_tid;
     DevBuf cnt2, scan_scratch, fdrp_scratch, me_lut, lpmd_total;
     DevBuf rowcnt[M_COUNT], value[M_COUNT];
@@ -397,7 +397,7 @@ int mth_ctx_destroy(mth_ctx* c) {
     if (!c) return MTH_OK;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    DevBuf* devs[] = {&c->a_start, &c->a_end, &c->a_meta, &c->a_off, &c->a_pos, &c->a_rel, &c->a_meth, &c->a_moff, &c->bitmap,
+    DevBuf* devs[] = {&c->a_start, &c->a_end, &c->a_meta, &c->a_off, &c->a_pos, &c->a_rel, &c->a_meth, &c->a_moff, &c->a_flags, &c->bitmap,
                       &c->word_prefix, &c->block_sums, &c->site_pos, &c->scalars, &c->totals, &c->ct_lin, &c->ct_tid, &c->cnt2,
                       &c->scan_scratch, &c->fdrp_scratch, &c->me_lut, &c->lpmd_total};
     for (DevBuf* b : devs) dev_free(*b);
@@ -582,6 +582,10 @@ int mth_submit(mth_ctx* c, const mth_batch* b) {
     ia.lin_hi = lin_off + (int32_t)c->ref_len[b->tid];
     ia.do_lpmd = lp ? 1 : 0;
     ia.lpmd = c->prm.lpmd;
+    ia.do_pdr = (c->prm.measures & MTH_PDR) ? 1 : 0;
+    ia.pdr = c->prm.pdr;
+    TRY(dev_reserve(c, c->a_flags, (size_t)c->I + 64, (size_t)i0));
+    ia.call_flags = (uint8_t*)c->a_flags.p;
     ia.sc = (RegionScalars*)c->scalars.p;
     {
         ProfScope ps(c, "k_ingest");
@@ -705,8 +709,8 @@ static int process_region(mth_ctx* c) {
             } else {
                 CUDA_TRY(c, cudaMemsetAsync(c->cnt2.p, 0, (size_t)C * 8, s));
                 ProfScope ps(c, "k_pdr_scatter");
-                ps.add(launch_pdr_scatter(rv, (const unsigned long long*)c->bitmap.p, (const uint32_t*)c->word_prefix.p,
-                                          (uint32_t*)c->cnt2.p, c->prm.pdr, s));
+                ps.add(launch_pdr_scatter(rv.cpg_pos, (const uint8_t*)c->a_flags.p, rv.I, (const unsigned long long*)c->bitmap.p, n_words,
+                                          (const uint32_t*)c->word_prefix.p, d_sc, (uint32_t*)c->cnt2.p, s));
             }
             ProfScope ps(c, "pdr_rows_count");
             ps.add(launch_pdr_rowcnt((const uint32_t*)c->cnt2.p, C, c->prm.pdr.min_depth, (uint32_t*)c->rowcnt[M_PDR].p, s));

@@ -8,25 +8,37 @@
 // k_pdr_rowcnt / k_pdr_emit turn the counters into rows: pdr = d as f32 / (c as f32 + d as f32) (pdr.rs:47-49).
 #include "gather.cuh"
 #include "kernels.h"
+#include "tma.cuh"
 
 namespace mth {
+
+static inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
 
 __device__ __forceinline__ bool pdr_read_ok(const mth_pdr_params& prm, uint32_t mapq, uint32_t n) {
     // pdr.rs:147 (n < min_cpgs), :150 (mapq < min_qual), :155 (no CpGs)
     return n >= prm.min_cpgs && mapq >= prm.min_qual && n > 0;
 }
 
-// One CTA = one tile of PDS_TILE consecutive reads (their CpG calls are one contiguous slice of cpg_pos).
-//   phase 1, one thread per read : filters + concordance state -> code {0 skip, 1 concordant, 2 discordant} and the
-//            owner table (call -> read of the tile) in shared memory;
-//   phase 2, one thread per call : coalesced cpg_pos load, site rank from the dictionary, shared-memory atomics into a
-//            window of PDS_WIN site ranks starting at the first site the tile can touch (reads are sorted, a 30x tile
-//            of 256 reads covers ~1.3 kb = a few dozen sites), direct global atomics for ranks outside the window;
-//   phase 3: non-zero window counters are flushed with one global atomic each.
-// Global atomics drop from one per CpG call to one per (tile, site, state).
-constexpr int PDS_TILE = 256;
-constexpr int PDS_CAP = 4096;   // calls per tile with an owner entry; beyond that the per-read fallback runs
-constexpr int PDS_WIN = 1024;   // site ranks aggregated in shared memory
+// k_pdr_scatter is a pure per-CALL kernel: k_ingest already classified every read (filters pdr.rs:147-155 + concordance
+// state readutil.rs:134-145) and replicated the verdict on each of its calls (call_flags, CF_PDR_C / CF_PDR_D), so the
+// scatter reads 5 bytes per call (position + flag byte) and no per-read data at all.
+// One CTA = PCS_TILE consecutive calls (vectorised int4 / uchar4 loads).  Reads are sorted, so the calls of a tile lie
+// in [P0 - lmax, ...) where P0 is the tile's first call (a later read starts at or after the read owning P0):
+//   * the 16 384-position window of the site bitmap starting there is loaded into shared memory and block-scanned, so
+//     rank(p) = rank0 + prefix[w] + popc(word & below) needs shared memory only;
+//   * counts go to shared-memory counters [local rank][state]; non-zero counters are flushed with one fire-and-forget
+//     global atomic each (one per (tile, site, state) instead of one per call);
+//   * calls outside the window / rank budget take the direct path (dictionary lookup + global atomic).
+#ifndef PCS_CPT
+#define PCS_CPT 8    // calls per thread, multiple of 4
+#endif
+#ifndef PCS_MINB
+#define PCS_MINB 6
+#endif
+constexpr int PCS_THREADS = 256;
+constexpr int PCS_TILE = PCS_THREADS * PCS_CPT;
+constexpr int PCS_WIN = 256;                   // 64-bit bitmap words in the window = 16 384 positions
+constexpr int PCS_RANKS = 64 * PCS_CPT;        // local site ranks with a shared-memory counter pair
 
 __device__ __forceinline__ uint32_t site_rank(const unsigned long long* __restrict__ bitmap,
                                               const uint32_t* __restrict__ word_prefix, int32_t pos) {
@@ -35,59 +47,89 @@ __device__ __forceinline__ uint32_t site_rank(const unsigned long long* __restri
     return __ldg(word_prefix + w) + (uint32_t)__popcll(__ldg(bitmap + w) & ((1ull << (bit & 63)) - 1ull));
 }
 
-__global__ void __launch_bounds__(PDS_TILE) k_pdr_scatter(ReadsView rv, const unsigned long long* __restrict__ bitmap,
-                                                          const uint32_t* __restrict__ word_prefix,
-                                                          uint32_t* __restrict__ cnt2, mth_pdr_params prm) {
-    __shared__ uint32_t s_cnt[2 * PDS_WIN];
-    __shared__ uint8_t s_owner[PDS_CAP];
-    __shared__ uint8_t s_code[PDS_TILE];
-    __shared__ uint32_t s_lo, s_hi, s_rank0;
+__global__ void __launch_bounds__(PCS_THREADS, PCS_MINB) k_pdr_scatter(const int32_t* __restrict__ cpg_pos,
+                                                                       const uint8_t* __restrict__ call_flags, int64_t n_calls,
+                                                                       const unsigned long long* __restrict__ bitmap, int64_t n_words,
+                                                                       const uint32_t* __restrict__ word_prefix,
+                                                                       const RegionScalars* __restrict__ sc,
+                                                                       uint32_t* __restrict__ cnt2) {
+    __shared__ unsigned long long s_bmw[PCS_WIN];
+    __shared__ uint32_t s_pref[PCS_WIN];
+    __shared__ __align__(16) uint32_t s_cnt[2 * PCS_RANKS];
+    __shared__ uint32_t s_wsum[PCS_THREADS / 32];
 
-    const int tid = threadIdx.x;
-    const int64_t tile0 = (int64_t)blockIdx.x * PDS_TILE;
-    const int64_t tile1 = min(rv.R, tile0 + PDS_TILE);
-    if (tid == 0) {
-        s_lo = rv.cpg_off[tile0];
-        s_hi = rv.cpg_off[tile1];
-        // every call of the tile lies at or after start[tile0] - 1 (reads sorted by start, calls in [start-1, end])
-        int32_t pmin = rv.start[tile0] - 1;
-        uint32_t bit = (uint32_t)(pmin + 1);
-        uint32_t w = bit >> 6;
-        s_rank0 = word_prefix[w] + (uint32_t)__popcll(bitmap[w] & ((1ull << (bit & 63)) - 1ull));
-    }
-    for (int k = tid; k < 2 * PDS_WIN; k += PDS_TILE) s_cnt[k] = 0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t x0 = (int64_t)blockIdx.x * PCS_TILE;
 
-    const int64_t j = tile0 + tid;
-    uint32_t o0 = 0, n = 0, code = 0;
-    if (j < tile1) {
-        o0 = rv.cpg_off[j];
-        n = rv.cpg_off[j + 1] - o0;
-        uint32_t mapq = rv.meta[j] & 0xFFu;
-        if (n > 0 && pdr_read_ok(prm, mapq, n)) code = read_discordant(rv, j, n) ? 2u : 1u;
+    // this thread's calls: groups of 4 consecutive calls, groups interleaved across the CTA (coalesced 16 B / 4 B loads)
+    int4 pv[PCS_CPT / 4];
+    uchar4 fv[PCS_CPT / 4];
+#pragma unroll
+    for (int g = 0; g < PCS_CPT / 4; g++) {
+        const int64_t x = x0 + (int64_t)(g * PCS_THREADS + tid) * 4;
+        pv[g] = make_int4(0, 0, 0, 0);
+        fv[g] = make_uchar4(0, 0, 0, 0);
+        if (x + 4 <= n_calls) {
+            pv[g] = *reinterpret_cast<const int4*>(cpg_pos + x);
+            fv[g] = *reinterpret_cast<const uchar4*>(call_flags + x);
+        } else if (x < n_calls) {
+            int32_t tp[4] = {0, 0, 0, 0};
+            uint8_t tf[4] = {0, 0, 0, 0};
+            for (int k = 0; k < 4 && x + k < n_calls; k++) { tp[k] = cpg_pos[x + k]; tf[k] = call_flags[x + k]; }
+            pv[g] = make_int4(tp[0], tp[1], tp[2], tp[3]);
+            fv[g] = make_uchar4(tf[0], tf[1], tf[2], tf[3]);
+        }
     }
-    s_code[tid] = (uint8_t)code;
-    __syncthreads();
-    const uint32_t lo = s_lo, hi = s_hi, rank0 = s_rank0;
-    const bool tabled = hi - lo <= (uint32_t)PDS_CAP;
-    if (tabled) {
-        for (uint32_t k = 0; k < n; k++) s_owner[o0 - lo + k] = (uint8_t)tid;
+    // window of the site bitmap: bit index of a call = position + 1 >= P0 - lmax + 1
+    const int32_t wlo = max(cpg_pos[x0] - sc->lmax + 1, 0);
+    const uint32_t w0 = (uint32_t)wlo >> 6;
+    unsigned long long bw = 0;
+    if ((int64_t)w0 + tid < n_words) bw = bitmap[w0 + tid];
+    const uint32_t rank0 = word_prefix[w0];
+    {
+        uint4* z = reinterpret_cast<uint4*>(s_cnt);
+        for (int k = tid; k < 2 * PCS_RANKS / 4; k += PCS_THREADS) z[k] = make_uint4(0, 0, 0, 0);
+    }
+    // local rank prefix of the window words (block exclusive scan of their popcounts)
+    {
+        uint32_t c = (uint32_t)__popcll(bw), inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(FULL, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) s_wsum[warp] = inc;
+        s_bmw[tid] = bw;
         __syncthreads();
-        for (uint32_t x = lo + tid; x < hi; x += PDS_TILE) {
-            uint32_t cd = s_code[s_owner[x - lo]];
-            if (!cd) continue;
-            uint32_t r = site_rank(bitmap, word_prefix, rv.cpg_pos[x]);
-            uint32_t rel = r - rank0;
-            if (rel < (uint32_t)PDS_WIN) atomicAdd(&s_cnt[2 * rel + (cd - 1)], 1u);
-            else atomicAdd(&cnt2[2 * (size_t)r + (cd - 1)], 1u);
-        }
-    } else if (code) {  // dense tile: one thread per read, straight to global memory
-        for (uint32_t k = 0; k < n; k++) {
-            uint32_t r = site_rank(bitmap, word_prefix, rv.cpg_pos[o0 + k]);
-            atomicAdd(&cnt2[2 * (size_t)r + (code - 1)], 1u);
-        }
+        uint32_t base = 0;
+#pragma unroll
+        for (int w = 0; w < PCS_THREADS / 32; w++) base += (w < warp) ? s_wsum[w] : 0u;
+        s_pref[tid] = base + inc - c;
     }
     __syncthreads();
-    for (int k = tid; k < 2 * PDS_WIN; k += PDS_TILE) {
+
+    auto count = [&](int32_t p, uint32_t f) {
+        const uint32_t cd = (f >> 3) & 3u;  // CF_PDR_C -> 1, CF_PDR_D -> 2
+        if (!cd) return;
+        const uint32_t bit = (uint32_t)(p + 1);
+        const uint32_t w = (bit >> 6) - w0;
+        if (w < (uint32_t)PCS_WIN) {
+            const uint32_t r = s_pref[w] + (uint32_t)__popcll(s_bmw[w] & ((1ull << (bit & 63)) - 1ull));
+            if (r < (uint32_t)PCS_RANKS) atomicAdd(&s_cnt[2 * r + (cd - 1)], 1u);
+            else atomicAdd(&cnt2[2 * (size_t)(rank0 + r) + (cd - 1)], 1u);
+        } else {
+            atomicAdd(&cnt2[2 * (size_t)site_rank(bitmap, word_prefix, p) + (cd - 1)], 1u);
+        }
+    };
+#pragma unroll
+    for (int g = 0; g < PCS_CPT / 4; g++) {
+        count(pv[g].x, fv[g].x);
+        count(pv[g].y, fv[g].y);
+        count(pv[g].z, fv[g].z);
+        count(pv[g].w, fv[g].w);
+    }
+    __syncthreads();
+    for (int k = tid; k < 2 * PCS_RANKS; k += PCS_THREADS) {
         uint32_t v = s_cnt[k];
         if (v) atomicAdd(&cnt2[2 * (size_t)rank0 + k], v);
     }
@@ -152,12 +194,10 @@ __global__ void k_pdr_emit(const uint32_t* __restrict__ cnt2, const uint32_t* __
     rows.n_disc[r] = d;
 }
 
-static inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
-
-int launch_pdr_scatter(const ReadsView& rv, const unsigned long long* bitmap, const uint32_t* word_prefix,
-                       uint32_t* cnt2, mth_pdr_params prm, cudaStream_t s) {
-    if (rv.R <= 0) return 0;
-    k_pdr_scatter<<<grid_for(rv.R, PDS_TILE), PDS_TILE, 0, s>>>(rv, bitmap, word_prefix, cnt2, prm);
+int launch_pdr_scatter(const int32_t* cpg_pos, const uint8_t* call_flags, int64_t n_calls, const unsigned long long* bitmap,
+                       int64_t n_words, const uint32_t* word_prefix, const RegionScalars* sc, uint32_t* cnt2, cudaStream_t s) {
+    if (n_calls <= 0) return 0;
+    k_pdr_scatter<<<grid_for(n_calls, PCS_TILE), PCS_THREADS, 0, s>>>(cpg_pos, call_flags, n_calls, bitmap, n_words, word_prefix, sc, cnt2);
     return 1;
 }
 

@@ -20,6 +20,9 @@ struct IngestArgs {
     int32_t lin_lo, lin_hi;   // valid position range of this contig in device coordinates: [lin_lo-1, lin_hi)
     int do_lpmd;
     mth_lpmd_params lpmd;
+    int do_pdr;               // also classify reads for PDR (CF_PDR_C / CF_PDR_D in call_flags)
+    mth_pdr_params pdr;
+    uint8_t* call_flags;      // region-wide, one byte per CpG call (common.cuh CF_*)
     RegionScalars* sc;
 };
 int launch_ingest(const IngestArgs& a, cudaStream_t s);
@@ -35,8 +38,8 @@ int launch_sites_emit(const unsigned long long* bitmap, int64_t n_words, const u
 int launch_exclusive_scan_u32(uint32_t* a, int64_t n, uint32_t* scratch, unsigned long long* total, cudaStream_t s);
 
 // ---- PDR (k_pdr.cu) -------------------------------------------------------------------------
-int launch_pdr_scatter(const ReadsView& rv, const unsigned long long* bitmap, const uint32_t* word_prefix,
-                       uint32_t* cnt2, mth_pdr_params prm, cudaStream_t s);
+int launch_pdr_scatter(const int32_t* cpg_pos, const uint8_t* call_flags, int64_t n_calls, const unsigned long long* bitmap,
+                       int64_t n_words, const uint32_t* word_prefix, const RegionScalars* sc, uint32_t* cnt2, cudaStream_t s);
 int launch_pdr_gather(const ReadsView& rv, const int32_t* site_pos, int64_t C, const RegionScalars* sc,
                       uint32_t* cnt2, mth_pdr_params prm, cudaStream_t s);
 // rowcnt[s] = 1 iff site s yields a row
