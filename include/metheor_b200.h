@@ -106,6 +106,40 @@ typedef struct {
     const uint32_t* meth_off;
 } mth_batch;
 
+/* The same reads in a compact wire format (~1/3 of the bytes of mth_batch: 9 B per read + 2.125 B per CpG call), for
+ * hosts whose link to the GPU is the bottleneck (PCIe: the SoA of a 30x chr19 is 468 MB, 172 MB in this form).  The
+ * engine expands it on the device into the layout above (k_expand) and proceeds identically.  Restrictions: at most 64
+ * CpG calls per read (use mth_batch for a batch that contains a denser read); end - start <= 65023.
+ *   start      : as in mth_batch
+ *   span       : end - start
+ *   mapq       : pdr.rs:150
+ *   n_cpg      : CpG calls of the read (replaces cpg_off; prefix-summed on the device)
+ *   flags      : bit 0 forward strand, bit 1 halo copy (MTH_META_HALO), bit 2 query indices given explicitly in rel_exc
+ *   cpg_delta  : per call, position - (start - 1)                       (a call lies in [start-1, end])
+ *   meth_bits  : per call, 1 bit: call x of the batch is bit (x & 7) of byte (x >> 3)
+ *   rel_exc    : only read when MTH_LPMD is set: the query indices (readutil.rs:335) of the calls of the reads that
+ *                have flag bit 2, in order.  All other reads are plain `<len>M` alignments, for which the query index
+ *                is implied: position - start (+1 on the reverse strand, readutil.rs:332-339).
+ */
+#define MTH_CFLAG_FORWARD 1u
+#define MTH_CFLAG_HALO 2u
+#define MTH_CFLAG_REL_EXPLICIT 4u
+typedef struct {
+    int32_t tid;
+    int32_t mem_kind;
+    int64_t n_reads;
+    int64_t n_cpg;
+    int64_t n_rel;            /* entries of rel_exc */
+    const int32_t* start;
+    const uint16_t* span;
+    const uint8_t* mapq;
+    const uint8_t* n_cpg8;
+    const uint8_t* flags;
+    const uint16_t* cpg_delta;
+    const uint8_t* meth_bits; /* (n_cpg + 7) / 8 bytes */
+    const uint16_t* rel_exc;
+} mth_batch_compact;
+
 /* Result rows.  Arrays are owned by the context and valid until the next mth_finish / mth_reset / mth_ctx_destroy. */
 typedef struct {          /* pdr.rs:102-116, mhl.rs:122-131, fdrp.rs:169-172, qfdrp.rs:181-184: sorted by (tid,pos) */
     int64_t n;
@@ -169,6 +203,8 @@ int mth_ctx_destroy(mth_ctx* ctx);
 int mth_set_stream(mth_ctx* ctx, void* cuda_stream);
 /* Asynchronous: enqueues the host->device copy on the copy stream and the ingest kernels behind it. */
 int mth_submit(mth_ctx* ctx, const mth_batch* batch);
+/* Same as mth_submit for the compact wire format (host or device memory). */
+int mth_submit_compact(mth_ctx* ctx, const mth_batch_compact* batch);
 /* Host reads that carried no CpG call were dropped before submit: only LPMD's n_read counts them (lpmd.rs:176). */
 int mth_add_skipped_reads(mth_ctx* ctx, int64_t n_reads, int64_t n_reads_mapq_ok);
 /* Closes the input, runs the measure kernels, brings the rows back (unless KEEP_ON_DEVICE) and synchronises. */

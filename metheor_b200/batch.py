@@ -72,3 +72,33 @@ def to_oracle_soa(batches):
     cat = np.concatenate
     return dict(tid=cat(tid), start=cat(start), end=cat(end), mapq=cat(mapq), cpg_off=cat(offs), cpg_pos=cat(pos),
                 cpg_rel=cat(rel), cpg_meth=cat(meth))
+
+
+def to_compact(b, with_rel=True):
+    """SoA batch -> the compact wire format of include/metheor_b200.h (mth_batch_compact).  Needs <= 64 calls per read."""
+    off = np.asarray(b["cpg_off"], np.int64)
+    cnt = np.diff(off)
+    if cnt.max(initial=0) > 64:
+        raise ValueError("compact wire format holds at most 64 CpG calls per read")
+    R = b["n_reads"]
+    start = np.asarray(b["start"], np.int64)
+    span = np.asarray(b["end"], np.int64) - start
+    if span.max(initial=0) > 65023 or span.min(initial=0) < 0:
+        raise ValueError("span outside the compact format")
+    meta = np.asarray(b["meta"], np.uint32)
+    fwd = ((meta >> 8) & 1).astype(np.int64)
+    ridx = np.repeat(np.arange(R, dtype=np.int64), cnt)
+    pos = np.asarray(b["cpg_pos"], np.int64)
+    delta = pos - (start[ridx] - 1)
+    flags = (fwd | (((meta >> 9) & 1) << 1)).astype(np.uint8)
+    rel_exc = np.zeros(0, np.uint16)
+    if with_rel and b.get("cpg_rel") is not None:
+        rel = np.asarray(b["cpg_rel"], np.int64)
+        odd = rel != delta - fwd[ridx]
+        explicit = np.zeros(R, bool)
+        explicit[np.unique(ridx[odd])] = True
+        flags = flags | (explicit.astype(np.uint8) << 2)
+        rel_exc = rel[explicit[ridx]].astype(np.uint16)
+    return dict(tid=b["tid"], n_reads=R, n_cpg=int(off[-1]), n_rel=len(rel_exc), start=np.asarray(b["start"], np.int32),
+                span=span.astype(np.uint16), mapq=(meta & 0xFF).astype(np.uint8), n_cpg8=cnt.astype(np.uint8), flags=flags,
+                cpg_delta=delta.astype(np.uint16), meth_bits=np.packbits(unpack_meth(b), bitorder="little"), rel_exc=rel_exc)

@@ -80,6 +80,9 @@ struct mth_ctx {
     DevBuf a_start, a_end, a_meta, a_off, a_pos, a_rel, a_meth, a_moff, a_flags;
     DevBuf bitmap, word_prefix, block_sums, site_pos, scalars, totals, ct_lin, ct_tid;
     DevBuf cnt2, scan_scratch, fdrp_scratch, me_lut, lpmd_total;
+    DevBuf stage[8], exp_blocks, exp_tot;  // compact wire format: staging + scan scratch
+    cudaEvent_t ev_stage_free = nullptr;
+    bool stage_busy = false;
     DevBuf rowcnt[M_COUNT], value[M_COUNT];
     size_t bitmap_words_valid = 0;
     HostBuf h_scalars, h_totals;
@@ -317,6 +320,58 @@ static int check_scalars_err(mth_ctx* c, uint32_t e) {
     return fail(c, MTH_ERR_INVALID, "device-side validation failed");
 }
 
+// Decides where a new batch goes: same region (possibly a new contig appended behind a gap) or a fresh region after the
+// current one has been processed.
+static int place_batch(mth_ctx* c, int32_t tid, int64_t n_reads, int64_t n_cpg, int64_t n_words) {
+    if (c->region_active) {
+        if (tid < c->last_tid) return fail(c, MTH_ERR_UNSORTED, "contigs must arrive in ascending tid order (coordinate-sorted input)");
+        if (tid != c->last_tid) {
+            int64_t noff = (((int64_t)c->cur_lin_off + c->ref_len[c->last_tid] + CONTIG_GAP) + 63) & ~63ll;
+            bool fits = noff + c->ref_len[tid] + 64 < (int64_t)INT32_MAX && c->I + n_cpg < (int64_t)UINT32_MAX - 64 &&
+                        c->R + n_reads < (int64_t)INT32_MAX - 64 && c->W + n_words < (int64_t)UINT32_MAX - 64;
+            if (fits) {
+                TRY(materialize(c));
+                TRY(add_contig(c, tid, (int32_t)noff));
+            } else {
+                TRY(process_region(c));
+            }
+        } else if (c->I + n_cpg >= (int64_t)UINT32_MAX - 64 || c->R + n_reads >= (int64_t)INT32_MAX - 64) {
+            return fail(c, MTH_ERR_UNSUPPORTED, "a single contig holds more than 2^32 CpG calls / 2^31 reads");
+        }
+    }
+    if (!c->region_active) TRY(begin_region(c, tid));
+    return MTH_OK;
+}
+
+// The ingest pass over reads [r0, r0+n) of the region (already in device memory, linear coordinates).
+static int run_ingest(mth_ctx* c, int32_t tid, int64_t r0, int64_t n, int64_t i0, int64_t n_cpg, const uint16_t* rel_dev) {
+    const bool lp = (c->prm.measures & MTH_LPMD) != 0;
+    IngestArgs ia;
+    ia.rv = make_view(c);
+    ia.r0 = r0;
+    ia.n = n;
+    ia.i0 = i0;
+    ia.cpg_rel = rel_dev;
+    ia.bitmap = (unsigned long long*)c->bitmap.p;
+    ia.lin_lo = c->cur_lin_off;
+    ia.lin_hi = c->cur_lin_off + (int32_t)c->ref_len[tid];
+    ia.do_lpmd = lp ? 1 : 0;
+    ia.lpmd = c->prm.lpmd;
+    ia.do_pdr = (c->prm.measures & MTH_PDR) ? 1 : 0;
+    ia.pdr = c->prm.pdr;
+    TRY(dev_reserve(c, c->a_flags, (size_t)c->I + 64, (size_t)i0));
+    ia.call_flags = (uint8_t*)c->a_flags.p;
+    ia.sc = (RegionScalars*)c->scalars.p;
+    {
+        ProfScope ps(c, "k_ingest");
+        ps.add(launch_ingest(ia, c->compute));
+    }
+    CUDA_TRY(c, cudaGetLastError());
+    c->stats.n_reads += n;
+    c->stats.n_cpg += n_cpg;
+    return MTH_OK;
+}
+
 // ---- C ABI -----------------------------------------------------------------------------------------
 extern "C" {
 
@@ -383,7 +438,8 @@ int mth_ctx_create(mth_ctx** out, int device, const mth_params* params, int32_t 
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->own_compute, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c->ev_compute, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&c->ev_compute, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_stage_free, cudaEventDisableTiming) != cudaSuccess) {
         g_create_err = std::string("CUDA initialisation failed: ") + cudaGetErrorString(cudaGetLastError());
         delete c;
         return MTH_ERR_CUDA;
@@ -401,6 +457,10 @@ int mth_ctx_destroy(mth_ctx* c) {
                       &c->word_prefix, &c->block_sums, &c->site_pos, &c->scalars, &c->totals, &c->ct_lin, &c->ct_tid, &c->cnt2,
                       &c->scan_scratch, &c->fdrp_scratch, &c->me_lut, &c->lpmd_total};
     for (DevBuf* b : devs) dev_free(*b);
+    for (DevBuf& b : c->stage) dev_free(b);
+    dev_free(c->exp_blocks);
+    dev_free(c->exp_tot);
+    if (c->ev_stage_free) cudaEventDestroy(c->ev_stage_free);
     for (int m = 0; m < M_COUNT; m++) { dev_free(c->rowcnt[m]); dev_free(c->value[m]); }
     for (SiteRowsBuf* r : {&c->rows_pdr, &c->rows_mhl, &c->rows_fdrp, &c->rows_qfdrp}) {
         dev_free(r->tid); dev_free(r->pos); dev_free(r->value); dev_free(r->nc); dev_free(r->nd);
@@ -492,23 +552,7 @@ int mth_submit(mth_ctx* c, const mth_batch* b) {
     int64_t bw = batch_words(b);
     if (bw < b->n_reads && b->meth_off == nullptr) return fail(c, MTH_ERR_INVALID, "n_meth_words inconsistent");
 
-    if (c->region_active) {
-        if (b->tid < c->last_tid) return fail(c, MTH_ERR_UNSORTED, "contigs must arrive in ascending tid order (coordinate-sorted input)");
-        if (b->tid != c->last_tid) {
-            int64_t noff = (((int64_t)c->cur_lin_off + c->ref_len[c->last_tid] + CONTIG_GAP) + 63) & ~63ll;
-            bool fits = noff + c->ref_len[b->tid] + 64 < (int64_t)INT32_MAX && c->I + b->n_cpg < (int64_t)UINT32_MAX - 64 &&
-                        c->R + b->n_reads < (int64_t)INT32_MAX - 64 && c->W + bw < (int64_t)UINT32_MAX - 64;
-            if (fits) {
-                TRY(materialize(c));
-                TRY(add_contig(c, b->tid, (int32_t)noff));
-            } else {
-                TRY(process_region(c));
-            }
-        } else if (c->I + b->n_cpg >= (int64_t)UINT32_MAX - 64 || c->R + b->n_reads >= (int64_t)INT32_MAX - 64) {
-            return fail(c, MTH_ERR_UNSUPPORTED, "a single contig holds more than 2^32 CpG calls / 2^31 reads");
-        }
-    }
-    if (!c->region_active) TRY(begin_region(c, b->tid));
+    TRY(place_batch(c, b->tid, b->n_reads, b->n_cpg, bw));
 
     const int32_t lin_off = c->cur_lin_off;
     const int64_t r0 = c->R, i0 = c->I, w0 = c->W;
@@ -571,30 +615,73 @@ int mth_submit(mth_ctx* c, const mth_batch* b) {
     c->I = i0 + b->n_cpg;
     c->W = w0 + bw;
 
-    IngestArgs ia;
-    ia.rv = make_view(c);
-    ia.r0 = r0;
-    ia.n = b->n_reads;
-    ia.i0 = i0;
-    ia.cpg_rel = rel_dev;
-    ia.bitmap = (unsigned long long*)c->bitmap.p;
-    ia.lin_lo = lin_off;
-    ia.lin_hi = lin_off + (int32_t)c->ref_len[b->tid];
-    ia.do_lpmd = lp ? 1 : 0;
-    ia.lpmd = c->prm.lpmd;
-    ia.do_pdr = (c->prm.measures & MTH_PDR) ? 1 : 0;
-    ia.pdr = c->prm.pdr;
-    TRY(dev_reserve(c, c->a_flags, (size_t)c->I + 64, (size_t)i0));
-    ia.call_flags = (uint8_t*)c->a_flags.p;
-    ia.sc = (RegionScalars*)c->scalars.p;
-    {
-        ProfScope ps(c, "k_ingest");
-        ps.add(launch_ingest(ia, c->compute));
-    }
-    CUDA_TRY(c, cudaGetLastError());
-    c->stats.n_reads += b->n_reads;
-    c->stats.n_cpg += b->n_cpg;
+    TRY(run_ingest(c, b->tid, r0, b->n_reads, i0, b->n_cpg, rel_dev));
     return MTH_OK;
+}
+
+int mth_submit_compact(mth_ctx* c, const mth_batch_compact* b) {
+    if (!c || !b) return MTH_ERR_INVALID;
+    if (c->finished) return fail(c, MTH_ERR_STATE, "mth_submit_compact after mth_finish (call mth_reset first)");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (b->n_reads < 0 || b->n_cpg < 0 || b->n_rel < 0) return fail(c, MTH_ERR_INVALID, "negative batch size");
+    if (b->n_reads == 0) return MTH_OK;
+    if (b->tid < 0 || (size_t)b->tid >= c->ref_len.size()) return fail(c, MTH_ERR_INVALID, "batch tid outside the reference list");
+    if (!b->start || !b->span || !b->mapq || !b->n_cpg8 || !b->flags || (b->n_cpg && (!b->cpg_delta || !b->meth_bits)))
+        return fail(c, MTH_ERR_INVALID, "null array in compact batch");
+    const bool lp = (c->prm.measures & MTH_LPMD) != 0;
+    if (lp && b->n_rel && !b->rel_exc) return fail(c, MTH_ERR_INVALID, "rel_exc is required when n_rel > 0");
+    if (b->mem_kind != 0 && b->mem_kind != 1) return fail(c, MTH_ERR_INVALID, "mem_kind must be 0 (host) or 1 (device)");
+    if (b->n_reads > (int64_t)INT32_MAX - 64 || b->n_cpg > (int64_t)UINT32_MAX - 64)
+        return fail(c, MTH_ERR_UNSUPPORTED, "batch too large (reads < 2^31, CpG calls < 2^32)");
+    TRY(place_batch(c, b->tid, b->n_reads, b->n_cpg, b->n_reads));
+    TRY(materialize(c));
+    const int64_t r0 = c->R, i0 = c->I, w0 = c->W;
+    const size_t nR = (size_t)b->n_reads, nI = (size_t)b->n_cpg, nE = lp ? (size_t)b->n_rel : 0;
+    TRY(ensure_arena(c, r0 + b->n_reads, i0 + b->n_cpg, w0 + b->n_reads, lp, c->has_meth_off));
+
+    ExpandArgs ea;
+    memset(&ea, 0, sizeof(ea));
+    if (b->mem_kind == 0) {
+        // staging buffers are reused by every batch: the copies of this batch wait for the expansion of the previous one
+        const size_t sz[8] = {nR * 4, nR * 2, nR, nR, nR, nI * 2, (nI + 7) / 8, nE * 2};
+        const void* src[8] = {b->start, b->span, b->mapq, b->n_cpg8, b->flags, b->cpg_delta, b->meth_bits, b->rel_exc};
+        for (int k = 0; k < 8; k++) TRY(dev_reserve(c, c->stage[k], sz[k] + 64, 0));
+        if (c->stage_busy) CUDA_TRY(c, cudaStreamWaitEvent(c->copy, c->ev_stage_free, 0));
+        for (int k = 0; k < 8; k++)
+            if (sz[k]) CUDA_TRY(c, cudaMemcpyAsync(c->stage[k].p, src[k], sz[k], cudaMemcpyHostToDevice, c->copy));
+        for (int k = 0; k < 8; k++) c->stats.h2d_bytes += (int64_t)sz[k];
+        CUDA_TRY(c, cudaEventRecord(c->ev_copy, c->copy));
+        CUDA_TRY(c, cudaStreamWaitEvent(c->compute, c->ev_copy, 0));
+        ea.start = (const int32_t*)c->stage[0].p; ea.span = (const uint16_t*)c->stage[1].p; ea.mapq = (const uint8_t*)c->stage[2].p;
+        ea.n_cpg8 = (const uint8_t*)c->stage[3].p; ea.flags = (const uint8_t*)c->stage[4].p; ea.cpg_delta = (const uint16_t*)c->stage[5].p;
+        ea.meth_bits = (const uint8_t*)c->stage[6].p; ea.rel_exc = (const uint16_t*)c->stage[7].p;
+    } else {
+        ea.start = b->start; ea.span = b->span; ea.mapq = b->mapq; ea.n_cpg8 = b->n_cpg8; ea.flags = b->flags;
+        ea.cpg_delta = b->cpg_delta; ea.meth_bits = b->meth_bits; ea.rel_exc = b->rel_exc;
+    }
+    const size_t nb = (nR + 255) / 256;
+    TRY(dev_reserve(c, c->exp_blocks, nb * 8 + 64, 0));
+    TRY(dev_reserve(c, c->exp_tot, 16, 0));
+    ea.n = b->n_reads;
+    ea.r0 = r0; ea.i0 = i0; ea.w0 = w0;
+    ea.lin_off = c->cur_lin_off;
+    ea.start_out = (int32_t*)c->a_start.p; ea.end_out = (int32_t*)c->a_end.p; ea.meta_out = (uint32_t*)c->a_meta.p;
+    ea.off_out = (uint32_t*)c->a_off.p; ea.pos_out = (int32_t*)c->a_pos.p; ea.rel_out = lp ? (uint16_t*)c->a_rel.p : nullptr;
+    ea.meth_out = (uint64_t*)c->a_meth.p; ea.moff_out = c->has_meth_off ? (uint32_t*)c->a_moff.p : nullptr;
+    ea.block_calls = (uint32_t*)c->exp_blocks.p; ea.block_rel = (uint32_t*)c->exp_blocks.p + nb;
+    ea.err = &((RegionScalars*)c->scalars.p)->err;
+    {
+        ProfScope ps(c, "k_expand");
+        ps.add(launch_expand(ea, (unsigned long long*)c->exp_tot.p, c->compute));
+    }
+    if (b->mem_kind == 0) {
+        CUDA_TRY(c, cudaEventRecord(c->ev_stage_free, c->compute));
+        c->stage_busy = true;
+    }
+    c->R = r0 + b->n_reads;
+    c->I = i0 + b->n_cpg;
+    c->W = w0 + b->n_reads;
+    return run_ingest(c, b->tid, r0, b->n_reads, i0, b->n_cpg, lp ? (const uint16_t*)c->a_rel.p : nullptr);
 }
 
 }  // extern "C"

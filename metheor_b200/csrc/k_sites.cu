@@ -98,6 +98,11 @@ __global__ void __launch_bounds__(SCAN_BLOCK) k_sites_emit(const unsigned long l
     }
 }
 
+int launch_scan_sums(uint32_t* sums, int64_t n, unsigned long long* total, cudaStream_t s) {
+    k_scan_sums<<<1, SCAN_BLOCK, 0, s>>>(sums, n, total);
+    return 1;
+}
+
 int launch_sites_count(const unsigned long long* bitmap, int64_t n_words, uint32_t* block_sums, RegionScalars* sc,
                        cudaStream_t s) {
     int64_t nb = (n_words + WORDS_PER_BLOCK - 1) / WORDS_PER_BLOCK;

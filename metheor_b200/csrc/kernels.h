@@ -27,6 +27,23 @@ struct IngestArgs {
 };
 int launch_ingest(const IngestArgs& a, cudaStream_t s);
 
+// ---- compact wire format -> SoA arena (k_expand.cu) ------------------------------------------
+struct ExpandArgs {
+    // compact batch (device copies)
+    int64_t n;
+    const int32_t* start; const uint16_t* span; const uint8_t* mapq; const uint8_t* n_cpg8; const uint8_t* flags;
+    const uint16_t* cpg_delta; const uint8_t* meth_bits; const uint16_t* rel_exc;
+    // destination: region arena, reads from r0, calls from i0, meth words from w0
+    int64_t r0, i0, w0;
+    int32_t lin_off;
+    int32_t* start_out; int32_t* end_out; uint32_t* meta_out; uint32_t* off_out; int32_t* pos_out; uint16_t* rel_out;  // rel_out: nullptr unless LPMD
+    uint64_t* meth_out; uint32_t* moff_out;  // moff_out: nullptr unless the region already uses meth_off
+    uint32_t* block_calls; uint32_t* block_rel;  // scratch, one entry per 256 reads
+    uint32_t* err;
+};
+int launch_expand(const ExpandArgs& a, unsigned long long* total_scratch, cudaStream_t s);
+int launch_scan_sums(uint32_t* sums, int64_t n, unsigned long long* total, cudaStream_t s);  // single block, in place
+
 // ---- site dictionary + scans (k_sites.cu) ---------------------------------------------------
 // phase 1: popcount per 1024-word block -> block_sums, scanned in place; total -> sc->n_sites
 int launch_sites_count(const unsigned long long* bitmap, int64_t n_words, uint32_t* block_sums, RegionScalars* sc,

@@ -6,7 +6,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import (FLAG_FORCE_GATHER, FLAG_KEEP_ON_DEVICE, FLAG_PROFILE, FLAG_QUARTET_COUNTS, MEASURE_BITS, Batch,
-                   LpmdResult, Params, Results, Stats)
+                   BatchCompact, LpmdResult, Params, Results, Stats)
 
 
 class EngineError(RuntimeError):
@@ -103,6 +103,27 @@ class Context:
             mb.n_meth_words = int(b["n_meth_words"]) if "n_meth_words" in b else int(len(b["meth"]))
         self._check(self._L.mth_submit(self._h, C.byref(mb)))
 
+    def submit_compact(self, b):
+        """b: dict in the compact wire format (batch.to_compact): numpy host arrays or torch CUDA tensors."""
+        mb = BatchCompact()
+        mb.tid, mb.n_reads, mb.n_cpg, mb.n_rel = int(b["tid"]), int(b["n_reads"]), int(b["n_cpg"]), int(b["n_rel"])
+        dt = dict(start=np.int32, span=np.uint16, mapq=np.uint8, n_cpg8=np.uint8, flags=np.uint8, cpg_delta=np.uint16,
+                  meth_bits=np.uint8, rel_exc=np.uint16)
+        dev = None
+        for f, t in dt.items():
+            x = b.get(f)
+            if isinstance(x, np.ndarray):
+                x = np.ascontiguousarray(x, t)
+            p, keep, is_dev = _as_ptr(x)
+            if p is not None and (not isinstance(x, np.ndarray) or x.size):
+                dev = is_dev if dev is None else dev
+                if dev != is_dev:
+                    raise ValueError("batch mixes host and device arrays")
+                self._keep.append(keep)
+            setattr(mb, f, p)
+        mb.mem_kind = 1 if dev else 0
+        self._check(self._L.mth_submit_compact(self._h, C.byref(mb)))
+
     def add_skipped_reads(self, n_reads, n_mapq_ok):
         self._check(self._L.mth_add_skipped_reads(self._h, n_reads, n_mapq_ok))
 
@@ -183,12 +204,18 @@ class Context:
         return d
 
 
-def run_batches(batches, ref_len, measures, device=0, flags=0, seed=0, **overrides):
-    """Convenience: one context, submit every batch, finish.  -> (results dict, stats dict)"""
+def run_batches(batches, ref_len, measures, device=0, flags=0, seed=0, compact=False, **overrides):
+    """Convenience: one context, submit every batch, finish.  -> (results dict, stats dict)
+    compact: send the batches in the compact wire format (True), or alternate between the two formats ("mix")."""
+    from .batch import to_compact
     ctx = Context(default_params(measures, flags=flags, seed=seed, **overrides), ref_len, device)
     try:
-        for b in batches:
-            ctx.submit(b)
+        for k, b in enumerate(batches):
+            dense = b["n_reads"] and np.diff(np.asarray(b["cpg_off"], np.int64)).max(initial=0) > 64
+            if compact and not dense and (compact != "mix" or k % 2 == 0):
+                ctx.submit_compact(to_compact(b))
+            else:
+                ctx.submit(b)
         res = ctx.finish()
         return res, ctx.stats()
     finally:

@@ -93,6 +93,7 @@ inline void emit_read(const ReadFields& r, NextOp&& next_op, const DecodeOptions
     int64_t ref = r.pos;
     size_t qi = 0;
     int32_t start = -1, end = -1;
+    bool plain = true;  // only M/=/X (and H/P): the query index of a call is implied by its position
     const size_t i0 = out->cpg_pos.size();
     CigarOp c;
     while (next_op(&c)) {
@@ -118,8 +119,8 @@ inline void emit_read(const ReadFields& r, NextOp&& next_op, const DecodeOptions
                 qi += c.len;
                 break;
             }
-            case 1: case 4: qi += c.len; break;   // I S: query only (None in reference_positions_full)
-            case 2: case 3: ref += c.len; break;  // D N: reference only
+            case 1: case 4: qi += c.len; plain = false; break;   // I S: query only (None in reference_positions_full)
+            case 2: case 3: ref += c.len; plain = false; break;  // D N: reference only
             default: break;                        // H P
         }
     }
@@ -130,10 +131,11 @@ inline void emit_read(const ReadFields& r, NextOp&& next_op, const DecodeOptions
         return;
     }
     if ((int32_t)n > cnt->max_cpgs) cnt->max_cpgs = (int32_t)n;
+    if ((int64_t)end - start + 1 > cnt->max_span) cnt->max_span = (int64_t)end - start + 1;
     out->tid.push_back(r.tid);
     out->start.push_back(start);
     out->end.push_back(end);
-    out->meta.push_back(r.mapq | ((uint32_t)fwd << 8));
+    out->meta.push_back(r.mapq | ((uint32_t)fwd << 8) | (plain ? 0u : SOA_META_COMPLEX));
     out->n_cpg.push_back((uint32_t)n);
 }
 

@@ -16,10 +16,13 @@ struct CpgSet {
     bool contains(int32_t tid, int32_t pos) const;
 };
 
+// host-internal meta bit: the alignment has indels / clips / skips, so query indices must be shipped explicitly
+constexpr uint32_t SOA_META_COMPLEX = 1u << 10;
+
 // Decoded reads of a contiguous run of records, in file order.
 struct SoaChunk {
     std::vector<int32_t> tid, start, end;
-    std::vector<uint32_t> meta;      // mapq | forward << 8
+    std::vector<uint32_t> meta;      // mapq | forward << 8 | SOA_META_COMPLEX
     std::vector<uint32_t> n_cpg;     // CpG calls kept per read
     std::vector<int32_t> cpg_pos;    // strand-adjusted positions (readutil.rs:332-339)
     std::vector<uint16_t> cpg_rel;   // query index (readutil.rs:335)
@@ -39,9 +42,11 @@ struct DecodeCounters {
     int64_t n_dropped = 0;           // records without a retained CpG call (not shipped to the GPU)
     int64_t n_dropped_mapq_ok = 0;   // ... of which mapq >= min_qual (LPMD n_valid_read, lpmd.rs:176-189)
     int32_t max_cpgs = 0;
+    int64_t max_span = 0;            // longest end - start + 1 among the kept reads
     void add(const DecodeCounters& o) {
         n_records += o.n_records; n_dropped += o.n_dropped; n_dropped_mapq_ok += o.n_dropped_mapq_ok;
         if (o.max_cpgs > max_cpgs) max_cpgs = o.max_cpgs;
+        if (o.max_span > max_span) max_span = o.max_span;
     }
 };
 

@@ -39,7 +39,7 @@ const size_t TASK_RECORDS = 4096;
 const int RING = 3;
 
 struct PinnedBatch {
-    enum { START, END, META, OFF, POS, REL, METH, MOFF, NARR };
+    enum { START, END, META, OFF, POS, REL, METH, MOFF, SPAN, MAPQ, NCPG, FLAGS, DELTA, BITS, RELX, NARR };
     void* p[NARR] = {nullptr};
     size_t cap[NARR] = {0};
     ~PinnedBatch() {
@@ -114,7 +114,7 @@ void assemble(ThreadPool& pool, std::vector<SoaChunk>& chunks, size_t c0, size_t
         if (!n) return;
         memcpy(start + r0, ch.start.data(), n * 4);
         memcpy(end + r0, ch.end.data(), n * 4);
-        memcpy(meta + r0, ch.meta.data(), n * 4);
+        for (size_t r = 0; r < n; r++) meta[r0 + r] = ch.meta[r] & ~SOA_META_COMPLEX;
         memcpy(pos + i0, ch.cpg_pos.data(), ch.cpg_pos.size() * 4);
         if (want_rel) memcpy(rel + i0, ch.cpg_rel.data(), ch.cpg_rel.size() * 2);
         size_t io = i0, wo = w_off[(size_t)k];
@@ -147,6 +147,73 @@ void assemble(ThreadPool& pool, std::vector<SoaChunk>& chunks, size_t c0, size_t
     b->cpg_rel = want_rel ? rel : nullptr;
     b->meth = meth;
     b->meth_off = multiword ? moff : nullptr;
+}
+
+// Same reads in the compact wire format (mth_batch_compact): 9 B per read + 2.125 B per call over PCIe instead of 24 + 6.
+void assemble_compact(ThreadPool& pool, std::vector<SoaChunk>& chunks, size_t nc, int32_t tid, bool want_rel, PinnedBatch& pb,
+                      mth_batch_compact* b) {
+    std::vector<size_t> r_off(nc + 1, 0), i_off(nc + 1, 0), e_off(nc + 1, 0);
+    for (size_t k = 0; k < nc; k++) {
+        const SoaChunk& ch = chunks[k];
+        r_off[k + 1] = r_off[k] + ch.start.size();
+        i_off[k + 1] = i_off[k] + ch.cpg_pos.size();
+        size_t e = 0;
+        if (want_rel)
+            for (size_t r = 0; r < ch.meta.size(); r++)
+                if (ch.meta[r] & SOA_META_COMPLEX) e += ch.n_cpg[r];
+        e_off[k + 1] = e_off[k] + e;
+    }
+    const size_t R = r_off[nc], I = i_off[nc], E = e_off[nc];
+    pb.reserve(PinnedBatch::START, R * 4); pb.reserve(PinnedBatch::SPAN, R * 2); pb.reserve(PinnedBatch::MAPQ, R);
+    pb.reserve(PinnedBatch::NCPG, R); pb.reserve(PinnedBatch::FLAGS, R); pb.reserve(PinnedBatch::DELTA, I * 2 + 64);
+    pb.reserve(PinnedBatch::BITS, (I + 7) / 8 + 64); pb.reserve(PinnedBatch::RELX, E * 2 + 64);
+    int32_t* start = (int32_t*)pb.p[PinnedBatch::START];
+    uint16_t* span = (uint16_t*)pb.p[PinnedBatch::SPAN];
+    uint8_t* mapq = (uint8_t*)pb.p[PinnedBatch::MAPQ];
+    uint8_t* ncpg = (uint8_t*)pb.p[PinnedBatch::NCPG];
+    uint8_t* flags = (uint8_t*)pb.p[PinnedBatch::FLAGS];
+    uint16_t* delta = (uint16_t*)pb.p[PinnedBatch::DELTA];
+    uint8_t* bits = (uint8_t*)pb.p[PinnedBatch::BITS];
+    uint16_t* relx = (uint16_t*)pb.p[PinnedBatch::RELX];
+    for (size_t k = 0; k <= nc; k++) bits[i_off[k] >> 3] = 0;  // bytes shared by two chunks are OR-ed atomically below
+    pool.run((int64_t)nc, [&](int64_t k, int) {
+        const SoaChunk& ch = chunks[(size_t)k];
+        const size_t r0 = r_off[(size_t)k], n = ch.start.size();
+        if (!n) return;
+        memcpy(start + r0, ch.start.data(), n * 4);
+        size_t x = i_off[(size_t)k], e = e_off[(size_t)k];
+        const size_t x_end = i_off[(size_t)k + 1];
+        const size_t first_byte = x >> 3, last_byte = x_end >> 3;
+        for (size_t by = first_byte + 1; by < last_byte; by++) bits[by] = 0;
+        size_t c = 0;  // call index within the chunk
+        for (size_t r = 0; r < n; r++) {
+            const uint32_t m = ch.meta[r], nr = ch.n_cpg[r];
+            const int32_t s = ch.start[r];
+            span[r0 + r] = (uint16_t)(ch.end[r] - s);
+            mapq[r0 + r] = (uint8_t)(m & 0xFFu);
+            ncpg[r0 + r] = (uint8_t)nr;
+            const bool cx = want_rel && (m & SOA_META_COMPLEX);
+            flags[r0 + r] = (uint8_t)(((m >> 8) & 1u) | (cx ? MTH_CFLAG_REL_EXPLICIT : 0u));
+            for (uint32_t q = 0; q < nr; q++, c++, x++) {
+                delta[x] = (uint16_t)(ch.cpg_pos[c] - (s - 1));
+                if (ch.cpg_meth[c]) {
+                    const size_t by = x >> 3;
+                    const uint8_t bit = (uint8_t)(1u << (x & 7));
+                    if (by == first_byte || by == last_byte) __atomic_fetch_or(&bits[by], bit, __ATOMIC_RELAXED);
+                    else bits[by] |= bit;
+                }
+                if (cx) relx[e++] = ch.cpg_rel[c];
+            }
+        }
+    });
+    memset(b, 0, sizeof(*b));
+    b->tid = tid;
+    b->mem_kind = 0;
+    b->n_reads = (int64_t)R;
+    b->n_cpg = (int64_t)I;
+    b->n_rel = (int64_t)E;
+    b->start = start; b->span = span; b->mapq = mapq; b->n_cpg8 = ncpg; b->flags = flags;
+    b->cpg_delta = delta; b->meth_bits = bits; b->rel_exc = relx;
 }
 
 // ---- TSV ----------------------------------------------------------------------------------------------------
@@ -363,17 +430,29 @@ void run(const mthh_options& o) {
                 }
                 PinnedBatch& pb = G.ring[G.next_slot];
                 G.next_slot = (G.next_slot + 1) % RING;
-                mth_batch b;
-                assemble(pool, chunks, 0, n_tasks, tid, want_rel, seg.max_cpgs, pb, &b);
-                s_assemble += now_s() - t0;
-                t0 = now_s();
-                int rc = mth_submit(G.ctx, &b);
+                int64_t nr_b, nc_b;
+                int rc;
+                if (seg.max_cpgs <= 64 && seg.max_span <= 65024) {  // compact wire format: ~1/3 of the PCIe bytes
+                    mth_batch_compact b;
+                    assemble_compact(pool, chunks, n_tasks, tid, want_rel, pb, &b);
+                    s_assemble += now_s() - t0;
+                    t0 = now_s();
+                    rc = mth_submit_compact(G.ctx, &b);
+                    nr_b = b.n_reads; nc_b = b.n_cpg;
+                } else {
+                    mth_batch b;
+                    assemble(pool, chunks, 0, n_tasks, tid, want_rel, seg.max_cpgs, pb, &b);
+                    s_assemble += now_s() - t0;
+                    t0 = now_s();
+                    rc = mth_submit(G.ctx, &b);
+                    nr_b = b.n_reads; nc_b = b.n_cpg;
+                }
                 if (rc != MTH_OK) engine_fail(G.ctx, rc, "mth_submit");
                 G.submitted++;
                 s_submit += now_s() - t0;
                 n_batches++;
-                n_shipped_reads += b.n_reads;
-                n_shipped_cpg += b.n_cpg;
+                n_shipped_reads += nr_b;
+                n_shipped_cpg += nc_b;
             }
             seg0 = seg1;
         }

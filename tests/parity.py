@@ -41,10 +41,11 @@ DEFAULTS = dict(pdr=dict(min_depth=10, min_cpgs=4, min_qual=10), mhl=dict(min_de
                 lpmd=dict(min_distance=2, max_distance=16, min_qual=10))
 
 
-def check_all(batches, ref_len, measures, seed=0, flags=0, **overrides):
+def check_all(batches, ref_len, measures, seed=0, flags=0, compact=False, **overrides):
     """Engine vs oracle, bit-exact, for every requested measure.  Returns (engine results, stats)."""
     prm = {m: dict(DEFAULTS[m], **overrides.get(m, {})) for m in measures}
-    res, stats = engine.run_batches(batches, ref_len, measures, flags=flags, seed=seed, **{k: dict(v) for k, v in prm.items()})
+    res, stats = engine.run_batches(batches, ref_len, measures, flags=flags, seed=seed, compact=compact,
+                                    **{k: dict(v) for k, v in prm.items()})
     orc = Oracle.from_soa(**B.to_oracle_soa(batches))
     if "pdr" in measures:
         w = orc.pdr(**prm["pdr"])

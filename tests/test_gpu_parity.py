@@ -238,3 +238,33 @@ def test_position_bin_sharding_with_halo_equals_one_pass():
                     if a.dtype == np.float32:
                         a, b2 = a.view(np.uint32), b2.view(np.uint32)
                     assert np.array_equal(a, b2), (m, k, world)
+
+
+def test_compact_wire_format_equals_soa(golden):
+    """mth_submit_compact (9 B/read + 2.125 B/call, expanded on the device) gives the same rows as mth_submit."""
+    ov = dict(pdr=dict(min_depth=3, min_cpgs=2), mhl=dict(min_depth=3, min_cpgs=2), fdrp=dict(min_depth=3), qfdrp=dict(min_depth=3),
+              pm=dict(min_depth=3), me=dict(min_depth=3), lpmd=dict(want_pairs=1))
+    b = parity.records_to_batch(golden["test4"]["reads"])
+    parity.check_all([b], CHR1, ALL, compact=True)
+    fx = golden["chr19_1000"]
+    parity.check_all([parity.records_to_batch(fx["reads"])], [l for _, l in fx["refs"]], ALL, compact=True, **ov)
+    # deletions: query indices are not implied by the positions -> rel_exc
+    s = _synth(110, read_len=140, del_frac=0.5, del_max=60, nocall=0.05, lowq=0.15)
+    c = B.to_compact(s)
+    assert c["n_rel"] > 0 and (c["flags"] & 4).any() and not (c["flags"] & 4).all()
+    parity.check_all([s], [200_000], ALL, compact=True, **ov)
+    # several batches and contigs, formats alternating
+    lens = [150_000, 80_000, 120_000]
+    batches = []
+    for tid, L in enumerate(lens):
+        x = _synth(120 + tid, length=L, cov=25.0, tid=tid)
+        cuts = [0, x["n_reads"] // 3, (2 * x["n_reads"]) // 3, x["n_reads"]]
+        batches += [B.slice_reads(x, lo, hi) for lo, hi in zip(cuts[:-1], cuts[1:])]
+    parity.check_all(batches, lens, ALL, compact=True)
+    parity.check_all(batches, lens, ALL, compact="mix")
+    # a read denser than the compact format allows falls back to the SoA batch; both kinds in one region
+    dense = synth.make_reads(17, np.arange(10, 20_000, 2, dtype=np.int32), 20_000, 12.0, nocall=0.02)
+    sparse = _synth(130, length=150_000, tid=1)
+    parity.check_all([dense, sparse], [20_000, 150_000], ALL, compact=True, pdr=dict(min_depth=4), mhl=dict(min_depth=4))
+    with pytest.raises(ValueError):
+        B.to_compact(dense)
