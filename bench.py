@@ -131,6 +131,42 @@ def run_reference(args, rank):
     print(json.dumps(line))
 
 
+def bam_leg(b, n_reads, length):
+    """BAM -> TSV through the shipped host (BGZF inflate + record decode on all cores, compact batches, GPU engine, TSV
+    writer) next to the oracle's CLI (single thread, its own BAM reader) on the same file; outputs must be identical."""
+    import tempfile
+    from metheor_b200 import batch as B
+    from metheor_b200 import host, synth_bam
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    oracle_lib.build()
+    sub = B.slice_reads(b, 0, min(n_reads, b["n_reads"]))
+    out = {}
+    with tempfile.TemporaryDirectory() as d:
+        bam = os.path.join(d, "synthetic.bam")
+        info = synth_bam.write_bam(bam, [("chr19", length)], [sub], threads=os.cpu_count() or 8)
+        out.update(records=info["records"], bam_bytes=info["bytes_compressed"], uncompressed_bytes=info["bytes_uncompressed"],
+                   host_threads=os.cpu_count())
+        for m in MEASURES:
+            tsv, st = os.path.join(d, f"{m}.tsv"), os.path.join(d, f"{m}.json")
+            best = None
+            for _ in range(3):
+                t0 = time.perf_counter()
+                host.run(m, bam, tsv, stats_json=st)
+                dt = time.perf_counter() - t0
+                if best is None or dt < best[0]:
+                    best = (dt, json.load(open(st)))
+            t0 = time.perf_counter()
+            r = subprocess.run([oracle_lib.CLI_PATH, m, "-i", bam, "-o", tsv + ".oracle"], capture_output=True, text=True)
+            dt_o = time.perf_counter() - t0
+            same = r.returncode == 0 and open(tsv, "rb").read() == open(tsv + ".oracle", "rb").read()
+            out[m] = {"reads_per_sec": info["records"] / best[0], "seconds": best[0],
+                      "uncompressed_MB_per_sec": info["bytes_uncompressed"] / best[0] / 1e6, "stage_seconds": best[1]["seconds"],
+                      "cpu_oracle_cli_seconds": dt_o, "cpu_oracle_cli_reads_per_sec": info["records"] / dt_o,
+                      "tsv_identical_to_oracle": bool(same)}
+    return out
+
+
 class _DevI64:
     def __init__(self, ptr, n):
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 2}
@@ -145,6 +181,8 @@ def main():
     ap.add_argument("--coverage", type=float, default=COVERAGE)
     ap.add_argument("--length", type=int, default=CONTIG_LEN)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--bam-reads", type=int, default=2_000_000,
+                    help="also time the BAM -> TSV path (C++ host + engine) on a BAM of the first N reads; 0 disables")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -306,6 +344,13 @@ def main():
                "sample": f"first {nn} reads of the workload (pdr+lpmd, defaults); C++ restatement of metheor 0.1.9, "
                          f"single-threaded like the reference; host has {os.cpu_count()} cores"}
 
+    bam = None
+    if rank == 0 and world == 1 and args.bam_reads > 0 and not args.no_cpu_baseline:
+        try:
+            bam = bam_leg(b, args.bam_reads, args.length)
+        except Exception as e:  # the extra leg must never cost the bench line
+            bam = {"error": repr(e)}
+
     if rank == 0:
         line = {"metric": "reads_per_sec", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -319,7 +364,7 @@ def main():
                 "e2e_soa": dict(e2e["soa"], wire_format="SoA (mth_submit)"),
                 "gpu_launches": int((st["kernel_launches"] - 0) * args.steps),
                 "launches_per_step": int(st["kernel_launches"]),
-                "roofline": roofline, "roofline_step": roofline_step, "kernels": kern, "cpu_baseline": cpu,
+                "roofline": roofline, "roofline_step": roofline_step, "kernels": kern, "cpu_baseline": cpu, "bam_end_to_end": bam,
                 "clocks": clocks, "pdr_path": {1: "scatter", 2: "gather"}.get(st["pdr_path"]), "lpmd": float(rows["lpmd"]["lpmd"])}
         print(json.dumps(line))
     ctx.close(); ectx.close()

@@ -211,8 +211,8 @@ def run_batches(batches, ref_len, measures, device=0, flags=0, seed=0, compact=F
     ctx = Context(default_params(measures, flags=flags, seed=seed, **overrides), ref_len, device)
     try:
         for k, b in enumerate(batches):
-            dense = b["n_reads"] and np.diff(np.asarray(b["cpg_off"], np.int64)).max(initial=0) > 64
-            if compact and not dense and (compact != "mix" or k % 2 == 0):
+            if compact and (compact != "mix" or k % 2 == 0) and b["n_reads"] and \
+                    np.diff(np.asarray(b["cpg_off"], np.int64)).max(initial=0) <= 64:
                 ctx.submit_compact(to_compact(b))
             else:
                 ctx.submit(b)
