@@ -286,7 +286,7 @@ def main():
     C = n_sites
     alg = {  # algorithmic bytes per launch, DESIGN.md §5
         "k_ingest": 16 * R + 6 * I + 32,          # LPMD: meta+cpg_off+meth per read, cpg_pos+cpg_rel per CpG call, 4 counters
-        "k_pdr_scatter": 16 * R + 4 * I + 8 * C,  # PDR: meta+cpg_off+meth per read, cpg_pos per call, 2 u32 counters per site
+        "k_pdr_scatter": 16 * R + 4 * I + 8 * C,  # PDR: per-read fields, cpg_pos per call, 2 u32 counters per site
         "k_pdr_gather": 16 * R + 4 * I + 8 * C,
         "k_sites_count": C * 4, "k_sites_emit": C * 4, "pdr_rows_count": C * 12, "k_pdr_emit": C * 8 + n_rows * 20,
     }
@@ -295,8 +295,14 @@ def main():
     ach = alg[hot] / (kern[hot]["ms_per_step"] * 1e-3) / 1e9
     step_alg = (16 * R + 4 * I + 12 * C) + (16 * R + 6 * I + 16)  # PDR + LPMD
     kern_ms_total = sum(v["ms_per_step"] for v in kern.values())
+    traffic = None
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(hot, {}).get("dram_bytes")
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": hot, "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                "frac": ach / peak, "traffic": None, "algorithmic_bytes_per_launch": alg[hot],
+                "frac": ach / peak, "traffic": traffic, "algorithmic_bytes_per_launch": alg[hot],
                 "ms_per_launch": kern[hot]["ms_per_step"]}
     roofline_step = {"algorithmic_bytes": step_alg, "kernel_ms_sum": kern_ms_total,
                      "achieved": step_alg / (kern_ms_total * 1e-3) / 1e9, "unit": "GB/s",

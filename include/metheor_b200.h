@@ -203,6 +203,9 @@ int mth_ctx_destroy(mth_ctx* ctx);
 int mth_set_stream(mth_ctx* ctx, void* cuda_stream);
 /* Asynchronous: enqueues the host->device copy on the copy stream and the ingest kernels behind it. */
 int mth_submit(mth_ctx* ctx, const mth_batch* batch);
+/* Capacity hint: pre-allocates the arena for about n_reads reads / n_cpg CpG calls so that a streaming host does not
+ * pay for re-allocations while batches arrive.  Never required; clamped to the free device memory. */
+int mth_reserve(mth_ctx* ctx, int64_t n_reads, int64_t n_cpg);
 /* Same as mth_submit for the compact wire format (host or device memory). */
 int mth_submit_compact(mth_ctx* ctx, const mth_batch_compact* batch);
 /* Host reads that carried no CpG call were dropped before submit: only LPMD's n_read counts them (lpmd.rs:176). */

@@ -87,7 +87,7 @@ class Stats(C.Structure):
                 ("n_kernel_stats", i32), ("kernel", KernelStat * 48)]
 
 
-EXPORTS = ["mth_params_default", "mth_ctx_create", "mth_ctx_destroy", "mth_set_stream", "mth_submit", "mth_submit_compact",
+EXPORTS = ["mth_params_default", "mth_ctx_create", "mth_ctx_destroy", "mth_set_stream", "mth_submit", "mth_submit_compact", "mth_reserve",
            "mth_add_skipped_reads", "mth_finish", "mth_results_device", "mth_lpmd_counters_device", "mth_lpmd_refresh",
            "mth_reset", "mth_sync", "mth_sync_copies", "mth_get_stats", "mth_last_error", "mth_host_alloc", "mth_host_free",
            "mth_device_count", "mth_version", "mth_reservoir_draw"]
@@ -118,6 +118,7 @@ def lib():
     L.mth_ctx_destroy.argtypes = [vp]; L.mth_ctx_destroy.restype = C.c_int
     L.mth_set_stream.argtypes = [vp, vp]; L.mth_set_stream.restype = C.c_int
     L.mth_submit.argtypes = [vp, P(Batch)]; L.mth_submit.restype = C.c_int
+    L.mth_reserve.argtypes = [vp, i64, i64]; L.mth_reserve.restype = C.c_int
     L.mth_submit_compact.argtypes = [vp, P(BatchCompact)]; L.mth_submit_compact.restype = C.c_int
     L.mth_add_skipped_reads.argtypes = [vp, i64, i64]; L.mth_add_skipped_reads.restype = C.c_int
     L.mth_finish.argtypes = [vp, P(Results)]; L.mth_finish.restype = C.c_int

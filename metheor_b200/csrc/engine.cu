@@ -12,6 +12,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -616,6 +617,28 @@ int mth_submit(mth_ctx* c, const mth_batch* b) {
     c->W = w0 + bw;
 
     TRY(run_ingest(c, b->tid, r0, b->n_reads, i0, b->n_cpg, rel_dev));
+    return MTH_OK;
+}
+
+int mth_reserve(mth_ctx* c, int64_t n_reads, int64_t n_cpg) {
+    if (!c || n_reads < 0 || n_cpg < 0) return MTH_ERR_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(c, cudaMemGetInfo(&free_b, &total_b));
+    const bool lp = (c->prm.measures & MTH_LPMD) != 0;
+    const double per_read = 24.0, per_call = lp ? 7.0 : 5.0;
+    double need = per_read * (double)n_reads + per_call * (double)n_cpg;
+    const double budget = 0.5 * (double)free_b;
+    if (need > budget) {  // keep the proportions, shrink to the budget
+        const double f = budget / need;
+        n_reads = (int64_t)((double)n_reads * f);
+        n_cpg = (int64_t)((double)n_cpg * f);
+    }
+    n_reads = std::min<int64_t>(n_reads, (int64_t)INT32_MAX - 128);
+    n_cpg = std::min<int64_t>(n_cpg, (int64_t)UINT32_MAX - 128);
+    if (n_reads <= c->R && n_cpg <= c->I) return MTH_OK;
+    TRY(ensure_arena(c, std::max(n_reads, c->R), std::max(n_cpg, c->I), std::max(n_reads, c->W), lp, c->has_meth_off));
+    TRY(dev_reserve(c, c->a_flags, (size_t)std::max(n_cpg, c->I) + 64, (size_t)c->I));
     return MTH_OK;
 }
 

@@ -312,7 +312,7 @@ int mthh_decode_file(const char* path, const char* cpg_set, int32_t threads, mth
     try {
         int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
         mthh::ThreadPool pool(nt < 1 ? 1 : nt);
-        mthh::RecordStream in(path, pool, 8u << 20);
+        mthh::RecordStream in(path, nt < 1 ? 1 : nt, 8u << 20);
         mthh::CpgSet set;
         if (cpg_set) set.load(cpg_set, in.header());
         mthh::DecodeOptions opt;

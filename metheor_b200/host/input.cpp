@@ -94,8 +94,8 @@ size_t bgzf_member(const uint8_t* d, size_t size, size_t o, size_t* cdata, size_
 
 }  // namespace
 
-RecordStream::RecordStream(const std::string& path, ThreadPool& pool, size_t window_bytes)
-    : path_(path), pool_(pool), window_bytes_(window_bytes) {
+RecordStream::RecordStream(const std::string& path, int n_threads, size_t window_bytes)
+    : path_(path), pool_(n_threads), window_bytes_(window_bytes) {
     file_.open(path);
     const uint8_t* d = file_.data();
     if (file_.size() >= 2 && d[0] == 31 && d[1] == 139) {
@@ -113,53 +113,106 @@ RecordStream::RecordStream(const std::string& path, ThreadPool& pool, size_t win
     }
 }
 
-bool RecordStream::fill_bam_window() {
+RecordStream::~RecordStream() {
+    if (prefetching_) next_.wait();
+}
+
+// Index the next members (up to window_bytes_ of output), inflate them on the reader's pool.  Touches only coff_,
+// which nobody else uses while a prefetch is in flight.
+RecordStream::Inflated RecordStream::inflate_next(size_t headroom) {
+    Inflated out;
     const uint8_t* d = file_.data();
-    size_t carry = buf_len_ - buf_pos_;
-    blocks_.clear();
+    std::vector<Block> blocks;
     size_t utotal = 0;
     while (coff_ < file_.size() && utotal < window_bytes_) {
         Block b;
         uint32_t crc;
         size_t total = bgzf_member(d, file_.size(), coff_, &b.cdata, &b.clen, &b.usize, &crc);
-        if (!total) throw open_error("corrupt or truncated BGZF block at offset " + std::to_string(coff_) + ": " + path_);
+        if (!total) {
+            out.ok = false;
+            out.err = "corrupt or truncated BGZF block at offset " + std::to_string(coff_) + ": " + path_;
+            return out;
+        }
         b.uoff = utotal;
         utotal += b.usize;
-        if (b.usize) blocks_.push_back(b);
+        if (b.usize) blocks.push_back(b);
         coff_ += total;
     }
-    if (blocks_.empty()) {
-        eof_ = true;
-        return false;
-    }
-    std::vector<uint8_t> nb(carry + utotal);
-    if (carry) memcpy(nb.data(), buf_.data() + buf_pos_, carry);
+    out.headroom = headroom;
+    out.len = utotal;
+    out.coff_end = coff_;
+    if (blocks.empty()) return out;
+    out.data.reset(new uint8_t[headroom + utotal]);  // deliberately uninitialised
     double t0 = now_s();
     std::vector<Inflater> infl((size_t)pool_.size());
     std::atomic<int> bad{0};
-    uint8_t* out = nb.data() + carry;
-    pool_.run((int64_t)blocks_.size(), [&](int64_t i, int w) {
-        const Block& b = blocks_[(size_t)i];
+    uint8_t* dst = out.data.get() + headroom;
+    pool_.run((int64_t)blocks.size(), [&](int64_t i, int w) {
+        const Block& b = blocks[(size_t)i];
         uint32_t crc = (uint32_t)le32(d + b.cdata + b.clen);
-        if (!infl[(size_t)w].run(d + b.cdata, b.clen, out + b.uoff, b.usize, crc)) bad.store(1);
+        if (!infl[(size_t)w].run(d + b.cdata, b.clen, dst + b.uoff, b.usize, crc)) bad.store(1);
     });
-    if (bad.load()) throw open_error("BGZF inflate / CRC failure: " + path_);
-    seconds_inflate += now_s() - t0;
-    bytes_uncompressed += utotal;
-    buf_.swap(nb);
-    buf_len_ = carry + utotal;
-    buf_pos_ = 0;
-    return true;
+    if (bad.load()) {
+        out.ok = false;
+        out.err = "BGZF inflate / CRC failure: " + path_;
+    }
+    out.seconds = now_s() - t0;
+    return out;
+}
+
+RecordStream::Window RecordStream::produce() {
+    Window w;
+    for (;;) {
+        Inflated in = inflate_next(carry_.size());
+        w.s_inflate += in.seconds;
+        if (!in.ok) { w.ok = false; w.err = in.err; return w; }
+        const bool last = in.len == 0;  // no members left: only the carried-over bytes remain
+        if (last) {
+            if (carry_.empty()) { w.eof = true; return w; }
+            in.data.reset(new uint8_t[carry_.size()]);
+        }
+        w.inflated += in.len;
+        w.coff_end = in.coff_end;
+        const size_t carry = carry_.size();
+        if (carry) memcpy(in.data.get(), carry_.data(), carry);
+        const uint8_t* b = in.data.get();
+        const size_t n = carry + in.len;
+        double t0 = now_s();
+        size_t o = 0;
+        w.recs.reserve(n / 256);
+        while (o + 4 <= n) {
+            int32_t bs = le32(b + o);
+            if (bs < 32) { w.ok = false; w.err = "corrupt BAM record (block_size < 32): " + path_; return w; }
+            if (o + 4 + (size_t)bs > n) break;
+            w.recs.push_back(RecordRef{b + o + 4, (uint32_t)bs});
+            o += 4 + (size_t)bs;
+        }
+        w.s_walk += now_s() - t0;
+        if (last && o != n) { w.ok = false; w.err = "truncated BAM record at end of file: " + path_; return w; }
+        carry_.assign(b + o, b + n);  // the partial record (if any) moves in front of the next run
+        if (!w.recs.empty()) {
+            w.data = std::move(in.data);
+            return w;
+        }
+        // a single record larger than one run: keep accumulating
+    }
 }
 
 void RecordStream::parse_bam_header() {
-    // the header may span several windows: keep appending until it is complete
+    // the header may span several runs: keep appending until it is complete
     for (;;) {
-        size_t before = buf_len_;
-        buf_pos_ = 0;
-        bool more = fill_bam_window();
-        const uint8_t* b = buf_.data();
-        size_t n = buf_len_;
+        Inflated in = inflate_next(carry_.size());
+        if (!in.ok) throw open_error(in.err);
+        seconds_inflate += in.seconds;
+        bytes_uncompressed += in.len;
+        consumed_ = in.coff_end;
+        const size_t carry = carry_.size();
+        if (in.len == 0 && carry == 0) throw open_error("not a BAM file (empty BGZF stream): " + path_);
+        std::vector<uint8_t> all(carry + in.len);
+        if (carry) memcpy(all.data(), carry_.data(), carry);
+        if (in.len) memcpy(all.data() + carry, in.data.get() + in.headroom, in.len);
+        const uint8_t* b = all.data();
+        const size_t n = all.size();
         if (n < 12 || memcmp(b, "BAM\1", 4) != 0) throw open_error("not a BAM file (bad magic): " + path_);
         bool ok = false;
         size_t o = 4;
@@ -187,10 +240,11 @@ void RecordStream::parse_bam_header() {
             ok = true;
         } while (false);
         if (ok) {
-            buf_pos_ = o;
+            carry_.assign(b + o, b + n);  // the records behind the header start the first window
             return;
         }
-        if (!more || buf_len_ == before) throw open_error("truncated BAM header: " + path_);
+        if (in.len == 0) throw open_error("truncated BAM header: " + path_);
+        carry_.swap(all);
     }
 }
 
@@ -244,28 +298,27 @@ bool RecordStream::next(std::vector<RecordRef>* recs) {
         seconds_walk += now_s() - t0;
         return true;
     }
-    for (;;) {
-        if (buf_pos_ + 4 > buf_len_ || (size_t)le32(buf_.data() + buf_pos_) + 4 + buf_pos_ > buf_len_) {
-            if (!fill_bam_window()) {
-                if (buf_pos_ != buf_len_) throw open_error("truncated BAM record at end of file: " + path_);
-                return false;
-            }
-        }
-        double t0 = now_s();
-        const uint8_t* b = buf_.data();
-        size_t o = buf_pos_;
-        while (o + 4 <= buf_len_) {
-            int32_t bs = le32(b + o);
-            if (bs < 32) throw open_error("corrupt BAM record (block_size < 32): " + path_);
-            if (o + 4 + (size_t)bs > buf_len_) break;
-            recs->push_back(RecordRef{b + o + 4, (uint32_t)bs});
-            o += 4 + (size_t)bs;
-        }
-        buf_pos_ = o;
-        seconds_walk += now_s() - t0;
-        if (!recs->empty()) return true;
-        // a single record larger than what is buffered: pull more blocks behind it
+    if (eof_) return false;
+    if (!prefetching_) {
+        next_ = std::async(std::launch::async, [this] { return produce(); });
+        prefetching_ = true;
     }
+    Window w = next_.get();
+    prefetching_ = false;
+    if (!w.ok) throw open_error(w.err);
+    seconds_inflate += w.s_inflate;
+    seconds_walk += w.s_walk;
+    bytes_uncompressed += w.inflated;
+    if (w.coff_end) consumed_ = w.coff_end;
+    if (w.eof) {
+        eof_ = true;
+        return false;
+    }
+    cur_ = std::move(w);  // keeps the buffer the records point into alive until the next call
+    recs->swap(cur_.recs);
+    next_ = std::async(std::launch::async, [this] { return produce(); });  // overlaps with the caller's decode
+    prefetching_ = true;
+    return true;
 }
 
 }  // namespace mthh

@@ -2,6 +2,8 @@
 // (zlib raw inflate), BAM header, record boundaries; SAM text as the second format bam::Reader::from_path
 // auto-detects (reference: src/bamutil.rs:4-25 over rust-htslib 0.50.0 / htslib).
 #pragma once
+#include <future>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -40,29 +42,53 @@ struct RecordRef {
 // Streams the file as "windows": each window is a contiguous buffer of whole records.
 class RecordStream {
 public:
-    RecordStream(const std::string& path, ThreadPool& pool, size_t window_bytes);
+    RecordStream(const std::string& path, int n_threads, size_t window_bytes);
+    ~RecordStream();
     const Header& header() const { return header_; }
     Format format() const { return format_; }
     // Fills `recs` with the records of the next window (pointers valid until the next call); false at end of file.
     bool next(std::vector<RecordRef>* recs);
+    size_t file_size() const { return file_.size(); }
+    size_t compressed_consumed() const { return consumed_; }  // compressed bytes behind the records handed out so far
     double seconds_inflate = 0, seconds_walk = 0;
     uint64_t bytes_compressed = 0, bytes_uncompressed = 0;
 
 private:
     struct Block { size_t cdata, clen; uint32_t usize; size_t uoff; };
-    bool fill_bam_window();   // inflates the next blocks behind the carried-over tail; false when nothing is left
+    // One inflated run of BGZF members (behind `headroom` free bytes).
+    struct Inflated {
+        std::unique_ptr<uint8_t[]> data;
+        size_t headroom = 0, len = 0, coff_end = 0;
+        bool ok = true;
+        std::string err;
+        double seconds = 0;
+    };
+    // One window of whole records.  The NEXT window is always produced (members inflated on the reader's own thread
+    // pool, record boundaries walked) on a background thread while the caller decodes the current one.
+    struct Window {
+        std::unique_ptr<uint8_t[]> data;
+        std::vector<RecordRef> recs;
+        bool ok = true, eof = false;
+        std::string err;
+        double s_inflate = 0, s_walk = 0;
+        size_t inflated = 0, coff_end = 0;
+    };
+    Inflated inflate_next(size_t headroom);
+    Window produce();         // background thread: inflate + walk; owns coff_ and carry_
     void parse_bam_header();
     void parse_sam_header();
     const std::string path_;
-    ThreadPool& pool_;
+    ThreadPool pool_;
+    std::future<Window> next_;
+    bool prefetching_ = false;
     size_t window_bytes_;
     MappedFile file_;
     Format format_ = Format::BAM;
     Header header_;
     size_t coff_ = 0;               // next compressed offset (BAM) / next text offset (SAM)
-    std::vector<uint8_t> buf_;      // uncompressed window: [carry | newly inflated blocks]
-    size_t buf_len_ = 0, buf_pos_ = 0;
-    std::vector<Block> blocks_;
+    std::vector<uint8_t> carry_;      // bytes of the record that straddles into the next run (producer only)
+    Window cur_;                      // the window whose records were handed out last
+    size_t consumed_ = 0;
     bool eof_ = false;
 };
 

@@ -14,6 +14,7 @@
 #include <charconv>
 #include <cmath>
 #include <cstdio>
+#include <future>
 #include <memory>
 
 #include "../../include/metheor_b200.h"
@@ -304,14 +305,16 @@ void run(const mthh_options& o) {
     int n_threads = o.threads > 0 ? o.threads : (int)std::thread::hardware_concurrency();
     if (n_threads < 1) n_threads = 1;
     ThreadPool pool(n_threads);
+    // the CUDA runtime takes a few hundred ms to come up: start it now, it overlaps with opening and inflating the file
+    std::future<int> cuda_up = std::async(std::launch::async, [] { return mth_device_count(); });
 
     // bamutil.rs:4-11: the input is opened first; a missing / non-BAM file panics with "Error opening BAM file. ..."
-    RecordStream in(o.input, pool, WINDOW_BYTES);
+    RecordStream in(o.input, n_threads, WINDOW_BYTES);  // inflates ahead on its own pool while `pool` decodes
     const Header& hdr = in.header();
     CpgSet cpg_set;
     if (o.cpg_set) cpg_set.load(o.cpg_set, hdr);  // readutil.rs:347-374
 
-    const int n_dev = mth_device_count();
+    const int n_dev = cuda_up.get();
     if (n_dev <= 0) throw HostError{1, "metheor_b200: no CUDA device found (this engine has no CPU path)"};
     const int n_gpus = std::max(1, o.n_gpus);
     if (o.device < 0 || o.device + n_gpus > n_dev)
@@ -372,6 +375,7 @@ void run(const mthh_options& o) {
     DecodeCounters total;
     double s_decode = 0, s_assemble = 0, s_submit = 0;
     int64_t n_batches = 0, n_shipped_reads = 0, n_shipped_cpg = 0;
+    bool reserved = false;
     const Format fmt = in.format();
 
     while (in.next(&recs)) {
@@ -418,8 +422,14 @@ void run(const mthh_options& o) {
             total.add(seg);
             s_decode += now_s() - t0;
 
-            size_t kept = 0;
-            for (size_t k = 0; k < n_tasks; k++) kept += chunks[k].start.size();
+            size_t kept = 0, kept_calls = 0;
+            for (size_t k = 0; k < n_tasks; k++) { kept += chunks[k].start.size(); kept_calls += chunks[k].cpg_pos.size(); }
+            if (!reserved && kept && fmt == Format::BAM && in.compressed_consumed() > 0 && n_gpus == 1) {
+                // size the device arena once from the first window: reads per compressed byte x file size (+15 %)
+                const double scale = 1.15 * (double)in.file_size() / (double)in.compressed_consumed();
+                if (scale > 1.5) mth_reserve(gpus[0]->ctx, (int64_t)((double)kept * scale) + 4096, (int64_t)((double)kept_calls * scale) + 4096);
+                reserved = true;
+            }
             if (kept && tid >= 0 && (size_t)tid < ref_len.size()) {
                 Gpu& G = *gpus[(size_t)gpu_of[(size_t)tid]];
                 t0 = now_s();

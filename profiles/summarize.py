@@ -103,6 +103,19 @@ def main():
                     md += ["", "top stall sites (share of warp-stall samples, SASS, dominant reason):", "```"]
                     md += [f"{p:5.1f}%  {s[:100]:100s} {r}" for p, s, r in st] + ["```"]
             md.append("")
+    # per-launch DRAM traffic of the captured kernels: bench.py quotes it as roofline.traffic
+    traffic = {}
+    for rep in sorted(glob.glob(os.path.join(d, "*.ncu-rep"))):
+        for k in full(rep):
+            def num(key):
+                v, u = (k.get(key, "0 byte").split() + ["byte"])[:2]
+                return float(v.replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+            traffic.setdefault(k["kernel"], {"dram_bytes": num("dram__bytes_read.sum") + num("dram__bytes_write.sum"),
+                                             "dram_read_bytes": num("dram__bytes_read.sum"), "dram_write_bytes": num("dram__bytes_write.sum"),
+                                             "source": f"profiles/{tag}_summary.md (ncu --set full, one launch)"})
+    if traffic:
+        with open(os.path.join(ROOT, "profiles", "traffic.json"), "w") as f:
+            json.dump(traffic, f, indent=1)
     out = os.path.join(ROOT, "profiles", f"{tag}_summary.md")
     with open(out, "w") as f:
         f.write("\n".join(md) + "\n")
