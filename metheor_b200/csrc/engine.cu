@@ -8,6 +8,7 @@
 //   region close (contig set full, or mth_finish): bitmap -> site dictionary -> one kernel family per measure ->
 //                row counts -> exclusive scan -> row emission into device row buffers.
 //   mth_finish : D2H of the rows into pinned buffers owned by the context.
+#include <emmintrin.h>
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
@@ -54,6 +55,8 @@ struct ProfSpan {
     int launches;
 };
 
+constexpr int64_t COMPACT_PIECE = 1 << 21;  // reads per H2D piece of a compact host batch
+
 enum { M_PDR = 0, M_MHL, M_FDRP, M_QFDRP, M_PM, M_ME, M_PAIRS, M_COUNT };
 
 }  // namespace
@@ -81,9 +84,10 @@ struct mth_ctx {
     DevBuf a_start, a_end, a_meta, a_off, a_pos, a_rel, a_meth, a_moff, a_flags;
     DevBuf bitmap, word_prefix, block_sums, site_pos, scalars, totals, ct_lin, ct_tid;
     DevBuf cnt2, scan_scratch, fdrp_scratch, me_lut, lpmd_total;
-    DevBuf stage[8], exp_blocks, exp_tot;  // compact wire format: staging + scan scratch
-    cudaEvent_t ev_stage_free = nullptr;
-    bool stage_busy = false;
+    DevBuf stage[2][8], exp_blocks, exp_tot;  // compact wire format: two staging sets + scan scratch
+    cudaEvent_t ev_stage_free[2] = {nullptr, nullptr};
+    bool stage_busy[2] = {false, false};
+    int stage_next = 0;
     DevBuf rowcnt[M_COUNT], value[M_COUNT];
     size_t bitmap_words_valid = 0;
     HostBuf h_scalars, h_totals;
@@ -321,6 +325,35 @@ static int check_scalars_err(mth_ctx* c, uint32_t e) {
     return fail(c, MTH_ERR_INVALID, "device-side validation failed");
 }
 
+// Host-side sums over one piece of a compact batch (SSE2 sum-of-absolute-differences: ~16 bytes per cycle, so that
+// slicing a large host batch into pieces costs microseconds, not milliseconds):
+//   *calls    = sum n8[r]
+//   *explicit = sum n8[r] over reads whose flags carry MTH_CFLAG_REL_EXPLICIT (flags == nullptr: 0)
+static void sum_call_counts(const uint8_t* n8, const uint8_t* flags, int64_t n, uint64_t* calls, uint64_t* explicit_rel) {
+    const __m128i zero = _mm_setzero_si128(), bit = _mm_set1_epi8((char)MTH_CFLAG_REL_EXPLICIT);
+    __m128i acc = zero, acc_e = zero;
+    int64_t r = 0;
+    for (; r + 16 <= n; r += 16) {
+        const __m128i v = _mm_loadu_si128((const __m128i*)(n8 + r));
+        acc = _mm_add_epi64(acc, _mm_sad_epu8(v, zero));
+        if (flags) {
+            const __m128i f = _mm_loadu_si128((const __m128i*)(flags + r));
+            const __m128i m = _mm_cmpeq_epi8(_mm_and_si128(f, bit), bit);
+            acc_e = _mm_add_epi64(acc_e, _mm_sad_epu8(_mm_and_si128(v, m), zero));
+        }
+    }
+    uint64_t t[2], te[2];
+    _mm_storeu_si128((__m128i*)t, acc);
+    _mm_storeu_si128((__m128i*)te, acc_e);
+    uint64_t c = t[0] + t[1], e = te[0] + te[1];
+    for (; r < n; r++) {
+        c += n8[r];
+        if (flags && (flags[r] & MTH_CFLAG_REL_EXPLICIT)) e += n8[r];
+    }
+    *calls = c;
+    *explicit_rel = e;
+}
+
 // Decides where a new batch goes: same region (possibly a new contig appended behind a gap) or a fresh region after the
 // current one has been processed.
 static int place_batch(mth_ctx* c, int32_t tid, int64_t n_reads, int64_t n_cpg, int64_t n_words) {
@@ -440,7 +473,8 @@ int mth_ctx_create(mth_ctx** out, int device, const mth_params* params, int32_t 
         cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_compute, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c->ev_stage_free, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&c->ev_stage_free[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_stage_free[1], cudaEventDisableTiming) != cudaSuccess) {
         g_create_err = std::string("CUDA initialisation failed: ") + cudaGetErrorString(cudaGetLastError());
         delete c;
         return MTH_ERR_CUDA;
@@ -458,10 +492,12 @@ int mth_ctx_destroy(mth_ctx* c) {
                       &c->word_prefix, &c->block_sums, &c->site_pos, &c->scalars, &c->totals, &c->ct_lin, &c->ct_tid, &c->cnt2,
                       &c->scan_scratch, &c->fdrp_scratch, &c->me_lut, &c->lpmd_total};
     for (DevBuf* b : devs) dev_free(*b);
-    for (DevBuf& b : c->stage) dev_free(b);
+    for (auto& set : c->stage)
+        for (DevBuf& b : set) dev_free(b);
     dev_free(c->exp_blocks);
     dev_free(c->exp_tot);
-    if (c->ev_stage_free) cudaEventDestroy(c->ev_stage_free);
+    for (cudaEvent_t e : c->ev_stage_free)
+        if (e) cudaEventDestroy(e);
     for (int m = 0; m < M_COUNT; m++) { dev_free(c->rowcnt[m]); dev_free(c->value[m]); }
     for (SiteRowsBuf* r : {&c->rows_pdr, &c->rows_mhl, &c->rows_fdrp, &c->rows_qfdrp}) {
         dev_free(r->tid); dev_free(r->pos); dev_free(r->value); dev_free(r->nc); dev_free(r->nd);
@@ -658,53 +694,78 @@ int mth_submit_compact(mth_ctx* c, const mth_batch_compact* b) {
         return fail(c, MTH_ERR_UNSUPPORTED, "batch too large (reads < 2^31, CpG calls < 2^32)");
     TRY(place_batch(c, b->tid, b->n_reads, b->n_cpg, b->n_reads));
     TRY(materialize(c));
-    const int64_t r0 = c->R, i0 = c->I, w0 = c->W;
-    const size_t nR = (size_t)b->n_reads, nI = (size_t)b->n_cpg, nE = lp ? (size_t)b->n_rel : 0;
-    TRY(ensure_arena(c, r0 + b->n_reads, i0 + b->n_cpg, w0 + b->n_reads, lp, c->has_meth_off));
+    TRY(ensure_arena(c, c->R + b->n_reads, c->I + b->n_cpg, c->W + b->n_reads, lp, c->has_meth_off));
+    TRY(dev_reserve(c, c->a_flags, (size_t)(c->I + b->n_cpg) + 64, (size_t)c->I));
 
-    ExpandArgs ea;
-    memset(&ea, 0, sizeof(ea));
-    if (b->mem_kind == 0) {
-        // staging buffers are reused by every batch: the copies of this batch wait for the expansion of the previous one
-        const size_t sz[8] = {nR * 4, nR * 2, nR, nR, nR, nI * 2, (nI + 7) / 8, nE * 2};
-        const void* src[8] = {b->start, b->span, b->mapq, b->n_cpg8, b->flags, b->cpg_delta, b->meth_bits, b->rel_exc};
-        for (int k = 0; k < 8; k++) TRY(dev_reserve(c, c->stage[k], sz[k] + 64, 0));
-        if (c->stage_busy) CUDA_TRY(c, cudaStreamWaitEvent(c->copy, c->ev_stage_free, 0));
-        for (int k = 0; k < 8; k++)
-            if (sz[k]) CUDA_TRY(c, cudaMemcpyAsync(c->stage[k].p, src[k], sz[k], cudaMemcpyHostToDevice, c->copy));
-        for (int k = 0; k < 8; k++) c->stats.h2d_bytes += (int64_t)sz[k];
-        CUDA_TRY(c, cudaEventRecord(c->ev_copy, c->copy));
-        CUDA_TRY(c, cudaStreamWaitEvent(c->compute, c->ev_copy, 0));
-        ea.start = (const int32_t*)c->stage[0].p; ea.span = (const uint16_t*)c->stage[1].p; ea.mapq = (const uint8_t*)c->stage[2].p;
-        ea.n_cpg8 = (const uint8_t*)c->stage[3].p; ea.flags = (const uint8_t*)c->stage[4].p; ea.cpg_delta = (const uint16_t*)c->stage[5].p;
-        ea.meth_bits = (const uint8_t*)c->stage[6].p; ea.rel_exc = (const uint16_t*)c->stage[7].p;
-    } else {
-        ea.start = b->start; ea.span = b->span; ea.mapq = b->mapq; ea.n_cpg8 = b->n_cpg8; ea.flags = b->flags;
-        ea.cpg_delta = b->cpg_delta; ea.meth_bits = b->meth_bits; ea.rel_exc = b->rel_exc;
+    // Host batches go over in pieces of COMPACT_PIECE reads through two staging sets, so that the H2D copy of piece k+1
+    // overlaps the expansion + ingest of piece k.  Device batches are expanded in place in one go.
+    const int64_t PIECE = b->mem_kind == 0 ? COMPACT_PIECE : b->n_reads;
+    int64_t x0 = 0, e0 = 0;  // calls / explicit query indices before the piece
+    for (int64_t ra = 0; ra < b->n_reads; ra += PIECE) {
+        const int64_t rb = std::min(b->n_reads, ra + PIECE);
+        int64_t nI = b->n_cpg, nE = lp ? b->n_rel : 0;
+        if (PIECE < b->n_reads) {  // host memory: count this piece's calls
+            uint64_t si = 0, se = 0;
+            sum_call_counts(b->n_cpg8 + ra, (lp && b->n_rel) ? b->flags + ra : nullptr, rb - ra, &si, &se);
+            nI = (int64_t)si;
+            nE = (int64_t)se;
+            if (x0 + nI > b->n_cpg || e0 + nE > b->n_rel) return fail(c, MTH_ERR_INVALID, "n_cpg8 / flags inconsistent with n_cpg / n_rel");
+        }
+        const int64_t r0 = c->R, i0 = c->I, w0 = c->W;
+        const size_t nR = (size_t)(rb - ra);
+        const int bit_base = (int)(x0 & 7);
+        ExpandArgs ea;
+        memset(&ea, 0, sizeof(ea));
+        if (b->mem_kind == 0) {
+            const int set = c->stage_next;
+            c->stage_next ^= 1;
+            DevBuf* st = c->stage[set];
+            const size_t sz[8] = {nR * 4, nR * 2, nR, nR, nR, (size_t)nI * 2, ((size_t)nI + bit_base + 7) / 8, (size_t)nE * 2};
+            const void* src[8] = {b->start + ra, b->span + ra, b->mapq + ra, b->n_cpg8 + ra, b->flags + ra, b->cpg_delta + x0,
+                                  b->meth_bits + (x0 >> 3), b->rel_exc ? b->rel_exc + e0 : nullptr};
+            for (int k = 0; k < 8; k++) TRY(dev_reserve(c, st[k], sz[k] + 64, 0));
+            if (c->stage_busy[set]) CUDA_TRY(c, cudaStreamWaitEvent(c->copy, c->ev_stage_free[set], 0));
+            for (int k = 0; k < 8; k++)
+                if (sz[k] && src[k]) CUDA_TRY(c, cudaMemcpyAsync(st[k].p, src[k], sz[k], cudaMemcpyHostToDevice, c->copy));
+            for (int k = 0; k < 8; k++) c->stats.h2d_bytes += (int64_t)sz[k];
+            CUDA_TRY(c, cudaEventRecord(c->ev_copy, c->copy));
+            CUDA_TRY(c, cudaStreamWaitEvent(c->compute, c->ev_copy, 0));
+            ea.start = (const int32_t*)st[0].p; ea.span = (const uint16_t*)st[1].p; ea.mapq = (const uint8_t*)st[2].p;
+            ea.n_cpg8 = (const uint8_t*)st[3].p; ea.flags = (const uint8_t*)st[4].p; ea.cpg_delta = (const uint16_t*)st[5].p;
+            ea.meth_bits = (const uint8_t*)st[6].p; ea.rel_exc = (const uint16_t*)st[7].p;
+            ea.bit_base = (uint32_t)bit_base;
+        } else {
+            ea.start = b->start; ea.span = b->span; ea.mapq = b->mapq; ea.n_cpg8 = b->n_cpg8; ea.flags = b->flags;
+            ea.cpg_delta = b->cpg_delta; ea.meth_bits = b->meth_bits; ea.rel_exc = b->rel_exc;
+        }
+        const size_t nb = (nR + 255) / 256;
+        TRY(dev_reserve(c, c->exp_blocks, nb * 8 + 64, 0));
+        TRY(dev_reserve(c, c->exp_tot, 16, 0));
+        ea.n = (int64_t)nR;
+        ea.r0 = r0; ea.i0 = i0; ea.w0 = w0;
+        ea.lin_off = c->cur_lin_off;
+        ea.start_out = (int32_t*)c->a_start.p; ea.end_out = (int32_t*)c->a_end.p; ea.meta_out = (uint32_t*)c->a_meta.p;
+        ea.off_out = (uint32_t*)c->a_off.p; ea.pos_out = (int32_t*)c->a_pos.p; ea.rel_out = lp ? (uint16_t*)c->a_rel.p : nullptr;
+        ea.meth_out = (uint64_t*)c->a_meth.p; ea.moff_out = c->has_meth_off ? (uint32_t*)c->a_moff.p : nullptr;
+        ea.block_calls = (uint32_t*)c->exp_blocks.p; ea.block_rel = (uint32_t*)c->exp_blocks.p + nb;
+        ea.err = &((RegionScalars*)c->scalars.p)->err;
+        {
+            ProfScope ps(c, "k_expand");
+            ps.add(launch_expand(ea, (unsigned long long*)c->exp_tot.p, c->compute));
+        }
+        if (b->mem_kind == 0) {
+            const int set = c->stage_next ^ 1;
+            CUDA_TRY(c, cudaEventRecord(c->ev_stage_free[set], c->compute));
+            c->stage_busy[set] = true;
+        }
+        c->R = r0 + (int64_t)nR;
+        c->I = i0 + nI;
+        c->W = w0 + (int64_t)nR;
+        TRY(run_ingest(c, b->tid, r0, (int64_t)nR, i0, nI, lp ? (const uint16_t*)c->a_rel.p : nullptr));
+        x0 += nI;
+        e0 += nE;
     }
-    const size_t nb = (nR + 255) / 256;
-    TRY(dev_reserve(c, c->exp_blocks, nb * 8 + 64, 0));
-    TRY(dev_reserve(c, c->exp_tot, 16, 0));
-    ea.n = b->n_reads;
-    ea.r0 = r0; ea.i0 = i0; ea.w0 = w0;
-    ea.lin_off = c->cur_lin_off;
-    ea.start_out = (int32_t*)c->a_start.p; ea.end_out = (int32_t*)c->a_end.p; ea.meta_out = (uint32_t*)c->a_meta.p;
-    ea.off_out = (uint32_t*)c->a_off.p; ea.pos_out = (int32_t*)c->a_pos.p; ea.rel_out = lp ? (uint16_t*)c->a_rel.p : nullptr;
-    ea.meth_out = (uint64_t*)c->a_meth.p; ea.moff_out = c->has_meth_off ? (uint32_t*)c->a_moff.p : nullptr;
-    ea.block_calls = (uint32_t*)c->exp_blocks.p; ea.block_rel = (uint32_t*)c->exp_blocks.p + nb;
-    ea.err = &((RegionScalars*)c->scalars.p)->err;
-    {
-        ProfScope ps(c, "k_expand");
-        ps.add(launch_expand(ea, (unsigned long long*)c->exp_tot.p, c->compute));
-    }
-    if (b->mem_kind == 0) {
-        CUDA_TRY(c, cudaEventRecord(c->ev_stage_free, c->compute));
-        c->stage_busy = true;
-    }
-    c->R = r0 + b->n_reads;
-    c->I = i0 + b->n_cpg;
-    c->W = w0 + b->n_reads;
-    return run_ingest(c, b->tid, r0, b->n_reads, i0, b->n_cpg, lp ? (const uint16_t*)c->a_rel.p : nullptr);
+    return MTH_OK;
 }
 
 }  // extern "C"

@@ -83,7 +83,8 @@ __global__ void __launch_bounds__(EXP_BLOCK) k_expand(ExpandArgs a) {
         const uint32_t x = o_local + k;
         const int32_t d = a.cpg_delta[x];
         a.pos_out[a.i0 + x] = s_lin - 1 + d;
-        mw |= (uint64_t)((a.meth_bits[x >> 3] >> (x & 7)) & 1u) << k;
+        const uint32_t xb = x + a.bit_base;
+        mw |= (uint64_t)((a.meth_bits[xb >> 3] >> (xb & 7)) & 1u) << k;
         if (a.rel_out) a.rel_out[a.i0 + x] = (fl & 4u) ? a.rel_exc[e_local + k] : (uint16_t)(d - fwd);
     }
     a.meth_out[a.w0 + r] = mw;

@@ -33,6 +33,7 @@ struct ExpandArgs {
     int64_t n;
     const int32_t* start; const uint16_t* span; const uint8_t* mapq; const uint8_t* n_cpg8; const uint8_t* flags;
     const uint16_t* cpg_delta; const uint8_t* meth_bits; const uint16_t* rel_exc;
+    uint32_t bit_base;        // bit of meth_bits[0] that belongs to the first call (pieces of a batch start mid-byte)
     // destination: region arena, reads from r0, calls from i0, meth words from w0
     int64_t r0, i0, w0;
     int32_t lin_off;
