@@ -12,7 +12,7 @@ constexpr int CONTIG_GAP = 1 << 16;        // spacing between contigs in the dev
 constexpr int MAX_REF_SPAN = CONTIG_GAP - 512;
 constexpr uint32_t META_HALO = 1u << 9;    // MTH_META_HALO
 // per-call flag byte written by k_ingest (call_flags[]): read-level decisions replicated on every call of the read
-constexpr uint32_t CF_METH = 1u, CF_FIRST = 2u, CF_LPMD = 4u, CF_PDR_C = 8u, CF_PDR_D = 16u;
+constexpr uint32_t CF_METH = 1u, CF_FIRST = 2u, CF_LPMD = 4u, CF_PDR_C = 8u, CF_PDR_D = 16u, CF_PM_OK = 32u, CF_ME_OK = 64u;
 
 // device error bits (ctx->d_err)
 enum : uint32_t {

@@ -84,6 +84,7 @@ struct mth_ctx {
     DevBuf a_start, a_end, a_meta, a_off, a_pos, a_rel, a_meth, a_moff, a_flags;
     DevBuf bitmap, word_prefix, block_sums, site_pos, scalars, totals, ct_lin, ct_tid;
     DevBuf cnt2, scan_scratch, fdrp_scratch, me_lut, lpmd_total;
+    DevBuf qhist[2], qmixed[2];  // PM / ME: per-site 16-pattern histograms of canonical quartets + mixed-site flags
     DevBuf stage[2][8], exp_blocks, exp_tot;  // compact wire format: two staging sets + scan scratch
     cudaEvent_t ev_stage_free[2] = {nullptr, nullptr};
     bool stage_busy[2] = {false, false};
@@ -393,6 +394,10 @@ static int run_ingest(mth_ctx* c, int32_t tid, int64_t r0, int64_t n, int64_t i0
     ia.lpmd = c->prm.lpmd;
     ia.do_pdr = (c->prm.measures & MTH_PDR) ? 1 : 0;
     ia.pdr = c->prm.pdr;
+    ia.do_pm = (c->prm.measures & MTH_PM) ? 1 : 0;
+    ia.do_me = (c->prm.measures & MTH_ME) ? 1 : 0;
+    ia.pm_min_qual = c->prm.pm.min_qual;
+    ia.me_min_qual = c->prm.me.min_qual;
     TRY(dev_reserve(c, c->a_flags, (size_t)c->I + 64, (size_t)i0));
     ia.call_flags = (uint8_t*)c->a_flags.p;
     ia.sc = (RegionScalars*)c->scalars.p;
@@ -496,6 +501,7 @@ int mth_ctx_destroy(mth_ctx* c) {
         for (DevBuf& b : set) dev_free(b);
     dev_free(c->exp_blocks);
     dev_free(c->exp_tot);
+    for (int q = 0; q < 2; q++) { dev_free(c->qhist[q]); dev_free(c->qmixed[q]); }
     for (cudaEvent_t e : c->ev_stage_free)
         if (e) cudaEventDestroy(e);
     for (int m = 0; m < M_COUNT; m++) { dev_free(c->rowcnt[m]); dev_free(c->value[m]); }
@@ -911,20 +917,35 @@ static int process_region(mth_ctx* c) {
             ProfScope ps(c, q ? "qfdrp_rows_count" : "fdrp_rows_count");
             ps.add(launch_exclusive_scan_u32((uint32_t*)c->rowcnt[m].p, C, scratch, d_tot + m, s));
         }
+        int q_set[2] = {0, 1};  // which histogram / mixed-site set PM and ME use
         for (int q = 0; q < 2; q++) {
             uint32_t bit = q ? MTH_ME : MTH_PM;
             int m = q ? M_ME : M_PM;
             if (!(M & bit)) continue;
             mth_quartet_params qp = q ? c->prm.me : c->prm.pm;
-            // PM and ME with identical thresholds share the count pass
+            // PM and ME with identical thresholds share the histogram and the count pass
             if (q == 1 && (M & MTH_PM) && c->prm.pm.min_depth == qp.min_depth && c->prm.pm.min_qual == qp.min_qual) {
                 CUDA_TRY(c, cudaMemcpyAsync(c->rowcnt[M_ME].p, c->rowcnt[M_PM].p, (size_t)C * 4, cudaMemcpyDeviceToDevice, s));
                 CUDA_TRY(c, cudaMemcpyAsync(d_tot + M_ME, d_tot + M_PM, 8, cudaMemcpyDeviceToDevice, s));
+                q_set[1] = 0;
                 continue;
+            }
+            q_set[q] = q;
+            TRY(dev_reserve(c, c->qhist[q], (size_t)(C + 4) * 256, 0));  // [site][4 key variants][16 patterns] u32
+            TRY(dev_reserve(c, c->qmixed[q], (size_t)C + 64, 0));
+            CUDA_TRY(c, cudaMemsetAsync(c->qhist[q].p, 0, (size_t)(C + 4) * 256, s));
+            CUDA_TRY(c, cudaMemsetAsync(c->qmixed[q].p, 0, (size_t)C + 64, s));
+            {
+                ProfScope ps(c, q ? "k_me_scatter" : "k_pm_scatter");
+                ps.add(launch_quartet_scatter(rv.cpg_pos, (const uint8_t*)c->a_flags.p, rv.I, (const unsigned long long*)c->bitmap.p, n_words,
+                                              (const uint32_t*)c->word_prefix.p, d_sc, q ? CF_ME_OK : CF_PM_OK, (uint32_t*)c->qhist[q].p,
+                                              (uint8_t*)c->qmixed[q].p, s));
             }
             {
                 ProfScope ps(c, q ? "k_me_count" : "k_pm_count");
-                ps.add(launch_quartet_count(rv, site_pos, C, d_sc, qp, (uint32_t*)c->rowcnt[m].p, s));
+                ps.add(launch_quartet_canon_count((const uint32_t*)c->qhist[q].p, (const uint8_t*)c->qmixed[q].p, C, qp.min_depth,
+                                                  (uint32_t*)c->rowcnt[m].p, s));
+                ps.add(launch_quartet_count(rv, site_pos, C, d_sc, qp, (const uint8_t*)c->qmixed[q].p, (uint32_t*)c->rowcnt[m].p, s));
             }
             ProfScope ps(c, q ? "me_rows_count" : "pm_rows_count");
             ps.add(launch_exclusive_scan_u32((uint32_t*)c->rowcnt[m].p, C, scratch, d_tot + m, s));
@@ -975,8 +996,13 @@ static int process_region(mth_ctx* c) {
             QuartetRowsDev rd = quartet_rows_dev(r);
             if (!counts) rd.counts = nullptr;
             ProfScope ps(c, q ? "k_me_emit" : "k_pm_emit");
-            ps.add(launch_quartet_emit(rv, site_pos, C, d_sc, q ? c->prm.me : c->prm.pm, q, (const uint32_t*)c->rowcnt[m].p,
-                                       (const float*)c->me_lut.p, c->me_lut_max, ct, rd, r.n, s));
+            const mth_quartet_params qp = q ? c->prm.me : c->prm.pm;
+            const uint32_t* qh = (const uint32_t*)c->qhist[q_set[q]].p;
+            const uint8_t* qm = (const uint8_t*)c->qmixed[q_set[q]].p;
+            ps.add(launch_quartet_canon_emit(qh, qm, site_pos, C, qp.min_depth, q, (const uint32_t*)c->rowcnt[m].p, (const float*)c->me_lut.p,
+                                             c->me_lut_max, ct, rd, r.n, s));
+            ps.add(launch_quartet_emit(rv, site_pos, C, d_sc, qp, q, qm, (const uint32_t*)c->rowcnt[m].p, (const float*)c->me_lut.p,
+                                       c->me_lut_max, ct, rd, r.n, s));
             r.n += (int64_t)tot[m];
         }
         if (want_pairs) {

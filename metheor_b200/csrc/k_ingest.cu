@@ -96,6 +96,8 @@ __device__ __forceinline__ ReadVerdict judge_read(const IngestArgs& a, int64_t j
     }
     const uint32_t mapq = meta & 0xFFu;
     if (a.do_lpmd && !(meta & META_HALO) && !v.bad && mapq >= a.lpmd.min_qual) v.flags |= CF_LPMD;  // lpmd.rs:177
+    if (a.do_pm && mapq >= a.pm_min_qual) v.flags |= CF_PM_OK;                                       // pm.rs:111
+    if (a.do_me && mapq >= a.me_min_qual) v.flags |= CF_ME_OK;                                       // me.rs:115
     return v;
 }
 

@@ -41,27 +41,40 @@ struct MhlPolicy {
         bool mine = (mask >> lane) & 1u;
         uint32_t n = mine ? lr.n : 0u;
         depth += __popc(mask);
-        maxn = max(maxn, __reduce_max_sync(FULL, n));
+        const uint32_t nmax = __reduce_max_sync(FULL, n);
+        maxn = max(maxn, nmax);
         if (mine) atomicAdd(&N[n], 1u);  // mhl.rs:75-80
-        uint64_t x[MAX_METH_WORDS];
-        uint32_t nw = (n + 63) >> 6;
+        if (nmax <= 64) {
+            // every contributor of this chunk fits one word: x_1 = methylation bits, x_l = x_{l-1} & (x_{l-1} >> 1)
+            uint64_t x = mine ? (meth_word(rv, lr.j, 0) & low_mask64(n)) : 0ull;
+            for (uint32_t l = 1; l <= 64; l++) {
+                uint32_t tot = __reduce_add_sync(FULL, (uint32_t)__popcll(x));
+                if (tot == 0) break;
+                if (lane == 0) S[l] += tot;  // mhl.rs:36-41
+                maxl = max(maxl, l);
+                x &= x >> 1;
+            }
+        } else {
+            uint64_t x[MAX_METH_WORDS];
+            uint32_t nw = (n + 63) >> 6;
 #pragma unroll
-        for (int w = 0; w < MAX_METH_WORDS; w++) {
-            x[w] = 0;
-            if ((uint32_t)w < nw) x[w] = meth_word(rv, lr.j, w) & low_mask64(min(64u, n - 64u * w));
-        }
-        for (uint32_t l = 1; l <= (uint32_t)MHL_LCAP; l++) {
-            uint32_t h = 0;
+            for (int w = 0; w < MAX_METH_WORDS; w++) {
+                x[w] = 0;
+                if ((uint32_t)w < nw) x[w] = meth_word(rv, lr.j, w) & low_mask64(min(64u, n - 64u * w));
+            }
+            for (uint32_t l = 1; l <= (uint32_t)MHL_LCAP; l++) {
+                uint32_t h = 0;
 #pragma unroll
-            for (int w = 0; w < MAX_METH_WORDS; w++) h += __popcll(x[w]);
-            uint32_t tot = __reduce_add_sync(FULL, h);
-            if (tot == 0) break;
-            if (lane == 0) S[l] += tot;  // mhl.rs:36-41
-            maxl = max(maxl, l);
+                for (int w = 0; w < MAX_METH_WORDS; w++) h += __popcll(x[w]);
+                uint32_t tot = __reduce_add_sync(FULL, h);
+                if (tot == 0) break;
+                if (lane == 0) S[l] += tot;
+                maxl = max(maxl, l);
 #pragma unroll
-            for (int w = 0; w < MAX_METH_WORDS; w++) {  // x &= x >> 1 across words
-                uint64_t hi = (w + 1 < MAX_METH_WORDS) ? x[w + 1] : 0ull;
-                x[w] &= (x[w] >> 1) | (hi << 63);
+                for (int w = 0; w < MAX_METH_WORDS; w++) {  // x &= x >> 1 across words
+                    uint64_t hi = (w + 1 < MAX_METH_WORDS) ? x[w + 1] : 0ull;
+                    x[w] &= (x[w] >> 1) | (hi << 63);
+                }
             }
         }
         __syncwarp();
@@ -70,31 +83,60 @@ struct MhlPolicy {
     __device__ __forceinline__ void close() {
         if (depth == 0) return;
         __syncwarp();
+        const int lane = lane_id();
         if (depth >= prm.min_depth) {  // mhl.rs:165
-            float res = 0.f;
-            if (lane_id() == 0) {
-                // D[l] for l = maxn..1, stored over N[l]
-                uint32_t cnt_ge = 0, dl = 0;
-                for (uint32_t l = maxn; l >= 1; l--) {
-                    cnt_ge += N[l];
-                    dl += cnt_ge;
-                    N[l] = dl;
+            float res;
+            if (maxn <= 32) {
+                // lane l-1 owns stretch length l: D[l] = sum_{n >= l} (n - l + 1) N[n] is a suffix sum of the suffix counts
+                const uint32_t l = (uint32_t)lane + 1;
+                uint32_t ge = l <= maxn ? N[l] : 0u;   // -> #reads with n >= l
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    uint32_t t = __shfl_down_sync(FULL, ge, o);
+                    if (lane + o < 32) ge += t;
                 }
-                float mhl = 0.f, l_sum = 0.f;
-                for (uint32_t l = 1; l <= maxn; l++) l_sum = __fadd_rn(l_sum, (float)l);  // mhl.rs:46-48
-                for (uint32_t l = 1; l <= maxl; l++) {                                     // mhl.rs:50-69
-                    uint32_t cnt = S[l];
-                    if (cnt == 0) continue;
-                    float term = __fdiv_rn(__fmul_rn((float)l, (float)cnt), (float)N[l]);
-                    mhl = __fadd_rn(mhl, term);
+                uint32_t dl = ge;                      // -> D[l]
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    uint32_t t = __shfl_down_sync(FULL, dl, o);
+                    if (lane + o < 32) dl += t;
                 }
-                res = __fdiv_rn(mhl, l_sum);  // mhl.rs:71
+                const uint32_t cnt = l <= maxl ? S[l] : 0u;
+                // mhl.rs:56-68: (l as f32 * count as f32) / denom ; terms with count 0 do not exist in the reference's map
+                const float term = cnt ? __fdiv_rn(__fmul_rn((float)l, (float)cnt), (float)dl) : 0.f;
+                float mhl = 0.f;
+                for (uint32_t k = 0; k < maxl; k++) {  // ascending l, sequential f32 adds (canonical order)
+                    const float t = __shfl_sync(FULL, term, (int)k);
+                    if (__shfl_sync(FULL, cnt, (int)k)) mhl = __fadd_rn(mhl, t);
+                }
+                // mhl.rs:46-48 sums 1..max_n in f32: every partial sum is an integer < 2^24, so the closed form is exact
+                const float l_sum = (float)(maxn * (maxn + 1) / 2);
+                res = __fdiv_rn(mhl, l_sum);           // mhl.rs:71
+            } else {
+                res = 0.f;
+                if (lane == 0) {
+                    uint32_t cnt_ge = 0, dl = 0;
+                    for (uint32_t l = maxn; l >= 1; l--) {  // D[l] for l = maxn..1, stored over N[l]
+                        cnt_ge += N[l];
+                        dl += cnt_ge;
+                        N[l] = dl;
+                    }
+                    float mhl = 0.f, l_sum = 0.f;
+                    for (uint32_t l = 1; l <= maxn; l++) l_sum = __fadd_rn(l_sum, (float)l);  // mhl.rs:46-48
+                    for (uint32_t l = 1; l <= maxl; l++) {                                     // mhl.rs:50-69
+                        uint32_t cnt = S[l];
+                        if (cnt == 0) continue;
+                        mhl = __fadd_rn(mhl, __fdiv_rn(__fmul_rn((float)l, (float)cnt), (float)N[l]));
+                    }
+                    res = __fdiv_rn(mhl, l_sum);
+                }
+                res = __shfl_sync(FULL, res, 0);
             }
             best = res;
             have = true;
         }
         __syncwarp();
-        for (uint32_t l = 1 + lane_id(); l <= max(maxn, maxl); l += 32) { S[l] = 0; N[l] = 0; }
+        for (uint32_t l = 1 + lane; l <= max(maxn, maxl); l += 32) { S[l] = 0; N[l] = 0; }
         __syncwarp();
         depth = maxn = maxl = 0;
     }

@@ -107,6 +107,7 @@ struct QuartetArgs {
     const RegionScalars* sc;
     mth_quartet_params prm;
     int kind;                 // 0 PM, 1 ME (EMIT only)
+    const uint8_t* mixed;     // nullptr: every site; else only the sites flagged by k_quartet_scatter
     uint32_t* rowcnt;         // COUNT: out
     const uint32_t* rowoff;   // EMIT: in
     const float* me_lut;
@@ -230,26 +231,184 @@ __global__ void __launch_bounds__(GATHER_BLOCK) k_quartet(QuartetArgs a) {
             }
         }
         if (!EMIT && lane == 0) a.rowcnt[s] = n_rows;
-    });
+    }, a.mixed);
+}
+
+// ---- streaming path: canonical quartets --------------------------------------------------------------------
+// A quartet observation is a call x with three more calls of the same read behind it (readutil.rs:97-132); its key is
+// (pos[x], pos[x+1], pos[x+2], pos[x+3]).  When those are four CONSECUTIVE sites of the dictionary — rank(pos[x+3]) ==
+// rank(pos[x]) + 3, true unless a read skipped a site (no-call, deletion) — the key is implied by the first site and the
+// observation is one atomic add into hist[rank][0][pattern].  A read that skipped exactly ONE of the next four sites (a
+// no-call) gives one of three other keys — (r+1,r+2,r+4), (r+1,r+3,r+4), (r+2,r+3,r+4) — which get the slots 1..3; in
+// that order the four keys are already sorted the way the rows must be.  Anything else (two skips, deletions) flags the
+// site as mixed and leaves it to the gather kernel.  Everything needed is in cpg_pos[] and call_flags[] (5 B per call):
+// methylation bits, read boundaries (CF_FIRST) and the mapq verdict; no per-read data is touched.
+constexpr int QV = 4;  // key variants with a histogram slot per site
+constexpr int QS_THREADS = 256;
+constexpr int QS_CPT = 8;
+constexpr int QS_TILE = QS_THREADS * QS_CPT;
+constexpr int QS_WIN = 256;  // 64-bit bitmap words in the shared window = 16 384 positions
+
+__global__ void __launch_bounds__(QS_THREADS) k_quartet_scatter(const int32_t* __restrict__ cpg_pos, const uint8_t* __restrict__ call_flags,
+                                                                int64_t n_calls, const unsigned long long* __restrict__ bitmap,
+                                                                int64_t n_words, const uint32_t* __restrict__ word_prefix,
+                                                                const RegionScalars* __restrict__ sc, uint32_t ok_bit,
+                                                                uint32_t* __restrict__ hist, uint8_t* __restrict__ mixed) {
+    __shared__ int32_t s_pos[QS_TILE + 4];
+    __shared__ uint8_t s_fl[QS_TILE + 4];
+    __shared__ unsigned long long s_bmw[QS_WIN];
+    __shared__ uint32_t s_pref[QS_WIN];
+    __shared__ uint32_t s_wsum[QS_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t x0 = (int64_t)blockIdx.x * QS_TILE;
+    const int nt = (int)min((int64_t)QS_TILE, n_calls - x0);
+    const int nh = (int)min((int64_t)QS_TILE + 3, n_calls - x0);  // with the 3-call halo
+    for (int y = tid; y < nh; y += QS_THREADS) {
+        s_pos[y] = cpg_pos[x0 + y];
+        s_fl[y] = call_flags[x0 + y];
+    }
+    const int32_t wlo = max(cpg_pos[x0] - sc->lmax + 1, 0);  // every call of the tile is at or after P0 - lmax (reads are sorted)
+    const uint32_t w0 = (uint32_t)wlo >> 6;
+    unsigned long long bw = 0;
+    if ((int64_t)w0 + tid < n_words) bw = bitmap[w0 + tid];
+    const uint32_t rank0 = word_prefix[w0];
+    {
+        uint32_t c = (uint32_t)__popcll(bw), inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(FULL, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) s_wsum[warp] = inc;
+        s_bmw[tid] = bw;
+        __syncthreads();
+        uint32_t base = 0;
+#pragma unroll
+        for (int w = 0; w < QS_THREADS / 32; w++) base += (w < warp) ? s_wsum[w] : 0u;
+        s_pref[tid] = base + inc - c;
+    }
+    __syncthreads();
+    auto rank_of = [&](int32_t p) -> uint32_t {
+        const uint32_t bit = (uint32_t)(p + 1);
+        const uint32_t w = (bit >> 6) - w0;
+        if (w < (uint32_t)QS_WIN) return rank0 + s_pref[w] + (uint32_t)__popcll(s_bmw[w] & ((1ull << (bit & 63)) - 1ull));
+        const uint32_t gw = bit >> 6;
+        return __ldg(word_prefix + gw) + (uint32_t)__popcll(__ldg(bitmap + gw) & ((1ull << (bit & 63)) - 1ull));
+    };
+    for (int y = tid; y < nt; y += QS_THREADS) {
+        const uint32_t f0 = s_fl[y];
+        if (!(f0 & ok_bit) || y + 3 >= nh) continue;
+        const uint32_t f1 = s_fl[y + 1], f2 = s_fl[y + 2], f3 = s_fl[y + 3];
+        if ((f1 | f2 | f3) & CF_FIRST) continue;  // fewer than four calls left in this read
+        const uint32_t pat = ((f0 & CF_METH) << 3) | ((f1 & CF_METH) << 2) | ((f2 & CF_METH) << 1) | (f3 & CF_METH);
+        const uint32_t r = rank_of(s_pos[y]);
+        const uint32_t g3 = rank_of(s_pos[y + 3]) - r;
+        int v = -1;  // variant slot: which of the dictionary's next sites the read called
+        if (g3 == 3) {
+            v = 0;                                             // (r+1, r+2, r+3)
+        } else if (g3 == 4) {
+            const uint32_t g1 = rank_of(s_pos[y + 1]) - r, g2 = rank_of(s_pos[y + 2]) - r;
+            if (g1 == 1) v = g2 == 2 ? 1 : 2;                  // (r+1, r+2, r+4) / (r+1, r+3, r+4)
+            else v = 3;                                        // (r+2, r+3, r+4)
+        }
+        if (v >= 0) atomicAdd(&hist[((size_t)r * QV + v) * 16 + pat], 1u);
+        else mixed[r] = 1;
+    }
+}
+
+template <bool EMIT>
+__global__ void __launch_bounds__(256) k_quartet_canon(const uint32_t* __restrict__ hist, const uint8_t* __restrict__ mixed,
+                                                       const int32_t* __restrict__ site_pos, int64_t C, uint32_t min_depth, int kind,
+                                                       uint32_t* __restrict__ rowcnt, const uint32_t* __restrict__ rowoff,
+                                                       const float* __restrict__ me_lut, int me_lut_max, ContigTable ct,
+                                                       QuartetRowsDev rows, int64_t row_base) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= C) return;
+    if (mixed[s]) {
+        if (!EMIT) rowcnt[s] = 0;  // overwritten by the gather pass
+        return;
+    }
+    uint32_t n_rows = 0;
+    int64_t r = 0;
+    int32_t tid = 0, pos = 0, off = 0;
+    if (EMIT) {
+        r = row_base + rowoff[s];
+        delinearize(ct, site_pos[s], &tid, &pos);
+        off = site_pos[s] - pos;
+    }
+#pragma unroll
+    for (int v = 0; v < QV; v++) {
+        uint32_t cnt[16];
+        const uint4* h = reinterpret_cast<const uint4*>(hist + ((size_t)s * QV + v) * 16);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint4 x = h[q];
+            cnt[4 * q] = x.x; cnt[4 * q + 1] = x.y; cnt[4 * q + 2] = x.z; cnt[4 * q + 3] = x.w;
+        }
+        uint32_t total = 0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) total += cnt[k];
+        if (!(total > 0 && total >= min_depth)) continue;  // pm.rs:77 / me.rs:82
+        if (EMIT) {
+            // the key of slot v: sites s+1..s+4 of the dictionary minus the one the reads skipped
+            const int d2 = v == 3 ? 2 : 1, d3 = v >= 2 ? 3 : 2, d4 = v >= 1 ? 4 : 3;
+            const int64_t o = r + n_rows;
+            rows.tid[o] = tid;
+            rows.p1[o] = pos;
+            rows.p2[o] = site_pos[s + d2] - off;
+            rows.p3[o] = site_pos[s + d3] - off;
+            rows.p4[o] = site_pos[s + d4] - off;
+            rows.value[o] = kind == 0 ? pm_value(cnt, total) : me_value(cnt, total, me_lut, me_lut_max);
+            if (rows.counts)
+                for (int k = 0; k < 16; k++) rows.counts[(size_t)o * 16 + k] = cnt[k];
+        }
+        n_rows++;
+    }
+    if (!EMIT) rowcnt[s] = n_rows;
+}
+
+int launch_quartet_scatter(const int32_t* cpg_pos, const uint8_t* call_flags, int64_t n_calls, const unsigned long long* bitmap,
+                           int64_t n_words, const uint32_t* word_prefix, const RegionScalars* sc, uint32_t ok_bit, uint32_t* hist,
+                           uint8_t* mixed, cudaStream_t s) {
+    if (n_calls <= 0) return 0;
+    k_quartet_scatter<<<(unsigned)((n_calls + QS_TILE - 1) / QS_TILE), QS_THREADS, 0, s>>>(cpg_pos, call_flags, n_calls, bitmap, n_words,
+                                                                                          word_prefix, sc, ok_bit, hist, mixed);
+    return 1;
+}
+
+int launch_quartet_canon_count(const uint32_t* hist, const uint8_t* mixed, int64_t C, uint32_t min_depth, uint32_t* rowcnt, cudaStream_t s) {
+    if (C <= 0) return 0;
+    k_quartet_canon<false><<<(unsigned)((C + 255) / 256), 256, 0, s>>>(hist, mixed, nullptr, C, min_depth, 0, rowcnt, nullptr, nullptr, 0,
+                                                                       ContigTable{0, nullptr, nullptr}, QuartetRowsDev{}, 0);
+    return 1;
+}
+
+int launch_quartet_canon_emit(const uint32_t* hist, const uint8_t* mixed, const int32_t* site_pos, int64_t C, uint32_t min_depth, int kind,
+                              const uint32_t* rowoff, const float* me_lut, int me_lut_max, ContigTable ct, QuartetRowsDev rows,
+                              int64_t row_base, cudaStream_t s) {
+    if (C <= 0) return 0;
+    k_quartet_canon<true><<<(unsigned)((C + 255) / 256), 256, 0, s>>>(hist, mixed, site_pos, C, min_depth, kind, nullptr, rowoff, me_lut,
+                                                                      me_lut_max, ct, rows, row_base);
+    return 1;
 }
 
 int launch_quartet_count(const ReadsView& rv, const int32_t* site_pos, int64_t C, const RegionScalars* sc,
-                         mth_quartet_params prm, uint32_t* rowcnt, cudaStream_t s) {
+                         mth_quartet_params prm, const uint8_t* mixed, uint32_t* rowcnt, cudaStream_t s) {
     if (C <= 0) return 0;
     QuartetArgs a;
     memset(&a, 0, sizeof(a));
-    a.rv = rv; a.site_pos = site_pos; a.C = C; a.sc = sc; a.prm = prm; a.rowcnt = rowcnt;
+    a.rv = rv; a.site_pos = site_pos; a.C = C; a.sc = sc; a.prm = prm; a.rowcnt = rowcnt; a.mixed = mixed;
     k_quartet<false><<<gather_grid(C), GATHER_BLOCK, 0, s>>>(a);
     return 1;
 }
 
 int launch_quartet_emit(const ReadsView& rv, const int32_t* site_pos, int64_t C, const RegionScalars* sc,
-                        mth_quartet_params prm, int kind, const uint32_t* rowoff, const float* me_lut, int me_lut_max,
-                        ContigTable ct, QuartetRowsDev rows, int64_t row_base, cudaStream_t s) {
+                        mth_quartet_params prm, int kind, const uint8_t* mixed, const uint32_t* rowoff, const float* me_lut,
+                        int me_lut_max, ContigTable ct, QuartetRowsDev rows, int64_t row_base, cudaStream_t s) {
     if (C <= 0) return 0;
     QuartetArgs a;
     memset(&a, 0, sizeof(a));
-    a.rv = rv; a.site_pos = site_pos; a.C = C; a.sc = sc; a.prm = prm; a.kind = kind; a.rowoff = rowoff;
+    a.rv = rv; a.site_pos = site_pos; a.C = C; a.sc = sc; a.prm = prm; a.kind = kind; a.rowoff = rowoff; a.mixed = mixed;
     a.me_lut = me_lut; a.me_lut_max = me_lut_max; a.ct = ct; a.rows = rows; a.row_base = row_base;
     k_quartet<true><<<gather_grid(C), GATHER_BLOCK, 0, s>>>(a);
     return 1;

@@ -22,6 +22,8 @@ struct IngestArgs {
     mth_lpmd_params lpmd;
     int do_pdr;               // also classify reads for PDR (CF_PDR_C / CF_PDR_D in call_flags)
     mth_pdr_params pdr;
+    int do_pm, do_me;         // mapq filter of pm.rs:111 / me.rs:115 -> CF_PM_OK / CF_ME_OK
+    uint32_t pm_min_qual, me_min_qual;
     uint8_t* call_flags;      // region-wide, one byte per CpG call (common.cuh CF_*)
     RegionScalars* sc;
 };
@@ -77,13 +79,25 @@ int gather_grid(int64_t C);  // grid size for the warp-per-site kernels
 
 // ---- PM / ME (k_quartet.cu) -----------------------------------------------------------------
 struct QuartetRowsDev { int32_t* tid; int32_t* p1; int32_t* p2; int32_t* p3; int32_t* p4; float* value; uint32_t* counts; };
-// pass 1: rowcnt[s] = number of quartets starting at site s whose depth >= min_depth
+// Streaming per-call pass: every call that starts a quartet inside its read adds its pattern to hist[rank][16] when the
+// quartet is CANONICAL (its four calls are four consecutive sites of the dictionary); otherwise mixed[rank] is set and
+// the site is left to the gather kernels below.  ok_bit = CF_PM_OK or CF_ME_OK.
+int launch_quartet_scatter(const int32_t* cpg_pos, const uint8_t* call_flags, int64_t n_calls, const unsigned long long* bitmap,
+                           int64_t n_words, const uint32_t* word_prefix, const RegionScalars* sc, uint32_t ok_bit, uint32_t* hist,
+                           uint8_t* mixed, cudaStream_t s);
+// rows of the canonical sites straight from the histogram (thread per site); mixed sites are skipped
+int launch_quartet_canon_count(const uint32_t* hist, const uint8_t* mixed, int64_t C, uint32_t min_depth, uint32_t* rowcnt, cudaStream_t s);
+int launch_quartet_canon_emit(const uint32_t* hist, const uint8_t* mixed, const int32_t* site_pos, int64_t C, uint32_t min_depth, int kind,
+                              const uint32_t* rowoff, const float* me_lut, int me_lut_max, ContigTable ct, QuartetRowsDev rows,
+                              int64_t row_base, cudaStream_t s);
+// gather pass 1: rowcnt[s] = number of quartets starting at site s whose depth >= min_depth.  `mixed` != nullptr restricts
+// both gather passes to the sites it flags (the others keep what the canonical kernels wrote).
 int launch_quartet_count(const ReadsView& rv, const int32_t* site_pos, int64_t C, const RegionScalars* sc,
-                         mth_quartet_params prm, uint32_t* rowcnt, cudaStream_t s);
+                         mth_quartet_params prm, const uint8_t* mixed, uint32_t* rowcnt, cudaStream_t s);
 // pass 2: write the rows (sorted by key within a site) at rowoff[s]; kind 0 = PM, 1 = ME
 int launch_quartet_emit(const ReadsView& rv, const int32_t* site_pos, int64_t C, const RegionScalars* sc,
-                        mth_quartet_params prm, int kind, const uint32_t* rowoff, const float* me_lut, int me_lut_max,
-                        ContigTable ct, QuartetRowsDev rows, int64_t row_base, cudaStream_t s);
+                        mth_quartet_params prm, int kind, const uint8_t* mixed, const uint32_t* rowoff, const float* me_lut,
+                        int me_lut_max, ContigTable ct, QuartetRowsDev rows, int64_t row_base, cudaStream_t s);
 
 // ---- LPMD --pairs (k_pairs.cu) ----------------------------------------------------------------
 struct PairRowsDev { int32_t* tid; int32_t* pos1; int32_t* pos2; float* lpmd; int32_t* n_conc; int32_t* n_disc; };
