@@ -13,7 +13,7 @@ view = {np.dtype("uint32"): np.int32, np.dtype("uint16"): np.int16, np.dtype("ui
 devb = dict(b)
 for k in ("start", "end", "meta", "cpg_off", "cpg_pos", "cpg_rel", "meth"):
     devb[k] = torch.from_numpy(b[k].view(view.get(b[k].dtype, b[k].dtype))).cuda()
-for m in (("mhl",), ("pm",), ("fdrp",), ("qfdrp",)):
+for m in [(x,) for x in (sys.argv[3].split(",") if len(sys.argv) > 3 else ("mhl", "pm", "fdrp", "qfdrp"))]:
     ctx = engine.Context(engine.default_params(m, flags=engine.FLAG_KEEP_ON_DEVICE), [length])
     for _ in range(2):
         ctx.reset(); ctx.submit(devb); ctx.finish()
