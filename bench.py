@@ -263,7 +263,6 @@ def main():
     if rank == 0:
         sampler.start()
     ms_dev, ms_wall = timed(step_resident, args.steps)
-    clocks = sampler.stop() if rank == 0 else None
     st = ctx.stats()
     n_sites = st["n_sites"]
     n_rows = rows["pdr"]["n"]
@@ -344,6 +343,9 @@ def main():
         assert (eres["lpmd"]["n_conc"], eres["lpmd"]["n_disc"]) == (rows["lpmd"]["n_conc"], rows["lpmd"]["n_disc"]) or world > 1
         e2e[name] = {"value": total_reads / (e_wall / e_steps * 1e-3), "unit": "reads/s", "ms_per_step": e_wall / e_steps,
                      "h2d_bytes_per_step": int(est["h2d_bytes"]), "d2h_bytes_per_step": int(est["d2h_bytes"]), "steps": e_steps}
+
+    # clocks / throttle reasons were sampled from the start of the resident timed region to the end of the e2e one
+    clocks = sampler.stop() if rank == 0 else None
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

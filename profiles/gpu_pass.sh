@@ -16,3 +16,4 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_ingest|k_pdr_scatter|k_sites_emit|k_pdr_emit' -s 12 -c 4 \
     -o $OUT/prof_pdr_lpmd python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_full.log 2>&1
 ls -la $OUT
+timeout 600 python profiles/measure_all.py > $OUT/measure_all.jsonl 2>> $OUT/bench.err
