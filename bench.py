@@ -105,6 +105,46 @@ def oracle_time(b, n_sample, steps=1):
     return sub["n_reads"] / best, best, sub["n_reads"]
 
 
+_ORACLE_PARTS = None
+_ORACLE_CACHE = {}
+
+
+def _oracle_slice(args):
+    """worker of oracle_all_cores: one oracle pass (pdr + lpmd) over one slice of the reads; returns its seconds"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_lib import Oracle
+    o = _ORACLE_CACHE.get(args)
+    if o is None:  # warm-up call: build this slice's read set once (inherited through fork: nothing is pickled)
+        o = _ORACLE_CACHE[args] = Oracle.from_soa(**_ORACLE_PARTS[args])
+    t0 = time.perf_counter()
+    o.pdr(10, 4, 10)
+    o.lpmd(2, 16, 10)
+    return time.perf_counter() - t0
+
+
+def oracle_all_cores(b, n_proc):
+    """What the CPU could do at best with every host core: the reads cut into n_proc position slices, one oracle process
+    each (the reference itself is single-threaded and could only be run per contig this way; slices of ONE contig are
+    not bit-identical at their edges, so this is an optimistic throughput bound, not a parity run)."""
+    import multiprocessing as mp
+    from metheor_b200 import batch as B
+    R = b["n_reads"]
+    cuts = [R * k // n_proc for k in range(n_proc + 1)]
+    global _ORACLE_PARTS
+    _ORACLE_PARTS = [B.to_oracle_soa([B.slice_reads(b, lo, hi)]) for lo, hi in zip(cuts[:-1], cuts[1:])]
+    with mp.get_context("fork").Pool(n_proc) as pool:
+        for _ in range(2):  # warm-up: every worker ends up holding every slice's decoded reads
+            pool.map(_oracle_slice, list(range(n_proc)) * 4, chunksize=1)
+        t0 = time.perf_counter()
+        secs = pool.map(_oracle_slice, range(n_proc), chunksize=1)
+        wall = time.perf_counter() - t0
+    _ORACLE_PARTS = None
+    return {"value": R / wall, "unit": "reads/s", "cores": n_proc, "kind": "port", "seconds": wall, "slowest_slice_seconds": max(secs),
+            "sample": f"all {R} reads in {n_proc} position slices, one single-threaded oracle process per slice, timed from "
+                      f"dispatch to the last slice done (decoded reads already in each worker's memory); optimistic bound: the "
+                      f"reference has no such mode and slice edges are not bit-identical"}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -354,6 +394,13 @@ def main():
                "sample": f"first {nn} reads of the workload (pdr+lpmd, defaults); C++ restatement of metheor 0.1.9, "
                          f"single-threaded like the reference; host has {os.cpu_count()} cores"}
 
+    cpu_all = None
+    if cpu is not None and (os.cpu_count() or 1) > 1:
+        try:
+            cpu_all = oracle_all_cores(b, os.cpu_count())
+        except Exception as e:
+            cpu_all = {"error": repr(e)}
+
     bam = None
     if rank == 0 and world == 1 and args.bam_reads > 0 and not args.no_cpu_baseline:
         try:
@@ -374,7 +421,7 @@ def main():
                 "e2e_soa": dict(e2e["soa"], wire_format="SoA (mth_submit)"),
                 "gpu_launches": int((st["kernel_launches"] - 0) * args.steps),
                 "launches_per_step": int(st["kernel_launches"]),
-                "roofline": roofline, "roofline_step": roofline_step, "kernels": kern, "cpu_baseline": cpu, "bam_end_to_end": bam,
+                "roofline": roofline, "roofline_step": roofline_step, "kernels": kern, "cpu_baseline": cpu, "cpu_baseline_all_cores": cpu_all, "bam_end_to_end": bam,
                 "clocks": clocks, "pdr_path": {1: "scatter", 2: "gather"}.get(st["pdr_path"]), "lpmd": float(rows["lpmd"]["lpmd"])}
         print(json.dumps(line))
     ctx.close(); ectx.close()
