@@ -157,15 +157,17 @@ struct FdrpPolicy {
                 int32_t ov = min(sc.en[i], sc.en[jj]) - max(sc.st[i], sc.st[jj]) + 1;
                 if (ov < 0) ov = 0;
                 if (ov >= prm.min_overlap) {  // fdrp.rs:133-136
-                    uint32_t ham = 0, shared = 0;
-                    for (uint32_t w = 0; w < NW; w++) {
-                        unsigned long long ci = sc.cm[w * Dp + i], cj = sc.cm[w * Dp + jj];
-                        unsigned long long both = ci & cj;
+                    // word 0 outside the loop: a pile's CpG positions almost always fit 64 ranks (NW == 1)
+                    unsigned long long both = sc.cm[i] & sc.cm[jj];
+                    uint32_t shared = __popcll(both);
+                    uint32_t ham = __popcll(both & sc.vm[i] & sc.vm[jj] & (sc.mm[i] ^ sc.mm[jj]));
+                    for (uint32_t w = 1; w < NW; w++) {
+                        both = sc.cm[w * Dp + i] & sc.cm[w * Dp + jj];
                         shared += __popcll(both);
                         ham += __popcll(both & sc.vm[w * Dp + i] & sc.vm[w * Dp + jj] & (sc.mm[w * Dp + i] ^ sc.mm[w * Dp + jj]));
                     }
-                    if (quant) term = __fdiv_rn((float)ham, (float)shared);  // qfdrp.rs:152
-                    else disc += (ham > 0) ? 1u : 0u;                         // fdrp.rs:138-140
+                    if (quant) { if (ham) term = __fdiv_rn((float)ham, (float)shared); }  // qfdrp.rs:152 (0 / shared adds nothing)
+                    else disc += (ham > 0) ? 1u : 0u;                                      // fdrp.rs:138-140
                 }
             }
             if (quant) {  // sequential f32 accumulation in pair order
@@ -208,7 +210,7 @@ struct FdrpPolicy {
     }
 };
 
-__global__ void __launch_bounds__(GATHER_BLOCK) k_fdrp(ReadsView rv, const int32_t* __restrict__ site_pos, int64_t C,
+__global__ void __launch_bounds__(GATHER_BLOCK, 4) k_fdrp(ReadsView rv, const int32_t* __restrict__ site_pos, int64_t C,
                                                        const RegionScalars* __restrict__ scal, mth_fdrp_params prm, int quant,
                                                        uint64_t seed, ContigTable ct, char* scratch, float* __restrict__ value,
                                                        uint32_t* __restrict__ rowcnt) {
