@@ -84,6 +84,7 @@ struct mth_ctx {
     DevBuf a_start, a_end, a_meta, a_off, a_pos, a_rel, a_meth, a_moff, a_flags;
     DevBuf bitmap, word_prefix, block_sums, site_pos, scalars, totals, ct_lin, ct_tid;
     DevBuf cnt2, scan_scratch, fdrp_scratch, me_lut, lpmd_total;
+    DevBuf gfallback;            // sites the thread-per-site gather kernels hand to the warp-per-site form
     DevBuf qhist[2], qmixed[2];  // PM / ME: per-site 16-pattern histograms of canonical quartets + mixed-site flags
     DevBuf stage[2][8], exp_blocks, exp_tot;  // compact wire format: two staging sets + scan scratch
     cudaEvent_t ev_stage_free[2] = {nullptr, nullptr};
@@ -502,6 +503,7 @@ int mth_ctx_destroy(mth_ctx* c) {
     dev_free(c->exp_blocks);
     dev_free(c->exp_tot);
     for (int q = 0; q < 2; q++) { dev_free(c->qhist[q]); dev_free(c->qmixed[q]); }
+    dev_free(c->gfallback);
     for (cudaEvent_t e : c->ev_stage_free)
         if (e) cudaEventDestroy(e);
     for (int m = 0; m < M_COUNT; m++) { dev_free(c->rowcnt[m]); dev_free(c->value[m]); }
@@ -863,6 +865,7 @@ static int process_region(mth_ctx* c) {
         ContigTable ct{(int32_t)nct, (const int32_t*)c->ct_lin.p, (const int32_t*)c->ct_tid.p};
         const int32_t* site_pos = (const int32_t*)c->site_pos.p;
 
+        TRY(dev_reserve(c, c->gfallback, (size_t)C + 64, 0));
         TRY(dev_reserve(c, c->totals, 8 * M_COUNT, 0));
         TRY(host_reserve(c, c->h_totals, 8 * M_COUNT));
         CUDA_TRY(c, cudaMemsetAsync(c->totals.p, 0, 8 * M_COUNT, s));
@@ -896,8 +899,11 @@ static int process_region(mth_ctx* c) {
         if (M & MTH_MHL) {
             {
                 ProfScope ps(c, "k_mhl");
+                CUDA_TRY(c, cudaMemsetAsync(c->gfallback.p, 0, (size_t)C, s));
+                ps.add(launch_mhl_site(rv, site_pos, C, d_sc, c->prm.mhl, (float*)c->value[M_MHL].p, (uint32_t*)c->rowcnt[M_MHL].p,
+                                       (uint8_t*)c->gfallback.p, s));
                 ps.add(launch_mhl(rv, site_pos, C, d_sc, c->prm.mhl, (float*)c->value[M_MHL].p, (uint32_t*)c->rowcnt[M_MHL].p,
-                                  &d_sc->err, s));
+                                  (const uint8_t*)c->gfallback.p, s));
             }
             ProfScope ps(c, "mhl_rows_count");
             ps.add(launch_exclusive_scan_u32((uint32_t*)c->rowcnt[M_MHL].p, C, scratch, d_tot + M_MHL, s));

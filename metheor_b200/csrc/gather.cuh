@@ -87,9 +87,10 @@ __device__ __forceinline__ void for_each_site(const ReadsView& rv, const int32_t
 //   static constexpr int SLACK;
 //   bool contrib_ok(mapq, n) / trigger_ok(mapq, n)
 //   void begin_site(p) ; void add(mask, lr) ; void close() ; void end_site(site_index)
+// `only` != nullptr: just the sites it flags (the ones a tile-form kernel handed back).
 template <class Policy>
 __device__ __forceinline__ void gather_sites(const ReadsView& rv, const int32_t* __restrict__ site_pos, int64_t C,
-                                             int32_t lmax, Policy& pol) {
+                                             int32_t lmax, Policy& pol, const uint8_t* __restrict__ only = nullptr) {
     for_each_site(rv, site_pos, C, lmax, [&](int64_t s, int32_t p, int64_t lo, int32_t target) {
         pol.begin_site(p);
         scan_window(rv, lo, p, target, [&](const LaneRead& lr) {
@@ -115,7 +116,7 @@ __device__ __forceinline__ void gather_sites(const ReadsView& rv, const int32_t*
         });
         pol.close();
         pol.end_site(s);
-    });
+    }, only);
 }
 
 }  // namespace mth

@@ -151,14 +151,15 @@ struct MhlPolicy {
 
 __global__ void __launch_bounds__(GATHER_BLOCK) k_mhl(ReadsView rv, const int32_t* __restrict__ site_pos, int64_t C,
                                                       const RegionScalars* __restrict__ sc, mth_mhl_params prm,
-                                                      float* __restrict__ value, uint32_t* __restrict__ rowcnt) {
+                                                      float* __restrict__ value, uint32_t* __restrict__ rowcnt,
+                                                      const uint8_t* __restrict__ only) {
     __shared__ uint32_t sS[MHL_WARPS][MHL_LCAP + 1];
     __shared__ uint32_t sN[MHL_WARPS][MHL_LCAP + 1];
     int warp = threadIdx.x >> 5;
     for (int l = lane_id(); l <= MHL_LCAP; l += 32) { sS[warp][l] = 0; sN[warp][l] = 0; }
     __syncwarp();
     MhlPolicy pol(rv, prm, value, rowcnt, sS[warp], sN[warp]);
-    gather_sites(rv, site_pos, C, sc->lmax, pol);
+    gather_sites(rv, site_pos, C, sc->lmax, pol, only);
 }
 
 __global__ void k_site_emit(const float* __restrict__ value, const uint32_t* __restrict__ rowoff, int64_t C,
@@ -179,9 +180,9 @@ __global__ void k_site_emit(const float* __restrict__ value, const uint32_t* __r
 }
 
 int launch_mhl(const ReadsView& rv, const int32_t* site_pos, int64_t C, const RegionScalars* sc, mth_mhl_params prm,
-               float* value, uint32_t* rowcnt, uint32_t*, cudaStream_t s) {
+               float* value, uint32_t* rowcnt, const uint8_t* only, cudaStream_t s) {
     if (C <= 0) return 0;
-    k_mhl<<<gather_grid(C), GATHER_BLOCK, 0, s>>>(rv, site_pos, C, sc, prm, value, rowcnt);
+    k_mhl<<<gather_grid(C), GATHER_BLOCK, 0, s>>>(rv, site_pos, C, sc, prm, value, rowcnt, only);
     return 1;
 }
 

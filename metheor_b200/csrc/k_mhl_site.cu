@@ -1,0 +1,174 @@
+// k_mhl_site.cu — methylation haplotype load (mhl.rs:135-208, AssociatedReads mhl.rs:12-81), one THREAD per CpG site.
+//
+// The warp-per-site form (k_mhl.cu) is issue-bound on cross-lane bookkeeping: a site only has ~30 reads to look at.
+// Here MS_SITES consecutive sites form a tile; the reads that can matter for them are one contiguous range of the sorted
+// read arrays and are staged in shared memory once (start, first call, call count | mapq, methylation word, and the
+// calls themselves); then every thread replays the reference's streaming loop for its own site, sequentially and in
+// file order, entirely out of shared memory: a read contributes if the site is among its calls, a read whose first
+// call lies behind the site closes the segment (mhl.rs:162-173), the per-read stretch histogram is the
+// x_l = x_{l-1} & (x_{l-1} >> 1) popcount chain, and the per-site S[l] / N[n] accumulators are two small
+// shared-memory arrays per thread.  32 sites advance per warp instruction instead of one.
+//
+// What does not fit — tiles with more than MS_RCAP reads or MS_CCAP calls, reads with more than MS_L calls (dense CpG
+// islands), > 64 calls per read — is flagged in `fallback` and done by the warp-per-site kernel afterwards.
+#include "gather.cuh"
+#include "kernels.h"
+
+namespace mth {
+
+constexpr int MS_SITES = 128;    // sites (= threads) per CTA
+constexpr int MS_RCAP = 2048;    // reads staged per tile
+constexpr int MS_CCAP = 6144;    // calls staged per tile
+constexpr int MS_L = 16;         // longest read (in calls) the per-thread accumulators hold
+constexpr int MS_SPAN = 60000;   // positions a tile may span (calls are staged as 16-bit offsets)
+
+// Shared-memory footprint decides how many sites are in flight per SM, so everything is packed: 10 bytes per read,
+// 2 bytes per call, 16-bit accumulators (a segment deeper than 65 535 reads goes to the per-site kernel).
+struct MsSmem {
+    int32_t start[MS_RCAP];
+    uint16_t meta[MS_RCAP];      // mapq | n << 8   (n <= MS_L)
+    uint16_t o0[MS_RCAP];        // first call of the read, tile-relative
+    uint16_t first[MS_RCAP];     // first call, as offset from the tile base (0xFFFF: no call)
+    uint16_t pos[MS_CCAP];       // calls, as offsets from the tile base
+    uint16_t S[MS_L + 1][MS_SITES];   // [l][thread]: bank-conflict-free
+    uint16_t N[MS_L + 1][MS_SITES];
+    long long ra;
+    unsigned int c0;
+    int nreads, ncalls, bad;
+};
+
+__global__ void __launch_bounds__(MS_SITES) k_mhl_site(ReadsView rv, const int32_t* __restrict__ site_pos, int64_t C,
+                                                       const RegionScalars* __restrict__ sc, mth_mhl_params prm,
+                                                       float* __restrict__ value, uint32_t* __restrict__ rowcnt,
+                                                       uint8_t* __restrict__ fallback) {
+    extern __shared__ __align__(16) unsigned char ms_raw[];
+    MsSmem& sh = *reinterpret_cast<MsSmem*>(ms_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int32_t lmax = sc->lmax;
+    const int64_t n_tiles = (C + MS_SITES - 1) / MS_SITES;
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t s0 = tile * MS_SITES;
+        const int ns = (int)min((int64_t)MS_SITES, C - s0);
+        __syncthreads();  // previous tile fully consumed
+        if (warp == 0) {
+            const int64_t ra = warp_lower_bound(rv.start, rv.R, site_pos[s0] - lmax + 1);
+            const int64_t rb = warp_lower_bound(rv.start, rv.R, site_pos[s0 + ns - 1] + 2);
+            if (lane == 0) {
+                const unsigned int c0 = rv.cpg_off[ra], c1 = rv.cpg_off[rb];
+                sh.ra = ra;
+                sh.c0 = c0;
+                sh.nreads = (int)min(rb - ra, (int64_t)MS_RCAP + 1);
+                sh.ncalls = (int)min(c1 - c0, (unsigned int)MS_CCAP + 1u);
+                // multi-word reads or a tile too wide for 16-bit offsets: per-site kernel
+                sh.bad = (rv.meth_off != nullptr || site_pos[s0 + ns - 1] - site_pos[s0] + 2 * lmax > MS_SPAN) ? 1 : 0;
+            }
+        }
+        __syncthreads();
+        const int64_t ra = sh.ra;
+        const uint32_t c0 = sh.c0;
+        const int nreads = sh.nreads, ncalls = sh.ncalls;
+        if (nreads > MS_RCAP || ncalls > MS_CCAP || sh.bad) {
+            if (tid < ns) fallback[s0 + tid] = 1;
+            continue;
+        }
+        const int32_t base = site_pos[s0] - lmax - 1;  // every call of a tile read is >= base
+        int toolong = 0;
+        for (int r = tid; r < nreads; r += MS_SITES) {
+            const int64_t j = ra + r;
+            const uint32_t o0 = rv.cpg_off[j], n = rv.cpg_off[j + 1] - o0;
+            sh.start[r] = rv.start[j];
+            sh.meta[r] = (uint16_t)((rv.meta[j] & 0xFFu) | (min(n, 255u) << 8));
+            sh.o0[r] = (uint16_t)(o0 - c0);
+            if (n > (uint32_t)MS_L) toolong = 1;
+        }
+        for (int y = tid; y < ncalls; y += MS_SITES) sh.pos[y] = (uint16_t)(rv.cpg_pos[c0 + y] - base);
+        if (__syncthreads_or(toolong)) {  // a read too long for the accumulators: this tile goes to the per-site kernel
+            if (tid < ns) fallback[s0 + tid] = 1;
+            continue;
+        }
+        for (int r = tid; r < nreads; r += MS_SITES) sh.first[r] = (sh.meta[r] >> 8) ? sh.pos[sh.o0[r]] : (uint16_t)0xFFFF;
+        __syncthreads();
+        if (tid >= ns) continue;
+
+        // ---- one thread per site: mhl.rs:155-205 over the site's window, in file order ----
+        const int32_t p = site_pos[s0 + tid];
+        const uint32_t pq = (uint32_t)(p - base);  // the site in tile offsets
+        bool deep = false;
+        int lo = 0, hi = nreads;  // first read with start >= p - lmax + 1
+        while (lo < hi) { int m = (lo + hi) >> 1; if (sh.start[m] < p - lmax + 1) lo = m + 1; else hi = m; }
+#pragma unroll
+        for (int l = 0; l <= MS_L; l++) { sh.S[l][tid] = 0; sh.N[l][tid] = 0; }
+        uint32_t depth = 0, maxn = 0;
+        float best = 0.f;
+        bool have = false;
+        auto close = [&]() {
+            if (depth == 0) return;
+            if (depth >= prm.min_depth) {  // mhl.rs:165
+                // D[l] = sum over reads of max(0, n - l + 1) = suffix sum of the suffix counts of N (mhl.rs:56-64)
+                uint32_t ge = 0, dl = 0;
+                uint32_t Dl[MS_L + 1];
+#pragma unroll
+                for (int l = MS_L; l >= 1; l--) {
+                    ge += sh.N[l][tid];
+                    dl += ge;
+                    Dl[l] = dl;
+                }
+                float mhl = 0.f;
+#pragma unroll
+                for (int l = 1; l <= MS_L; l++) {  // ascending l, sequential f32 adds (canonical order)
+                    const uint32_t cnt = sh.S[l][tid];
+                    if (cnt) mhl = __fadd_rn(mhl, __fdiv_rn(__fmul_rn((float)l, (float)cnt), (float)Dl[l]));
+                }
+                // mhl.rs:46-48 sums 1..max_n in f32: every partial sum is an integer < 2^24, so the closed form is exact
+                best = __fdiv_rn(mhl, (float)(maxn * (maxn + 1) / 2));  // mhl.rs:71
+                have = true;
+            }
+#pragma unroll
+            for (int l = 1; l <= MS_L; l++) { sh.S[l][tid] = 0; sh.N[l][tid] = 0; }
+            depth = maxn = 0;
+        };
+        for (int r = lo; r < nreads && sh.start[r] <= p + 1; r++) {
+            const uint32_t m = sh.meta[r], n = m >> 8;
+            if (n == 0) continue;
+            if ((uint32_t)sh.first[r] > pq) { close(); continue; }  // mhl.rs:162-173: ANY read with >= 1 CpG flushes what lies before its first CpG
+            // does the read call p?  (its calls are sorted; n <= MS_L)
+            const uint16_t* cp = sh.pos + sh.o0[r];
+            bool calls = false;
+            for (uint32_t k = 0; k < n; k++) {
+                const uint32_t x = cp[k];
+                if (x >= pq) { calls = x == pq; break; }
+            }
+            if (!calls) continue;
+            if ((m & 0xFFu) < prm.min_qual || n < prm.min_cpgs) continue;  // mhl.rs:176, :181
+            if (++depth >= 4000u) deep = true;  // 16 calls x 4000 reads still fit the 16-bit accumulators
+            maxn = max(maxn, n);
+            sh.N[n][tid]++;  // mhl.rs:75-80
+            unsigned long long x = rv.meth[ra + r] & low_mask64(n);
+            for (uint32_t l = 1; x; l++) {  // stretch_info[l] = popc(x_l), readutil.rs:147-164
+                sh.S[l][tid] += (uint32_t)__popcll(x);
+                x &= x >> 1;
+            }
+        }
+        close();
+        if (deep) { fallback[s0 + tid] = 1; continue; }  // deeper than the 16-bit accumulators allow: per-site kernel
+        value[s0 + tid] = best;
+        rowcnt[s0 + tid] = have ? 1u : 0u;
+    }
+}
+
+int launch_mhl_site(const ReadsView& rv, const int32_t* site_pos, int64_t C, const RegionScalars* sc, mth_mhl_params prm,
+                    float* value, uint32_t* rowcnt, uint8_t* fallback, cudaStream_t s) {
+    if (C <= 0) return 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_mhl_site, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MsSmem));
+        attr_set = true;
+    }
+    int64_t tiles = (C + MS_SITES - 1) / MS_SITES;
+    if (tiles > 148 * 64) tiles = 148 * 64;
+    k_mhl_site<<<(unsigned)tiles, MS_SITES, sizeof(MsSmem), s>>>(rv, site_pos, C, sc, prm, value, rowcnt, fallback);
+    return 1;
+}
+
+}  // namespace mth

@@ -71,7 +71,11 @@ int launch_pdr_emit(const uint32_t* cnt2, const uint32_t* rowoff, const int32_t*
 // ---- MHL (k_mhl.cu) -------------------------------------------------------------------------
 // value[s], rowcnt[s] in {0,1}
 int launch_mhl(const ReadsView& rv, const int32_t* site_pos, int64_t C, const RegionScalars* sc, mth_mhl_params prm,
-               float* value, uint32_t* rowcnt, uint32_t* err, cudaStream_t s);
+               float* value, uint32_t* rowcnt, const uint8_t* only, cudaStream_t s);  // only != nullptr: just the flagged sites
+// thread-per-site form (k_mhl_site.cu): takes every site whose tile fits shared memory, flags the rest in fallback[] (C bytes,
+// zeroed by the caller) for launch_mhl(..., only = fallback)
+int launch_mhl_site(const ReadsView& rv, const int32_t* site_pos, int64_t C, const RegionScalars* sc, mth_mhl_params prm,
+                    float* value, uint32_t* rowcnt, uint8_t* fallback, cudaStream_t s);
 // generic: rows for sites with rowcnt (pre-scan value kept in `flag`), value from dense array
 int launch_site_emit(const float* value, const uint32_t* rowoff, uint64_t n_rows_region, const int32_t* site_pos,
                      int64_t C, ContigTable ct, SiteRowsDev rows, int64_t row_base, cudaStream_t s);
