@@ -115,16 +115,18 @@ RecordStream::RecordStream(const std::string& path, int n_threads, size_t window
 
 RecordStream::~RecordStream() {
     if (prefetching_) next_.wait();
+    if (inflating_) inflate_fut_.wait();
 }
 
 // Index the next members (up to window_bytes_ of output), inflate them on the reader's pool.  Touches only coff_,
 // which nobody else uses while a prefetch is in flight.
-RecordStream::Inflated RecordStream::inflate_next(size_t headroom) {
+RecordStream::Inflated RecordStream::inflate_next(size_t headroom, size_t max_bytes) {
+    if (!max_bytes) max_bytes = window_bytes_;
     Inflated out;
     const uint8_t* d = file_.data();
     std::vector<Block> blocks;
     size_t utotal = 0;
-    while (coff_ < file_.size() && utotal < window_bytes_) {
+    while (coff_ < file_.size() && utotal < max_bytes) {
         Block b;
         uint32_t crc;
         size_t total = bgzf_member(d, file_.size(), coff_, &b.cdata, &b.clen, &b.usize, &crc);
@@ -163,7 +165,23 @@ RecordStream::Inflated RecordStream::inflate_next(size_t headroom) {
 RecordStream::Window RecordStream::produce() {
     Window w;
     for (;;) {
-        Inflated in = inflate_next(carry_.size());
+        // two-deep: the NEXT run is already inflating on the pool while this one is walked below
+        if (!inflating_) {
+            inflate_fut_ = std::async(std::launch::async, [this] { return inflate_next(kHeadroom); });
+            inflating_ = true;
+        }
+        Inflated in = inflate_fut_.get();
+        inflating_ = false;
+        if (in.ok && in.len) {
+            inflate_fut_ = std::async(std::launch::async, [this] { return inflate_next(kHeadroom); });
+            inflating_ = true;
+        }
+        if (in.ok && carry_.size() > in.headroom) {  // rare: the carried-over record is larger than the headroom
+            std::unique_ptr<uint8_t[]> nb(new uint8_t[carry_.size() + in.len]);
+            if (in.len) memcpy(nb.get() + carry_.size(), in.data.get() + in.headroom, in.len);
+            in.data = std::move(nb);
+            in.headroom = carry_.size();
+        }
         w.s_inflate += in.seconds;
         if (!in.ok) { w.ok = false; w.err = in.err; return w; }
         const bool last = in.len == 0;  // no members left: only the carried-over bytes remain
@@ -174,8 +192,9 @@ RecordStream::Window RecordStream::produce() {
         w.inflated += in.len;
         w.coff_end = in.coff_end;
         const size_t carry = carry_.size();
-        if (carry) memcpy(in.data.get(), carry_.data(), carry);
-        const uint8_t* b = in.data.get();
+        uint8_t* front = in.data.get() + (last ? 0 : in.headroom - carry);
+        if (carry) memcpy(front, carry_.data(), carry);
+        const uint8_t* b = front;
         const size_t n = carry + in.len;
         double t0 = now_s();
         size_t o = 0;
@@ -201,7 +220,7 @@ RecordStream::Window RecordStream::produce() {
 void RecordStream::parse_bam_header() {
     // the header may span several runs: keep appending until it is complete
     for (;;) {
-        Inflated in = inflate_next(carry_.size());
+        Inflated in = inflate_next(carry_.size(), 1u << 18);  // small runs: the header is usually a few KB
         if (!in.ok) throw open_error(in.err);
         seconds_inflate += in.seconds;
         bytes_uncompressed += in.len;

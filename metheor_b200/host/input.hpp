@@ -73,7 +73,7 @@ private:
         double s_inflate = 0, s_walk = 0;
         size_t inflated = 0, coff_end = 0;
     };
-    Inflated inflate_next(size_t headroom);
+    Inflated inflate_next(size_t headroom, size_t max_bytes = 0);  // max_bytes 0: one window
     Window produce();         // background thread: inflate + walk; owns coff_ and carry_
     void parse_bam_header();
     void parse_sam_header();
@@ -81,6 +81,9 @@ private:
     ThreadPool pool_;
     std::future<Window> next_;
     bool prefetching_ = false;
+    std::future<Inflated> inflate_fut_;   // the run after the one being walked (producer thread only)
+    bool inflating_ = false;
+    static constexpr size_t kHeadroom = 4u << 20;  // room in front of a run for the record carried over from the previous one
     size_t window_bytes_;
     MappedFile file_;
     Format format_ = Format::BAM;

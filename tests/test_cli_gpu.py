@@ -116,3 +116,27 @@ def test_missing_xm_aborts_like_the_reference(tmp_path):
     bamio.write_bam(ok, REFS, recgen.random_records(32, REFS, 300))
     r = host.cli("pdr", "-i", ok, "-o", "/nonexistent_directory/readonly_output.tsv")
     assert r.returncode != 0
+
+
+def test_edge_inputs(tmp_path):
+    """Header-only BAM, unmapped reads behind the mapped ones, a CpG set that filters everything, reads at contig ends."""
+    empty = str(tmp_path / "empty.bam")
+    bamio.write_bam(empty, REFS, [])
+    for m in MEASURES:
+        t = _both(tmp_path, m, empty)
+        assert t == ("name\tlpmd\n" + empty + "\tNaN\n" if m == "lpmd" else "")
+    reads = recgen.random_records(41, REFS, 1500, p_simple=0.8)
+    reads += [dict(tid=-1, pos=-1, flag=4, mapq=0, cigar="", xm="....z...Z.") for _ in range(20)]
+    # reads touching both ends of a contig (forward and reverse strand)
+    edge = [dict(tid=2, pos=0, flag=f, mapq=42, cigar="20M", xm="Z..z....Z.....z....Z") for f in (0, 16)] + \
+           [dict(tid=2, pos=REFS[2][1] - 20, flag=f, mapq=42, cigar="20M", xm="Z..z....Z.....z....Z") for f in (0, 16)]
+    mapped = [r for r in reads if r["tid"] >= 0]
+    mapped = sorted(mapped + edge, key=lambda r: (r["tid"], r["pos"]))
+    bam = str(tmp_path / "u.bam")
+    bamio.write_bam(bam, REFS, mapped + [r for r in reads if r["tid"] < 0])
+    for m in MEASURES:
+        _both(tmp_path, m, bam, *(() if m == "lpmd" else ("-d", 1)))
+    bed = str(tmp_path / "none.bed")
+    open(bed, "w").write("chr1\t199999\t200001\n")
+    for m in ("pdr", "lpmd", "pm"):
+        _both(tmp_path, m, bam, "-c", bed)

@@ -169,3 +169,21 @@ def test_cli_usage_matches_clap_contract(tmp_path):
     junk.write_text("[package]\n")
     r = host.cli("pdr", "-i", str(junk), "-o", str(tmp_path / "o.tsv"))
     assert r.returncode == 101 and "Error opening BAM file" in r.stderr
+
+
+def test_multi_window_stream_matches_generator(tmp_path):
+    """~18 MB of records = several 8 MiB windows of the decode-only API: records straddle window and BGZF member
+    boundaries, the producer thread inflates and walks ahead of the decoder."""
+    from metheor_b200 import synth, synth_bam
+    L = 200_000
+    sites = synth.make_sites(91, L)
+    b = synth.make_reads(92, sites, L, 30.0)
+    p = str(tmp_path / "big.bam")
+    info = synth_bam.write_bam(p, [("chr19", L)], [b], threads=4)
+    assert info["bytes_uncompressed"] > 17_000_000
+    for threads in (1, 5):
+        d = host.decode_file(p, threads=threads)
+        assert d["n_reads"] == b["n_reads"]
+        for k in ("start", "end", "cpg_pos", "cpg_rel"):
+            assert np.array_equal(d[k], b[k]), k
+        assert np.array_equal(d["mapq"], (b["meta"] & 0xFF).astype(np.uint8))
