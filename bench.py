@@ -212,7 +212,17 @@ class _DevI64:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 2}
 
 
+def ensure_built():
+    """The libraries are built in-tree by __graft_entry__.build() and travel with the snapshot; a bare checkout builds them here."""
+    need = [os.path.join(ROOT, "metheor_b200", "csrc", "libmetheor_b200.so"), os.path.join(ROOT, "metheor_b200", "host", "libmetheor_host.so"),
+            os.path.join(ROOT, "oracle", "_build", "liboracle.so")]
+    if not all(os.path.exists(p) for p in need):
+        import __graft_entry__
+        __graft_entry__.build()
+
+
 def main():
+    ensure_built()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
