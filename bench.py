@@ -217,8 +217,14 @@ def ensure_built():
     need = [os.path.join(ROOT, "metheor_b200", "csrc", "libmetheor_b200.so"), os.path.join(ROOT, "metheor_b200", "host", "libmetheor_host.so"),
             os.path.join(ROOT, "oracle", "_build", "liboracle.so")]
     if not all(os.path.exists(p) for p in need):
-        import __graft_entry__
-        __graft_entry__.build()
+        if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+            import __graft_entry__
+            __graft_entry__.build()
+        else:  # under torchrun only one rank builds
+            t0 = time.time()
+            while not all(os.path.exists(p) for p in need) and time.time() - t0 < 600:
+                time.sleep(1.0)
+            time.sleep(2.0)
 
 
 def main():
