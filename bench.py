@@ -366,15 +366,25 @@ def main():
                      "frac": step_alg / (kern_ms_total * 1e-3) / 1e9 / peak}
 
     # ---------------- end to end through host buffers ----------------
-    # The shipped host (metheor_b200/host) hands batches over in the compact wire format (mth_submit_compact): 9 B per
-    # read + 2.125 B per call cross PCIe and the device expands them.  `e2e` times exactly that call sequence with
-    # pinned host arrays; `e2e_soa` is the same through mth_submit with the full SoA layout (24 B + 6 B).
+    # The shipped host (metheor_b200/host) hands batches over in the compact wire format (mth_submit_compact) with the
+    # dense block encodings: ~7 B per read + 1.125 B per call cross PCIe and the device expands them.  `e2e` times exactly
+    # that call sequence with pinned host arrays; `e2e_compact` is the plain compact format (9 B + 2.125 B) and `e2e_soa`
+    # mth_submit with the full SoA layout (24 B + 6 B).
     from metheor_b200 import batch as B
-    hostc = B.to_compact(b)
-    for k, v in list(hostc.items()):
-        if isinstance(v, np.ndarray):
-            t = torch.from_numpy(v.view({np.dtype("uint16"): np.int16}.get(v.dtype, v.dtype)))
-            hostc[k] = t.pin_memory() if t.numel() else t
+
+    def pin(d):
+        d = dict(d)
+        for k, v in list(d.items()):
+            if isinstance(v, np.ndarray):
+                t = torch.from_numpy(v.view({np.dtype("uint16"): np.int16, np.dtype("uint32"): np.int32}.get(v.dtype, v.dtype)))
+                d[k] = t.pin_memory() if t.numel() else t
+        return d
+
+    hostc = pin(B.to_compact(b))
+    # dense block encodings (MTH_CENC_START16 | MTH_CENC_DELTA8), handed over like the streaming host does: a few
+    # batches of <= 2 M reads, so that the copy of one overlaps the expansion + ingest of the previous one
+    CH = 1 << 21
+    hostd = [pin(B.to_compact(B.slice_reads(b, lo, min(R, lo + CH)), dense=True)) for lo in range(0, R, CH)]
     ectx = make_ctx(0)
     eres = {}
 
@@ -382,7 +392,7 @@ def main():
         def step():
             ectx.reset()
             submit(payload)
-            eres.update(ectx.finish())
+            eres.update(ectx.finish(copy=False))  # rows are read where the C ABI leaves them: the context's pinned host buffers
             allreduce_lpmd(ectx)
             if world > 1:
                 eres["lpmd"] = ectx.lpmd_refresh()
@@ -390,7 +400,12 @@ def main():
 
     e_steps = max(3, min(args.steps, 10))
     e2e = {}
-    for name, st_fn in (("soa", make_step(ectx.submit, host)), ("compact", make_step(ectx.submit_compact, hostc))):
+    def submit_dense(chunks):
+        for hc in chunks:
+            ectx.submit_compact(hc)
+
+    for name, st_fn in (("soa", make_step(ectx.submit, host)), ("compact", make_step(ectx.submit_compact, hostc)),
+                        ("dense", make_step(submit_dense, hostd))):
         for _ in range(args.warmup):
             st_fn()
         _, e_wall = timed(st_fn, e_steps)
@@ -433,8 +448,10 @@ def main():
                            "l2": "inputs (%.0f MB per step) larger than L2" % ((16 * R + 6 * I + 8 * R) / 1e6),
                            "parallelism": f"genomic sharding x{world}, NCCL all-reduce of 4 LPMD counters"},
                 "cpgs_per_sec": C * world / (ms_step * 1e-3), "wall_ms_per_step": ms_wall / args.steps,
-                "e2e": dict(e2e["compact"], wire_format="compact (mth_submit_compact)"),
-                "e2e_soa": dict(e2e["soa"], wire_format="SoA (mth_submit)"),
+                "e2e": dict(e2e["dense"], wire_format="compact + dense block encodings (mth_submit_compact, enc = START16 | DELTA8), "
+                                                      f"{len(hostd)} batches of <= {CH} reads"),
+                "e2e_compact": dict(e2e["compact"], wire_format="compact (mth_submit_compact, enc = 0), one batch"),
+                "e2e_soa": dict(e2e["soa"], wire_format="SoA (mth_submit), one batch"),
                 "gpu_launches": int((st["kernel_launches"] - 0) * args.steps),
                 "launches_per_step": int(st["kernel_launches"]),
                 "roofline": roofline, "roofline_step": roofline_step, "kernels": kern, "cpu_baseline": cpu, "cpu_baseline_all_cores": cpu_all, "bam_end_to_end": bam,

@@ -138,7 +138,29 @@ typedef struct {
     const uint16_t* cpg_delta;
     const uint8_t* meth_bits; /* (n_cpg + 7) / 8 bytes */
     const uint16_t* rel_exc;
+    /* ---- optional denser encodings (enc != 0): 7 B per read + 1.125 B per call on sorted short-read data ----------
+     * Reads are grouped in blocks of MTH_CBLOCK = 256 (block b = reads [256 b, 256 b + 256) of this batch); a block that
+     * does not fit the narrow type falls back to the wide one, block by block, so nothing needs an escape code.
+     * MTH_CENC_START16: `start` above is not read.  start = blk_start[b] + start_off16[r]; a block whose starts span
+     *   more than 65535 has blk_start[b] = -(1 + e) and its 256 absolute starts are start_exc[256 e .. 256 e + 255].
+     * MTH_CENC_DELTA8: call positions are deltas from the PREVIOUS call of the read (first call: from start - 1).
+     *   blk_call_off[b] = offset of the block's first call in cpg_delta8; with bit 31 set the block holds a delta > 255
+     *   and its calls are 16-bit deltas in `cpg_delta` at offset (blk_call_off[b] & 0x7FFFFFFF) instead.  Without this
+     *   bit of `enc`, `cpg_delta` keeps its meaning above (one 16-bit offset from start - 1 per call). */
+    uint32_t enc;
+    uint32_t reserved;
+    const uint16_t* start_off16;
+    const int32_t* blk_start;
+    const int32_t* start_exc;
+    int64_t n_start_exc;      /* entries of start_exc (256 per exception block) */
+    const uint8_t* cpg_delta8;
+    const uint32_t* blk_call_off;
+    int64_t n_delta8;         /* entries of cpg_delta8 */
+    int64_t n_delta16;        /* entries of cpg_delta when MTH_CENC_DELTA8 is set */
 } mth_batch_compact;
+#define MTH_CENC_START16 1u
+#define MTH_CENC_DELTA8 2u
+#define MTH_CBLOCK 256
 
 /* Result rows.  Arrays are owned by the context and valid until the next mth_finish / mth_reset / mth_ctx_destroy. */
 typedef struct {          /* pdr.rs:102-116, mhl.rs:122-131, fdrp.rs:169-172, qfdrp.rs:181-184: sorted by (tid,pos) */

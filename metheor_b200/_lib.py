@@ -53,7 +53,9 @@ class Batch(C.Structure):
 
 class BatchCompact(C.Structure):
     _fields_ = [("tid", i32), ("mem_kind", i32), ("n_reads", i64), ("n_cpg", i64), ("n_rel", i64), ("start", vp), ("span", vp),
-                ("mapq", vp), ("n_cpg8", vp), ("flags", vp), ("cpg_delta", vp), ("meth_bits", vp), ("rel_exc", vp)]
+                ("mapq", vp), ("n_cpg8", vp), ("flags", vp), ("cpg_delta", vp), ("meth_bits", vp), ("rel_exc", vp),
+                ("enc", u32), ("reserved", u32), ("start_off16", vp), ("blk_start", vp), ("start_exc", vp), ("n_start_exc", i64),
+                ("cpg_delta8", vp), ("blk_call_off", vp), ("n_delta8", i64), ("n_delta16", i64)]
 
 
 class SiteRows(C.Structure):

@@ -74,8 +74,12 @@ def to_oracle_soa(batches):
                 cpg_rel=cat(rel), cpg_meth=cat(meth))
 
 
-def to_compact(b, with_rel=True):
-    """SoA batch -> the compact wire format of include/metheor_b200.h (mth_batch_compact).  Needs <= 64 calls per read."""
+CBLOCK = 256  # MTH_CBLOCK
+
+
+def to_compact(b, with_rel=True, dense=False):
+    """SoA batch -> the compact wire format of include/metheor_b200.h (mth_batch_compact).  Needs <= 64 calls per read.
+    dense=True adds the block encodings MTH_CENC_START16 | MTH_CENC_DELTA8 (7 B per read + 1.125 B per call)."""
     off = np.asarray(b["cpg_off"], np.int64)
     cnt = np.diff(off)
     if cnt.max(initial=0) > 64:
@@ -99,6 +103,41 @@ def to_compact(b, with_rel=True):
         explicit[np.unique(ridx[odd])] = True
         flags = flags | (explicit.astype(np.uint8) << 2)
         rel_exc = rel[explicit[ridx]].astype(np.uint16)
-    return dict(tid=b["tid"], n_reads=R, n_cpg=int(off[-1]), n_rel=len(rel_exc), start=np.asarray(b["start"], np.int32),
-                span=span.astype(np.uint16), mapq=(meta & 0xFF).astype(np.uint8), n_cpg8=cnt.astype(np.uint8), flags=flags,
-                cpg_delta=delta.astype(np.uint16), meth_bits=np.packbits(unpack_meth(b), bitorder="little"), rel_exc=rel_exc)
+    out = dict(tid=b["tid"], n_reads=R, n_cpg=int(off[-1]), n_rel=len(rel_exc), start=np.asarray(b["start"], np.int32),
+               span=span.astype(np.uint16), mapq=(meta & 0xFF).astype(np.uint8), n_cpg8=cnt.astype(np.uint8), flags=flags,
+               cpg_delta=delta.astype(np.uint16), meth_bits=np.packbits(unpack_meth(b), bitorder="little"), rel_exc=rel_exc, enc=0)
+    if not dense or R == 0:
+        return out
+    nb = (R + CBLOCK - 1) // CBLOCK
+    blk = np.arange(R, dtype=np.int64) // CBLOCK
+    # starts: 16-bit offsets from the block's first (= smallest) start; blocks spanning more than 65535 keep 32-bit starts
+    first = start[np.arange(nb, dtype=np.int64) * CBLOCK]
+    last = start[np.minimum((np.arange(nb, dtype=np.int64) + 1) * CBLOCK, R) - 1]
+    wide_s = (last - first) > 65535
+    exc_rank = np.cumsum(wide_s) - 1
+    blk_start = np.where(wide_s, -(1 + exc_rank), first).astype(np.int32)
+    off16 = np.where(wide_s[blk], 0, start - first[blk]).astype(np.uint16)
+    start_exc = np.zeros(int(wide_s.sum()) * CBLOCK, np.int32)
+    for e, bidx in enumerate(np.flatnonzero(wide_s)):
+        seg = start[bidx * CBLOCK:(bidx + 1) * CBLOCK]
+        start_exc[e * CBLOCK:e * CBLOCK + len(seg)] = seg
+    # calls: deltas from the previous call of the read (first call: from start - 1); a block with a delta > 255 stays 16-bit
+    is_first = np.zeros(len(pos), bool)
+    is_first[off[:-1][cnt > 0]] = True
+    prev = np.where(is_first, start[ridx] - 1, np.concatenate([[0], pos[:-1]]))
+    dch = pos - prev
+    cblk = blk[ridx]
+    blk_max = np.zeros(nb, np.int64)
+    np.maximum.at(blk_max, cblk, dch)
+    wide_c = blk_max > 255
+    ncall_blk = np.bincount(cblk, minlength=nb)
+    n8 = np.where(wide_c, 0, ncall_blk)
+    n16 = np.where(wide_c, ncall_blk, 0)
+    off8 = np.cumsum(n8) - n8
+    off16c = np.cumsum(n16) - n16
+    blk_call_off = np.where(wide_c, off16c | 0x80000000, off8).astype(np.uint32)
+    out.update(enc=3, start_off16=off16, blk_start=blk_start, start_exc=start_exc, n_start_exc=len(start_exc),
+               cpg_delta8=dch[~wide_c[cblk]].astype(np.uint8), cpg_delta=dch[wide_c[cblk]].astype(np.uint16), blk_call_off=blk_call_off)
+    out["n_delta8"], out["n_delta16"] = len(out["cpg_delta8"]), len(out["cpg_delta"])
+    del out["start"]
+    return out

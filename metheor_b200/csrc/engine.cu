@@ -86,7 +86,7 @@ struct mth_ctx {
     DevBuf cnt2, scan_scratch, fdrp_scratch, me_lut, lpmd_total;
     DevBuf gfallback;            // sites the thread-per-site gather kernels hand to the warp-per-site form
     DevBuf qhist[2], qmixed[2];  // PM / ME: per-site 16-pattern histograms of canonical quartets + mixed-site flags
-    DevBuf stage[2][8], exp_blocks, exp_tot;  // compact wire format: two staging sets + scan scratch
+    DevBuf stage[2][13], exp_blocks, exp_tot;  // compact wire format: two staging sets + scan scratch
     cudaEvent_t ev_stage_free[2] = {nullptr, nullptr};
     bool stage_busy[2] = {false, false};
     int stage_next = 0;
@@ -693,8 +693,16 @@ int mth_submit_compact(mth_ctx* c, const mth_batch_compact* b) {
     if (b->n_reads < 0 || b->n_cpg < 0 || b->n_rel < 0) return fail(c, MTH_ERR_INVALID, "negative batch size");
     if (b->n_reads == 0) return MTH_OK;
     if (b->tid < 0 || (size_t)b->tid >= c->ref_len.size()) return fail(c, MTH_ERR_INVALID, "batch tid outside the reference list");
-    if (!b->start || !b->span || !b->mapq || !b->n_cpg8 || !b->flags || (b->n_cpg && (!b->cpg_delta || !b->meth_bits)))
+    const bool enc_s16 = (b->enc & MTH_CENC_START16) != 0, enc_d8 = (b->enc & MTH_CENC_DELTA8) != 0;
+    if (b->enc & ~(MTH_CENC_START16 | MTH_CENC_DELTA8)) return fail(c, MTH_ERR_INVALID, "unknown bits in mth_batch_compact.enc");
+    if ((!enc_s16 && !b->start) || !b->span || !b->mapq || !b->n_cpg8 || !b->flags || (b->n_cpg && !b->meth_bits) ||
+        (b->n_cpg && !enc_d8 && !b->cpg_delta))
         return fail(c, MTH_ERR_INVALID, "null array in compact batch");
+    if (enc_s16 && (!b->start_off16 || !b->blk_start || (b->n_start_exc && !b->start_exc) || b->n_start_exc < 0))
+        return fail(c, MTH_ERR_INVALID, "MTH_CENC_START16 needs start_off16, blk_start (and start_exc)");
+    if (enc_d8 && (!b->blk_call_off || (b->n_delta8 && !b->cpg_delta8) || (b->n_delta16 && !b->cpg_delta) || b->n_delta8 < 0 ||
+                   b->n_delta16 < 0 || b->n_delta8 + b->n_delta16 != b->n_cpg))
+        return fail(c, MTH_ERR_INVALID, "MTH_CENC_DELTA8 needs blk_call_off, cpg_delta8 / cpg_delta with n_delta8 + n_delta16 == n_cpg");
     const bool lp = (c->prm.measures & MTH_LPMD) != 0;
     if (lp && b->n_rel && !b->rel_exc) return fail(c, MTH_ERR_INVALID, "rel_exc is required when n_rel > 0");
     if (b->mem_kind != 0 && b->mem_kind != 1) return fail(c, MTH_ERR_INVALID, "mem_kind must be 0 (host) or 1 (device)");
@@ -707,7 +715,9 @@ int mth_submit_compact(mth_ctx* c, const mth_batch_compact* b) {
 
     // Host batches go over in pieces of COMPACT_PIECE reads through two staging sets, so that the H2D copy of piece k+1
     // overlaps the expansion + ingest of piece k.  Device batches are expanded in place in one go.
-    const int64_t PIECE = b->mem_kind == 0 ? COMPACT_PIECE : b->n_reads;
+    // (the dense encodings address their arrays by block of the whole batch: no slicing — hand them over in batches of a
+    // few million reads, as the streaming host does anyway)
+    const int64_t PIECE = (b->mem_kind == 0 && b->enc == 0) ? COMPACT_PIECE : b->n_reads;
     int64_t x0 = 0, e0 = 0;  // calls / explicit query indices before the piece
     for (int64_t ra = 0; ra < b->n_reads; ra += PIECE) {
         const int64_t rb = std::min(b->n_reads, ra + PIECE);
@@ -724,28 +734,48 @@ int mth_submit_compact(mth_ctx* c, const mth_batch_compact* b) {
         const int bit_base = (int)(x0 & 7);
         ExpandArgs ea;
         memset(&ea, 0, sizeof(ea));
+        const size_t nblk = (nR + 255) / 256;
+        const bool s16 = (b->enc & MTH_CENC_START16) != 0, d8 = (b->enc & MTH_CENC_DELTA8) != 0;
+        // the arrays of this piece: {source, bytes}; order fixed, absent ones have 0 bytes
+        const void* src[12] = {s16 ? nullptr : (const void*)(b->start + ra), b->span + ra, b->mapq + ra, b->n_cpg8 + ra, b->flags + ra,
+                               d8 ? (const void*)b->cpg_delta : (const void*)(b->cpg_delta + x0), b->meth_bits + (x0 >> 3),
+                               b->rel_exc ? b->rel_exc + e0 : nullptr, b->start_off16, b->blk_start, b->start_exc, b->cpg_delta8};
+        const size_t sz[12] = {s16 ? 0 : nR * 4, nR * 2, nR, nR, nR, d8 ? (size_t)b->n_delta16 * 2 : (size_t)nI * 2,
+                               ((size_t)nI + bit_base + 7) / 8, (size_t)nE * 2, s16 ? nR * 2 : 0, s16 ? nblk * 4 : 0,
+                               s16 ? (size_t)b->n_start_exc * 4 : 0, d8 ? (size_t)b->n_delta8 : 0};
+        const void* ptr[13];  // device addresses the expansion reads (12 arrays + blk_call_off)
         if (b->mem_kind == 0) {
             const int set = c->stage_next;
             c->stage_next ^= 1;
             DevBuf* st = c->stage[set];
-            const size_t sz[8] = {nR * 4, nR * 2, nR, nR, nR, (size_t)nI * 2, ((size_t)nI + bit_base + 7) / 8, (size_t)nE * 2};
-            const void* src[8] = {b->start + ra, b->span + ra, b->mapq + ra, b->n_cpg8 + ra, b->flags + ra, b->cpg_delta + x0,
-                                  b->meth_bits + (x0 >> 3), b->rel_exc ? b->rel_exc + e0 : nullptr};
-            for (int k = 0; k < 8; k++) TRY(dev_reserve(c, st[k], sz[k] + 64, 0));
+            for (int k = 0; k < 12; k++) TRY(dev_reserve(c, st[k], sz[k] + 64, 0));
+            TRY(dev_reserve(c, st[12], (d8 ? nblk * 4 : 0) + 64, 0));
             if (c->stage_busy[set]) CUDA_TRY(c, cudaStreamWaitEvent(c->copy, c->ev_stage_free[set], 0));
-            for (int k = 0; k < 8; k++)
+            for (int k = 0; k < 12; k++) {
                 if (sz[k] && src[k]) CUDA_TRY(c, cudaMemcpyAsync(st[k].p, src[k], sz[k], cudaMemcpyHostToDevice, c->copy));
-            for (int k = 0; k < 8; k++) c->stats.h2d_bytes += (int64_t)sz[k];
+                c->stats.h2d_bytes += (int64_t)sz[k];
+                ptr[k] = st[k].p;
+            }
+            if (d8) {
+                CUDA_TRY(c, cudaMemcpyAsync(st[12].p, b->blk_call_off, nblk * 4, cudaMemcpyHostToDevice, c->copy));
+                c->stats.h2d_bytes += (int64_t)nblk * 4;
+            }
+            ptr[12] = st[12].p;
             CUDA_TRY(c, cudaEventRecord(c->ev_copy, c->copy));
             CUDA_TRY(c, cudaStreamWaitEvent(c->compute, c->ev_copy, 0));
-            ea.start = (const int32_t*)st[0].p; ea.span = (const uint16_t*)st[1].p; ea.mapq = (const uint8_t*)st[2].p;
-            ea.n_cpg8 = (const uint8_t*)st[3].p; ea.flags = (const uint8_t*)st[4].p; ea.cpg_delta = (const uint16_t*)st[5].p;
-            ea.meth_bits = (const uint8_t*)st[6].p; ea.rel_exc = (const uint16_t*)st[7].p;
             ea.bit_base = (uint32_t)bit_base;
         } else {
-            ea.start = b->start; ea.span = b->span; ea.mapq = b->mapq; ea.n_cpg8 = b->n_cpg8; ea.flags = b->flags;
-            ea.cpg_delta = b->cpg_delta; ea.meth_bits = b->meth_bits; ea.rel_exc = b->rel_exc;
+            for (int k = 0; k < 12; k++) ptr[k] = src[k];
+            ptr[0] = b->start; ptr[1] = b->span; ptr[2] = b->mapq; ptr[3] = b->n_cpg8; ptr[4] = b->flags; ptr[5] = b->cpg_delta;
+            ptr[6] = b->meth_bits; ptr[7] = b->rel_exc;
+            ptr[12] = b->blk_call_off;
         }
+        ea.start = (const int32_t*)ptr[0]; ea.span = (const uint16_t*)ptr[1]; ea.mapq = (const uint8_t*)ptr[2];
+        ea.n_cpg8 = (const uint8_t*)ptr[3]; ea.flags = (const uint8_t*)ptr[4]; ea.cpg_delta = (const uint16_t*)ptr[5];
+        ea.meth_bits = (const uint8_t*)ptr[6]; ea.rel_exc = (const uint16_t*)ptr[7];
+        ea.enc = b->enc;
+        ea.start_off16 = (const uint16_t*)ptr[8]; ea.blk_start = (const int32_t*)ptr[9]; ea.start_exc = (const int32_t*)ptr[10];
+        ea.cpg_delta8 = (const uint8_t*)ptr[11]; ea.blk_call_off = (const uint32_t*)ptr[12];
         const size_t nb = (nR + 255) / 256;
         TRY(dev_reserve(c, c->exp_blocks, nb * 8 + 64, 0));
         TRY(dev_reserve(c, c->exp_tot, 16, 0));

@@ -62,11 +62,18 @@ __global__ void __launch_bounds__(EXP_BLOCK) k_expand(ExpandArgs a) {
         if (a.rel_out && (fl & 4u)) ne = n;
     }
     uint32_t tot;
-    const uint32_t o_local = block_excl_scan(n, s_warp, &tot) + a.block_calls[blockIdx.x];  // block_calls: scanned in place
+    const uint32_t o_blk = block_excl_scan(n, s_warp, &tot);                 // call offset within this block of 256 reads
+    const uint32_t o_local = o_blk + a.block_calls[blockIdx.x];              // ... within the batch (block_calls: scanned in place)
     const uint32_t e_local = block_excl_scan(ne, s_warp, &tot) + a.block_rel[blockIdx.x];
     if (!in) return;
     const int64_t j = a.r0 + r;
-    const int32_t s = a.start[r];
+    int32_t s;
+    if (a.enc & MTH_CENC_START16) {
+        const int32_t bs = a.blk_start[blockIdx.x];
+        s = bs >= 0 ? bs + (int32_t)a.start_off16[r] : a.start_exc[(size_t)(-(bs + 1)) * EXP_BLOCK + threadIdx.x];
+    } else {
+        s = a.start[r];
+    }
     const int32_t s_lin = s + a.lin_off;
     a.start_out[j] = s_lin;
     a.end_out[j] = s_lin + (int32_t)a.span[r];
@@ -79,9 +86,16 @@ __global__ void __launch_bounds__(EXP_BLOCK) k_expand(ExpandArgs a) {
     }
     uint64_t mw = 0;
     const int32_t fwd = (int32_t)(fl & 1u);
+    // where this read's call deltas live: 16-bit offsets from start - 1, or (dense) 8/16-bit deltas from the previous call
+    const bool chained = (a.enc & MTH_CENC_DELTA8) != 0;
+    const uint32_t bco = chained ? a.blk_call_off[blockIdx.x] : 0u;
+    const bool wide = !chained || (bco & 0x80000000u);
+    const size_t dbase = chained ? (size_t)(bco & 0x7FFFFFFFu) + o_blk : (size_t)o_local;
+    int32_t d_acc = 0;
     for (uint32_t k = 0; k < n; k++) {
         const uint32_t x = o_local + k;
-        const int32_t d = a.cpg_delta[x];
+        int32_t d = wide ? (int32_t)a.cpg_delta[dbase + k] : (int32_t)a.cpg_delta8[dbase + k];
+        if (chained) { d_acc += d; d = d_acc; }
         a.pos_out[a.i0 + x] = s_lin - 1 + d;
         const uint32_t xb = x + a.bit_base;
         mw |= (uint64_t)((a.meth_bits[xb >> 3] >> (xb & 7)) & 1u) << k;

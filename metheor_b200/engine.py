@@ -60,6 +60,7 @@ class Context:
         if rc != 0:
             raise EngineError(rc, L.mth_last_error(None).decode())
         self._keep = []
+        self._copy_rows = True
 
     def _check(self, rc):
         if rc != 0:
@@ -108,7 +109,10 @@ class Context:
         mb = BatchCompact()
         mb.tid, mb.n_reads, mb.n_cpg, mb.n_rel = int(b["tid"]), int(b["n_reads"]), int(b["n_cpg"]), int(b["n_rel"])
         dt = dict(start=np.int32, span=np.uint16, mapq=np.uint8, n_cpg8=np.uint8, flags=np.uint8, cpg_delta=np.uint16,
-                  meth_bits=np.uint8, rel_exc=np.uint16)
+                  meth_bits=np.uint8, rel_exc=np.uint16, start_off16=np.uint16, blk_start=np.int32, start_exc=np.int32,
+                  cpg_delta8=np.uint8, blk_call_off=np.uint32)
+        mb.enc = int(b.get("enc", 0))
+        mb.n_start_exc, mb.n_delta8, mb.n_delta16 = int(b.get("n_start_exc", 0)), int(b.get("n_delta8", 0)), int(b.get("n_delta16", 0))
         dev = None
         for f, t in dt.items():
             x = b.get(f)
@@ -127,16 +131,20 @@ class Context:
     def add_skipped_reads(self, n_reads, n_mapq_ok):
         self._check(self._L.mth_add_skipped_reads(self._h, n_reads, n_mapq_ok))
 
-    @staticmethod
-    def _np(ptr, n, dtype, cols=None):
+    def _np(self, ptr, n, dtype, cols=None):
         if not ptr or n == 0:
             return np.zeros((0,) if cols is None else (0, cols), dtype)
         count = n * (cols or 1)
-        a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(np.ctypeslib.as_ctypes_type(dtype))), shape=(count,)).copy()
+        a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(np.ctypeslib.as_ctypes_type(dtype))), shape=(count,))
+        if self._copy_rows:
+            a = a.copy()
         return a if cols is None else a.reshape(n, cols)
 
     def finish(self, copy=True):
-        """-> dict measure -> rows (numpy copies).  With FLAG_KEEP_ON_DEVICE only row counts are returned."""
+        """-> dict measure -> rows.  copy=True: numpy copies owned by the caller; copy=False: zero-copy views of the
+        context's pinned result buffers (the C ABI's own contract: valid until the next finish / reset / close).
+        With FLAG_KEEP_ON_DEVICE only row counts are returned."""
+        self._copy_rows = bool(copy)
         r = Results()
         self._check(self._L.mth_finish(self._h, C.byref(r)))
         self._keep.clear()
@@ -213,7 +221,7 @@ def run_batches(batches, ref_len, measures, device=0, flags=0, seed=0, compact=F
         for k, b in enumerate(batches):
             if compact and (compact != "mix" or k % 2 == 0) and b["n_reads"] and \
                     np.diff(np.asarray(b["cpg_off"], np.int64)).max(initial=0) <= 64:
-                ctx.submit_compact(to_compact(b))
+                ctx.submit_compact(to_compact(b, dense=(compact == "dense" or (compact == "mix" and k % 4 == 0))))
             else:
                 ctx.submit(b)
         res = ctx.finish()

@@ -268,3 +268,36 @@ def test_compact_wire_format_equals_soa(golden):
     parity.check_all([dense, sparse], [20_000, 150_000], ALL, compact=True, pdr=dict(min_depth=4), mhl=dict(min_depth=4))
     with pytest.raises(ValueError):
         B.to_compact(dense)
+
+
+def test_dense_block_encodings_equal_soa(golden):
+    """MTH_CENC_START16 | MTH_CENC_DELTA8: 16-bit start offsets per block of 256 reads and 8-bit chained call deltas, with
+    per-block fall-back to the wide types (coverage gaps, long reads)."""
+    ov = dict(pdr=dict(min_depth=3, min_cpgs=2), mhl=dict(min_depth=3, min_cpgs=2), fdrp=dict(min_depth=3), qfdrp=dict(min_depth=3),
+              pm=dict(min_depth=3), me=dict(min_depth=3), lpmd=dict(want_pairs=1))
+    parity.check_all([parity.records_to_batch(golden["test4"]["reads"])], CHR1, ALL, compact="dense")
+    s = _synth(140, read_len=140, del_frac=0.5, del_max=60, nocall=0.05, lowq=0.15)
+    d = B.to_compact(s, dense=True)
+    assert d["enc"] == 3 and d["n_delta8"] > 0 and "start" not in d
+    parity.check_all([s], [200_000], ALL, compact="dense", **ov)
+    # a coverage gap wider than 65535 inside a block (32-bit start block) and a read with a 300-bp gap between calls (16-bit block)
+    a = _synth(141, length=400_000, cov=6.0)
+    keep = (a["start"] < 120_000) | (a["start"] > 260_000)
+    a = B.select_reads(a, keep)
+    longr = dict(tid=0, pos=395_000, flag=0, mapq=42, cigar="10M300N20M", xm="Z........." + "." * 10 + "Z........z")
+    lb = parity.records_to_batch([longr])
+    a2 = B.select_reads(a, a["start"] < 394_000)
+    d = B.to_compact(a2, dense=True)
+    assert d["n_start_exc"] == 256 and (d["blk_start"] < 0).sum() == 1
+    dl = B.to_compact(lb, dense=True)
+    assert dl["n_delta16"] == 3 and dl["n_delta8"] == 0
+    parity.check_all([a2, lb], [400_000], ALL, compact="dense", **ov)
+    # several batches / contigs, all three wire formats interleaved
+    lens = [150_000, 80_000, 120_000]
+    batches = []
+    for tid, L in enumerate(lens):
+        x = _synth(150 + tid, length=L, cov=25.0, tid=tid)
+        cuts = [0, x["n_reads"] // 4, x["n_reads"] // 2, (3 * x["n_reads"]) // 4, x["n_reads"]]
+        batches += [B.slice_reads(x, lo, hi) for lo, hi in zip(cuts[:-1], cuts[1:])]
+    parity.check_all(batches, lens, ALL, compact="dense")
+    parity.check_all(batches, lens, ALL, compact="mix")
