@@ -40,7 +40,8 @@ const size_t TASK_RECORDS = 4096;
 const int RING = 3;
 
 struct PinnedBatch {
-    enum { START, END, META, OFF, POS, REL, METH, MOFF, SPAN, MAPQ, NCPG, FLAGS, DELTA, BITS, RELX, NARR };
+    enum { START, END, META, OFF, POS, REL, METH, MOFF, SPAN, MAPQ, NCPG, FLAGS, DELTA, BITS, RELX, SOFF16, BLKSTART, STARTEXC, DELTA8,
+           BLKCALL, DELTA16, NARR };
     void* p[NARR] = {nullptr};
     size_t cap[NARR] = {0};
     ~PinnedBatch() {
@@ -151,8 +152,9 @@ void assemble(ThreadPool& pool, std::vector<SoaChunk>& chunks, size_t c0, size_t
 }
 
 // Same reads in the compact wire format (mth_batch_compact): 9 B per read + 2.125 B per call over PCIe instead of 24 + 6.
-void assemble_compact(ThreadPool& pool, std::vector<SoaChunk>& chunks, size_t nc, int32_t tid, bool want_rel, PinnedBatch& pb,
-                      mth_batch_compact* b) {
+// dense = also the block encodings MTH_CENC_START16 | MTH_CENC_DELTA8 (7 B per read + 1.125 B per call on short-read data).
+void assemble_compact(ThreadPool& pool, std::vector<SoaChunk>& chunks, size_t nc, int32_t tid, bool want_rel, bool dense,
+                      PinnedBatch& pb, mth_batch_compact* b) {
     std::vector<size_t> r_off(nc + 1, 0), i_off(nc + 1, 0), e_off(nc + 1, 0);
     for (size_t k = 0; k < nc; k++) {
         const SoaChunk& ch = chunks[k];
@@ -195,8 +197,11 @@ void assemble_compact(ThreadPool& pool, std::vector<SoaChunk>& chunks, size_t nc
             ncpg[r0 + r] = (uint8_t)nr;
             const bool cx = want_rel && (m & SOA_META_COMPLEX);
             flags[r0 + r] = (uint8_t)(((m >> 8) & 1u) | (cx ? MTH_CFLAG_REL_EXPLICIT : 0u));
+            int32_t prev = s - 1;
             for (uint32_t q = 0; q < nr; q++, c++, x++) {
-                delta[x] = (uint16_t)(ch.cpg_pos[c] - (s - 1));
+                // dense: delta from the previous call of the read (MTH_CENC_DELTA8); plain: offset from start - 1
+                delta[x] = (uint16_t)(ch.cpg_pos[c] - (dense ? prev : s - 1));
+                prev = ch.cpg_pos[c];
                 if (ch.cpg_meth[c]) {
                     const size_t by = x >> 3;
                     const uint8_t bit = (uint8_t)(1u << (x & 7));
@@ -215,6 +220,72 @@ void assemble_compact(ThreadPool& pool, std::vector<SoaChunk>& chunks, size_t nc
     b->n_rel = (int64_t)E;
     b->start = start; b->span = span; b->mapq = mapq; b->n_cpg8 = ncpg; b->flags = flags;
     b->cpg_delta = delta; b->meth_bits = bits; b->rel_exc = relx;
+    if (!dense || R == 0) return;
+
+    // ---- block encodings: blocks of MTH_CBLOCK reads; `start` (32-bit) and `delta` (16-bit, chained) are the wide forms ----
+    const size_t nb = (R + MTH_CBLOCK - 1) / MTH_CBLOCK;
+    pb.reserve(PinnedBatch::SOFF16, R * 2); pb.reserve(PinnedBatch::BLKSTART, nb * 4); pb.reserve(PinnedBatch::BLKCALL, nb * 4);
+    pb.reserve(PinnedBatch::DELTA8, I + 64); pb.reserve(PinnedBatch::DELTA16, I * 2 + 64);
+    uint16_t* soff = (uint16_t*)pb.p[PinnedBatch::SOFF16];
+    int32_t* blk_start = (int32_t*)pb.p[PinnedBatch::BLKSTART];
+    uint32_t* blk_call = (uint32_t*)pb.p[PinnedBatch::BLKCALL];
+    uint8_t* d8 = (uint8_t*)pb.p[PinnedBatch::DELTA8];
+    uint16_t* d16 = (uint16_t*)pb.p[PinnedBatch::DELTA16];
+    std::vector<size_t> call0(nb + 1, 0);       // first call of each block
+    std::vector<uint8_t> wide_s(nb, 0), wide_c(nb, 0);
+    {
+        size_t x = 0;
+        for (size_t blk = 0; blk < nb; blk++) {
+            call0[blk] = x;
+            const size_t r1 = std::min(R, (blk + 1) * (size_t)MTH_CBLOCK);
+            for (size_t r = blk * MTH_CBLOCK; r < r1; r++) x += ncpg[r];
+        }
+        call0[nb] = x;
+    }
+    pool.run((int64_t)nb, [&](int64_t blk, int) {
+        const size_t r0 = (size_t)blk * MTH_CBLOCK, r1 = std::min(R, r0 + (size_t)MTH_CBLOCK);
+        wide_s[(size_t)blk] = (int64_t)start[r1 - 1] - (int64_t)start[r0] > 65535;  // reads are sorted: first = smallest
+        uint16_t mx = 0;
+        for (size_t x = call0[(size_t)blk]; x < call0[(size_t)blk + 1]; x++) mx = std::max(mx, delta[x]);
+        wide_c[(size_t)blk] = mx > 255;
+    });
+    size_t n_exc = 0, n8 = 0, n16 = 0;
+    std::vector<size_t> off8(nb), off16(nb), exc_idx(nb);
+    for (size_t blk = 0; blk < nb; blk++) {
+        const size_t ncall = call0[blk + 1] - call0[blk];
+        exc_idx[blk] = n_exc;
+        if (wide_s[blk]) n_exc++;
+        off8[blk] = n8; off16[blk] = n16;
+        if (wide_c[blk]) n16 += ncall; else n8 += ncall;
+    }
+    pb.reserve(PinnedBatch::STARTEXC, n_exc * MTH_CBLOCK * 4 + 64);
+    int32_t* start_exc = (int32_t*)pb.p[PinnedBatch::STARTEXC];
+    pool.run((int64_t)nb, [&](int64_t blk_, int) {
+        const size_t blk = (size_t)blk_;
+        const size_t r0 = blk * MTH_CBLOCK, r1 = std::min(R, r0 + (size_t)MTH_CBLOCK);
+        if (wide_s[blk]) {
+            blk_start[blk] = -(int32_t)(1 + exc_idx[blk]);
+            int32_t* e = start_exc + exc_idx[blk] * MTH_CBLOCK;
+            for (size_t r = r0; r < r0 + MTH_CBLOCK; r++) e[r - r0] = r < r1 ? start[r] : 0;
+            for (size_t r = r0; r < r1; r++) soff[r] = 0;
+        } else {
+            blk_start[blk] = start[r0];
+            for (size_t r = r0; r < r1; r++) soff[r] = (uint16_t)(start[r] - start[r0]);
+        }
+        const size_t c0 = call0[blk], c1 = call0[blk + 1];
+        if (wide_c[blk]) {
+            blk_call[blk] = (uint32_t)off16[blk] | 0x80000000u;
+            memcpy(d16 + off16[blk], delta + c0, (c1 - c0) * 2);
+        } else {
+            blk_call[blk] = (uint32_t)off8[blk];
+            for (size_t x = c0; x < c1; x++) d8[off8[blk] + (x - c0)] = (uint8_t)delta[x];
+        }
+    });
+    b->enc = MTH_CENC_START16 | MTH_CENC_DELTA8;
+    b->start = nullptr;
+    b->start_off16 = soff; b->blk_start = blk_start; b->start_exc = start_exc; b->n_start_exc = (int64_t)(n_exc * MTH_CBLOCK);
+    b->cpg_delta8 = d8; b->blk_call_off = blk_call; b->cpg_delta = d16;
+    b->n_delta8 = (int64_t)n8; b->n_delta16 = (int64_t)n16;
 }
 
 // ---- TSV ----------------------------------------------------------------------------------------------------
@@ -444,7 +515,7 @@ void run(const mthh_options& o) {
                 int rc;
                 if (seg.max_cpgs <= 64 && seg.max_span <= 65024) {  // compact wire format: ~1/3 of the PCIe bytes
                     mth_batch_compact b;
-                    assemble_compact(pool, chunks, n_tasks, tid, want_rel, pb, &b);
+                    assemble_compact(pool, chunks, n_tasks, tid, want_rel, /*dense=*/true, pb, &b);
                     s_assemble += now_s() - t0;
                     t0 = now_s();
                     rc = mth_submit_compact(G.ctx, &b);

@@ -24,10 +24,20 @@ def _oracle_cli(*args):
     return subprocess.run([oracle_lib.CLI_PATH, *map(str, args)], capture_output=True, text=True)
 
 
-def _both(tmp_path, measure, bam, *flags, expect_rows=None):
+_FLAG_FIELD = {"-d": "min_depth", "-p": "min_cpgs", "-q": "min_qual", "-D": "max_depth", "-l": "min_overlap", "-m": "min_distance",
+               "-M": "max_distance", "-c": "cpg_set", "--seed": "seed"}
+
+
+def _both(tmp_path, measure, bam, *flags, expect_rows=None, binary=False):
+    """Engine vs oracle CLI on the same file.  binary=True spawns `metheor`; otherwise the same code runs through the
+    library entry point mthh_run (what the binary calls), which saves a process + CUDA start-up per case."""
     a, b = str(tmp_path / f"{measure}.engine.tsv"), str(tmp_path / f"{measure}.oracle.tsv")
-    r = host.cli(measure, "-i", bam, "-o", a, *flags)
-    assert r.returncode == 0, r.stderr
+    if binary:
+        r = host.cli(measure, "-i", bam, "-o", a, *flags)
+        assert r.returncode == 0, r.stderr
+    else:
+        kw = {_FLAG_FIELD[flags[i]]: (flags[i + 1] if flags[i] == "-c" else int(flags[i + 1])) for i in range(0, len(flags), 2)}
+        host.run(measure, bam, a, **kw)
     o = _oracle_cli(measure, "-i", bam, "-o", b, *flags)
     assert o.returncode == 0, o.stderr
     ta, tb = open(a).read(), open(b).read()
@@ -40,7 +50,7 @@ def _both(tmp_path, measure, bam, *flags, expect_rows=None):
 @pytest.mark.parametrize("name", ["test1", "test2", "test3", "test4", "test5", "test6"])
 def test_fixture_bams_default_flags(fixture_bams, tmp_path, name):
     for m in MEASURES:
-        _both(tmp_path, m, fixture_bams[name])
+        _both(tmp_path, m, fixture_bams[name], binary=(name == "test1"))
 
 
 def test_fixture_expected_rows_from_survey_appendix_b(fixture_bams, tmp_path):
@@ -73,7 +83,7 @@ def test_random_records_three_contigs(tmp_path):
     assert open(pa).read() == open(pb).read() and open(pa).read().count("\n") > 100
     sam = str(tmp_path / "r.sam")
     bamio.write_sam(sam, REFS, reads)
-    _both(tmp_path, "pdr", sam, "-d", 2, "-p", 2)
+    _both(tmp_path, "pdr", sam, "-d", 2, "-p", 2, binary=True)
 
 
 def test_synthetic_wgbs_default_flags_and_cpg_set(tmp_path):
