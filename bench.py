@@ -168,7 +168,7 @@ def run_reference(args, rank):
                                        f"like the reference), not the Rust binary"},
             "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "host": {"nproc": os.cpu_count()}, "wall_s": time.perf_counter() - t_all0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def bam_leg(b, n_reads, length):
@@ -227,7 +227,23 @@ def ensure_built():
             time.sleep(2.0)
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line on stdout.  Everything else any library prints (NCCL's version banner, ...) was routed to stderr."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # stray prints of libraries go to stderr; emit() writes the result to the real stdout
     ensure_built()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -456,7 +472,7 @@ def main():
                 "launches_per_step": int(st["kernel_launches"]),
                 "roofline": roofline, "roofline_step": roofline_step, "kernels": kern, "cpu_baseline": cpu, "cpu_baseline_all_cores": cpu_all, "bam_end_to_end": bam,
                 "clocks": clocks, "pdr_path": {1: "scatter", 2: "gather"}.get(st["pdr_path"]), "lpmd": float(rows["lpmd"]["lpmd"])}
-        print(json.dumps(line))
+        emit(line)
     ctx.close(); ectx.close()
     if world > 1:
         dist.destroy_process_group()
