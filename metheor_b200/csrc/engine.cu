@@ -774,6 +774,7 @@ int mth_submit_compact(mth_ctx* c, const mth_batch_compact* b) {
         ea.n_cpg8 = (const uint8_t*)ptr[3]; ea.flags = (const uint8_t*)ptr[4]; ea.cpg_delta = (const uint16_t*)ptr[5];
         ea.meth_bits = (const uint8_t*)ptr[6]; ea.rel_exc = (const uint16_t*)ptr[7];
         ea.enc = b->enc;
+        ea.n_calls = nI; ea.n_delta8 = b->n_delta8; ea.n_delta16 = b->n_delta16; ea.n_rel = nE; ea.n_start_exc = b->n_start_exc;
         ea.start_off16 = (const uint16_t*)ptr[8]; ea.blk_start = (const int32_t*)ptr[9]; ea.start_exc = (const int32_t*)ptr[10];
         ea.cpg_delta8 = (const uint8_t*)ptr[11]; ea.blk_call_off = (const uint32_t*)ptr[12];
         const size_t nb = (nR + 255) / 256;

@@ -70,7 +70,13 @@ __global__ void __launch_bounds__(EXP_BLOCK) k_expand(ExpandArgs a) {
     int32_t s;
     if (a.enc & MTH_CENC_START16) {
         const int32_t bs = a.blk_start[blockIdx.x];
-        s = bs >= 0 ? bs + (int32_t)a.start_off16[r] : a.start_exc[(size_t)(-(bs + 1)) * EXP_BLOCK + threadIdx.x];
+        const int64_t xi = bs >= 0 ? 0 : (int64_t)(-(bs + 1)) * EXP_BLOCK + threadIdx.x;
+        if (xi >= a.n_start_exc && bs < 0) {
+            atomicOr(a.err, ERRBIT_BAD_OFFSETS);
+            s = 0;
+        } else {
+            s = bs >= 0 ? bs + (int32_t)a.start_off16[r] : a.start_exc[xi];
+        }
     } else {
         s = a.start[r];
     }
@@ -84,6 +90,10 @@ __global__ void __launch_bounds__(EXP_BLOCK) k_expand(ExpandArgs a) {
         atomicOr(a.err, ERRBIT_TOO_MANY_CPGS);
         n = 64;
     }
+    if ((int64_t)o_local + n > a.n_calls) {  // per-read counts exceed the declared number of calls: corrupt batch
+        atomicOr(a.err, ERRBIT_BAD_OFFSETS);
+        n = 0;
+    }
     uint64_t mw = 0;
     const int32_t fwd = (int32_t)(fl & 1u);
     // where this read's call deltas live: 16-bit offsets from start - 1, or (dense) 8/16-bit deltas from the previous call
@@ -91,6 +101,11 @@ __global__ void __launch_bounds__(EXP_BLOCK) k_expand(ExpandArgs a) {
     const uint32_t bco = chained ? a.blk_call_off[blockIdx.x] : 0u;
     const bool wide = !chained || (bco & 0x80000000u);
     const size_t dbase = chained ? (size_t)(bco & 0x7FFFFFFFu) + o_blk : (size_t)o_local;
+    if ((chained && (int64_t)(dbase + n) > (wide ? a.n_delta16 : a.n_delta8)) ||
+        (a.rel_out && (fl & 4u) && (int64_t)e_local + n > a.n_rel)) {
+        atomicOr(a.err, ERRBIT_BAD_OFFSETS);
+        n = 0;
+    }
     int32_t d_acc = 0;
     for (uint32_t k = 0; k < n; k++) {
         const uint32_t x = o_local + k;

@@ -36,6 +36,7 @@ struct ExpandArgs {
     const int32_t* start; const uint16_t* span; const uint8_t* mapq; const uint8_t* n_cpg8; const uint8_t* flags;
     const uint16_t* cpg_delta; const uint8_t* meth_bits; const uint16_t* rel_exc;
     uint32_t bit_base;        // bit of meth_bits[0] that belongs to the first call (pieces of a batch start mid-byte)
+    int64_t n_calls, n_delta8, n_delta16, n_rel, n_start_exc;  // declared sizes: a batch whose per-read counts disagree is reported, never read out of bounds
     uint32_t enc;             // MTH_CENC_* dense encodings (whole batches only)
     const uint16_t* start_off16; const int32_t* blk_start; const int32_t* start_exc;
     const uint8_t* cpg_delta8; const uint32_t* blk_call_off;

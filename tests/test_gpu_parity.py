@@ -301,3 +301,40 @@ def test_dense_block_encodings_equal_soa(golden):
         batches += [B.slice_reads(x, lo, hi) for lo, hi in zip(cuts[:-1], cuts[1:])]
     parity.check_all(batches, lens, ALL, compact="dense")
     parity.check_all(batches, lens, ALL, compact="mix")
+
+
+def test_compact_error_paths_and_reserve():
+    b = _synth(160, length=60_000, cov=8.0)
+    c = B.to_compact(b, dense=True)
+    ctx = engine.Context(engine.default_params(ALL), [60_000])
+    try:
+        assert ctx._L.mth_reserve(ctx._h, 10_000_000, 40_000_000) == 0  # capacity hint: harmless, clamped to free memory
+        bad = dict(c, enc=8)
+        with pytest.raises(engine.EngineError) as e:
+            ctx.submit_compact(bad)
+        assert e.value.code == engine._lib.ERR_INVALID
+        ctx.reset()
+        bad = dict(c, n_delta8=c["n_delta8"] - 1)  # n_delta8 + n_delta16 != n_cpg
+        with pytest.raises(engine.EngineError):
+            ctx.submit_compact(bad)
+        ctx.reset()
+        bad = dict(c)
+        bad["n_cpg8"] = c["n_cpg8"].copy()
+        bad["n_cpg8"][5] = 200  # more than 64 calls in a compact read: reported, never silently truncated
+        with pytest.raises(engine.EngineError) as e:
+            ctx.submit_compact(bad)
+            ctx.finish()
+        assert e.value.code in (engine._lib.ERR_UNSUPPORTED, engine._lib.ERR_INVALID)
+        ctx.reset()
+        plain = B.to_compact(b)
+        unsorted_ = dict(plain, start=plain["start"][::-1].copy())
+        with pytest.raises(engine.EngineError) as e:
+            ctx.submit_compact(unsorted_)
+            ctx.finish()
+        assert e.value.code in (engine._lib.ERR_UNSORTED, engine._lib.ERR_INVALID)
+        ctx.reset()
+        ctx.submit_compact(c)  # the context is still usable after the failures
+        res = ctx.finish()
+        assert res["pdr"]["n"] >= 0 and res["lpmd"]["n_read"] == b["n_reads"]
+    finally:
+        ctx.close()
