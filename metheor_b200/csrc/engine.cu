@@ -948,8 +948,12 @@ static int process_region(mth_ctx* c) {
             TRY(dev_reserve(c, c->fdrp_scratch, sb, 0));
             {
                 ProfScope ps(c, q ? "k_qfdrp" : "k_fdrp");
+                CUDA_TRY(c, cudaMemsetAsync(c->gfallback.p, 0, (size_t)C, s));
+                ps.add(launch_fdrp_tile(rv, site_pos, C, (const unsigned long long*)c->bitmap.p, n_words, (const uint32_t*)c->word_prefix.p,
+                                        d_sc, fp, q, c->prm.seed, ct, (float*)c->value[m].p, (uint32_t*)c->rowcnt[m].p,
+                                        (uint8_t*)c->gfallback.p, s));
                 ps.add(launch_fdrp(rv, site_pos, C, d_sc, fp, q, c->prm.seed, ct, c->fdrp_scratch.p, sb, (float*)c->value[m].p,
-                                   (uint32_t*)c->rowcnt[m].p, &d_sc->err, s));
+                                   (uint32_t*)c->rowcnt[m].p, (const uint8_t*)c->gfallback.p, s));
             }
             ProfScope ps(c, q ? "qfdrp_rows_count" : "fdrp_rows_count");
             ps.add(launch_exclusive_scan_u32((uint32_t*)c->rowcnt[m].p, C, scratch, d_tot + m, s));

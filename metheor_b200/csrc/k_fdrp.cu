@@ -213,7 +213,7 @@ struct FdrpPolicy {
 __global__ void __launch_bounds__(GATHER_BLOCK, 4) k_fdrp(ReadsView rv, const int32_t* __restrict__ site_pos, int64_t C,
                                                        const RegionScalars* __restrict__ scal, mth_fdrp_params prm, int quant,
                                                        uint64_t seed, ContigTable ct, char* scratch, float* __restrict__ value,
-                                                       uint32_t* __restrict__ rowcnt) {
+                                                       uint32_t* __restrict__ rowcnt, const uint8_t* __restrict__ only) {
     __shared__ uint32_t sU[FDRP_WARPS][FDRP_UWORDS + 1];
     __shared__ uint32_t sP[FDRP_WARPS][FDRP_UWORDS + 1];
     const int warp = threadIdx.x >> 5;
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(GATHER_BLOCK, 4) k_fdrp(ReadsView rv, const in
     fs.mm = fs.cm + Dp * FDRP_MAXW;
     fs.vm = fs.mm + Dp * FDRP_MAXW;
     FdrpPolicy pol(rv, prm, quant != 0, seed, ct, value, rowcnt, fs, sU[warp], sP[warp]);
-    gather_sites(rv, site_pos, C, scal->lmax, pol);
+    gather_sites(rv, site_pos, C, scal->lmax, pol, only);
 }
 
 // grid is bounded so that the per-warp scratch stays below ~2 GB even for very large max_depth
@@ -253,11 +253,11 @@ size_t fdrp_scratch_bytes(mth_fdrp_params prm, int) {
 
 int launch_fdrp(const ReadsView& rv, const int32_t* site_pos, int64_t C, const RegionScalars* sc, mth_fdrp_params prm,
                 int quantitative, uint64_t seed, ContigTable ct, void* scratch, size_t scratch_bytes, float* value,
-                uint32_t* rowcnt, uint32_t*, cudaStream_t s) {
+                uint32_t* rowcnt, const uint8_t* only, cudaStream_t s) {
     if (C <= 0) return 0;
     int g = fdrp_grid(C, prm.max_depth);
     if ((size_t)g * fdrp_per_warp_bytes(prm.max_depth) * FDRP_WARPS > scratch_bytes) return 0;
-    k_fdrp<<<g, GATHER_BLOCK, 0, s>>>(rv, site_pos, C, sc, prm, quantitative, seed, ct, (char*)scratch, value, rowcnt);
+    k_fdrp<<<g, GATHER_BLOCK, 0, s>>>(rv, site_pos, C, sc, prm, quantitative, seed, ct, (char*)scratch, value, rowcnt, only);
     return 1;
 }
 

@@ -118,7 +118,12 @@ int launch_lpmd_pairs_emit(const ReadsView& rv, const uint16_t* rel, const int32
 // ---- FDRP / qFDRP (k_fdrp.cu) ---------------------------------------------------------------
 int launch_fdrp(const ReadsView& rv, const int32_t* site_pos, int64_t C, const RegionScalars* sc, mth_fdrp_params prm,
                 int quantitative, uint64_t seed, ContigTable ct, void* scratch, size_t scratch_bytes, float* value,
-                uint32_t* rowcnt, uint32_t* err, cudaStream_t s);
+                uint32_t* rowcnt, const uint8_t* only, cudaStream_t s);  // only != nullptr: just the flagged sites
+// tile form (k_fdrp_tile.cu): takes every site whose tile fits shared memory, flags the rest in fallback[] (C bytes, zeroed by
+// the caller) for launch_fdrp(..., only = fallback)
+int launch_fdrp_tile(const ReadsView& rv, const int32_t* site_pos, int64_t C, const unsigned long long* bitmap, int64_t n_words,
+                     const uint32_t* word_prefix, const RegionScalars* sc, mth_fdrp_params prm, int quantitative, uint64_t seed,
+                     ContigTable ct, float* value, uint32_t* rowcnt, uint8_t* fallback, cudaStream_t s);
 size_t fdrp_scratch_bytes(mth_fdrp_params prm, int quantitative);
 
 }  // namespace mth
