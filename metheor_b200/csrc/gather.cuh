@@ -58,23 +58,34 @@ __device__ __forceinline__ void scan_window(const ReadsView& rv, int64_t lo, int
 }
 
 // Iterate the sites owned by this warp; body(s, p, lo, target) is called with the window lower bound maintained.
-// `only` != nullptr restricts the walk to the sites it flags (groups without a flagged site cost one load + ballot).
+// `only` != nullptr restricts the walk to the sites it flags.  Flagged sites cluster (CpG islands), so in that mode sites
+// are dealt to the warps one by one, round robin, instead of in runs of SITES_PER_WARP: neighbours land on different warps.
 template <class Body>
 __device__ __forceinline__ void for_each_site(const ReadsView& rv, const int32_t* __restrict__ site_pos, int64_t C,
                                               int32_t lmax, Body&& body, const uint8_t* __restrict__ only = nullptr) {
     const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    if (only) {
+        for (int64_t base = 0; base < C; base += n_warps * 32) {
+            // 32 candidate sites per warp and step: lane l looks at site base + (l * n_warps + warp_global)
+            const int64_t sl = base + (int64_t)lane_id() * n_warps + warp_global;
+            uint32_t want = __ballot_sync(FULL, sl < C && only[sl] != 0);
+            while (want) {
+                const int l = __ffs(want) - 1;
+                want &= want - 1;
+                const int64_t s = base + (int64_t)l * n_warps + warp_global;
+                const int32_t p = site_pos[s];
+                const int32_t target = p - lmax + 1;
+                const int64_t lo = warp_lower_bound(rv.start, rv.R, target);
+                body(s, p, lo, target);
+            }
+        }
+        return;
+    }
     for (int64_t s0 = warp_global * SITES_PER_WARP; s0 < C; s0 += n_warps * SITES_PER_WARP) {
         int64_t s1 = min(C, s0 + SITES_PER_WARP);
-        uint32_t want = FULL;
-        if (only) {
-            const int64_t sl = s0 + lane_id();
-            want = __ballot_sync(FULL, sl < s1 && only[sl] != 0);
-            if (!want) continue;
-        }
         int64_t lo = warp_lower_bound(rv.start, rv.R, site_pos[s0] - lmax + 1);
         for (int64_t s = s0; s < s1; s++) {
-            if (!((want >> (s - s0)) & 1u)) continue;
             const int32_t p = site_pos[s];
             const int32_t target = p - lmax + 1;
             while (lo + 32 <= rv.R && rv.start[lo + 31] < target) lo += 32;  // warp-uniform
