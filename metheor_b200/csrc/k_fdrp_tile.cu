@@ -164,10 +164,16 @@ __global__ void __launch_bounds__(FT_THREADS, 3) k_fdrp_tile(ReadsView rv, const
                     }
                     if (quant) {  // sequential f32 accumulation in pair order
                         uint32_t nz = __ballot_sync(FULL, term != 0.f);
-                        while (nz) {
-                            const int src = __ffs(nz) - 1;
-                            acc = __fadd_rn(acc, __shfl_sync(FULL, term, src));
-                            nz &= nz - 1;
+                        if (__popc(nz) > 8) {
+                            // dense step: fold all 32 lanes in order, branch-free (x + 0.0f == x exactly, acc >= 0)
+#pragma unroll
+                            for (int src = 0; src < 32; src++) acc = __fadd_rn(acc, __shfl_sync(FULL, term, src));
+                        } else {
+                            while (nz) {
+                                const int src = __ffs(nz) - 1;
+                                acc = __fadd_rn(acc, __shfl_sync(FULL, term, src));
+                                nz &= nz - 1;
+                            }
                         }
                     }
                 }
