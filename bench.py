@@ -501,7 +501,7 @@ def main():
                 "gpu_launches": int((st["kernel_launches"] - 0) * args.steps),
                 "launches_per_step": int(st["kernel_launches"]),
                 "roofline": roofline, "roofline_step": roofline_step, "kernels": kern, "cpu_baseline": cpu, "cpu_baseline_all_cores": cpu_all, "bam_end_to_end": bam,
-                "clocks": clocks, "pdr_path": {1: "scatter", 2: "gather"}.get(st["pdr_path"]), "lpmd": float(rows["lpmd"]["lpmd"]),
+                "clocks": clocks, "pdr_path": {1: "scatter", 2: "gather", 3: "scatter+gather(hazard sites)"}.get(st["pdr_path"]), "lpmd": float(rows["lpmd"]["lpmd"]),
                 "lpmd_all_ranks": lpmd_all}
         emit(line)
     ctx.close(); ectx.close()

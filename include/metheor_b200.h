@@ -211,7 +211,7 @@ typedef struct {
     int64_t kernel_launches;      /* engine kernels launched since create/reset */
     int64_t h2d_bytes, d2h_bytes; /* bytes copied since create/reset */
     int32_t max_ref_span;         /* longest end-start+1 seen */
-    int32_t pdr_path;             /* 0 none, 1 scatter (no segment hazard possible), 2 gather */
+    int32_t pdr_path;             /* 0 none, 1 scatter (no flush possible), 2 gather everywhere (MTH_FLAG_FORCE_GATHER), 3 scatter + gather on hazard sites */
     int32_t n_kernel_stats;
     struct { char name[32]; int64_t launches; double ms; } kernel[MTH_MAX_KERNEL_STATS]; /* MTH_FLAG_PROFILE */
 } mth_stats;

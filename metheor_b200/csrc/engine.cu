@@ -912,16 +912,27 @@ static int process_region(mth_ctx* c) {
         // ---------------- phase A: measure kernels + row counts + scans ----------------
         if (M & MTH_PDR) {
             TRY(dev_reserve(c, c->cnt2, (size_t)C * 8 + 8, 0));
-            bool gather = (c->prm.flags & MTH_FLAG_FORCE_GATHER) || sc.lmax > 150;
-            c->stats.pdr_path = gather ? 2 : 1;
-            if (gather) {
+            // 1 = scatter only (no read spans > 150 bases: no flush possible), 2 = gather everywhere (testing flag),
+            // 3 = scatter + segment-exact gather on the hazard sites only
+            const bool force = (c->prm.flags & MTH_FLAG_FORCE_GATHER) != 0;
+            c->stats.pdr_path = force ? 2 : (sc.lmax > 150 ? 3 : 1);
+            if (force) {
                 ProfScope ps(c, "k_pdr_gather");
-                ps.add(launch_pdr_gather(rv, site_pos, C, d_sc, (uint32_t*)c->cnt2.p, c->prm.pdr, s));
+                ps.add(launch_pdr_gather(rv, site_pos, C, d_sc, (uint32_t*)c->cnt2.p, c->prm.pdr, nullptr, s));
             } else {
                 CUDA_TRY(c, cudaMemsetAsync(c->cnt2.p, 0, (size_t)C * 8, s));
-                ProfScope ps(c, "k_pdr_scatter");
-                ps.add(launch_pdr_scatter(rv.cpg_pos, (const uint8_t*)c->a_flags.p, rv.I, (const unsigned long long*)c->bitmap.p, n_words,
-                                          (const uint32_t*)c->word_prefix.p, d_sc, (uint32_t*)c->cnt2.p, s));
+                {
+                    ProfScope ps(c, "k_pdr_scatter");
+                    ps.add(launch_pdr_scatter(rv.cpg_pos, (const uint8_t*)c->a_flags.p, rv.I, (const unsigned long long*)c->bitmap.p, n_words,
+                                              (const uint32_t*)c->word_prefix.p, d_sc, (uint32_t*)c->cnt2.p, s));
+                }
+                if (sc.lmax > 150) {
+                    ProfScope ps(c, "k_pdr_gather");
+                    CUDA_TRY(c, cudaMemsetAsync(c->gfallback.p, 0, (size_t)C, s));
+                    ps.add(launch_pdr_hazard(rv, (const unsigned long long*)c->bitmap.p, (const uint32_t*)c->word_prefix.p,
+                                             (uint8_t*)c->gfallback.p, s));
+                    ps.add(launch_pdr_gather(rv, site_pos, C, d_sc, (uint32_t*)c->cnt2.p, c->prm.pdr, (const uint8_t*)c->gfallback.p, s));
+                }
             }
             ProfScope ps(c, "pdr_rows_count");
             ps.add(launch_pdr_rowcnt((const uint32_t*)c->cnt2.p, C, c->prm.pdr.min_depth, (uint32_t*)c->rowcnt[M_PDR].p, s));

@@ -163,9 +163,28 @@ struct PdrGatherPolicy {
 
 __global__ void __launch_bounds__(GATHER_BLOCK) k_pdr_gather(ReadsView rv, const int32_t* __restrict__ site_pos, int64_t C,
                                                              const RegionScalars* __restrict__ sc,
-                                                             uint32_t* __restrict__ cnt2, mth_pdr_params prm) {
+                                                             uint32_t* __restrict__ cnt2, mth_pdr_params prm,
+                                                             const uint8_t* __restrict__ only) {
     PdrGatherPolicy pol(rv, prm, cnt2);
-    gather_sites(rv, site_pos, C, sc->lmax, pol);
+    gather_sites(rv, site_pos, C, sc->lmax, pol, only);
+}
+
+// Which sites can see a PDR flush at all?  A read j flushes the live CpG p (pdr.rs:160-177) iff p + 150 < first_cpg(j), and
+// that only matters if a LATER read still contributes to p, i.e. starts at or before p + 1 — so start(j) <= p + 1 as well.
+// Hence p lies in [start(j) - 1, first_cpg(j) - 151]: only reads whose first CpG call sits >= 150 bases behind their start
+// (long reads / reads with deletions and a CpG-free head) create hazard sites, and only those few sites need the
+// segment-exact gather kernel; everywhere else the scatter counts are provably what the reference reports.
+__global__ void __launch_bounds__(256) k_pdr_hazard(ReadsView rv, const unsigned long long* __restrict__ bitmap,
+                                                    const uint32_t* __restrict__ word_prefix, uint8_t* __restrict__ hazard) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= rv.R) return;
+    const uint32_t o0 = rv.cpg_off[j];
+    if (rv.cpg_off[j + 1] == o0) return;
+    const int32_t s = rv.start[j], first = rv.cpg_pos[o0];
+    if (first - s < 150) return;
+    // ranks of the sites with position in [s - 1, first - 151]: site_rank(x) = number of sites below x
+    const uint32_t r0 = site_rank(bitmap, word_prefix, s - 1), r1 = site_rank(bitmap, word_prefix, first - 150);
+    for (uint32_t r = r0; r < r1; r++) hazard[r] = 1;
 }
 
 __global__ void k_pdr_rowcnt(const uint32_t* __restrict__ cnt2, int64_t C, uint32_t min_depth,
@@ -210,9 +229,16 @@ int gather_grid(int64_t C) {
 }
 
 int launch_pdr_gather(const ReadsView& rv, const int32_t* site_pos, int64_t C, const RegionScalars* sc,
-                      uint32_t* cnt2, mth_pdr_params prm, cudaStream_t s) {
+                      uint32_t* cnt2, mth_pdr_params prm, const uint8_t* only, cudaStream_t s) {
     if (C <= 0) return 0;
-    k_pdr_gather<<<gather_grid(C), GATHER_BLOCK, 0, s>>>(rv, site_pos, C, sc, cnt2, prm);
+    k_pdr_gather<<<gather_grid(C), GATHER_BLOCK, 0, s>>>(rv, site_pos, C, sc, cnt2, prm, only);
+    return 1;
+}
+
+int launch_pdr_hazard(const ReadsView& rv, const unsigned long long* bitmap, const uint32_t* word_prefix, uint8_t* hazard,
+                      cudaStream_t s) {
+    if (rv.R <= 0) return 0;
+    k_pdr_hazard<<<grid_for(rv.R, 256), 256, 0, s>>>(rv, bitmap, word_prefix, hazard);
     return 1;
 }
 

@@ -65,7 +65,10 @@ int launch_exclusive_scan_u32(uint32_t* a, int64_t n, uint32_t* scratch, unsigne
 int launch_pdr_scatter(const int32_t* cpg_pos, const uint8_t* call_flags, int64_t n_calls, const unsigned long long* bitmap,
                        int64_t n_words, const uint32_t* word_prefix, const RegionScalars* sc, uint32_t* cnt2, cudaStream_t s);
 int launch_pdr_gather(const ReadsView& rv, const int32_t* site_pos, int64_t C, const RegionScalars* sc,
-                      uint32_t* cnt2, mth_pdr_params prm, cudaStream_t s);
+                      uint32_t* cnt2, mth_pdr_params prm, const uint8_t* only, cudaStream_t s);  // only != nullptr: flagged sites
+// hazard[rank] = 1 for the sites a PDR flush can touch (k_pdr.cu): the scatter counts are exact everywhere else
+int launch_pdr_hazard(const ReadsView& rv, const unsigned long long* bitmap, const uint32_t* word_prefix, uint8_t* hazard,
+                      cudaStream_t s);
 // rowcnt[s] = 1 iff site s yields a row
 int launch_pdr_rowcnt(const uint32_t* cnt2, int64_t C, uint32_t min_depth, uint32_t* rowcnt, cudaStream_t s);
 struct SiteRowsDev { int32_t* tid; int32_t* pos; float* value; uint32_t* n_conc; uint32_t* n_disc; };

@@ -98,7 +98,7 @@ def test_synthetic_long_spans_segment_hazards():
     b = _synth(14, read_len=140, del_frac=0.5, del_max=60, nocall=0.05, lowq=0.15)
     res, st = parity.check_all([b], [200_000], ALL, pdr=dict(min_depth=3, min_cpgs=2), mhl=dict(min_depth=3, min_cpgs=2),
                                fdrp=dict(min_depth=3), qfdrp=dict(min_depth=3), pm=dict(min_depth=3), me=dict(min_depth=3))
-    assert st["pdr_path"] == 2 and st["max_ref_span"] > 150
+    assert st["pdr_path"] == 3 and st["max_ref_span"] > 150  # scatter + segment-exact gather on the hazard sites
 
 
 def test_synthetic_dense_islands_many_cpgs_per_read():
@@ -338,3 +338,19 @@ def test_compact_error_paths_and_reserve():
         assert res["pdr"]["n"] >= 0 and res["lpmd"]["n_read"] == b["n_reads"]
     finally:
         ctx.close()
+
+
+def test_pdr_flush_segment_is_replayed_on_hazard_sites_only():
+    """A constructed PDR flush (pdr.rs:160-177): read T (a 200-base skip, first CpG 212 bases behind its start) flushes the
+    CpGs of read A before read B contributes to the same CpG again -> the reference reports B's segment only."""
+    reads = [dict(tid=0, pos=100, flag=0, mapq=42, cigar="20M", xm=".....Z....Z........."),   # A: CpGs 105 (Z), 110 (Z)
+             dict(tid=0, pos=101, flag=0, mapq=42, cigar="10M200N20M", xm="." * 10 + "..Z......z.........."),  # T: first CpG 313
+             dict(tid=0, pos=104, flag=0, mapq=42, cigar="20M", xm=".z....Z............."),    # B: CpGs 105 (z), 110 (Z) -> discordant
+             dict(tid=0, pos=300, flag=0, mapq=42, cigar="20M", xm=".............Z......")]    # C: CpG 313
+    b = parity.records_to_batch(reads)
+    res, st = parity.check_all([b], [10_000], ("pdr",), pdr=dict(min_depth=1, min_cpgs=1, min_qual=10))
+    assert st["pdr_path"] == 3
+    r = res["pdr"]
+    got = {int(p): (int(c), int(d)) for p, c, d in zip(r["pos"], r["n_conc"], r["n_disc"])}
+    assert got[105] == (0, 1) and got[110] == (0, 1), got   # only B's segment survives (A's was flushed, then overwritten)
+    assert got[313] == (1, 1)                               # T (discordant) + C
