@@ -150,3 +150,19 @@ def test_edge_inputs(tmp_path):
     open(bed, "w").write("chr1\t199999\t200001\n")
     for m in ("pdr", "lpmd", "pm"):
         _both(tmp_path, m, bam, "-c", bed)
+
+
+def test_reads_with_more_than_64_calls_take_the_soa_batch(tmp_path):
+    """A window that holds a read with > 64 CpG calls cannot use the compact wire format: the host falls back to the SoA
+    batch with meth_off for it (DESIGN.md 'Limits': up to 256 calls per read)."""
+    rng = np.random.default_rng(5)
+    reads = []
+    for i in range(400):
+        n = 120
+        xm = "".join(rng.choice(list("zZ"), n)) if i % 3 == 0 else "".join(rng.choice(list("zZ.."), n))
+        reads.append(dict(tid=0, pos=int(100 + i // 4), flag=int(rng.choice([0, 16])), mapq=42, cigar=f"{n}M", xm=xm))
+    bam = str(tmp_path / "dense.bam")
+    bamio.write_bam(bam, REFS, reads)
+    for m in MEASURES:
+        t = _both(tmp_path, m, bam, *(() if m == "lpmd" else ("-d", 5)))
+        assert t.count("\n") > (1 if m == "lpmd" else 50), m
