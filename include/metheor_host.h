@@ -78,6 +78,12 @@ void mthh_decoded_free(mthh_decoded* d);
 /* Rust `{}` formatting of an f32 (shortest round-trip digits, positional, "NaN", "inf", "-0"); returns length. */
 int mthh_format_f32(float v, char* buf, int cap);
 
+/* The host's own raw-DEFLATE decoder (host/inflate_fast.cpp), exposed for its tests: decodes in[0,in_len) into exactly
+ * out_len bytes; 1 on success, 0 if it rejects the stream (the BGZF reader then falls back to zlib).
+ * mthh_zlib_fallbacks: how many BGZF members this process handed to zlib after the fast decoder rejected them. */
+int mthh_inflate_raw(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_len);
+int64_t mthh_zlib_fallbacks(void);
+
 #ifdef __cplusplus
 }
 #endif

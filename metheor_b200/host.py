@@ -28,7 +28,8 @@ class Decoded(C.Structure):
                 ("cpg_meth", C.c_void_p)]
 
 
-EXPORTS = ["mthh_options_default", "mthh_run", "mthh_main", "mthh_decode_file", "mthh_decoded_free", "mthh_format_f32"]
+EXPORTS = ["mthh_options_default", "mthh_run", "mthh_main", "mthh_decode_file", "mthh_decoded_free", "mthh_format_f32", "mthh_inflate_raw",
+           "mthh_zlib_fallbacks"]
 
 
 class HostError(RuntimeError):
@@ -57,6 +58,8 @@ def lib():
         L.mthh_decode_file.restype = C.c_int
         L.mthh_decoded_free.argtypes = [C.POINTER(Decoded)]; L.mthh_decoded_free.restype = None
         L.mthh_format_f32.argtypes = [C.c_float, C.c_char_p, C.c_int]; L.mthh_format_f32.restype = C.c_int
+        L.mthh_inflate_raw.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]; L.mthh_inflate_raw.restype = C.c_int
+        L.mthh_zlib_fallbacks.argtypes = []; L.mthh_zlib_fallbacks.restype = C.c_int64
         _lib = L
     return _lib
 
@@ -108,6 +111,17 @@ def format_f32(v):
     buf = C.create_string_buffer(128)
     n = lib().mthh_format_f32(C.c_float(v), buf, 128)
     return buf.raw[:n].decode()
+
+
+def inflate_raw(data, out_len):
+    """The host's own DEFLATE decoder on one raw stream -> bytes, or None if it rejects the stream."""
+    out = C.create_string_buffer(max(out_len, 1))
+    ok = lib().mthh_inflate_raw(data, len(data), out, out_len)
+    return out.raw[:out_len] if ok else None
+
+
+def zlib_fallbacks():
+    return int(lib().mthh_zlib_fallbacks())
 
 
 def cli(*args, **kw):

@@ -13,6 +13,7 @@
 #include "../../include/metheor_b200.h"
 #include "../../include/metheor_host.h"
 #include "decode.hpp"
+#include "inflate_fast.hpp"
 #include "input.hpp"
 
 namespace mthh {
@@ -181,6 +182,11 @@ int mthh_run(const mthh_options* o, char* err, size_t errcap) {
 }
 
 int mthh_format_f32(float v, char* buf, int cap) { return mthh::format_f32(v, buf, cap); }
+
+int mthh_inflate_raw(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_len) {
+    return mthh::inflate_fast(in, in_len, out, out_len) ? 1 : 0;
+}
+int64_t mthh_zlib_fallbacks(void) { return mthh::g_zlib_fallbacks.load(); }
 
 int mthh_main(int argc, char** argv) {
     const std::vector<CmdSpec> cmds = commands();

@@ -1,0 +1,441 @@
+// inflate_fast.cpp — a raw-DEFLATE decoder for BGZF members (RFC 1951), written for throughput: 64-bit bit buffer refilled
+// with unaligned 8-byte loads, one table lookup per symbol (11-bit literal/length table and 8-bit distance table with
+// second-level subtables for longer codes), word-wise match copies.  BGZF inflate bounds the BAM -> TSV path,
+// stock zlib needs ~4 ns per output byte, this decoder roughly half of that.
+//
+// Safety net: the caller (input.cpp) verifies the CRC32 of every member; a member this decoder rejects or decodes wrongly
+// is inflated again with zlib, so the worst a bug here can cost is speed.
+#include "inflate_fast.hpp"
+
+#include <cstring>
+
+namespace mthh {
+
+namespace {
+
+constexpr int LIT_TB = 11;   // primary table bits of the literal/length code
+constexpr int DIST_TB = 8;   // primary table bits of the distance code
+constexpr int PRE_TB = 7;    // the code-length code has codewords of at most 7 bits
+constexpr int MAX_CODE = 15;
+
+// A table entry, one 32-bit word:
+//   bits 0-4   bits to consume: codeword + extra bits (two codewords for a literal pair; the primary index bits for F_SUB)
+//   bits 5-8   codeword bits alone (extra bits sit above them in the bit buffer); for F_SUB: index bits of the subtable
+//   bit  9     F_LIT2: a literal entry carrying TWO literals (second byte in bits 24-31) — both codewords fit in the
+//              primary index, so literal runs decode two symbols per look-up
+//   bits 12-15 kind flag;  bits 16-31 literal byte(s) / base length / base distance / offset of the subtable.
+// Keeping "codeword + extra" in one field means ONE shift of the bit buffer per symbol on the serial dependency chain
+// (index -> load -> shift -> index ...) that bounds a Huffman decoder; the extra bits are read from a saved copy.
+using Entry = uint32_t;
+constexpr Entry F_LIT = 0x1000, F_LEN = 0x2000, F_EOB = 0x4000, F_SUB = 0x8000, F_LIT2 = 0x0200;
+constexpr Entry INVALID = 1 | (1 << 5);  // consumes one bit, no kind flag
+// while a table is built the low five bits hold the symbol's extra-bit count; build_table() adds the codeword length
+inline Entry mk(uint32_t val, uint32_t flag, uint32_t extra) { return (val << 16) | flag | extra; }
+inline Entry with_len(Entry e, int l) { return (e & ~31u) | ((e & 31u) + (uint32_t)l) | ((uint32_t)l << 5); }
+inline int e_total(Entry e) { return (int)(e & 31); }
+inline int e_cw(Entry e) { return (int)((e >> 5) & 15); }
+inline uint32_t e_val(Entry e) { return e >> 16; }
+// value of a length / distance entry: base + the extra bits that follow the codeword in `saved` (the unshifted buffer)
+inline uint32_t e_value(Entry e, uint64_t saved) {
+    return e_val(e) + (uint32_t)((saved >> e_cw(e)) & ((1u << (e_total(e) - e_cw(e))) - 1u));
+}
+inline uint32_t sub_index(Entry e, uint64_t bitbuf) { return e_val(e) + (uint32_t)(bitbuf & ((1u << e_cw(e)) - 1u)); }
+
+const uint16_t LEN_BASE[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+const uint8_t LEN_EXTRA[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+const uint16_t DIST_BASE[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073,
+                                4097, 6145, 8193, 12289, 16385, 24577};
+const uint8_t DIST_EXTRA[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+
+inline uint32_t bit_reverse(uint32_t v, int n) {
+    uint32_t r = 0;
+    for (int i = 0; i < n; i++) { r = (r << 1) | (v & 1); v >>= 1; }
+    return r;
+}
+
+// Builds a decode table from codeword lengths (canonical Huffman, RFC 1951 3.2.2).  `table` holds (1 << tb) primary
+// entries followed by the subtables; returns false for an over-subscribed code.  `make(sym)` gives the payload of a symbol.
+template <class Make>
+bool build_table(const uint8_t* lens, int n_syms, int tb, Entry* table, int table_cap, Make&& make) {
+    int count[MAX_CODE + 1] = {0};
+    for (int s = 0; s < n_syms; s++) count[lens[s]]++;
+    count[0] = 0;
+    int left = 1;
+    for (int l = 1; l <= MAX_CODE; l++) {
+        left = (left << 1) - count[l];
+        if (left < 0) return false;  // over-subscribed
+    }
+    uint32_t next_code[MAX_CODE + 2];
+    uint32_t code = 0;
+    for (int l = 1; l <= MAX_CODE; l++) {
+        code = (code + (uint32_t)count[l - 1]) << 1;
+        next_code[l] = code;
+    }
+    for (int i = 0; i < (1 << tb); i++) table[i] = INVALID;
+    // subtables: for every primary prefix, how many extra bits its longest code needs
+    int sub_bits[1 << LIT_TB];
+    bool any_long = false;
+    for (int l = tb + 1; l <= MAX_CODE; l++) any_long |= count[l] != 0;
+    if (any_long) {
+        memset(sub_bits, 0, sizeof(int) * (size_t)(1 << tb));
+        uint32_t nc[MAX_CODE + 2];
+        memcpy(nc, next_code, sizeof(nc));
+        for (int s = 0; s < n_syms; s++) {
+            const int l = lens[s];
+            if (l <= tb) { if (l) nc[l]++; continue; }
+            const uint32_t c = nc[l]++;
+            const uint32_t prefix = bit_reverse(c >> (l - tb), tb);  // first tb bits of the codeword, as they arrive
+            if (l - tb > sub_bits[prefix]) sub_bits[prefix] = l - tb;
+        }
+    }
+    int used = 1 << tb;
+    int sub_off[1 << LIT_TB];
+    if (any_long) {
+        for (int p = 0; p < (1 << tb); p++) {
+            if (!sub_bits[p]) continue;
+            if (used + (1 << sub_bits[p]) > table_cap) return false;
+            sub_off[p] = used;
+            for (int i = 0; i < (1 << sub_bits[p]); i++) table[used + i] = INVALID;
+            table[p] = ((uint32_t)used << 16) | F_SUB | ((uint32_t)sub_bits[p] << 5) | (uint32_t)tb;
+            used += 1 << sub_bits[p];
+        }
+    }
+    for (int s = 0; s < n_syms; s++) {
+        const int l = lens[s];
+        if (!l) continue;
+        const uint32_t c = next_code[l]++;
+        Entry e = make(s);
+        if (l <= tb) {
+            e = with_len(e, l);
+            const uint32_t r = bit_reverse(c, l);
+            for (uint32_t i = r; i < (1u << tb); i += 1u << l) table[i] = e;
+        } else {
+            const uint32_t prefix = bit_reverse(c >> (l - tb), tb);
+            const int sb = sub_bits[prefix], rest = l - tb;
+            e = with_len(e, rest);
+            const uint32_t r = bit_reverse(c & ((1u << rest) - 1u), rest);
+            for (uint32_t i = r; i < (1u << sb); i += 1u << rest) table[sub_off[prefix] + i] = e;
+        }
+    }
+    return true;
+}
+
+Entry make_litlen(int s) {
+    if (s < 256) return mk((uint32_t)s, F_LIT, 0);
+    if (s == 256) return mk(0, F_EOB, 0);
+    if (s <= 285) return mk(LEN_BASE[s - 257], F_LEN, LEN_EXTRA[s - 257]);
+    return 0;  // symbols 286/287 of the fixed code: no kind flag, rejected when met
+}
+Entry make_dist(int s) { return s < 30 ? mk(DIST_BASE[s], F_LEN, DIST_EXTRA[s]) : 0; }
+Entry make_pre(int s) { return mk((uint32_t)s, F_LIT, 0); }
+
+// Second pass over the primary literal/length table: where a literal of l1 bits is followed, within the same index, by a
+// complete second literal codeword, store both.  Indices are visited from the top so that look-ups see single entries.
+void pair_literals(Entry* table) {
+    for (int i = (1 << LIT_TB) - 1; i >= 0; i--) {
+        const Entry e1 = table[i];
+        if (!(e1 & F_LIT)) continue;
+        const int l1 = e_total(e1);
+        const Entry e2 = table[i >> l1];  // index bits above l1, zero-extended; i >> l1 <= i, == i only for i == 0
+        if ((i >> l1) == i || !(e2 & F_LIT)) continue;
+        const int l2 = e_total(e2);  // e2 is still a single literal: its index is smaller than i and not yet visited
+        if (l1 + l2 > LIT_TB) continue;
+        table[i] = ((e_val(e1) | (e_val(e2) << 8)) << 16) | F_LIT | F_LIT2 | ((uint32_t)(l1 + l2) << 5) | (uint32_t)(l1 + l2);
+    }
+}
+
+constexpr int LIT_CAP = (1 << LIT_TB) + 1024;   // worst case subtable space for 288 symbols of <= 15 bits
+constexpr int DIST_CAP = (1 << DIST_TB) + 512;
+
+struct Tables {
+    Entry lit[LIT_CAP];
+    Entry dist[DIST_CAP];
+};
+
+struct FixedTables {
+    Tables t;
+    bool ok;
+    FixedTables() {
+        uint8_t l[288];
+        for (int i = 0; i < 144; i++) l[i] = 8;
+        for (int i = 144; i < 256; i++) l[i] = 9;
+        for (int i = 256; i < 280; i++) l[i] = 7;
+        for (int i = 280; i < 288; i++) l[i] = 8;
+        uint8_t d[32];
+        for (int i = 0; i < 32; i++) d[i] = 5;
+        ok = build_table(l, 288, LIT_TB, t.lit, LIT_CAP, make_litlen) && build_table(d, 32, DIST_TB, t.dist, DIST_CAP, make_dist);
+        if (ok) pair_literals(t.lit);
+    }
+};
+
+inline uint64_t load64(const uint8_t* p) {
+    uint64_t v;
+    memcpy(&v, p, 8);
+    return v;
+}
+
+}  // namespace
+
+// Copies a match of `len` bytes from `distance` back.  `slack` = the caller guarantees len + 16 writable bytes at op.
+inline void copy_match(uint8_t* op, uint32_t distance, uint32_t len, bool slack) {
+    const uint8_t* src = op - distance;
+    if (slack && distance >= 8) {
+        uint8_t* dst = op;
+        uint8_t* const stop = op + len;
+        if (distance >= 16) {
+            do {
+                memcpy(dst, src, 16);
+                dst += 16;
+                src += 16;
+            } while (dst < stop);
+        } else {
+            do {
+                memcpy(dst, src, 8);
+                dst += 8;
+                src += 8;
+            } while (dst < stop);
+        }
+    } else if (distance == 1) {
+        memset(op, *src, len);
+    } else {
+        for (uint32_t i = 0; i < len; i++) op[i] = src[i];
+    }
+}
+
+bool inflate_fast(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_len) {
+    static const FixedTables fixed;  // thread-safe initialisation (C++11)
+    const uint8_t* ip = in;
+    const uint8_t* const iend = in + in_len;
+    uint8_t* op = out;
+    uint8_t* const oend = out + out_len;
+    uint64_t bitbuf = 0;
+    int bitcnt = 0;
+    Tables dyn;
+    constexpr uint32_t LMASK = (1u << LIT_TB) - 1u, DMASK = (1u << DIST_TB) - 1u;
+    // the unchecked loop runs while a whole step (four look-ups of up to two literals, then one match of 258 bytes + copy
+    // slack; two refills that advance by <= 8 bytes and read 8) fits: FAST_OUT bytes of output and FAST_IN bytes of input
+    constexpr ptrdiff_t FAST_OUT = 8 + 1 + 258 + 16 + 16, FAST_IN = 24;
+
+    // REFILL_FAST needs ip + 8 <= iend; afterwards 56..63 bits are available.  REFILL falls back to byte-wise loads near
+    // the end of the input (missing bits read as zero; the overrun shows as bitcnt < 0 and is rejected).
+#define REFILL_FAST()                        \
+    do {                                     \
+        bitbuf |= load64(ip) << bitcnt;      \
+        ip += (63 - bitcnt) >> 3;            \
+        bitcnt |= 56;                        \
+    } while (0)
+#define REFILL()                                             \
+    do {                                                     \
+        if (ip + 8 <= iend) {                                \
+            REFILL_FAST();                                   \
+        } else {                                             \
+            while (bitcnt <= 56 && ip < iend) {              \
+                bitbuf |= (uint64_t)*ip++ << bitcnt;         \
+                bitcnt += 8;                                 \
+            }                                                \
+        }                                                    \
+    } while (0)
+#define TAKE(n) (bitbuf >>= (n), bitcnt -= (n))
+
+    for (;;) {
+        REFILL();
+        if (bitcnt < 3) return false;
+        const int bfinal = (int)(bitbuf & 1), btype = (int)((bitbuf >> 1) & 3);
+        TAKE(3);
+        if (btype == 0) {  // stored: byte-align, hand the whole bytes still in the bit buffer back to the input
+            TAKE(bitcnt & 7);
+            ip -= bitcnt >> 3;
+            bitbuf = 0;
+            bitcnt = 0;
+            if (ip + 4 > iend) return false;
+            const uint32_t len = (uint32_t)ip[0] | ((uint32_t)ip[1] << 8), nlen = (uint32_t)ip[2] | ((uint32_t)ip[3] << 8);
+            ip += 4;
+            if ((len ^ nlen) != 0xFFFFu || len > (size_t)(iend - ip) || len > (size_t)(oend - op)) return false;
+            memcpy(op, ip, len);
+            ip += len;
+            op += len;
+        } else if (btype == 1 || btype == 2) {
+            const Tables* T = &fixed.t;
+            if (btype == 2) {
+                if (bitcnt < 14) return false;
+                const int hlit = (int)(bitbuf & 31) + 257, hdist = (int)((bitbuf >> 5) & 31) + 1, hclen = (int)((bitbuf >> 10) & 15) + 4;
+                TAKE(14);
+                if (hlit > 286 || hdist > 30) return false;
+                static const uint8_t ORDER[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+                uint8_t pl[19] = {0};
+                for (int i = 0; i < hclen; i++) {
+                    if (bitcnt < 3) REFILL();
+                    if (bitcnt < 3) return false;
+                    pl[ORDER[i]] = (uint8_t)(bitbuf & 7);
+                    TAKE(3);
+                }
+                Entry pre[1 << PRE_TB];
+                if (!build_table(pl, 19, PRE_TB, pre, 1 << PRE_TB, make_pre)) return false;
+                uint8_t lens[286 + 30 + 16] = {0};
+                int n = 0;
+                const int total = hlit + hdist;
+                while (n < total) {
+                    REFILL();
+                    const Entry e = pre[bitbuf & ((1u << PRE_TB) - 1u)];
+                    if (!(e & F_LIT) || e_total(e) > bitcnt) return false;
+                    TAKE(e_total(e));
+                    const int sym = (int)e_val(e);
+                    if (sym < 16) {
+                        lens[n++] = (uint8_t)sym;
+                    } else {
+                        int rep, val = 0;
+                        if (sym == 16) {
+                            if (n == 0) return false;
+                            val = lens[n - 1];
+                            rep = 3 + (int)(bitbuf & 3);
+                            TAKE(2);
+                        } else if (sym == 17) {
+                            rep = 3 + (int)(bitbuf & 7);
+                            TAKE(3);
+                        } else {
+                            rep = 11 + (int)(bitbuf & 127);
+                            TAKE(7);
+                        }
+                        if (bitcnt < 0 || n + rep > total) return false;
+                        for (int i = 0; i < rep; i++) lens[n++] = (uint8_t)val;
+                    }
+                }
+                if (lens[256] == 0) return false;  // no end-of-block code
+                if (!build_table(lens, hlit, LIT_TB, dyn.lit, LIT_CAP, make_litlen)) return false;
+                if (!build_table(lens + hlit, hdist, DIST_TB, dyn.dist, DIST_CAP, make_dist)) return false;
+                pair_literals(dyn.lit);
+                T = &dyn;
+            } else if (!fixed.ok) {
+                return false;
+            }
+            const Entry* const lit = T->lit;
+            const Entry* const dist = T->dist;
+            bool eob = false;
+
+            // ---- unchecked loop: far enough from both buffer ends that one step cannot overrun either ----
+#define IN_FAST_RANGE() (iend - ip >= FAST_IN && oend - op >= FAST_OUT)
+#define LOOK() lit[bitbuf & LMASK]
+#define PUT_LITERALS()                                   \
+    do {                                                 \
+        TAKE(e_total(e));                                \
+        const uint16_t two = (uint16_t)(e >> 16);        \
+        memcpy(op, &two, 2);                             \
+        op += 1 + ((e >> 9) & 1);                        \
+    } while (0)
+            if (IN_FAST_RANGE()) {
+                REFILL_FAST();
+                Entry e = LOOK();
+                for (;;) {  // invariant: >= 56 bits in the buffer, e looked up from them and not yet consumed
+                    if (e & F_LIT) {  // up to four look-ups (<= 11 bits, one or two literals each) from one refill
+                        PUT_LITERALS();
+                        e = LOOK();
+                        if (e & F_LIT) {
+                            PUT_LITERALS();
+                            e = LOOK();
+                            if (e & F_LIT) {
+                                PUT_LITERALS();
+                                e = LOOK();
+                                if (e & F_LIT) {
+                                    PUT_LITERALS();
+                                    e = LOOK();  // >= 12 bits are left: a primary index is still fully defined
+                                }
+                            }
+                        }
+                        REFILL_FAST();  // only adds bits above those e was looked up from
+                        if (e & F_LIT) {
+                            if (!IN_FAST_RANGE()) break;
+                            continue;
+                        }
+                    }
+                    if (e & F_SUB) {
+                        TAKE(LIT_TB);
+                        e = lit[sub_index(e, bitbuf)];
+                        if (e & F_LIT) {
+                            PUT_LITERALS();
+                            REFILL_FAST();
+                            e = LOOK();
+                            if (!IN_FAST_RANGE()) break;
+                            continue;
+                        }
+                    }
+                    uint64_t saved = bitbuf;
+                    TAKE(e_total(e));
+                    if (e & F_EOB) {
+                        eob = true;
+                        break;
+                    }
+                    if (!(e & F_LEN)) return false;
+                    const uint32_t len = e_value(e, saved);
+                    Entry d = dist[bitbuf & DMASK];  // >= 56 - 11 - 20 bits left: enough for a distance code + extra (28)
+                    if (d & F_SUB) {
+                        TAKE(DIST_TB);
+                        d = dist[sub_index(d, bitbuf)];
+                    }
+                    saved = bitbuf;
+                    TAKE(e_total(d));
+                    if (!(d & F_LEN)) return false;
+                    const uint32_t distance = e_value(d, saved);
+                    if (distance > (size_t)(op - out)) return false;
+                    REFILL_FAST();  // next symbol's look-up goes ahead of the copy
+                    e = LOOK();
+                    copy_match(op, distance, len, true);
+                    op += len;
+                    if (!IN_FAST_RANGE()) break;
+                }
+            }
+
+            // ---- checked loop: the last bytes of either buffer ----
+            while (!eob) {
+                REFILL();
+                Entry e = LOOK();
+                if (e & F_SUB) {
+                    TAKE(LIT_TB);
+                    e = lit[sub_index(e, bitbuf)];
+                }
+                uint64_t saved = bitbuf;
+                TAKE(e_total(e));
+                if (bitcnt < 0) return false;  // ran past the end of the input
+                if (e & F_LIT) {
+                    const size_t nl = 1 + ((e >> 9) & 1);
+                    if ((size_t)(oend - op) < nl) return false;
+                    *op++ = (uint8_t)e_val(e);
+                    if (nl == 2) *op++ = (uint8_t)(e >> 24);
+                    continue;
+                }
+                if (e & F_EOB) break;
+                if (!(e & F_LEN)) return false;
+                const uint32_t len = e_value(e, saved);
+                if (bitcnt < 28) REFILL();  // distance code (<= 15) + extra (<= 13)
+                Entry d = dist[bitbuf & DMASK];
+                if (d & F_SUB) {
+                    TAKE(DIST_TB);
+                    d = dist[sub_index(d, bitbuf)];
+                }
+                saved = bitbuf;
+                TAKE(e_total(d));
+                if (!(d & F_LEN)) return false;
+                const uint32_t distance = e_value(d, saved);
+                if (bitcnt < 0) return false;
+                if (distance > (size_t)(op - out) || len > (size_t)(oend - op)) return false;
+                copy_match(op, distance, len, (size_t)(oend - op) >= (size_t)len + 16);
+                op += len;
+            }
+            if (bitcnt < 0) return false;
+        } else {
+            return false;
+        }
+        if (bfinal) break;
+    }
+#undef REFILL
+#undef REFILL_FAST
+#undef TAKE
+#undef PUT_LITERALS
+#undef LOOK
+#undef IN_FAST_RANGE
+    // all output produced, and the input was not overrun (whole unread bytes still in the bit buffer are given back)
+    if (bitcnt < 0) return false;
+    ip -= bitcnt >> 3;
+    return op == oend && ip <= iend;
+}
+
+}  // namespace mthh

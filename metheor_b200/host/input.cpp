@@ -9,8 +9,13 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <cstdlib>
+
+#include "inflate_fast.hpp"
 
 namespace mthh {
+
+std::atomic<int64_t> g_zlib_fallbacks{0};
 
 int Header::tid_of(const std::string& n) const {
     for (size_t i = 0; i < names.size(); i++)
@@ -52,6 +57,11 @@ struct Inflater {
     }
     // raw DEFLATE payload of one BGZF member -> exactly usize bytes; CRC32 checked like htslib's bgzf reader does
     bool run(const uint8_t* in, size_t clen, uint8_t* out, uint32_t usize, uint32_t crc_expected) {
+        static const bool zlib_only = getenv("METHEOR_ZLIB_INFLATE") != nullptr;  // A/B switch for measurements
+        if (!zlib_only) {
+            if (inflate_fast(in, clen, out, usize) && (uint32_t)crc32(crc32(0L, Z_NULL, 0), out, usize) == crc_expected) return true;
+            g_zlib_fallbacks.fetch_add(1, std::memory_order_relaxed);  // rejected or wrong: let zlib have the last word
+        }
         if (!ready) {
             memset(&zs, 0, sizeof(zs));
             if (inflateInit2(&zs, -15) != Z_OK) return false;

@@ -11,6 +11,9 @@
 
 namespace mthh {
 
+extern std::atomic<int64_t> g_zlib_fallbacks;  // BGZF members the fast decoder rejected (input.cpp)
+
+
 struct Header {  // bamutil.rs:13-25 — the binary reference list gives tid <-> name
     std::vector<std::string> names;
     std::vector<int64_t> lengths;

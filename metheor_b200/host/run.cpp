@@ -639,12 +639,12 @@ void run(const mthh_options& o) {
             const double wall = t_end - t_begin;
             fprintf(f, "{\"input\": \""); json_escape(f, o.input);
             fprintf(f, "\", \"format\": \"%s\", \"threads\": %d, \"gpus\": %d, \"records\": %lld, \"reads_shipped\": %lld, "
-                       "\"cpg_calls_shipped\": %lld, \"batches\": %lld, \"rows\": %lld, \"bytes_uncompressed\": %llu, "
+                       "\"cpg_calls_shipped\": %lld, \"batches\": %lld, \"rows\": %lld, \"bytes_uncompressed\": %llu, \"zlib_fallbacks\": %lld, "
                        "\"seconds\": {\"total\": %.6f, \"stream\": %.6f, \"inflate\": %.6f, \"walk\": %.6f, \"decode\": %.6f, "
                        "\"assemble\": %.6f, \"submit\": %.6f, \"finish\": %.6f, \"write\": %.6f}, \"reads_per_sec\": %.1f, \"gpu\": [",
                     fmt == Format::BAM ? "bam" : "sam", n_threads, n_gpus, (long long)total.n_records, (long long)n_shipped_reads,
                     (long long)n_shipped_cpg, (long long)n_batches, (long long)n_rows_total, (unsigned long long)in.bytes_uncompressed,
-                    wall, t_decoded - t_begin, in.seconds_inflate, in.seconds_walk, s_decode, s_assemble, s_submit,
+                    (long long)g_zlib_fallbacks.load(), wall, t_decoded - t_begin, in.seconds_inflate, in.seconds_walk, s_decode, s_assemble, s_submit,
                     t_finished - t_decoded, t_end - t_finished, (double)total.n_records / wall);
             for (size_t g = 0; g < gpus.size(); g++) {
                 const mth_stats& st = gpus[g]->stats;
