@@ -207,6 +207,62 @@ def bam_leg(b, n_reads, length):
     return out
 
 
+def tag_leg(n_reads, length, read_len=150, seed=7):
+    """`tag` (XM synthesis): synthetic plain-`150M` reads over a random chr19-sized genome through the C ABI
+    (mth_tag: host arrays in, XM strings in pinned host memory out), with the kernel's own device time and the Python oracle
+    (single thread, bounded sample) beside it; the sample's tags must be identical."""
+    from metheor_b200 import tag
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import tag_oracle
+    rng = np.random.default_rng(seed)
+    genome = rng.choice(np.frombuffer(b"ACGT", np.uint8), length, p=[0.29, 0.21, 0.21, 0.29])
+    genome[rng.integers(0, length, length // 500)] = ord("N")
+    pos = np.sort(rng.integers(0, length - read_len, n_reads)).astype(np.int32)
+    tid = np.zeros(n_reads, np.int32)
+    rc = (rng.random(n_reads) < 0.5).astype(np.uint8)
+    l_seq = np.full(n_reads, read_len, np.int32)
+    cigar_off = np.arange(n_reads + 1, dtype=np.uint32)
+    cigar = np.full(n_reads, read_len << 4, np.uint32)
+    nb = (read_len + 1) // 2
+    seq_off = (np.arange(n_reads + 1, dtype=np.uint64) * np.uint64(nb))
+    codes = np.array([1, 2, 4, 8, 8, 8, 15], np.uint8)  # A C G T T T N: bisulfite-like
+    seq4 = (codes[rng.integers(0, 7, n_reads * nb)] << 4) | codes[rng.integers(0, 7, n_reads * nb)]
+    out = {"reads": n_reads, "read_len": read_len, "genome_bases": length}
+    with tag.Genome([length]) as g:
+        t0 = time.perf_counter()
+        g.set_contig(0, genome)
+        out["genome_upload_seconds"] = time.perf_counter() - t0
+        best, kms = None, None
+        for _ in range(4):
+            t0 = time.perf_counter()
+            off, ln, xm, status = g.tag_arrays(tid, pos, rc, l_seq, cigar_off, cigar, seq_off, seq4, raw=True)
+            dt = time.perf_counter() - t0
+            if best is None or dt < best:
+                best, kms = dt, g.last_kernel_ms()
+        assert not status.any()
+        bytes_per_read = nb + (read_len + 4) + read_len + 4 + 4 + 1 + 4 + 4 + 8 + 8 + 8 + 4 + 1  # SEQ, genome, tag, scalars / offsets
+        out.update(reads_per_sec=n_reads / best, seconds=best, kernel_ms=kms, kernel_reads_per_sec=n_reads / (kms * 1e-3),
+                   kernel_algorithmic_GBps=bytes_per_read * n_reads / (kms * 1e-3) / 1e9, algorithmic_bytes_per_read=bytes_per_read,
+                   h2d_bytes=int(tid.nbytes + pos.nbytes + rc.nbytes + l_seq.nbytes + cigar_off.nbytes + cigar.nbytes + seq_off.nbytes + seq4.nbytes
+                                 + 16 * (n_reads + 1)), d2h_bytes=int(xm.nbytes + 5 * n_reads))
+        # CPU oracle on a bounded sample, tags compared
+        m = min(n_reads, 20000)
+        text = bytes(genome).decode()
+        nt = "=ACMGRSVTWYHKDBN"
+        t0 = time.perf_counter()
+        same = True
+        for i in range(m):
+            sq = seq4[i * nb:(i + 1) * nb]
+            s = "".join(nt[c >> 4] + nt[c & 15] for c in sq)[:read_len]
+            want = tag_oracle.xm_string(16 if rc[i] else 0, int(pos[i]), [(read_len, "M")], s, text, length, False)
+            got = bytes(xm[int(off[i]):int(off[i]) + int(ln[i])]).decode()
+            same = same and (got == want)
+        dt = time.perf_counter() - t0
+        out.update(cpu_oracle_reads_per_sec=m / dt, cpu_oracle_sample=f"first {m} reads, single-threaded Python restatement of tag.rs",
+                   tags_identical_to_oracle=bool(same))
+    return out
+
+
 class _DevI64:
     def __init__(self, ptr, n):
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 2}
@@ -253,6 +309,7 @@ def main():
     ap.add_argument("--coverage", type=float, default=COVERAGE)
     ap.add_argument("--length", type=int, default=CONTIG_LEN)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tag-reads", type=int, default=2_000_000, help="reads of the extra `tag` (XM synthesis) leg; 0 disables it")
     ap.add_argument("--bam-reads", type=int, default=2_000_000,
                     help="also time the BAM -> TSV path (C++ host + engine) on a BAM of the first N reads; 0 disables")
     args = ap.parse_args()
@@ -478,6 +535,13 @@ def main():
         except Exception as e:  # the extra leg must never cost the bench line
             bam = {"error": repr(e)}
 
+    tag_res = None
+    if rank == 0 and world == 1 and args.tag_reads > 0 and not args.no_cpu_baseline:
+        try:
+            tag_res = tag_leg(args.tag_reads, args.length)
+        except Exception as e:
+            tag_res = {"error": repr(e)}
+
     lpmd_all = None
     if world > 1 and ar_state.get("result") is not None:
         torch.cuda.synchronize()
@@ -500,7 +564,7 @@ def main():
                 "e2e_soa": dict(e2e["soa"], wire_format="SoA (mth_submit), one batch"),
                 "gpu_launches": int((st["kernel_launches"] - 0) * args.steps),
                 "launches_per_step": int(st["kernel_launches"]),
-                "roofline": roofline, "roofline_step": roofline_step, "kernels": kern, "cpu_baseline": cpu, "cpu_baseline_all_cores": cpu_all, "bam_end_to_end": bam,
+                "roofline": roofline, "roofline_step": roofline_step, "kernels": kern, "cpu_baseline": cpu, "cpu_baseline_all_cores": cpu_all, "bam_end_to_end": bam, "tag": tag_res,
                 "clocks": clocks, "pdr_path": {1: "scatter", 2: "gather", 3: "scatter+gather(hazard sites)"}.get(st["pdr_path"]), "lpmd": float(rows["lpmd"]["lpmd"]),
                 "lpmd_all_ranks": lpmd_all}
         emit(line)

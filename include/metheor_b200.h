@@ -253,6 +253,56 @@ void mth_host_free(void* p);
 int mth_device_count(void);
 const char* mth_version(void);
 
+/* ---------------------------------------------------------------------------------------------------------------------
+ * `tag`: Bismark XM strings synthesised from read sequence + reference genome (replaces determine_xm_tag_string,
+ * src/tag.rs:130-384, called per record from tag::run, src/tag.rs:408-424).  The genome lives in HBM (one upper-cased
+ * byte per base, every contig of the header), a batch ships CIGAR + 4-bit SEQ as a BAM record stores them, one warp per
+ * read builds the aligned read/reference columns and classifies every reference C by its 3-base context.
+ * ------------------------------------------------------------------------------------------------------------------- */
+typedef struct mth_genome mth_genome;
+
+/* per-read status of mth_tag: where the reference panics, the read gets a non-zero status and an empty tag */
+enum {
+    MTH_TAG_OK = 0,
+    MTH_TAG_NO_COMPLEMENT = 1, /* reverse-strand read with a base outside the complement map, e.g. '=' (tag.rs:23) */
+    MTH_TAG_NO_CONTEXT = 2,    /* look-ahead over deletions found no second base (tag.rs:301) */
+    MTH_TAG_BAD_CONTIG = 3,    /* tid outside the genome, or contig not loaded (tag.rs:152) */
+    MTH_TAG_PAST_END = 4,      /* alignment ends past the contig (tag.rs:167-172) */
+    MTH_TAG_SHORT_SEQ = 5      /* SEQ shorter than the CIGAR's M + I bases */
+};
+
+typedef struct mth_tag_batch {
+    int64_t n_reads;
+    const int32_t* tid;        /* [n_reads] */
+    const int32_t* pos;        /* [n_reads] 0-based leftmost position (Record::reference_start) */
+    const uint8_t* rc;         /* [n_reads] 1: work on the reverse complement (tag.rs:141-144; need_reverse_complement for pairs) */
+    const int32_t* l_seq;      /* [n_reads] number of bases in SEQ */
+    const uint32_t* cigar_off; /* [n_reads + 1] offsets into cigar[] */
+    const uint32_t* cigar;     /* BAM encoding: len << 4 | op, op index into "MIDNSHP=X" */
+    const uint64_t* seq_off;   /* [n_reads + 1] byte offsets into seq4[] */
+    const uint8_t* seq4;       /* BAM encoding: two bases per byte, high nibble first, codes of "=ACMGRSVTWYHKDBN" */
+} mth_tag_batch;
+
+typedef struct mth_tag_result {
+    int64_t n_reads;
+    int64_t n_failed;          /* reads with status != MTH_TAG_OK */
+    const uint64_t* xm_off;    /* [n_reads + 1] read r's tag is xm[xm_off[r] .. xm_off[r] + xm_len[r]) */
+    const uint32_t* xm_len;    /* [n_reads] (can be shorter than the M + I bases: tag.rs:300-331 has no final else) */
+    const uint8_t* xm;         /* tag characters, not NUL-terminated */
+    const uint8_t* status;     /* [n_reads] MTH_TAG_* */
+} mth_tag_result;
+
+/* ref_len: the header's @SQ LN values (tag.rs:58-77).  Contigs are loaded one by one, any letter case (upper-cased on the
+ * device like tag.rs:162).  `len` may differ from ref_len[tid] only by being longer (extra bases are ignored). */
+int mth_genome_create(mth_genome** out, int device, int32_t n_ref, const int64_t* ref_len);
+int mth_genome_set_contig(mth_genome* g, int32_t tid, const uint8_t* seq, int64_t len);
+/* Tags one batch; result arrays are pinned host memory owned by the genome until the next mth_tag / destroy. */
+int mth_tag(mth_genome* g, const mth_tag_batch* batch, mth_tag_result* out);
+/* Device time of the last mth_tag's kernel (CUDA events around the launch), milliseconds; < 0 if none ran yet. */
+double mth_genome_last_kernel_ms(mth_genome* g);
+int mth_genome_destroy(mth_genome* g);
+const char* mth_genome_last_error(mth_genome* g); /* g may be NULL: last create error */
+
 /* Seeded replacement draw used for reservoir sampling: returns j in 1..=total (documented in DESIGN.md). */
 uint32_t mth_reservoir_draw(uint64_t seed, int32_t tid, int32_t pos, uint32_t total);
 

@@ -75,6 +75,12 @@ typedef struct {
 int mthh_decode_file(const char* path, const char* cpg_set, int32_t threads, mthh_decoded** out, char* err, size_t errcap);
 void mthh_decoded_free(mthh_decoded* d);
 
+/* `metheor tag` (reference src/tag.rs:386-443): XM tags synthesised on the GPU from SEQ + CIGAR + the FASTA `genome`,
+ * appended as the last aux field, written as SAM text.  threads 0 = all cores; stats_json may be NULL.
+ * 0 on success, otherwise the exit status (101 where the reference panics) with the message in `err`. */
+int mthh_tag(const char* input, const char* output, const char* genome, int32_t device, int32_t threads,
+             const char* stats_json, char* err, size_t errcap);
+
 /* Rust `{}` formatting of an f32 (shortest round-trip digits, positional, "NaN", "inf", "-0"); returns length. */
 int mthh_format_f32(float v, char* buf, int cap);
 

@@ -89,10 +89,20 @@ class Stats(C.Structure):
                 ("n_kernel_stats", i32), ("kernel", KernelStat * 48)]
 
 
+class TagBatch(C.Structure):
+    _fields_ = [("n_reads", i64), ("tid", vp), ("pos", vp), ("rc", vp), ("l_seq", vp), ("cigar_off", vp), ("cigar", vp),
+                ("seq_off", vp), ("seq4", vp)]
+
+
+class TagResult(C.Structure):
+    _fields_ = [("n_reads", i64), ("n_failed", i64), ("xm_off", vp), ("xm_len", vp), ("xm", vp), ("status", vp)]
+
+
 EXPORTS = ["mth_params_default", "mth_ctx_create", "mth_ctx_destroy", "mth_set_stream", "mth_submit", "mth_submit_compact", "mth_reserve",
            "mth_add_skipped_reads", "mth_finish", "mth_results_device", "mth_lpmd_counters_device", "mth_lpmd_refresh",
            "mth_reset", "mth_sync", "mth_sync_copies", "mth_get_stats", "mth_last_error", "mth_host_alloc", "mth_host_free",
-           "mth_device_count", "mth_version", "mth_reservoir_draw"]
+           "mth_device_count", "mth_version", "mth_reservoir_draw", "mth_genome_create", "mth_genome_set_contig", "mth_tag",
+           "mth_genome_destroy", "mth_genome_last_error", "mth_genome_last_kernel_ms"]
 
 
 def build(force=False):
@@ -137,5 +147,11 @@ def lib():
     L.mth_device_count.argtypes = []; L.mth_device_count.restype = C.c_int
     L.mth_version.argtypes = []; L.mth_version.restype = C.c_char_p
     L.mth_reservoir_draw.argtypes = [u64, i32, i32, u32]; L.mth_reservoir_draw.restype = u32
+    L.mth_genome_create.argtypes = [P(vp), C.c_int, i32, P(i64)]; L.mth_genome_create.restype = C.c_int
+    L.mth_genome_set_contig.argtypes = [vp, i32, vp, i64]; L.mth_genome_set_contig.restype = C.c_int
+    L.mth_tag.argtypes = [vp, P(TagBatch), P(TagResult)]; L.mth_tag.restype = C.c_int
+    L.mth_genome_destroy.argtypes = [vp]; L.mth_genome_destroy.restype = C.c_int
+    L.mth_genome_last_error.argtypes = [vp]; L.mth_genome_last_error.restype = C.c_char_p
+    L.mth_genome_last_kernel_ms.argtypes = [vp]; L.mth_genome_last_kernel_ms.restype = C.c_double
     _lib = L
     return L

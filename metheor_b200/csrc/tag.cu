@@ -1,0 +1,587 @@
+// tag.cu — XM synthesis (`metheor tag`): the genome resident in HBM, one warp per read.
+//
+// Replaces determine_xm_tag_string (reference src/tag.rs:130-384).  The reference materialises two aligned strings per
+// read (read bases / reference bases, '-' for gaps) with two context columns on either side, reverse-complements both for
+// reverse-strand reads, walks them once and reverses the tag back.  Here:
+//   phase A  the warp walks the CIGAR once and writes the body columns (M, I, D only — tag.rs:186-233 ignores every other
+//            op) to an L2-resident scratch line of the read; the four context bases come straight from the genome
+//            (N outside the contig, tag.rs:165-173);
+//   phase B  lane i classifies target column i (index arithmetic stands in for the reverse complement), the warp
+//            compacts the emitted characters in order with a ballot (a column can emit nothing: deletion columns and
+//            contexts outside CG/CHG/CHH/unknown, tag.rs:300-331), and reverse-strand tags are reversed in place.
+// HBM traffic per read: l_seq/2 B of SEQ + ~l_seq B of genome in, ~l_seq B of tag out; the columns stay in L2.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/metheor_b200.h"
+
+namespace {
+
+constexpr uint32_t FULL = 0xffffffffu;
+constexpr int TAG_BLOCK = 256;
+
+struct TagArgs {
+    int64_t n_reads;
+    const int32_t* tid;
+    const int32_t* pos;
+    const uint8_t* rc;
+    const int32_t* l_seq;
+    const uint32_t* cigar_off;
+    const uint32_t* cigar;
+    const uint64_t* seq_off;
+    const uint8_t* seq4;
+    const uint64_t* col_off;   // [n+1] body columns (M + I + D) per read
+    const uint64_t* xm_off;    // [n+1] tag capacity (M + I) per read
+    const uint8_t* genome;     // upper-cased bases, contigs back to back
+    const int64_t* contig_off; // [n_ref]
+    const int64_t* contig_len; // [n_ref] header LN
+    const int64_t* loaded_len; // [n_ref] bases actually loaded (-1: contig missing)
+    int32_t n_ref;
+    uint8_t* col_read;
+    uint8_t* col_ref;
+    uint8_t* xm;
+    uint32_t* xm_len;
+    uint8_t* status;
+};
+
+// tag.rs:78-99; 0 = not in the map (the reference panics on the HashMap index)
+__device__ __forceinline__ uint8_t complement(uint8_t c) {
+    switch (c) {
+        case 'A': return 'T'; case 'C': return 'G'; case 'G': return 'C'; case 'T': return 'A'; case 'N': return 'N';
+        case 'M': return 'K'; case 'R': return 'Y'; case 'W': return 'W'; case 'S': return 'S'; case 'Y': return 'R';
+        case 'K': return 'M'; case 'V': return 'B'; case 'H': return 'D'; case 'D': return 'H'; case 'B': return 'V';
+        case '-': return '-';
+        default: return 0;
+    }
+}
+
+__device__ __forceinline__ bool is_h(uint8_t c) { return c == 'A' || c == 'T' || c == 'C'; }
+__device__ __forceinline__ bool is_unknown(uint8_t c) { return c == '-' || c == 'N'; }
+
+// Context of a reference C -> tag character for read base rd, or 0 when the reference emits nothing.  n_ctx: how many
+// context characters exist after the C (2 normally, 1 when the look-ahead ran into the end of the columns).
+__device__ __forceinline__ uint8_t classify(uint8_t c1, uint8_t c2, int n_ctx, uint8_t rd) {
+    uint8_t lower;
+    if (c1 == 'G') lower = 'z';                                               // tag.rs:301, 339
+    else if (n_ctx == 2 && is_h(c1) && c2 == 'G') lower = 'x';                // CHG, tag.rs:32-34
+    else if (n_ctx == 2 && is_h(c1) && is_h(c2)) lower = 'h';                 // CHH, tag.rs:36-41
+    else if (is_unknown(c1) || (n_ctx == 2 && is_unknown(c2))) lower = 'u';   // tag.rs:43-52
+    else return 0;
+    return rd == 'C' ? (uint8_t)(lower - 32) : rd == 'T' ? lower : (uint8_t)'.';
+}
+
+// One read, any number of columns: the columns go through the global scratch line of the read (long reads, huge deletions).
+__device__ __noinline__ void tag_read_generic(const TagArgs& a, const int64_t r, const int lane) {
+    do {
+        const int32_t tid = a.tid[r];
+        const int64_t start = a.pos[r];
+        const bool rc = a.rc[r] != 0;
+        const int32_t l_seq = a.l_seq[r];
+        const uint32_t c_lo = a.cigar_off[r], c_hi = a.cigar_off[r + 1];
+        const uint64_t col0 = a.col_off[r];
+        const int64_t B = (int64_t)(a.col_off[r + 1] - col0);
+        uint8_t* const xm = a.xm + a.xm_off[r];
+        uint8_t st = MTH_TAG_OK;
+        if (tid < 0 || tid >= a.n_ref || a.loaded_len[tid] < 0 || start < 0) st = MTH_TAG_BAD_CONTIG;
+        if (st) {
+            if (lane == 0) { a.status[r] = st; a.xm_len[r] = 0; }
+            continue;
+        }
+        const int64_t chrom = a.contig_len[tid], loaded = a.loaded_len[tid];
+        const uint8_t* const g = a.genome + a.contig_off[tid];
+        auto ref_at = [&](int64_t p) -> uint8_t { return (p < 0 || p >= chrom || p >= loaded) ? (uint8_t)'N' : g[p]; };
+        const uint8_t* const sq = a.seq4 + a.seq_off[r];
+        auto base_at = [&](int64_t i) -> uint8_t {
+            if (i >= l_seq) return 'N';
+            const uint32_t code = (sq[i >> 1] >> ((~i & 1) << 2)) & 15u;
+            return (uint8_t)"=ACMGRSVTWYHKDBN"[code];
+        };
+        uint8_t* const cr = a.col_read + col0;
+        uint8_t* const cf = a.col_ref + col0;
+
+        // ---- phase A: body columns ----
+        int64_t c0 = 0, ur = 0, uf = 0, ref_span = 0;
+        bool unmappable = false;
+        for (uint32_t k = c_lo; k < c_hi; k++) {
+            const uint32_t v = a.cigar[k];
+            const int64_t len = v >> 4;
+            const uint32_t op = v & 15u;
+            if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) ref_span += len;  // bam_endpos: M D N = X
+            if (op > 2) continue;  // tag.rs:232 `_ => {}`
+            if (c0 + len > B) break;  // offsets inconsistent with the CIGAR (rejected on the host; never write outside)
+            for (int64_t j = lane; j < len; j += 32) {
+                const uint8_t rd = op == 2 ? (uint8_t)'-' : base_at(ur + j);
+                const uint8_t rf = op == 1 ? (uint8_t)'-' : ref_at(start + uf + j);
+                cr[c0 + j] = rd;
+                cf[c0 + j] = rf;
+                if (rc && (!complement(rd) || !complement(rf))) unmappable = true;
+            }
+            c0 += len;
+            if (op != 2) ur += len;
+            if (op != 1) uf += len;
+        }
+        const int64_t end = start + (ref_span ? ref_span : 1);
+        const uint8_t p0 = ref_at(start - 2), p1 = ref_at(start - 1), s0 = ref_at(end), s1 = ref_at(end + 1);
+        if (rc && (!complement(p0) || !complement(p1))) unmappable = true;
+        if (end > chrom || (end + 2 < chrom ? end + 2 : chrom) > loaded) st = MTH_TAG_PAST_END;
+        else if (ur > l_seq) st = MTH_TAG_SHORT_SEQ;
+        else if (__any_sync(FULL, unmappable)) st = MTH_TAG_NO_COMPLEMENT;
+        __syncwarp();
+        if (st) {
+            if (lane == 0) { a.status[r] = st; a.xm_len[r] = 0; }
+            continue;
+        }
+
+        // ---- phase B: classify target column i, compact in order ----
+        const int64_t L = B + 2;
+        auto R = [&](int64_t i) -> uint8_t { return i >= B ? (uint8_t)'-' : rc ? complement(cr[B - 1 - i]) : cr[i]; };
+        auto F = [&](int64_t i) -> uint8_t {
+            if (i < B) return rc ? complement(cf[B - 1 - i]) : cf[i];
+            if (rc) return complement(i == B ? p1 : p0);
+            return i == B ? s0 : s1;
+        };
+        uint32_t n_out = 0;
+        bool no_context = false;
+        for (int64_t base = 0; base < B; base += 32) {
+            const int64_t i = base + lane;
+            uint8_t ch = 0;
+            if (i < B) {
+                const uint8_t rd = R(i);
+                if (rd == '-') {
+                    ch = 0;
+                } else if (rd == 'N') {
+                    ch = '.';
+                } else if (F(i) == 'C') {
+                    if ((R(i + 1) == '-' || R(i + 2) == '-') && i != L - 3 && i != L - 4) {  // tag.rs:268-299
+                        uint8_t ctx[2] = {0, 0};
+                        int found = 0;
+                        for (int64_t k = 1; found != 2 && i + k <= L - 1; k++)
+                            if (R(i + k) != '-') ctx[found++] = F(i + k);
+                        if (found == 0) no_context = true;
+                        else ch = classify(ctx[0], ctx[1], found, rd);
+                    } else {
+                        ch = classify(F(i + 1), F(i + 2), 2, rd);
+                    }
+                } else {
+                    ch = '.';
+                }
+            }
+            const uint32_t m = __ballot_sync(FULL, ch != 0);
+            if (ch) xm[n_out + __popc(m & ((1u << lane) - 1u))] = ch;
+            n_out += __popc(m);
+        }
+        if (__any_sync(FULL, no_context)) {
+            if (lane == 0) { a.status[r] = MTH_TAG_NO_CONTEXT; a.xm_len[r] = 0; }
+            continue;
+        }
+        __syncwarp();
+        if (rc) {  // tag.rs:380-383
+            for (uint32_t k = lane; k < n_out / 2; k += 32) {
+                const uint8_t x = xm[k], y = xm[n_out - 1 - k];
+                xm[k] = y;
+                xm[n_out - 1 - k] = x;
+            }
+        }
+        if (lane == 0) { a.status[r] = MTH_TAG_OK; a.xm_len[r] = n_out; }
+    } while (false);
+}
+
+constexpr int TAG_CAP = 512;  // target columns (body + 2) a warp keeps in shared memory
+
+// One warp per read.  Reads of up to TAG_CAP - 2 body columns (all short-read data) stay in shared memory: phase A writes
+// the TARGET columns (already reverse-complemented for reverse-strand reads, tag.rs:244-257), phase B classifies them
+// into a shared character line and counts, phase C writes the tag (reversed for reverse-strand reads, tag.rs:380-383).
+__global__ void __launch_bounds__(TAG_BLOCK, 4) k_tag(const __grid_constant__ TagArgs a) {
+    __shared__ uint8_t s_comp[256];
+    __shared__ uint8_t s_read[TAG_BLOCK / 32][TAG_CAP + 4];
+    __shared__ uint8_t s_ref[TAG_BLOCK / 32][TAG_CAP + 4];
+    __shared__ uint8_t s_out[TAG_BLOCK / 32][TAG_CAP];
+    for (int c = threadIdx.x; c < 256; c += blockDim.x) s_comp[c] = complement((uint8_t)c);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    uint8_t* const tr = s_read[wib];
+    uint8_t* const tf = s_ref[wib];
+    uint8_t* const to = s_out[wib];
+    for (int64_t r = warp; r < a.n_reads; r += n_warps) {
+        const int64_t B64 = (int64_t)(a.col_off[r + 1] - a.col_off[r]);
+        if (B64 + 2 > TAG_CAP) {
+            tag_read_generic(a, r, lane);
+            __syncwarp();
+            continue;
+        }
+        const int B = (int)B64;
+        const int32_t tid = a.tid[r];
+        const int64_t start = a.pos[r];
+        const bool rc = a.rc[r] != 0;
+        const int32_t l_seq = a.l_seq[r];
+        const uint32_t c_lo = a.cigar_off[r], c_hi = a.cigar_off[r + 1];
+        if (tid < 0 || tid >= a.n_ref || a.loaded_len[tid] < 0 || start < 0) {
+            if (lane == 0) { a.status[r] = MTH_TAG_BAD_CONTIG; a.xm_len[r] = 0; }
+            continue;
+        }
+        const int64_t chrom = a.contig_len[tid], loaded = a.loaded_len[tid];
+        const int64_t lim = chrom < loaded ? chrom : loaded;
+        const uint8_t* const g = a.genome + a.contig_off[tid];
+        const uint8_t* const sq = a.seq4 + a.seq_off[r];
+
+        // ---- phase A: target columns ----
+        int c0 = 0;
+        int64_t ur = 0, uf = 0, ref_span = 0;
+        bool unmappable = false;
+        for (uint32_t k = c_lo; k < c_hi; k++) {
+            const uint32_t v = a.cigar[k];
+            const int len = (int)(v >> 4);
+            const uint32_t op = v & 15u;
+            if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) ref_span += v >> 4;
+            if (op > 2) continue;
+            if (c0 + len > B) break;
+            for (int j = lane; j < len; j += 32) {
+                uint8_t rd = '-', rf = '-';
+                if (op != 2) {
+                    const int64_t i = ur + j;
+                    rd = i < l_seq ? (uint8_t)"=ACMGRSVTWYHKDBN"[(sq[i >> 1] >> ((~i & 1) << 2)) & 15u] : (uint8_t)'N';
+                }
+                if (op != 1) {
+                    const int64_t p = start + uf + j;
+                    rf = p < lim ? g[p] : (uint8_t)'N';
+                }
+                int t = c0 + j;
+                if (rc) {
+                    rd = s_comp[rd];
+                    rf = s_comp[rf];
+                    unmappable |= !rd || !rf;
+                    t = B - 1 - t;
+                }
+                tr[t] = rd;
+                tf[t] = rf;
+            }
+            c0 += len;
+            if (op != 2) ur += len;
+            if (op != 1) uf += len;
+        }
+        const int64_t end = start + (ref_span ? ref_span : 1);
+        if (lane < 2) {  // the two context columns behind the body
+            int64_t p = rc ? start - 1 - lane : end + lane;
+            uint8_t c = (p >= 0 && p < lim) ? g[p] : (uint8_t)'N';
+            if (rc) {
+                c = s_comp[c];
+                unmappable |= !c;
+            }
+            tr[B + lane] = '-';
+            tf[B + lane] = c;
+        }
+        uint8_t st = MTH_TAG_OK;
+        if (end > chrom || (end + 2 < chrom ? end + 2 : chrom) > loaded) st = MTH_TAG_PAST_END;
+        else if (ur > l_seq) st = MTH_TAG_SHORT_SEQ;
+        else if (__any_sync(FULL, unmappable)) st = MTH_TAG_NO_COMPLEMENT;
+        __syncwarp();
+        if (st) {
+            if (lane == 0) { a.status[r] = st; a.xm_len[r] = 0; }
+            __syncwarp();
+            continue;
+        }
+
+        // ---- phase B: classify ----
+        const int L = B + 2;
+        int n_out = 0;
+        bool no_context = false;
+        for (int base = 0; base < B; base += 32) {
+            const int i = base + lane;
+            uint8_t ch = 0;
+            if (i < B) {
+                const uint8_t rd = tr[i];
+                if (rd == '-') {
+                    ch = 0;
+                } else if (rd == 'N') {
+                    ch = '.';
+                } else if (tf[i] == 'C') {
+                    if ((tr[i + 1] == '-' || tr[i + 2] == '-') && i != L - 3 && i != L - 4) {  // tag.rs:268-299
+                        uint8_t ctx[2] = {0, 0};
+                        int found = 0;
+                        for (int k = 1; found != 2 && i + k <= L - 1; k++)
+                            if (tr[i + k] != '-') ctx[found++] = tf[i + k];
+                        if (found == 0) no_context = true;
+                        else ch = classify(ctx[0], ctx[1], found, rd);
+                    } else {
+                        ch = classify(tf[i + 1], tf[i + 2], 2, rd);
+                    }
+                } else {
+                    ch = '.';
+                }
+            }
+            const uint32_t m = __ballot_sync(FULL, ch != 0);
+            if (ch) to[n_out + __popc(m & ((1u << lane) - 1u))] = ch;
+            n_out += __popc(m);
+        }
+        if (__any_sync(FULL, no_context)) {
+            if (lane == 0) { a.status[r] = MTH_TAG_NO_CONTEXT; a.xm_len[r] = 0; }
+            __syncwarp();
+            continue;
+        }
+        __syncwarp();
+        // ---- phase C: the tag, in read orientation ----
+        uint8_t* const xm = a.xm + a.xm_off[r];
+        for (int k = lane; k < n_out; k += 32) xm[k] = to[rc ? n_out - 1 - k : k];
+        if (lane == 0) { a.status[r] = MTH_TAG_OK; a.xm_len[r] = (uint32_t)n_out; }
+        __syncwarp();
+    }
+}
+
+// to_uppercase of tag.rs:162 (ASCII letters), 16 bases per thread step
+__global__ void k_upper(uint8_t* p, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint8_t c = p[i];
+        if (c >= 'a' && c <= 'z') p[i] = (uint8_t)(c - 32);
+    }
+}
+
+std::string g_genome_create_err;
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    bool pinned_host;
+    explicit DevBuf(bool host = false) : pinned_host(host) {}
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        release();
+        size_t want = n + n / 4 + 64;
+        cudaError_t e = pinned_host ? cudaHostAlloc((void**)&p, want * sizeof(T), cudaHostAllocDefault) : cudaMalloc((void**)&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want; else p = nullptr;
+        return e;
+    }
+    void release() {
+        if (p) { if (pinned_host) cudaFreeHost(p); else cudaFree(p); }
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+}  // namespace
+
+struct mth_genome {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int32_t n_ref = 0;
+    std::vector<int64_t> ref_len, contig_off, loaded;
+    uint8_t* d_genome = nullptr;
+    int64_t total = 0;
+    int64_t *d_contig_off = nullptr, *d_contig_len = nullptr, *d_loaded = nullptr;
+    bool tables_dirty = true;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double last_kernel_ms = -1.0;
+    std::string err;
+    int sm_count = 148;
+    // per-batch device buffers
+    DevBuf<int32_t> d_tid, d_pos, d_lseq;
+    DevBuf<uint8_t> d_rc, d_seq4, d_colr, d_colf, d_xm, d_status;
+    DevBuf<uint32_t> d_cigar_off, d_cigar, d_xm_len;
+    DevBuf<uint64_t> d_seq_off, d_col_off, d_xm_off;
+    // pinned results
+    DevBuf<uint64_t> h_xm_off{true}, h_col_off{true};
+    DevBuf<uint32_t> h_xm_len{true};
+    DevBuf<uint8_t> h_xm{true}, h_status{true};
+};
+
+#define G_CUDA(call)                                                                        \
+    do {                                                                                    \
+        cudaError_t e_ = (call);                                                            \
+        if (e_ != cudaSuccess) {                                                            \
+            g->err = std::string(#call) + ": " + cudaGetErrorString(e_);                    \
+            return MTH_ERR_CUDA;                                                            \
+        }                                                                                   \
+    } while (0)
+
+extern "C" {
+
+const char* mth_genome_last_error(mth_genome* g) { return g ? g->err.c_str() : g_genome_create_err.c_str(); }
+
+int mth_genome_create(mth_genome** out, int device, int32_t n_ref, const int64_t* ref_len) {
+    if (!out || n_ref < 0 || (n_ref && !ref_len)) { g_genome_create_err = "mth_genome_create: bad arguments"; return MTH_ERR_INVALID; }
+    *out = nullptr;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+        g_genome_create_err = "no CUDA device: the metheor_b200 engine has no CPU fallback";
+        return MTH_ERR_CUDA;
+    }
+    if (device < 0 || device >= n_dev) { g_genome_create_err = "mth_genome_create: no such device"; return MTH_ERR_INVALID; }
+    mth_genome* g = new mth_genome();
+    g->device = device;
+    g->n_ref = n_ref;
+    int64_t off = 0;
+    for (int32_t t = 0; t < n_ref; t++) {
+        if (ref_len[t] < 0) { delete g; g_genome_create_err = "mth_genome_create: negative contig length"; return MTH_ERR_INVALID; }
+        g->ref_len.push_back(ref_len[t]);
+        g->contig_off.push_back(off);
+        g->loaded.push_back(-1);
+        off += ref_len[t];
+    }
+    g->total = off;
+    auto fail = [&](const char* what, cudaError_t e) {
+        g_genome_create_err = std::string(what) + ": " + cudaGetErrorString(e);
+        mth_genome_destroy(g);
+        return MTH_ERR_CUDA;
+    };
+    cudaError_t e;
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return fail("cudaSetDevice", e);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) g->sm_count = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+    if ((e = cudaMalloc((void**)&g->d_genome, (size_t)(off ? off : 1))) != cudaSuccess) return fail("cudaMalloc(genome)", e);
+    const size_t tb = sizeof(int64_t) * (size_t)(n_ref ? n_ref : 1);
+    if ((e = cudaMalloc((void**)&g->d_contig_off, tb)) != cudaSuccess) return fail("cudaMalloc", e);
+    if ((e = cudaMalloc((void**)&g->d_contig_len, tb)) != cudaSuccess) return fail("cudaMalloc", e);
+    if ((e = cudaMalloc((void**)&g->d_loaded, tb)) != cudaSuccess) return fail("cudaMalloc", e);
+    *out = g;
+    return MTH_OK;
+}
+
+int mth_genome_set_contig(mth_genome* g, int32_t tid, const uint8_t* seq, int64_t len) {
+    if (!g) return MTH_ERR_INVALID;
+    if (tid < 0 || tid >= g->n_ref || len < 0 || (len && !seq)) { g->err = "mth_genome_set_contig: bad arguments"; return MTH_ERR_INVALID; }
+    G_CUDA(cudaSetDevice(g->device));
+    const int64_t n = len < g->ref_len[(size_t)tid] ? len : g->ref_len[(size_t)tid];
+    uint8_t* dst = g->d_genome + g->contig_off[(size_t)tid];
+    if (n) {
+        G_CUDA(cudaMemcpyAsync(dst, seq, (size_t)n, cudaMemcpyHostToDevice, g->stream));
+        int64_t blocks = (n + 256 * 16 - 1) / (256 * 16);
+        const int64_t cap = (int64_t)g->sm_count * 16;
+        if (blocks > cap) blocks = cap;
+        k_upper<<<(unsigned)blocks, 256, 0, g->stream>>>(dst, n);
+        G_CUDA(cudaGetLastError());
+        G_CUDA(cudaStreamSynchronize(g->stream));  // `seq` is the caller's again
+    }
+    g->loaded[(size_t)tid] = n;
+    g->tables_dirty = true;
+    return MTH_OK;
+}
+
+int mth_tag(mth_genome* g, const mth_tag_batch* b, mth_tag_result* out) {
+    if (!g) return MTH_ERR_INVALID;
+    if (!b || !out || b->n_reads < 0) { g->err = "mth_tag: bad arguments"; return MTH_ERR_INVALID; }
+    const int64_t n = b->n_reads;
+    memset(out, 0, sizeof(*out));
+    if (n == 0) return MTH_OK;
+    if (!b->tid || !b->pos || !b->rc || !b->l_seq || !b->cigar_off || !b->seq_off) { g->err = "mth_tag: null array"; return MTH_ERR_INVALID; }
+    if (n > (int64_t)1 << 31) { g->err = "mth_tag: more than 2^31 reads in one batch"; return MTH_ERR_UNSUPPORTED; }
+    G_CUDA(cudaSetDevice(g->device));
+    const uint32_t n_cigar = b->cigar_off[n];
+    const uint64_t n_seq = b->seq_off[n];
+    if ((n_cigar && !b->cigar) || (n_seq && !b->seq4)) { g->err = "mth_tag: null cigar / seq4"; return MTH_ERR_INVALID; }
+    // offsets of the column scratch (M + I + D) and of the tag buffer (M + I), from the CIGARs
+    G_CUDA(g->h_col_off.ensure((size_t)n + 1));
+    G_CUDA(g->h_xm_off.ensure((size_t)n + 1));
+    uint64_t cols = 0, xms = 0;
+    for (int64_t r = 0; r < n; r++) {
+        g->h_col_off.p[r] = cols;
+        g->h_xm_off.p[r] = xms;
+        const uint32_t lo = b->cigar_off[r], hi = b->cigar_off[r + 1];
+        if (hi < lo || hi > n_cigar || b->seq_off[r + 1] < b->seq_off[r] || b->l_seq[r] < 0 ||
+            (uint64_t)(b->seq_off[r + 1] - b->seq_off[r]) < ((uint64_t)b->l_seq[r] + 1) / 2) {
+            g->err = "mth_tag: inconsistent offsets at read " + std::to_string(r);
+            return MTH_ERR_INVALID;
+        }
+        for (uint32_t k = lo; k < hi; k++) {
+            const uint32_t v = b->cigar[k], op = v & 15u;
+            if (op <= 2) cols += v >> 4;
+            if (op <= 1) xms += v >> 4;
+        }
+    }
+    g->h_col_off.p[n] = cols;
+    g->h_xm_off.p[n] = xms;
+
+    if (g->tables_dirty) {
+        const size_t tb = sizeof(int64_t) * (size_t)g->n_ref;
+        if (tb) {
+            G_CUDA(cudaMemcpyAsync(g->d_contig_off, g->contig_off.data(), tb, cudaMemcpyHostToDevice, g->stream));
+            G_CUDA(cudaMemcpyAsync(g->d_contig_len, g->ref_len.data(), tb, cudaMemcpyHostToDevice, g->stream));
+            G_CUDA(cudaMemcpyAsync(g->d_loaded, g->loaded.data(), tb, cudaMemcpyHostToDevice, g->stream));
+            G_CUDA(cudaStreamSynchronize(g->stream));
+        }
+        g->tables_dirty = false;
+    }
+    const size_t N = (size_t)n;
+    G_CUDA(g->d_tid.ensure(N)); G_CUDA(g->d_pos.ensure(N)); G_CUDA(g->d_lseq.ensure(N)); G_CUDA(g->d_rc.ensure(N));
+    G_CUDA(g->d_cigar_off.ensure(N + 1)); G_CUDA(g->d_cigar.ensure(n_cigar ? n_cigar : 1));
+    G_CUDA(g->d_seq_off.ensure(N + 1)); G_CUDA(g->d_seq4.ensure(n_seq ? n_seq : 1));
+    G_CUDA(g->d_col_off.ensure(N + 1)); G_CUDA(g->d_xm_off.ensure(N + 1));
+    G_CUDA(g->d_colr.ensure(cols ? cols : 1)); G_CUDA(g->d_colf.ensure(cols ? cols : 1));
+    G_CUDA(g->d_xm.ensure(xms ? xms : 1)); G_CUDA(g->d_xm_len.ensure(N)); G_CUDA(g->d_status.ensure(N));
+    G_CUDA(g->h_xm.ensure(xms ? xms : 1)); G_CUDA(g->h_xm_len.ensure(N)); G_CUDA(g->h_status.ensure(N));
+    cudaStream_t s = g->stream;
+    const auto H2D = cudaMemcpyHostToDevice;
+    G_CUDA(cudaMemcpyAsync(g->d_tid.p, b->tid, N * 4, H2D, s));
+    G_CUDA(cudaMemcpyAsync(g->d_pos.p, b->pos, N * 4, H2D, s));
+    G_CUDA(cudaMemcpyAsync(g->d_lseq.p, b->l_seq, N * 4, H2D, s));
+    G_CUDA(cudaMemcpyAsync(g->d_rc.p, b->rc, N, H2D, s));
+    G_CUDA(cudaMemcpyAsync(g->d_cigar_off.p, b->cigar_off, (N + 1) * 4, H2D, s));
+    if (n_cigar) G_CUDA(cudaMemcpyAsync(g->d_cigar.p, b->cigar, (size_t)n_cigar * 4, H2D, s));
+    G_CUDA(cudaMemcpyAsync(g->d_seq_off.p, b->seq_off, (N + 1) * 8, H2D, s));
+    if (n_seq) G_CUDA(cudaMemcpyAsync(g->d_seq4.p, b->seq4, (size_t)n_seq, H2D, s));
+    G_CUDA(cudaMemcpyAsync(g->d_col_off.p, g->h_col_off.p, (N + 1) * 8, H2D, s));
+    G_CUDA(cudaMemcpyAsync(g->d_xm_off.p, g->h_xm_off.p, (N + 1) * 8, H2D, s));
+
+    TagArgs a;
+    a.n_reads = n;
+    a.tid = g->d_tid.p; a.pos = g->d_pos.p; a.rc = g->d_rc.p; a.l_seq = g->d_lseq.p;
+    a.cigar_off = g->d_cigar_off.p; a.cigar = g->d_cigar.p; a.seq_off = g->d_seq_off.p; a.seq4 = g->d_seq4.p;
+    a.col_off = g->d_col_off.p; a.xm_off = g->d_xm_off.p;
+    a.genome = g->d_genome; a.contig_off = g->d_contig_off; a.contig_len = g->d_contig_len; a.loaded_len = g->d_loaded;
+    a.n_ref = g->n_ref;
+    a.col_read = g->d_colr.p; a.col_ref = g->d_colf.p; a.xm = g->d_xm.p; a.xm_len = g->d_xm_len.p; a.status = g->d_status.p;
+    int64_t blocks = (n + (TAG_BLOCK / 32) - 1) / (TAG_BLOCK / 32);
+    const int64_t cap = (int64_t)g->sm_count * 4;  // 4 resident CTAs of 256 threads per SM (launch bounds)
+    if (blocks > cap) blocks = cap;
+    if (!g->ev0) { G_CUDA(cudaEventCreate(&g->ev0)); G_CUDA(cudaEventCreate(&g->ev1)); }
+    G_CUDA(cudaEventRecord(g->ev0, s));
+    k_tag<<<(unsigned)blocks, TAG_BLOCK, 0, s>>>(a);
+    G_CUDA(cudaGetLastError());
+    G_CUDA(cudaEventRecord(g->ev1, s));
+    const auto D2H = cudaMemcpyDeviceToHost;
+    if (xms) G_CUDA(cudaMemcpyAsync(g->h_xm.p, g->d_xm.p, (size_t)xms, D2H, s));
+    G_CUDA(cudaMemcpyAsync(g->h_xm_len.p, g->d_xm_len.p, N * 4, D2H, s));
+    G_CUDA(cudaMemcpyAsync(g->h_status.p, g->d_status.p, N, D2H, s));
+    G_CUDA(cudaStreamSynchronize(s));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g->ev0, g->ev1) == cudaSuccess) g->last_kernel_ms = ms;
+    int64_t failed = 0;
+    for (int64_t r = 0; r < n; r++) failed += g->h_status.p[r] != MTH_TAG_OK;
+    out->n_reads = n;
+    out->n_failed = failed;
+    out->xm_off = g->h_xm_off.p;
+    out->xm_len = g->h_xm_len.p;
+    out->xm = g->h_xm.p;
+    out->status = g->h_status.p;
+    return MTH_OK;
+}
+
+double mth_genome_last_kernel_ms(mth_genome* g) { return g ? g->last_kernel_ms : -1.0; }
+
+int mth_genome_destroy(mth_genome* g) {
+    if (!g) return MTH_OK;
+    cudaSetDevice(g->device);
+    if (g->ev0) cudaEventDestroy(g->ev0);
+    if (g->ev1) cudaEventDestroy(g->ev1);
+    if (g->stream) { cudaStreamSynchronize(g->stream); cudaStreamDestroy(g->stream); }
+    if (g->d_genome) cudaFree(g->d_genome);
+    if (g->d_contig_off) cudaFree(g->d_contig_off);
+    if (g->d_contig_len) cudaFree(g->d_contig_len);
+    if (g->d_loaded) cudaFree(g->d_loaded);
+    g->d_tid.release(); g->d_pos.release(); g->d_lseq.release(); g->d_rc.release(); g->d_seq4.release();
+    g->d_colr.release(); g->d_colf.release(); g->d_xm.release(); g->d_status.release(); g->d_cigar_off.release();
+    g->d_cigar.release(); g->d_xm_len.release(); g->d_seq_off.release(); g->d_col_off.release(); g->d_xm_off.release();
+    g->h_xm_off.release(); g->h_col_off.release(); g->h_xm_len.release(); g->h_xm.release(); g->h_status.release();
+    delete g;
+    return MTH_OK;
+}
+
+}  // extern "C"

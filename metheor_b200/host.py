@@ -29,7 +29,7 @@ class Decoded(C.Structure):
 
 
 EXPORTS = ["mthh_options_default", "mthh_run", "mthh_main", "mthh_decode_file", "mthh_decoded_free", "mthh_format_f32", "mthh_inflate_raw",
-           "mthh_zlib_fallbacks"]
+           "mthh_zlib_fallbacks", "mthh_tag"]
 
 
 class HostError(RuntimeError):
@@ -60,6 +60,8 @@ def lib():
         L.mthh_format_f32.argtypes = [C.c_float, C.c_char_p, C.c_int]; L.mthh_format_f32.restype = C.c_int
         L.mthh_inflate_raw.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]; L.mthh_inflate_raw.restype = C.c_int
         L.mthh_zlib_fallbacks.argtypes = []; L.mthh_zlib_fallbacks.restype = C.c_int64
+        L.mthh_tag.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int32, C.c_int32, C.c_char_p, C.c_char_p, C.c_size_t]
+        L.mthh_tag.restype = C.c_int
         _lib = L
     return _lib
 
@@ -111,6 +113,15 @@ def format_f32(v):
     buf = C.create_string_buffer(128)
     n = lib().mthh_format_f32(C.c_float(v), buf, 128)
     return buf.raw[:n].decode()
+
+
+def tag(input, output, genome, device=0, threads=0, stats_json=None):
+    """`metheor tag -i input -o output -g genome` in-process (reference src/tag.rs:386-443); raises HostError."""
+    err = C.create_string_buffer(4096)
+    rc = lib().mthh_tag(str(input).encode(), str(output).encode(), str(genome).encode(), device, threads,
+                        stats_json.encode() if stats_json else None, err, 4096)
+    if rc != 0:
+        raise HostError(rc, err.value.decode())
 
 
 def inflate_raw(data, out_len):

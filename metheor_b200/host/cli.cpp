@@ -18,6 +18,7 @@
 
 namespace mthh {
 void run(const mthh_options& o);
+void run_tag(const char* input, const char* output, const char* genome, int device, int threads, const char* stats_json);
 int format_f32(float v, char* buf, int cap);
 }  // namespace mthh
 
@@ -88,7 +89,7 @@ std::vector<CmdSpec> commands() {
                   {'M', "max-distance", A_I32, false, "16", "Maximum distance between CpG pairs to consider", "MAX_DISTANCE"}, q, CPGSET}});
     c.push_back({"tag", "Add bismark XM tag to BAM file", -1,
                  {{'i', "input", A_STR, true, nullptr, "", "INPUT"}, {'o', "output", A_STR, true, nullptr, "", "OUTPUT"},
-                  {'g', "genome", A_STR, true, nullptr, "", "GENOME"}}});
+                  {'g', "genome", A_STR, true, nullptr, "", "GENOME"}, E_DEVICE, E_THREADS, E_STATS}});
     for (auto& cmd : c)
         if (cmd.measure >= 0) {
             cmd.args.push_back(E_DEVICE); cmd.args.push_back(E_GPUS); cmd.args.push_back(E_THREADS); cmd.args.push_back(E_STATS);
@@ -171,6 +172,21 @@ void mthh_options_default(mthh_options* o, int32_t measure) {
 int mthh_run(const mthh_options* o, char* err, size_t errcap) {
     try {
         mthh::run(*o);
+        return 0;
+    } catch (const HostError& e) {
+        if (err && errcap) snprintf(err, errcap, "%s", e.msg.c_str());
+        return e.status ? e.status : 1;
+    } catch (const std::exception& e) {
+        if (err && errcap) snprintf(err, errcap, "%s", e.what());
+        return 1;
+    }
+}
+
+int mthh_tag(const char* input, const char* output, const char* genome, int32_t device, int32_t threads, const char* stats_json,
+             char* err, size_t errcap) {
+    try {
+        if (!input || !output || !genome) throw HostError{2, "mthh_tag: input, output and genome are required"};
+        mthh::run_tag(input, output, genome, device, threads, stats_json);
         return 0;
     } catch (const HostError& e) {
         if (err && errcap) snprintf(err, errcap, "%s", e.msg.c_str());
@@ -285,14 +301,16 @@ int mthh_main(int argc, char** argv) {
         else if (n == "seed") o.seed = u;
         else if (n == "stats") o.stats_json = v;
     }
-    if (cmd->measure < 0) {
-        // `tag` (tag.rs:386-443) recomputes XM tags from a FASTA: a pre-processing utility outside the GPU hot path
-        // (DESIGN.md "Out of scope").  The flags are parsed like the reference's so that usage errors match.
-        fprintf(stderr, "metheor_b200: the 'tag' subcommand is not provided by this engine; run the reference's `metheor tag` to add XM tags.\n");
-        return 1;
-    }
     char err[4096];
     err[0] = 0;
+    if (cmd->measure < 0) {  // tag: -i -o -g (src/lib.rs:219-230)
+        const char* genome = nullptr;
+        for (size_t k = 0; k < cmd->args.size(); k++)
+            if (!strcmp(cmd->args[k].longn, "genome")) genome = val[k];
+        int rc = mthh_tag(o.input, o.output, genome, o.device, o.threads, o.stats_json, err, sizeof(err));
+        if (rc != 0) fprintf(stderr, "%s\n", err);
+        return rc;
+    }
     int rc = mthh_run(&o, err, sizeof(err));
     if (rc != 0) fprintf(stderr, "%s\n", err);
     return rc;

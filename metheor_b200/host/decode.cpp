@@ -1,6 +1,10 @@
 // decode.cpp — see decode.hpp.
 #include "decode.hpp"
 
+#ifdef __AVX2__
+#include <immintrin.h>
+#endif
+
 #include <algorithm>
 #include <cerrno>
 #include <cstdlib>
@@ -104,16 +108,30 @@ inline void emit_read(const ReadFields& r, NextOp&& next_op, const DecodeOptions
                 end = (int32_t)(ref + c.len - 1);
                 if (qi < r.xm_len) {
                     size_t stop = std::min(r.xm_len, qi + (size_t)c.len);  // zip() stops at the shorter side
-                    for (size_t x = qi; x < stop; x++) {
-                        char ch = r.xm[x];
-                        if ((ch | 0x20) != 'z') continue;  // readutil.rs:327-329 keeps 'z' / 'Z'
+                    auto call = [&](size_t x) {
+                        const char ch = r.xm[x];
                         int32_t p = (int32_t)(ref + (int64_t)(x - qi)) - (fwd ? 0 : 1);
-                        if (opt.cpg_set && !opt.cpg_set->contains(r.tid, p)) continue;  // readutil.rs:87-95
+                        if (opt.cpg_set && !opt.cpg_set->contains(r.tid, p)) return;  // readutil.rs:87-95
                         if (x > 65535) throw HostError{101, "read longer than 65535 query bases is not supported"};
                         out->cpg_pos.push_back(p);
                         out->cpg_rel.push_back((uint16_t)x);
                         out->cpg_meth.push_back(ch == 'Z');
+                    };
+                    size_t x = qi;
+#ifdef __AVX2__
+                    // readutil.rs:327-329 keeps 'z' / 'Z': 32 XM characters per compare, then only the hits are visited
+                    const __m256i fold = _mm256_set1_epi8(0x20), zed = _mm256_set1_epi8('z');
+                    for (; x + 32 <= stop; x += 32) {
+                        const __m256i v = _mm256_loadu_si256((const __m256i*)(r.xm + x));
+                        uint32_t hits = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(_mm256_or_si256(v, fold), zed));
+                        while (hits) {
+                            call(x + (size_t)__builtin_ctz(hits));
+                            hits &= hits - 1;
+                        }
                     }
+#endif
+                    for (; x < stop; x++)
+                        if ((r.xm[x] | 0x20) == 'z') call(x);
                 }
                 ref += c.len;
                 qi += c.len;

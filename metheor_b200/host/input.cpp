@@ -248,11 +248,13 @@ void RecordStream::parse_bam_header() {
         do {
             int32_t l_text = le32(b + o);
             if (l_text < 0) throw open_error("corrupt BAM header: " + path_);
+            const size_t o_text = o + 4;
             o += 4 + (size_t)l_text;
             if (o + 4 > n) break;
             int32_t n_ref = le32(b + o);
             o += 4;
             Header h;
+            h.text.assign((const char*)b + o_text, strnlen((const char*)b + o_text, (size_t)l_text));
             bool complete = true;
             for (int32_t i = 0; i < n_ref; i++) {
                 if (o + 4 > n) { complete = false; break; }
@@ -302,6 +304,8 @@ void RecordStream::parse_sam_header() {
         }
         o = e + 1;
     }
+    if (o > n) o = n;
+    header_.text.assign((const char*)d, o);
     coff_ = o;
 }
 

@@ -17,6 +17,7 @@ extern std::atomic<int64_t> g_zlib_fallbacks;  // BGZF members the fast decoder 
 struct Header {  // bamutil.rs:13-25 — the binary reference list gives tid <-> name
     std::vector<std::string> names;
     std::vector<int64_t> lengths;
+    std::string text;  // the SAM header text (BAM: the l_text bytes; SAM: the '@' lines), what `tag` copies to its output
     int tid_of(const std::string& n) const;
 };
 
