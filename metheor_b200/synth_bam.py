@@ -18,8 +18,9 @@ def _bgzf_block(data, level=1):
             struct.pack("<II", zlib.crc32(data) & 0xFFFFFFFF, len(data)))
 
 
-def write_bam(path, refs, batches, read_len=150, seed=0, threads=16, block=0xFF00):
-    """batches: SoA dicts (one contig each, ascending tid) whose reads are plain `read_len`M alignments."""
+def write_bam(path, refs, batches, read_len=150, seed=0, threads=16, block=0xFF00, with_xm=True):
+    """batches: SoA dicts (one contig each, ascending tid) whose reads are plain `read_len`M alignments.
+    with_xm=False leaves the XM:Z field out (input of `metheor tag`)."""
     rng = np.random.default_rng(seed)
     ht = ("@HD\tVN:1.0\tSO:coordinate\n" + "".join(f"@SQ\tSN:{n}\tLN:{l}\n" for n, l in refs)).encode()
     head = bytearray(b"BAM\x01" + struct.pack("<i", len(ht)) + ht + struct.pack("<i", len(refs)))
@@ -33,7 +34,7 @@ def write_bam(path, refs, batches, read_len=150, seed=0, threads=16, block=0xFF0
     o_seq = o_cigar + 4
     o_qual = o_seq + n_seq
     o_xm = o_qual + read_len
-    o_tail = o_xm + 3 + read_len + 1
+    o_tail = o_xm + (3 + read_len + 1 if with_xm else 0)
     tail = b"XRZCT\0XGZCT\0NMC\x03"
     rec_len = o_tail + len(tail)
     chunks = [bytes(head)]
@@ -63,6 +64,11 @@ def write_bam(path, refs, batches, read_len=150, seed=0, threads=16, block=0xFF0
         rec[:, o_cigar:o_cigar + 4] = np.frombuffer(struct.pack("<I", read_len << 4), np.uint8)
         rec[:, o_seq:o_seq + n_seq] = rng.choice(np.array([0x11, 0x12, 0x14, 0x18, 0x21, 0x28, 0x41, 0x48, 0x81, 0x88], np.uint8), (R, n_seq))
         rec[:, o_qual:o_qual + read_len] = rng.integers(28, 41, (R, read_len), dtype=np.uint8)
+        if not with_xm:
+            rec[:, o_tail:] = np.frombuffer(tail, np.uint8)
+            chunks.append(rec.tobytes())
+            n_total += R
+            continue
         rec[:, o_xm:o_xm + 3] = np.frombuffer(b"XMZ", np.uint8)
         xm = rec[:, o_xm + 3:o_xm + 3 + read_len]
         xm[:] = ord(".")
