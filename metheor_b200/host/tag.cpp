@@ -224,8 +224,15 @@ void pack_bam(const RecordRef& r, bool paired, TagBatchHost* b) {
 // ---- SAM text of a BAM record (what htslib's sam_format1 prints) ----
 inline void put_int(std::string* s, long long v) {
     char buf[24];
-    int n = snprintf(buf, sizeof(buf), "%lld", v);
-    s->append(buf, (size_t)n);
+    char* e = buf + sizeof(buf);
+    char* p = e;
+    unsigned long long u = v < 0 ? 0ull - (unsigned long long)v : (unsigned long long)v;
+    do {
+        *--p = (char)('0' + u % 10);
+        u /= 10;
+    } while (u);
+    if (v < 0) *--p = '-';
+    s->append(p, (size_t)(e - p));
 }
 inline void put_g(std::string* s, double v) {
     char buf[40];
