@@ -89,6 +89,7 @@ int mthh_format_f32(float v, char* buf, int cap);
  * mthh_zlib_fallbacks: how many BGZF members this process handed to zlib after the fast decoder rejected them. */
 int mthh_inflate_raw(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_len);
 int64_t mthh_zlib_fallbacks(void);
+uint32_t mthh_crc32(const uint8_t* p, size_t n); /* the BGZF reader's CRC-32 (PCLMULQDQ folding), == zlib crc32(0, p, n) */
 
 #ifdef __cplusplus
 }

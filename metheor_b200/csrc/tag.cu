@@ -24,6 +24,9 @@ namespace {
 
 constexpr uint32_t FULL = 0xffffffffu;
 constexpr int TAG_BLOCK = 256;
+#ifndef TAG_MINB
+#define TAG_MINB 3  // resident CTAs per SM the register budget is capped for
+#endif
 
 struct TagArgs {
     int64_t n_reads;
@@ -191,52 +194,87 @@ __device__ __noinline__ void tag_read_generic(const TagArgs& a, const int64_t r,
     } while (false);
 }
 
-constexpr int TAG_CAP = 512;  // target columns (body + 2) a warp keeps in shared memory
+constexpr int TAG_CAP = 512;     // target columns (body + 2) a warp keeps in shared memory
+constexpr int TAG_MAXREF = 512;  // contig tables of up to this many contigs are copied to shared memory
+
+// Per-read scalars.  The warp loads the NEXT read's header while it works on the current one, so the chain of dependent
+// global loads (offsets -> first CIGAR op / SEQ pointer) is off the critical path.
+struct ReadHdr {
+    uint64_t col_lo, col_hi, seq_off, xm_off;
+    int32_t tid, pos, l_seq;
+    uint32_t c_lo, c_hi, first_op;
+    bool rc;
+};
+__device__ __forceinline__ ReadHdr load_hdr(const TagArgs& a, int64_t r) {
+    ReadHdr h;
+    h.col_lo = a.col_off[r]; h.col_hi = a.col_off[r + 1];
+    h.seq_off = a.seq_off[r]; h.xm_off = a.xm_off[r];
+    h.tid = a.tid[r]; h.pos = a.pos[r]; h.l_seq = a.l_seq[r];
+    h.c_lo = a.cigar_off[r]; h.c_hi = a.cigar_off[r + 1];
+    h.first_op = h.c_hi > h.c_lo ? a.cigar[h.c_lo] : 0u;
+    h.rc = a.rc[r] != 0;
+    return h;
+}
 
 // One warp per read.  Reads of up to TAG_CAP - 2 body columns (all short-read data) stay in shared memory: phase A writes
 // the TARGET columns (already reverse-complemented for reverse-strand reads, tag.rs:244-257), phase B classifies them
 // into a shared character line and counts, phase C writes the tag (reversed for reverse-strand reads, tag.rs:380-383).
-__global__ void __launch_bounds__(TAG_BLOCK, 4) k_tag(const __grid_constant__ TagArgs a) {
+__global__ void __launch_bounds__(TAG_BLOCK, TAG_MINB) k_tag(const __grid_constant__ TagArgs a) {
     __shared__ uint8_t s_comp[256];
     __shared__ uint8_t s_read[TAG_BLOCK / 32][TAG_CAP + 4];
     __shared__ uint8_t s_ref[TAG_BLOCK / 32][TAG_CAP + 4];
     __shared__ uint8_t s_out[TAG_BLOCK / 32][TAG_CAP];
+    __shared__ int64_t s_tab[3][TAG_MAXREF];
     for (int c = threadIdx.x; c < 256; c += blockDim.x) s_comp[c] = complement((uint8_t)c);
+    const bool tab_smem = a.n_ref <= TAG_MAXREF;
+    if (tab_smem)
+        for (int c = threadIdx.x; c < a.n_ref; c += blockDim.x) {
+            s_tab[0][c] = a.contig_off[c];
+            s_tab[1][c] = a.contig_len[c];
+            s_tab[2][c] = a.loaded_len[c];
+        }
     __syncthreads();
+    const int64_t* const t_off = tab_smem ? s_tab[0] : a.contig_off;
+    const int64_t* const t_len = tab_smem ? s_tab[1] : a.contig_len;
+    const int64_t* const t_loaded = tab_smem ? s_tab[2] : a.loaded_len;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     uint8_t* const tr = s_read[wib];
     uint8_t* const tf = s_ref[wib];
     uint8_t* const to = s_out[wib];
+    ReadHdr nxt;
+    if (warp < a.n_reads) nxt = load_hdr(a, warp);
     for (int64_t r = warp; r < a.n_reads; r += n_warps) {
-        const int64_t B64 = (int64_t)(a.col_off[r + 1] - a.col_off[r]);
+        const ReadHdr h = nxt;
+        if (r + n_warps < a.n_reads) nxt = load_hdr(a, r + n_warps);
+        const int64_t B64 = (int64_t)(h.col_hi - h.col_lo);
         if (B64 + 2 > TAG_CAP) {
             tag_read_generic(a, r, lane);
             __syncwarp();
             continue;
         }
         const int B = (int)B64;
-        const int32_t tid = a.tid[r];
-        const int64_t start = a.pos[r];
-        const bool rc = a.rc[r] != 0;
-        const int32_t l_seq = a.l_seq[r];
-        const uint32_t c_lo = a.cigar_off[r], c_hi = a.cigar_off[r + 1];
-        if (tid < 0 || tid >= a.n_ref || a.loaded_len[tid] < 0 || start < 0) {
+        const int32_t tid = h.tid;
+        const int64_t start = h.pos;
+        const bool rc = h.rc;
+        const int32_t l_seq = h.l_seq;
+        const uint32_t c_lo = h.c_lo, c_hi = h.c_hi;
+        if (tid < 0 || tid >= a.n_ref || t_loaded[tid] < 0 || start < 0) {
             if (lane == 0) { a.status[r] = MTH_TAG_BAD_CONTIG; a.xm_len[r] = 0; }
             continue;
         }
-        const int64_t chrom = a.contig_len[tid], loaded = a.loaded_len[tid];
+        const int64_t chrom = t_len[tid], loaded = t_loaded[tid];
         const int64_t lim = chrom < loaded ? chrom : loaded;
-        const uint8_t* const g = a.genome + a.contig_off[tid];
-        const uint8_t* const sq = a.seq4 + a.seq_off[r];
+        const uint8_t* const g = a.genome + t_off[tid];
+        const uint8_t* const sq = a.seq4 + h.seq_off;
 
         // ---- phase A: target columns ----
         int c0 = 0;
         int64_t ur = 0, uf = 0, ref_span = 0;
         bool unmappable = false;
         for (uint32_t k = c_lo; k < c_hi; k++) {
-            const uint32_t v = a.cigar[k];
+            const uint32_t v = k == c_lo ? h.first_op : a.cigar[k];
             const int len = (int)(v >> 4);
             const uint32_t op = v & 15u;
             if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) ref_span += v >> 4;
@@ -327,7 +365,7 @@ __global__ void __launch_bounds__(TAG_BLOCK, 4) k_tag(const __grid_constant__ Ta
         }
         __syncwarp();
         // ---- phase C: the tag, in read orientation ----
-        uint8_t* const xm = a.xm + a.xm_off[r];
+        uint8_t* const xm = a.xm + h.xm_off;
         for (int k = lane; k < n_out; k += 32) xm[k] = to[rc ? n_out - 1 - k : k];
         if (lane == 0) { a.status[r] = MTH_TAG_OK; a.xm_len[r] = (uint32_t)n_out; }
         __syncwarp();
@@ -539,7 +577,7 @@ int mth_tag(mth_genome* g, const mth_tag_batch* b, mth_tag_result* out) {
     a.n_ref = g->n_ref;
     a.col_read = g->d_colr.p; a.col_ref = g->d_colf.p; a.xm = g->d_xm.p; a.xm_len = g->d_xm_len.p; a.status = g->d_status.p;
     int64_t blocks = (n + (TAG_BLOCK / 32) - 1) / (TAG_BLOCK / 32);
-    const int64_t cap = (int64_t)g->sm_count * 4;  // 4 resident CTAs of 256 threads per SM (launch bounds)
+    const int64_t cap = (int64_t)g->sm_count * TAG_MINB;  // resident CTAs of 256 threads per SM (launch bounds)
     if (blocks > cap) blocks = cap;
     if (!g->ev0) { G_CUDA(cudaEventCreate(&g->ev0)); G_CUDA(cudaEventCreate(&g->ev1)); }
     G_CUDA(cudaEventRecord(g->ev0, s));

@@ -29,7 +29,7 @@ class Decoded(C.Structure):
 
 
 EXPORTS = ["mthh_options_default", "mthh_run", "mthh_main", "mthh_decode_file", "mthh_decoded_free", "mthh_format_f32", "mthh_inflate_raw",
-           "mthh_zlib_fallbacks", "mthh_tag"]
+           "mthh_zlib_fallbacks", "mthh_tag", "mthh_crc32"]
 
 
 class HostError(RuntimeError):
@@ -60,6 +60,7 @@ def lib():
         L.mthh_format_f32.argtypes = [C.c_float, C.c_char_p, C.c_int]; L.mthh_format_f32.restype = C.c_int
         L.mthh_inflate_raw.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]; L.mthh_inflate_raw.restype = C.c_int
         L.mthh_zlib_fallbacks.argtypes = []; L.mthh_zlib_fallbacks.restype = C.c_int64
+        L.mthh_crc32.argtypes = [C.c_char_p, C.c_size_t]; L.mthh_crc32.restype = C.c_uint32
         L.mthh_tag.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int32, C.c_int32, C.c_char_p, C.c_char_p, C.c_size_t]
         L.mthh_tag.restype = C.c_int
         _lib = L
@@ -129,6 +130,10 @@ def inflate_raw(data, out_len):
     out = C.create_string_buffer(max(out_len, 1))
     ok = lib().mthh_inflate_raw(data, len(data), out, out_len)
     return out.raw[:out_len] if ok else None
+
+
+def crc32(data):
+    return int(lib().mthh_crc32(data, len(data)))
 
 
 def zlib_fallbacks():

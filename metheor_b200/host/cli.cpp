@@ -202,6 +202,7 @@ int mthh_format_f32(float v, char* buf, int cap) { return mthh::format_f32(v, bu
 int mthh_inflate_raw(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_len) {
     return mthh::inflate_fast(in, in_len, out, out_len) ? 1 : 0;
 }
+uint32_t mthh_crc32(const uint8_t* p, size_t n) { return mthh::crc32_fast(p, n); }
 int64_t mthh_zlib_fallbacks(void) { return mthh::g_zlib_fallbacks.load(); }
 
 int mthh_main(int argc, char** argv) {

@@ -10,4 +10,7 @@ namespace mthh {
 // out[0, out_len) and never reads outside in[0, in_len).
 bool inflate_fast(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_len);
 
+// CRC-32 (gzip polynomial, as zlib's crc32(0, p, n)); PCLMULQDQ folding when the CPU has it.
+uint32_t crc32_fast(const uint8_t* p, size_t n);
+
 }  // namespace mthh

@@ -59,7 +59,7 @@ struct Inflater {
     bool run(const uint8_t* in, size_t clen, uint8_t* out, uint32_t usize, uint32_t crc_expected) {
         static const bool zlib_only = getenv("METHEOR_ZLIB_INFLATE") != nullptr;  // A/B switch for measurements
         if (!zlib_only) {
-            if (inflate_fast(in, clen, out, usize) && (uint32_t)crc32(crc32(0L, Z_NULL, 0), out, usize) == crc_expected) return true;
+            if (inflate_fast(in, clen, out, usize) && crc32_fast(out, usize) == crc_expected) return true;
             g_zlib_fallbacks.fetch_add(1, std::memory_order_relaxed);  // rejected or wrong: let zlib have the last word
         }
         if (!ready) {
@@ -75,7 +75,7 @@ struct Inflater {
         zs.avail_out = usize;
         int rc = inflate(&zs, Z_FINISH);
         if (rc != Z_STREAM_END || zs.avail_out != 0) return false;
-        return (uint32_t)crc32(crc32(0L, Z_NULL, 0), out, usize) == crc_expected;
+        return crc32_fast(out, usize) == crc_expected;
     }
 };
 

@@ -5,7 +5,7 @@ set -e
 cd "$(dirname "$0")/../metheor_b200/csrc"
 NAME=$1; DEFS=$2
 mkdir -p build/var_$NAME
-for f in engine k_ingest k_sites k_pdr k_mhl k_mhl_site k_quartet k_fdrp k_fdrp_tile k_pairs k_expand; do
+for f in engine k_ingest k_sites k_pdr k_mhl k_mhl_site k_quartet k_fdrp k_fdrp_tile k_pairs k_expand tag; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=false -Xcompiler -fPIC,-ffp-contract=off $DEFS -c $f.cu -o build/var_$NAME/$f.o -Xptxas -v 2> build/var_$NAME/$f.log &
 done
 wait

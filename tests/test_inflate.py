@@ -44,6 +44,13 @@ def test_every_block_type_level_and_strategy_matches_zlib():
     assert n > 1000
 
 
+def test_crc32_matches_zlib_at_every_length_class():
+    rng = np.random.default_rng(2)
+    for n in list(range(0, 200)) + [255, 256, 1023, 4096, 65279, 65280, 65535, 100003]:
+        d = bytes(rng.integers(0, 256, n, dtype=np.uint8))
+        assert host.crc32(d) == (zlib.crc32(d) & 0xFFFFFFFF), n
+
+
 def test_multi_block_streams_and_sync_flushes():
     rng = np.random.default_rng(5)
     parts = [bytes(rng.integers(65, 70, 3000, dtype=np.uint8)), os.urandom(500), b"x" * 4000, b""]
