@@ -25,7 +25,7 @@ namespace {
 constexpr uint32_t FULL = 0xffffffffu;
 constexpr int TAG_BLOCK = 256;
 #ifndef TAG_MINB
-#define TAG_MINB 3  // resident CTAs per SM the register budget is capped for
+#define TAG_MINB 4  // resident CTAs per SM the register budget is capped for
 #endif
 
 struct TagArgs {
