@@ -12,6 +12,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <future>
+#include <memory>
 #include <string>
 #include <thread>
 #include <vector>
@@ -374,7 +376,7 @@ void run_tag(const char* input, const char* output, const char* genome, int devi
     const double t_begin = now_s();
     int n_threads = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
     if (n_threads < 1) n_threads = 1;
-    RecordStream rs(input, n_threads, (size_t)256 << 20);  // tag.rs:387 (get_reader panics when the file is missing)
+    RecordStream rs(input, n_threads, (size_t)64 << 20);  // tag.rs:387 (get_reader panics when the file is missing)
     const Header& h = rs.header();
     const std::string dir = parent_dir(output);
     if (!is_dir(dir)) panic("No such directory for output alignment file: " + dir);  // tag.rs:396-404
@@ -413,6 +415,7 @@ void run_tag(const char* input, const char* output, const char* genome, int devi
     bool first = true, paired = false;
     int64_t n_records = 0, n_batches = 0;
     double s_pack = 0, s_gpu = 0, s_format = 0, s_write = 0;
+    std::future<bool> writing;  // declared after `closer`: a pending write is joined before the file is closed
     std::string last_name;
     int last_tid = -1;
     const bool bam = rs.format() == Format::BAM;
@@ -475,13 +478,22 @@ void run_tag(const char* input, const char* output, const char* genome, int devi
         if (dup.load() >= 0)  // rust-htslib's push_aux refuses a tag that is already there (tag.rs:417-421)
             panic("Error adding XM tag to alignment record. the record already carries an XM tag");
         double t3 = now_s();
-        for (const std::string& s : parts)
-            if (!s.empty() && fwrite(s.data(), 1, s.size(), out) != s.size()) panic("Error writing to output file.");  // tag.rs:423
-        double t4 = now_s();
-        s_pack += t1 - t0; s_gpu += t2 - t1; s_format += t3 - t2; s_write += t4 - t3;
+        // the text of this window is written on a second thread while the next window is inflated, packed and tagged
+        if (writing.valid() && !writing.get()) panic("Error writing to output file.");  // tag.rs:423
+        auto owned = std::make_shared<std::vector<std::string>>(std::move(parts));
+        writing = std::async(std::launch::async, [owned, out, &s_write] {
+            const double w0 = now_s();
+            bool ok = true;
+            for (const std::string& s : *owned)
+                if (!s.empty() && fwrite(s.data(), 1, s.size(), out) != s.size()) ok = false;
+            s_write += now_s() - w0;
+            return ok;
+        });
+        s_pack += t1 - t0; s_gpu += t2 - t1; s_format += t3 - t2;
         n_records += n;
         n_batches++;
     }
+    if (writing.valid() && !writing.get()) panic("Error writing to output file.");
     if (fflush(out) != 0) panic("Error writing to output file.");
     const double t_end = now_s();
     if (stats_json) {

@@ -17,3 +17,9 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_i
     -o $OUT/prof_pdr_lpmd python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_full.log 2>&1
 ls -la $OUT
 timeout 600 python profiles/measure_all.py > $OUT/measure_all.jsonl 2>> $OUT/bench.err
+# `tag` (XM synthesis): CLI profile, launch time and one full capture of k_tag
+timeout 300 python profiles/tag_cli.py 1000000 2>> $OUT/bench.err | tail -1 > $OUT/tag_cli.json
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'k_tag|k_upper' -c 8 --csv --log-file $OUT/tag_launches.csv \
+    python -c "import bench; bench.tag_leg(2000000, 58617616)" > $OUT/tag_under_ncu.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:'k_tag' -s 1 -c 1 -o $OUT/prof_tag \
+    python -c "import bench; bench.tag_leg(2000000, 58617616)" >> $OUT/tag_under_ncu.log 2>&1
