@@ -197,8 +197,8 @@ __device__ __noinline__ void tag_read_generic(const TagArgs& a, const int64_t r,
 constexpr int TAG_CAP = 512;     // target columns (body + 2) a warp keeps in shared memory
 constexpr int TAG_MAXREF = 512;  // contig tables of up to this many contigs are copied to shared memory
 
-// Per-read scalars.  The warp loads the NEXT read's header while it works on the current one, so the chain of dependent
-// global loads (offsets -> first CIGAR op / SEQ pointer) is off the critical path.
+// Per-read scalars, loaded together at the top of the read so that the independent global loads overlap.  (Loading the
+// NEXT read's header one iteration ahead was measured: no gain, the kernel is issue-bound, and it cost spills.)
 struct ReadHdr {
     uint64_t col_lo, col_hi, seq_off, xm_off;
     int32_t tid, pos, l_seq;
@@ -225,7 +225,20 @@ __global__ void __launch_bounds__(TAG_BLOCK, TAG_MINB) k_tag(const __grid_consta
     __shared__ uint8_t s_ref[TAG_BLOCK / 32][TAG_CAP + 4];
     __shared__ uint8_t s_out[TAG_BLOCK / 32][TAG_CAP];
     __shared__ int64_t s_tab[3][TAG_MAXREF];
-    for (int c = threadIdx.x; c < 256; c += blockDim.x) s_comp[c] = complement((uint8_t)c);
+    // classify() as three byte look-ups: context class of each of the two bases behind the C (0 'G', 1 A/T/C, 2 '-'/'N',
+    // 3 anything else), class of the read base (0 'C', 1 'T', 2 other), and the 4 x 4 x 3 table of tag characters
+    __shared__ uint8_t s_cls[256], s_rdc[256], s_ctx[48], s_nt[16];
+    for (int c = threadIdx.x; c < 256; c += blockDim.x) {
+        s_comp[c] = complement((uint8_t)c);
+        s_cls[c] = c == 'G' ? 0 : is_h((uint8_t)c) ? 1 : is_unknown((uint8_t)c) ? 2 : 3;
+        s_rdc[c] = c == 'C' ? 0 : c == 'T' ? 1 : 2;
+    }
+    if (threadIdx.x < 48) {
+        static const char probe[4] = {'G', 'A', 'N', 'R'};  // one representative per context class
+        const int k1 = threadIdx.x / 12, k2 = (threadIdx.x / 3) & 3, kr = threadIdx.x % 3;
+        s_ctx[threadIdx.x] = classify((uint8_t)probe[k1], (uint8_t)probe[k2], 2, kr == 0 ? (uint8_t)'C' : kr == 1 ? (uint8_t)'T' : (uint8_t)'A');
+    }
+    if (threadIdx.x < 16) s_nt[threadIdx.x] = (uint8_t)"=ACMGRSVTWYHKDBN"[threadIdx.x];
     const bool tab_smem = a.n_ref <= TAG_MAXREF;
     if (tab_smem)
         for (int c = threadIdx.x; c < a.n_ref; c += blockDim.x) {
@@ -243,11 +256,8 @@ __global__ void __launch_bounds__(TAG_BLOCK, TAG_MINB) k_tag(const __grid_consta
     uint8_t* const tr = s_read[wib];
     uint8_t* const tf = s_ref[wib];
     uint8_t* const to = s_out[wib];
-    ReadHdr nxt;
-    if (warp < a.n_reads) nxt = load_hdr(a, warp);
     for (int64_t r = warp; r < a.n_reads; r += n_warps) {
-        const ReadHdr h = nxt;
-        if (r + n_warps < a.n_reads) nxt = load_hdr(a, r + n_warps);
+        const ReadHdr h = load_hdr(a, r);
         const int64_t B64 = (int64_t)(h.col_hi - h.col_lo);
         if (B64 + 2 > TAG_CAP) {
             tag_read_generic(a, r, lane);
@@ -284,7 +294,7 @@ __global__ void __launch_bounds__(TAG_BLOCK, TAG_MINB) k_tag(const __grid_consta
                 uint8_t rd = '-', rf = '-';
                 if (op != 2) {
                     const int64_t i = ur + j;
-                    rd = i < l_seq ? (uint8_t)"=ACMGRSVTWYHKDBN"[(sq[i >> 1] >> ((~i & 1) << 2)) & 15u] : (uint8_t)'N';
+                    rd = i < l_seq ? s_nt[(sq[i >> 1] >> ((~i & 1) << 2)) & 15u] : (uint8_t)'N';
                 }
                 if (op != 1) {
                     const int64_t p = start + uf + j;
@@ -348,7 +358,7 @@ __global__ void __launch_bounds__(TAG_BLOCK, TAG_MINB) k_tag(const __grid_consta
                         if (found == 0) no_context = true;
                         else ch = classify(ctx[0], ctx[1], found, rd);
                     } else {
-                        ch = classify(tf[i + 1], tf[i + 2], 2, rd);
+                        ch = s_ctx[s_cls[tf[i + 1]] * 12 + s_cls[tf[i + 2]] * 3 + s_rdc[rd]];
                     }
                 } else {
                     ch = '.';
