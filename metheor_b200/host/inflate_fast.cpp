@@ -50,10 +50,21 @@ const uint16_t DIST_BASE[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97,
                                 4097, 6145, 8193, 12289, 16385, 24577};
 const uint8_t DIST_EXTRA[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
 
+struct Rev8 {
+    uint8_t t[256];
+    Rev8() {
+        for (int i = 0; i < 256; i++) {
+            int r = 0;
+            for (int b = 0; b < 8; b++) r |= ((i >> b) & 1) << (7 - b);
+            t[i] = (uint8_t)r;
+        }
+    }
+};
+const Rev8 REV8;
+// the low n (<= 15) bits of v, reversed
 inline uint32_t bit_reverse(uint32_t v, int n) {
-    uint32_t r = 0;
-    for (int i = 0; i < n; i++) { r = (r << 1) | (v & 1); v >>= 1; }
-    return r;
+    const uint32_t r16 = ((uint32_t)REV8.t[v & 255u] << 8) | REV8.t[(v >> 8) & 255u];
+    return r16 >> (16 - n);
 }
 
 // Builds a decode table from codeword lengths (canonical Huffman, RFC 1951 3.2.2).  `table` holds (1 << tb) primary
