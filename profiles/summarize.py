@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Turn one GPU pass (gpurun_out/<tag>/, written by profiles/gpu_pass.sh) into the tracked summary profiles/<tag>_*.
    python profiles/summarize.py r01a          (needs `ncu` on PATH for the .ncu-rep -> csv step; no GPU needed)"""
-import csv
+import csv, re
 import glob
 import json
 import os
@@ -17,6 +17,14 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__shared_mem_per_block_static", "launch__shared_mem_per_block_dynamic"]
 
 
+def kname(full_name):
+    """'void mth::k_ingest<(bool)0, (bool)1>(mth::IngestArgs)' -> 'k_ingest' (instances of a template are one kernel here)."""
+    n = full_name[5:] if full_name.startswith("void ") else full_name
+    for pre in ("mth::", "<unnamed>::"):
+        n = n.replace(pre, "")
+    return re.split(r"[<(]", n)[0].strip()
+
+
 def launches(path):
     """-> OrderedDict kernel -> [n, total_ns] from an `ncu --metrics gpu__time_duration.sum --csv` log."""
     agg = OrderedDict()
@@ -25,7 +33,7 @@ def launches(path):
     hdr = rows[0]
     ik, iv = hdr.index("Kernel Name"), hdr.index("Metric Value")
     for r in rows[1:]:
-        name = r[ik].split("(")[0]
+        name = kname(r[ik])
         a = agg.setdefault(name, [0, 0.0])
         a[0] += 1
         a[1] += float(r[iv].replace(",", ""))
@@ -38,7 +46,7 @@ def full(rep):
     hdr, units = rows[0], rows[1]
     out = []
     for r in rows[2:]:
-        d = {"kernel": r[hdr.index("Kernel Name")].split("(")[0]}
+        d = {"kernel": kname(r[hdr.index("Kernel Name")])}
         for k in KEYS:
             if k in hdr:
                 d[k] = f"{r[hdr.index(k)]} {units[hdr.index(k)]}".strip()
