@@ -1,12 +1,13 @@
 // k_ingest.cu — per-batch kernels: offset/coordinate fix-ups, validation, CpG-site marking and LPMD.
 //
-// k_ingest is one pass over a freshly copied batch (16 B/read + 4 B/CpG [+2 B/CpG for LPMD] of HBM reads):
+// k_ingest is one pass over a freshly copied batch (24 B/read + 4 B/CpG [+2 B/CpG for LPMD] of HBM reads):
 //   * validates what every later kernel relies on (sorted starts, monotone offsets, CpG positions strictly
 //     increasing and inside [start-1, end]) and records max(end-start+1) for the gather windows;
-//   * marks each CpG position in the region's site bitmap (load-test then atomicOr: bits are only ever set,
-//     so a stale 0 only costs a redundant atomic);
+//   * marks each CpG position in the region's site bitmap (shared-memory window per tile, merged with atomicOr:
+//     bits are only ever set);
+//   * writes one flag byte per call (call_flags) carrying the read-level verdicts the per-call kernels need;
 //   * LPMD (lpmd.rs:175-199 + readutil.rs:166-224): all in-read CpG pairs with min <= d(query index) <= max,
-//     concordant iff equal methylation; warp-reduced into four 64-bit device counters.
+//     concordant iff equal methylation; block-reduced into four 64-bit device counters.
 #include "kernels.h"
 #include "tma.cuh"
 
