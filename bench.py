@@ -98,11 +98,32 @@ def oracle_time(b, n_sample, steps=1):
     best = None
     for _ in range(steps):
         t0 = time.perf_counter()
-        o.pdr(10, 4, 10)
-        o.lpmd(2, 16, 10)
+        _ORACLE_LAST["pdr"] = o.pdr(10, 4, 10)
+        _ORACLE_LAST["lpmd"] = o.lpmd(2, 16, 10)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
+    _ORACLE_LAST["reads"] = sub["n_reads"]
     return sub["n_reads"] / best, best, sub["n_reads"]
+
+
+_ORACLE_LAST = {}  # results of the last oracle_time pass: the checker of `parity_full_size`
+
+
+def parity_full_size(eng, R):
+    """Engine rows of the end-to-end leg (whole bench workload, through the C ABI with host buffers) against the oracle pass
+    that was timed as cpu_baseline: bit-exact rows and LPMD counters at BASELINE.json's full size."""
+    w, wl = _ORACLE_LAST.get("pdr"), _ORACLE_LAST.get("lpmd")
+    if w is None or _ORACLE_LAST.get("reads") != R:
+        return None
+    g, gl = eng["pdr"], eng["lpmd"]
+    f32 = lambda a: np.asarray(a, np.float32).view(np.uint32)
+    n = int(g["n"])
+    rows_ok = (n == len(w["pos"]) and all(np.array_equal(np.asarray(g[k])[:n], w[k]) for k in ("tid", "pos", "n_conc", "n_disc"))
+               and np.array_equal(f32(g["value"])[:n], f32(w["pdr"])))
+    lpmd_ok = all(int(gl[k]) == int(wl[k]) for k in ("n_read", "n_valid_read", "n_conc", "n_disc")) and \
+        (f32(gl["lpmd"]) == f32(wl["lpmd"]) or (np.isnan(gl["lpmd"]) and np.isnan(wl["lpmd"])))
+    return {"reads": int(R), "pdr_rows": n, "pdr_rows_bit_identical_to_oracle": bool(rows_ok), "lpmd_identical_to_oracle": bool(lpmd_ok),
+            "checked": "rows and counters of the e2e leg vs the oracle pass timed as cpu_baseline (tid, pos, n_conc, n_disc, f32 bit patterns)"}
 
 
 _ORACLE_PARTS = None
@@ -521,6 +542,13 @@ def main():
                "sample": f"first {nn} reads of the workload (pdr+lpmd, defaults); C++ restatement of metheor 0.1.9, "
                          f"single-threaded like the reference; host has {os.cpu_count()} cores"}
 
+    parity_full = None
+    if cpu is not None:
+        try:
+            parity_full = parity_full_size(eres, R)
+        except Exception as e:  # a checker problem must never cost the bench line
+            parity_full = {"error": repr(e)}
+
     cpu_all = None
     if cpu is not None and (os.cpu_count() or 1) > 1:
         try:
@@ -564,7 +592,7 @@ def main():
                 "e2e_soa": dict(e2e["soa"], wire_format="SoA (mth_submit), one batch"),
                 "gpu_launches": int((st["kernel_launches"] - 0) * args.steps),
                 "launches_per_step": int(st["kernel_launches"]),
-                "roofline": roofline, "roofline_step": roofline_step, "kernels": kern, "cpu_baseline": cpu, "cpu_baseline_all_cores": cpu_all, "bam_end_to_end": bam, "tag": tag_res,
+                "roofline": roofline, "roofline_step": roofline_step, "kernels": kern, "cpu_baseline": cpu, "parity_full_size": parity_full, "cpu_baseline_all_cores": cpu_all, "bam_end_to_end": bam, "tag": tag_res,
                 "clocks": clocks, "pdr_path": {1: "scatter", 2: "gather", 3: "scatter+gather(hazard sites)"}.get(st["pdr_path"]), "lpmd": float(rows["lpmd"]["lpmd"]),
                 "lpmd_all_ranks": lpmd_all}
         emit(line)
