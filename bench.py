@@ -1,44 +1,221 @@
 #!/usr/bin/env python
-"""bench.py — BASELINE.json configs[1]: `pdr` + `lpmd` over synthetic 30x WGBS of a chr19-sized contig.
+"""bench.py — metheor_b200 on BASELINE.json's whole-genome configuration, per measure.
 
-One "step" = one full pass of the hot path over the whole read set (11.7 M reads, ~31 M CpG calls): ingest
-(validation + site marking + LPMD), site dictionary, PDR counters, row emission.
+Workload (`config.workload`): BASELINE.json configs[2] — synthetic 30x WGBS over 24 contigs with the hg38 chromosome
+lengths (3.09 Gb, ~28 M CpG sites, ~0.62 G 150-bp single-end reads on both strands, ~0.82 G CpG calls), generated on the
+GPU from an integer hash (metheor_b200/synth_gpu.py; bit-identical on CPU and CUDA).  The headline measure set is that
+config's `pm` + `me`; the line also carries one block per measure (pdr, lpmd, mhl, pm, me, fdrp, qfdrp) on the SAME
+workload, the combined passes, and — as secondary legs — configs[1] (pdr + lpmd on a chr19-sized contig: the round-1
+headline), configs[3] (fdrp + qfdrp at 60x), the BAM -> TSV path and `tag`.
 
-  value : reads/s with the SoA batch already resident in HBM (device pointers handed to mth_submit, rows left in HBM)
-  e2e   : reads/s through the same C-ABI calls with HOST (pinned) buffers: H2D of the batch and D2H of the rows inside
-          the timed region
-  roofline : the slowest kernel of the step, algorithmic bytes / its CUDA-event time, vs MEASURED_PEAKS.json
-  cpu_baseline : the CPU oracle (C++ restatement of metheor 0.1.9, NOT the Rust binary) on a bounded sample, 1 core
+One "step" = one full pass of the hot path over the whole read set: per contig mth_submit (ingest: validation, site
+bitmap, LPMD) -> site dictionary -> measure kernels -> row emission, then mth_finish.
+  value     : reads/s, SoA batches already resident in HBM (device pointers handed to mth_submit, rows left in HBM)
+  e2e       : reads/s through the same C-ABI calls with HOST buffers: pinned SoA arrays in the layout north_star names
+              (per-read int32 CpG positions + packed uint64 methylation words), H2D of every batch and D2H of the rows inside
+              the timed region; nothing is pre-encoded on the host
+  roofline  : the measure's dominant kernel: algorithmic bytes (SURVEY 8d / DESIGN.md §4) over its CUDA-event time, against
+              MEASURED_PEAKS.json; `roofline_measure` = SURVEY 8d bytes of the measure over the sum of its kernels
+  cpu_baseline : the CPU oracle (C++ restatement of metheor 0.1.9 — the Rust binary cannot be built here), one thread like
+              the reference, on a stated bounded sample of the same workload
+  parity_full_size : the rows the engine produced in the FULL pass, restricted to one whole contig (chr21; a prefix of it
+              for fdrp / qfdrp), bit-identical to the oracle run on that contig's reads (contigs are independent in the
+              reference: a tid change flushes every accumulator, readutil.rs:290-295), plus digests that tie every
+              single-measure pass to the all-seven pass that was checked
 
-N > 1 (torchrun): every rank processes its own chr19-sized contig (weak scaling, genomic sharding needs no data-path
-collective); LPMD's four int64 counters are all-reduced over NCCL each step.
-`--impl reference` times the CPU oracle alone (rank 0 only).
+N > 1 (torchrun): STRONG scaling — the same genome is cut into N position bins (+ halo reads, MTH_META_HALO), one bin per
+rank, no data-path collective; the one exchange is the library's NCCL all-reduce of LPMD's counters (mth_allreduce), once
+per pass.  Rank 0 then runs the whole genome alone (untimed) and checks that the owned rows of all ranks together have
+the same digest.
+`--impl reference`: the CPU oracle alone on the parity contig (rank 0 only; no GPU needed).
 """
 import argparse
 import json
 import os
-import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-SEED = 20260101
-CONTIG_LEN = 58_617_616
+SEED = 20260102
 COVERAGE = 30.0
-WORKLOAD = "pdr+lpmd, synthetic 30x WGBS, chr19-sized contig (58.6 Mb, ~1.1 M CpG sites, 150-bp SE reads, both strands)"
-MEASURES = ("pdr", "lpmd")
-CPU_SAMPLE_READS = 12_000_000  # the whole chr19-sized read set: a full pass takes the oracle only a few seconds
+HEADLINE = ("pm", "me")
+ALL7 = ("pdr", "lpmd", "mhl", "pm", "me", "fdrp", "qfdrp")
+SINGLE = tuple((m,) for m in ALL7)
+COMBOS = (("pm", "me"), ("pdr", "lpmd"), ("fdrp", "qfdrp"), ALL7)
+PARITY_TID = 20                      # chr21: the smallest contig (46.7 Mb, ~9.3 M reads at 30x)
+FDRP_PARITY_SPAN = 8_000_000         # fdrp / qfdrp rows are checked on the first 8 Mb of the parity contig (oracle: O(d^2 * 403) per site)
+HALO = 1024                          # reads starting up to this far before a bin also go to its rank (>= longest reference span + 2)
+DTYPE = "u32/u64 integer + f32 finalisation"
 
 
-def make_workload(rank, coverage=COVERAGE, length=CONTIG_LEN):
-    from metheor_b200 import synth
-    b, sites = synth.chr19_like(seed=SEED + 1000 * rank, coverage=coverage, length=length)
-    return b, sites
+def workload_name(cov, scale):
+    s = (f"synthetic {cov:g}x WGBS whole genome: 24 contigs with the hg38 chromosome lengths (3.09 Gb), ~28 M CpG sites, "
+         f"150-bp SE reads on both strands (BASELINE.json configs[2]), seed {SEED}")
+    return s if scale == 1.0 else s + f", contig lengths x {scale:g}"
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
+_REAL_STDOUT = None
+
+
+def ensure_built():
+    need = [os.path.join(ROOT, "metheor_b200", "csrc", "libmetheor_b200.so"), os.path.join(ROOT, "metheor_b200", "host", "libmetheor_host.so"),
+            os.path.join(ROOT, "oracle", "_build", "liboracle.so")]
+    if not all(os.path.exists(p) for p in need):
+        if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+            import __graft_entry__
+            __graft_entry__.build()
+        else:
+            t0 = time.time()
+            while not all(os.path.exists(p) for p in need) and time.time() - t0 < 600:
+                time.sleep(1.0)
+            time.sleep(2.0)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# workload
+# ---------------------------------------------------------------------------------------------------------------------
+def plan_bins_by_length(ref_len, world):
+    from metheor_b200 import shard
+    return shard.plan_bins(ref_len, world)
+
+
+def gen_shard(torch, dev, contigs, coverage, intervals, world):
+    """The reads a rank needs for its intervals [(tid, lo, hi)]: start in [lo - HALO, hi]; halo copies carry MTH_META_HALO.
+    -> (list of torch batches, owned reads, owned calls)"""
+    from metheor_b200 import synth_gpu as G
+    out, owned_r, owned_i = [], 0, 0
+    for tid, lo, hi in intervals:
+        length = contigs[tid][1]
+        whole = world == 1 or (lo == 0 and hi >= length)
+        b = G.make_contig(dev, SEED, tid, length, coverage, start_range=None if whole else (lo - HALO, hi + 1))
+        if not whole:
+            st = b["start"]
+            halo = (st < lo) | (st >= hi)
+            b["meta"] = torch.where(halo, b["meta"] | (1 << 9), b["meta"])
+            cnt = (b["cpg_off"][1:] - b["cpg_off"][:-1]).to(torch.int64)
+            owned_r += int((~halo).sum()); owned_i += int(cnt[~halo].sum())
+        else:
+            owned_r += b["n_reads"]; owned_i += b["n_cpg"]
+        out.append(b)
+    return out, owned_r, owned_i
+
+
+def batch_bytes(b, with_rel):
+    return 24 * b["n_reads"] + 4 + (6 if with_rel else 4) * b["n_cpg"]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# device-side digests of result rows (order-independent 64-bit sums: shards add up to the whole)
+# ---------------------------------------------------------------------------------------------------------------------
+class _DevArr:
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def _dt(torch, dev, ptr, n, typestr):
+    if not ptr or n == 0:
+        return torch.zeros(0, dtype=torch.int64, device=dev)
+    return torch.as_tensor(_DevArr(ptr, n, typestr), device=dev).to(torch.int64)
+
+
+_K = [-7046029254386353131, -4658895280553007687, -7723592293110705685, 0x2545F4914F6CDD1D, 0x27D4EB2F165667C5, 0x165667B19E3779F9,
+      -3750763034362895579]
+
+
+def _mix(torch, cols):
+    x = torch.zeros_like(cols[0])
+    for k, c in zip(_K, cols):
+        x = (x ^ c) * k
+        x = x ^ ((x >> 29) & ((1 << 35) - 1))
+    return x
+
+
+def rows_digest(torch, dev, ctx, measures, owned=None):
+    """{measure: [n_rows, digest]} from the device-resident rows of the last finish(); owned = [(tid, lo, hi)] keeps only the
+    rows whose (first) position lies in one of the intervals (position-bin sharding)."""
+    r = ctx.results_device()
+    out = {}
+
+    def own_mask(tid, pos):
+        if owned is None:
+            return None
+        m = torch.zeros_like(tid, dtype=torch.bool)
+        for t, lo, hi in owned:
+            m |= (tid == t) & (pos >= lo) & (pos < hi)
+        return m
+
+    for name in ("pdr", "mhl", "fdrp", "qfdrp"):
+        if name not in measures:
+            continue
+        s = getattr(r, name)
+        n = int(s.n)
+        cols = [_dt(torch, dev, s.tid, n, "<i4"), _dt(torch, dev, s.pos, n, "<i4"), _dt(torch, dev, s.value, n, "<i4")]
+        if name == "pdr":
+            cols += [_dt(torch, dev, s.n_conc, n, "<i4"), _dt(torch, dev, s.n_disc, n, "<i4")]
+        x = _mix(torch, cols)
+        m = own_mask(cols[0], cols[1])
+        if m is not None:
+            x = x[m]
+        out[name] = [int(x.numel()), int(x.sum())]
+    for name in ("pm", "me"):
+        if name not in measures:
+            continue
+        s = getattr(r, name)
+        n = int(s.n)
+        cols = [_dt(torch, dev, getattr(s, k), n, "<i4") for k in ("tid", "p1", "p2", "p3", "p4", "value")]
+        x = _mix(torch, cols)
+        m = own_mask(cols[0], cols[1])
+        if m is not None:
+            x = x[m]
+        out[name] = [int(x.numel()), int(x.sum())]
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# algorithmic bytes and kernel attribution
+# ---------------------------------------------------------------------------------------------------------------------
+def survey_bytes(m, R, I, C, Q):
+    return {"pdr": 16 * R + 4 * I + 12 * C, "lpmd": 16 * R + 6 * I + 16, "mhl": 24 * R + 4 * I + 8 * C, "pm": 16 * R + 4 * I + 20 * Q,
+            "me": 16 * R + 4 * I + 20 * Q, "fdrp": 24 * R + 4 * I + 8 * C, "qfdrp": 24 * R + 4 * I + 8 * C}[m]
+
+
+def kernel_bytes(k, measures, R, I, C, Q):
+    """Compulsory bytes of ONE kernel family over a pass (what it must read and write at least once), never more than the
+    SURVEY 8d figure of the measure it serves."""
+    lp = "lpmd" in measures
+    if k == "k_ingest":
+        return 16 * R + (6 if lp else 4) * I + (32 if lp else 0)
+    if k in ("k_pdr_scatter", "k_pdr_tile"):
+        return 5 * I + 8 * C                      # cpg_pos + flag byte per call, two u32 counters per site
+    if k == "k_pdr_gather":
+        return 16 * R + 4 * I + 8 * C
+    if k == "k_mhl":
+        return 24 * R + 4 * I + 8 * C
+    if k in ("k_fdrp", "k_qfdrp"):
+        return 24 * R + 4 * I + 8 * C
+    if k == "k_fdrp_qfdrp":
+        return 24 * R + 4 * I + 16 * C
+    if k in ("k_pm_scatter", "k_me_scatter"):
+        return 5 * I + 64 * C                     # cpg_pos + flag byte per call, one 16-bin u32 histogram per site
+    if k in ("k_pm_count", "k_me_count", "k_pm_emit", "k_me_emit"):
+        return 64 * C + 24 * Q
+    return None
+
+
+MEASURE_KERNELS = {"pdr": ("k_pdr",), "lpmd": (), "mhl": ("k_mhl",), "pm": ("k_pm",), "me": ("k_me",), "fdrp": ("k_fdrp",), "qfdrp": ("k_qfdrp",)}
 
 
 def peaks():
@@ -49,273 +226,112 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-
-    def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
-
-    def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
-            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        self.t.join(timeout=2)
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+def load_traffic():
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
 
 
-def oracle_time(b, n_sample, steps=1):
-    """CPU oracle (pdr + lpmd, reference defaults) on the first n_sample reads. -> (reads/s, seconds per pass)"""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU oracle legs
+# ---------------------------------------------------------------------------------------------------------------------
+ORACLE_PRM = dict(pdr=dict(min_depth=10, min_cpgs=4, min_qual=10), mhl=dict(min_depth=10, min_cpgs=4, min_qual=10),
+                  pm=dict(min_depth=10, min_qual=10), me=dict(min_depth=10, min_qual=10),
+                  fdrp=dict(min_qual=10, min_depth=10, max_depth=40, min_overlap=35),
+                  qfdrp=dict(min_qual=10, min_depth=10, max_depth=40, min_overlap=35), lpmd=dict(min_distance=2, max_distance=16, min_qual=10))
+CPU_SAMPLE = dict(pdr=None, lpmd=None, mhl=None, pm=None, me=None, fdrp=250_000, qfdrp=150_000)  # reads; None = the whole parity contig
+
+
+def oracle_single(nb, m, n_reads=None, repeat=1):
+    """One thread, like the reference: -> (reads/s, seconds, reads) for measure m on the first n_reads reads of nb."""
     from metheor_b200 import batch as B
     from oracle_lib import Oracle
-    sub = B.slice_reads(b, 0, min(n_sample, b["n_reads"]))
+    n = nb["n_reads"] if n_reads is None else min(n_reads, nb["n_reads"])
+    sub = nb if n == nb["n_reads"] else B.slice_range(nb, 0, n)
     o = Oracle.from_soa(**B.to_oracle_soa([sub]))
     best = None
-    for _ in range(steps):
+    for _ in range(repeat):
         t0 = time.perf_counter()
-        _ORACLE_LAST["pdr"] = o.pdr(10, 4, 10)
-        _ORACLE_LAST["lpmd"] = o.lpmd(2, 16, 10)
+        if m == "pdr": o.pdr(**ORACLE_PRM["pdr"])
+        elif m == "lpmd": o.lpmd(**ORACLE_PRM["lpmd"])
+        elif m == "mhl": o.mhl(**ORACLE_PRM["mhl"])
+        elif m in ("pm", "me", "pm+me"): o.quartets(**ORACLE_PRM["pm"])
+        elif m in ("fdrp", "qfdrp"): o.fdrp(quantitative=(m == "qfdrp"), **ORACLE_PRM[m])
+        else: raise ValueError(m)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
-    _ORACLE_LAST["reads"] = sub["n_reads"]
-    return sub["n_reads"] / best, best, sub["n_reads"]
+    o.close()
+    return n / best, best, n
 
 
-_ORACLE_LAST = {}  # results of the last oracle_time pass: the checker of `parity_full_size`
+def f32bits(a):
+    return np.asarray(a, np.float32).view(np.uint32)
 
 
-def parity_full_size(eng, R):
-    """Engine rows of the end-to-end leg (whole bench workload, through the C ABI with host buffers) against the oracle pass
-    that was timed as cpu_baseline: bit-exact rows and LPMD counters at BASELINE.json's full size."""
-    w, wl = _ORACLE_LAST.get("pdr"), _ORACLE_LAST.get("lpmd")
-    if w is None or _ORACLE_LAST.get("reads") != R:
-        return None
-    g, gl = eng["pdr"], eng["lpmd"]
-    f32 = lambda a: np.asarray(a, np.float32).view(np.uint32)
-    n = int(g["n"])
-    rows_ok = (n == len(w["pos"]) and all(np.array_equal(np.asarray(g[k])[:n], w[k]) for k in ("tid", "pos", "n_conc", "n_disc"))
-               and np.array_equal(f32(g["value"])[:n], f32(w["pdr"])))
-    lpmd_ok = all(int(gl[k]) == int(wl[k]) for k in ("n_read", "n_valid_read", "n_conc", "n_disc")) and \
-        (f32(gl["lpmd"]) == f32(wl["lpmd"]) or (np.isnan(gl["lpmd"]) and np.isnan(wl["lpmd"])))
-    return {"reads": int(R), "pdr_rows": n, "pdr_rows_bit_identical_to_oracle": bool(rows_ok), "lpmd_identical_to_oracle": bool(lpmd_ok),
-            "checked": "rows and counters of the e2e leg vs the oracle pass timed as cpu_baseline (tid, pos, n_conc, n_disc, f32 bit patterns)"}
-
-
-_ORACLE_PARTS = None
-_ORACLE_CACHE = {}
-
-
-def _oracle_slice(args):
-    """worker of oracle_all_cores: one oracle pass (pdr + lpmd) over one slice of the reads; returns its seconds"""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from oracle_lib import Oracle
-    o = _ORACLE_CACHE.get(args)
-    if o is None:  # warm-up call: build this slice's read set once (inherited through fork: nothing is pickled)
-        o = _ORACLE_CACHE[args] = Oracle.from_soa(**_ORACLE_PARTS[args])
-    t0 = time.perf_counter()
-    o.pdr(10, 4, 10)
-    o.lpmd(2, 16, 10)
-    return time.perf_counter() - t0
-
-
-def oracle_all_cores(b, n_proc):
-    """What the CPU could do at best with every host core: the reads cut into n_proc position slices, one oracle process
-    each (the reference itself is single-threaded and could only be run per contig this way; slices of ONE contig are
-    not bit-identical at their edges, so this is an optimistic throughput bound, not a parity run)."""
-    import multiprocessing as mp
-    from metheor_b200 import batch as B
-    R = b["n_reads"]
-    cuts = [R * k // n_proc for k in range(n_proc + 1)]
-    global _ORACLE_PARTS
-    _ORACLE_PARTS = [B.to_oracle_soa([B.slice_reads(b, lo, hi)]) for lo, hi in zip(cuts[:-1], cuts[1:])]
-    with mp.get_context("fork").Pool(n_proc) as pool:
-        for _ in range(2):  # warm-up: every worker ends up holding every slice's decoded reads
-            pool.map(_oracle_slice, list(range(n_proc)) * 4, chunksize=1)
+def parity_contig(rows, nb, tid, n_proc):
+    """Engine rows of the full pass (host arrays) restricted to contig `tid` against the oracle on that contig's reads."""
+    import oracle_parallel as OP
+    out = {}
+    L = int(nb["start"][-1]) + 4096 if nb["n_reads"] else 1
+    for m in ALL7:
+        if m not in rows:
+            continue
         t0 = time.perf_counter()
-        secs = pool.map(_oracle_slice, range(n_proc), chunksize=1)
-        wall = time.perf_counter() - t0
-    _ORACLE_PARTS = None
-    return {"value": R / wall, "unit": "reads/s", "cores": n_proc, "kind": "port", "seconds": wall, "slowest_slice_seconds": max(secs),
-            "sample": f"all {R} reads in {n_proc} position slices, one single-threaded oracle process per slice, timed from "
-                      f"dispatch to the last slice done (decoded reads already in each worker's memory); optimistic bound: the "
-                      f"reference has no such mode and slice edges are not bit-identical"}
+        try:
+            if m == "lpmd":
+                continue  # global scalar: checked by additivity below
+            span = (0, min(FDRP_PARITY_SPAN, L)) if m in ("fdrp", "qfdrp") else None
+            key = "p1" if m in ("pm", "me") else "pos"
+            g = rows[m]
+            sel = np.asarray(g["tid"]) == tid
+            if span is not None:
+                sel &= np.asarray(g[key]) < span[1]
+            want, info = OP.run(nb, "quartets" if m in ("pm", "me") else m, ORACLE_PRM[m], n_proc=n_proc, interval=span)
+            ok, n_w = False, 0
+            if want is not None:
+                n_w = len(want[key])
+                vkey = {"pdr": "pdr", "pm": "pm", "me": "me"}.get(m, "value")
+                cols = [key] + (["p2", "p3", "p4"] if key == "p1" else []) + (["n_conc", "n_disc"] if m == "pdr" else [])
+                ok = int(sel.sum()) == n_w and all(np.array_equal(np.asarray(g[c])[sel], want[c]) for c in cols) and \
+                    np.array_equal(f32bits(np.asarray(g["value"])[sel]), f32bits(want[vkey]))
+            out[m] = {"contig": f"tid {tid}" + (f", sites < {span[1]}" if span else ", whole contig"), "rows": int(sel.sum()), "oracle_rows": int(n_w),
+                      "rows_bit_identical_to_oracle": bool(ok), "oracle_wall_s": round(info["wall_s"], 2), "oracle_cpu_s": round(info["cpu_s"], 2),
+                      "oracle_procs": info["procs"], "seconds": round(time.perf_counter() - t0, 2)}
+        except Exception as e:  # a checker problem must never cost the bench line
+            out[m] = {"error": repr(e)}
+    return out
 
 
-def run_reference(args, rank):
-    if rank != 0:
-        return
-    b, _ = make_workload(0)
-    n = CPU_SAMPLE_READS
-    times = []
-    for _ in range(args.warmup):
-        oracle_time(b, n // 8)
-    t_all0 = time.perf_counter()
-    rps = []
+def run_reference(args):
+    """`--impl reference`: the CPU oracle (port of metheor 0.1.9, one thread like the reference) on the headline measure set,
+    each step = the whole parity contig of the same workload (regenerated on the CPU, bit-identical to the GPU's)."""
+    import torch
+    from metheor_b200 import synth_gpu as G
+    contigs = G.genome(args.scale)
+    t_all = time.perf_counter()
+    nb = G.to_numpy_batch(G.make_contig("cpu", SEED, PARITY_TID, contigs[PARITY_TID][1], args.coverage))
+    for _ in range(min(args.warmup, 2)):
+        oracle_single(nb, "pm+me", 1_000_000)
+    rps, times = [], []
     for _ in range(args.steps):
-        r, dt, nn = oracle_time(b, n)
+        r, dt, n = oracle_single(nb, "pm+me")
         rps.append(r); times.append(dt)
     v = float(np.mean(rps))
-    line = {"impl": "reference", "metric": "reads_per_sec", "value": v, "unit": "reads/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u32/u64 integer + f32 finalisation", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "measures": list(MEASURES)},
-            "cpu_baseline": {"value": v, "unit": "reads/s", "cores": 1, "kind": "port",
-                             "sample": f"first {n} reads of the workload; C++ restatement of metheor 0.1.9 (single-threaded "
-                                       f"like the reference), not the Rust binary"},
-            "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "host": {"nproc": os.cpu_count()}, "wall_s": time.perf_counter() - t_all0}
-    emit(line)
+    emit({"impl": "reference", "metric": "reads_per_sec", "value": v, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps,
+          "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True,
+          "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
+          "config": {"workload": workload_name(args.coverage, args.scale), "measures": list(HEADLINE)},
+          "cpu_baseline": {"value": v, "unit": "reads/s", "cores": 1, "kind": "port",
+                           "sample": f"each step = all {nb['n_reads']} reads of contig tid {PARITY_TID} (chr21) of the workload, pm + me "
+                                     f"(one quartet pass, pm.rs:85-128 / me.rs:90-132); C++ restatement of metheor 0.1.9, "
+                                     f"single-threaded like the reference, not the Rust binary"},
+          "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+          "host": {"nproc": os.cpu_count()}, "wall_s": time.perf_counter() - t_all})
 
 
-def bam_leg(b, n_reads, length):
-    """BAM -> TSV through the shipped host (BGZF inflate + record decode on all cores, compact batches, GPU engine, TSV
-    writer) next to the oracle's CLI (single thread, its own BAM reader) on the same file; outputs must be identical."""
-    import tempfile
-    from metheor_b200 import batch as B
-    from metheor_b200 import host, synth_bam
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import oracle_lib
-    oracle_lib.build()
-    sub = B.slice_reads(b, 0, min(n_reads, b["n_reads"]))
-    out = {}
-    with tempfile.TemporaryDirectory() as d:
-        bam = os.path.join(d, "synthetic.bam")
-        info = synth_bam.write_bam(bam, [("chr19", length)], [sub], threads=os.cpu_count() or 8)
-        out.update(records=info["records"], bam_bytes=info["bytes_compressed"], uncompressed_bytes=info["bytes_uncompressed"],
-                   host_threads=os.cpu_count())
-        for m in MEASURES:
-            tsv, st = os.path.join(d, f"{m}.tsv"), os.path.join(d, f"{m}.json")
-            best = None
-            for _ in range(3):
-                t0 = time.perf_counter()
-                host.run(m, bam, tsv, stats_json=st)
-                dt = time.perf_counter() - t0
-                if best is None or dt < best[0]:
-                    best = (dt, json.load(open(st)))
-            t0 = time.perf_counter()
-            r = subprocess.run([oracle_lib.CLI_PATH, m, "-i", bam, "-o", tsv + ".oracle"], capture_output=True, text=True)
-            dt_o = time.perf_counter() - t0
-            same = r.returncode == 0 and open(tsv, "rb").read() == open(tsv + ".oracle", "rb").read()
-            out[m] = {"reads_per_sec": info["records"] / best[0], "seconds": best[0],
-                      "uncompressed_MB_per_sec": info["bytes_uncompressed"] / best[0] / 1e6, "stage_seconds": best[1]["seconds"],
-                      "cpu_oracle_cli_seconds": dt_o, "cpu_oracle_cli_reads_per_sec": info["records"] / dt_o,
-                      "tsv_identical_to_oracle": bool(same)}
-    return out
-
-
-def tag_leg(n_reads, length, read_len=150, seed=7):
-    """`tag` (XM synthesis): synthetic plain-`150M` reads over a random chr19-sized genome through the C ABI
-    (mth_tag: host arrays in, XM strings in pinned host memory out), with the kernel's own device time and the Python oracle
-    (single thread, bounded sample) beside it; the sample's tags must be identical."""
-    from metheor_b200 import tag
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import tag_oracle
-    rng = np.random.default_rng(seed)
-    genome = rng.choice(np.frombuffer(b"ACGT", np.uint8), length, p=[0.29, 0.21, 0.21, 0.29])
-    genome[rng.integers(0, length, length // 500)] = ord("N")
-    pos = np.sort(rng.integers(0, length - read_len, n_reads)).astype(np.int32)
-    tid = np.zeros(n_reads, np.int32)
-    rc = (rng.random(n_reads) < 0.5).astype(np.uint8)
-    l_seq = np.full(n_reads, read_len, np.int32)
-    cigar_off = np.arange(n_reads + 1, dtype=np.uint32)
-    cigar = np.full(n_reads, read_len << 4, np.uint32)
-    nb = (read_len + 1) // 2
-    seq_off = (np.arange(n_reads + 1, dtype=np.uint64) * np.uint64(nb))
-    codes = np.array([1, 2, 4, 8, 8, 8, 15], np.uint8)  # A C G T T T N: bisulfite-like
-    seq4 = (codes[rng.integers(0, 7, n_reads * nb)] << 4) | codes[rng.integers(0, 7, n_reads * nb)]
-    out = {"reads": n_reads, "read_len": read_len, "genome_bases": length}
-    with tag.Genome([length]) as g:
-        t0 = time.perf_counter()
-        g.set_contig(0, genome)
-        out["genome_upload_seconds"] = time.perf_counter() - t0
-        best, kms = None, None
-        for _ in range(4):
-            t0 = time.perf_counter()
-            off, ln, xm, status = g.tag_arrays(tid, pos, rc, l_seq, cigar_off, cigar, seq_off, seq4, raw=True)
-            dt = time.perf_counter() - t0
-            if best is None or dt < best:
-                best, kms = dt, g.last_kernel_ms()
-        assert not status.any()
-        bytes_per_read = nb + (read_len + 4) + read_len + 4 + 4 + 1 + 4 + 4 + 8 + 8 + 8 + 4 + 1  # SEQ, genome, tag, scalars / offsets
-        out.update(reads_per_sec=n_reads / best, seconds=best, kernel_ms=kms, kernel_reads_per_sec=n_reads / (kms * 1e-3),
-                   kernel_algorithmic_GBps=bytes_per_read * n_reads / (kms * 1e-3) / 1e9, algorithmic_bytes_per_read=bytes_per_read,
-                   h2d_bytes=int(tid.nbytes + pos.nbytes + rc.nbytes + l_seq.nbytes + cigar_off.nbytes + cigar.nbytes + seq_off.nbytes + seq4.nbytes
-                                 + 16 * (n_reads + 1)), d2h_bytes=int(xm.nbytes + 5 * n_reads))
-        # CPU oracle on a bounded sample, tags compared
-        m = min(n_reads, 20000)
-        text = bytes(genome).decode()
-        nt = "=ACMGRSVTWYHKDBN"
-        t0 = time.perf_counter()
-        same = True
-        for i in range(m):
-            sq = seq4[i * nb:(i + 1) * nb]
-            s = "".join(nt[c >> 4] + nt[c & 15] for c in sq)[:read_len]
-            want = tag_oracle.xm_string(16 if rc[i] else 0, int(pos[i]), [(read_len, "M")], s, text, length, False)
-            got = bytes(xm[int(off[i]):int(off[i]) + int(ln[i])]).decode()
-            same = same and (got == want)
-        dt = time.perf_counter() - t0
-        out.update(cpu_oracle_reads_per_sec=m / dt, cpu_oracle_sample=f"first {m} reads, single-threaded Python restatement of tag.rs",
-                   tags_identical_to_oracle=bool(same))
-    return out
-
-
-class _DevI64:
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 2}
-
-
-def ensure_built():
-    """The libraries are built in-tree by __graft_entry__.build() and travel with the snapshot; a bare checkout builds them here."""
-    need = [os.path.join(ROOT, "metheor_b200", "csrc", "libmetheor_b200.so"), os.path.join(ROOT, "metheor_b200", "host", "libmetheor_host.so"),
-            os.path.join(ROOT, "oracle", "_build", "liboracle.so")]
-    if not all(os.path.exists(p) for p in need):
-        if int(os.environ.get("LOCAL_RANK", "0")) == 0:
-            import __graft_entry__
-            __graft_entry__.build()
-        else:  # under torchrun only one rank builds
-            t0 = time.time()
-            while not all(os.path.exists(p) for p in need) and time.time() - t0 < 600:
-                time.sleep(1.0)
-            time.sleep(2.0)
-
-
-_REAL_STDOUT = None
-
-
-def emit(line):
-    """The ONE JSON line on stdout.  Everything else any library prints (NCCL's version banner, ...) was routed to stderr."""
-    data = (json.dumps(line) + "\n").encode()
-    if _REAL_STDOUT is None:
-        sys.stdout.write(data.decode()); sys.stdout.flush()
-    else:
-        os.write(_REAL_STDOUT, data)
-
-
+# ---------------------------------------------------------------------------------------------------------------------
 def main():
     global _REAL_STDOUT
     sys.stdout.flush()
@@ -324,27 +340,32 @@ def main():
     ensure_built()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--coverage", type=float, default=COVERAGE)
-    ap.add_argument("--length", type=int, default=CONTIG_LEN)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--tag-reads", type=int, default=2_000_000, help="reads of the extra `tag` (XM synthesis) leg; 0 disables it")
-    ap.add_argument("--bam-reads", type=int, default=2_000_000,
-                    help="also time the BAM -> TSV path (C++ host + engine) on a BAM of the first N reads; 0 disables")
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink every contig (quick runs); 1.0 = the BASELINE workload")
+    ap.add_argument("--measure-steps", type=int, default=5, help="timed passes of every non-headline measure set")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip every CPU oracle leg (cpu_baseline, parity)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary legs (chr19 configs[1], 60x, BAM, tag)")
+    ap.add_argument("--chr19-coverage", type=float, default=30.0)
+    ap.add_argument("--wg60", type=float, default=60.0, help="coverage of the configs[3] leg (fdrp + qfdrp); 0 disables")
+    ap.add_argument("--tag-reads", type=int, default=2_000_000)
+    ap.add_argument("--bam-reads", type=int, default=2_000_000)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank)
+        if rank == 0:
+            run_reference(args)
         return
     args.warmup = max(args.warmup, 3)
 
     import torch
     import torch.distributed as dist
     from metheor_b200 import engine
+    from metheor_b200 import synth_gpu as G
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the engine has no CPU fallback)")
     torch.cuda.set_device(local_rank)
@@ -352,52 +373,35 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
-
-    b, sites = make_workload(rank, args.coverage, args.length)
-    R, I = b["n_reads"], b["n_cpg"]
-    view = {np.dtype("uint32"): np.int32, np.dtype("uint16"): np.int16, np.dtype("uint64"): np.int64}
-    host, devb = dict(b), dict(b)
-    for k in ("start", "end", "meta", "cpg_off", "cpg_pos", "cpg_rel", "meth"):
-        t = torch.from_numpy(b[k].view(view.get(b[k].dtype, b[k].dtype)))
-        host[k] = t.pin_memory()
-        devb[k] = t.to(dev)
     stream = torch.cuda.current_stream()
+    t_begin = time.perf_counter()
+    import bench_chr19 as X
 
-    def make_ctx(flags):
-        c = engine.Context(engine.default_params(MEASURES, flags=flags), [args.length], device=local_rank)
+    contigs = G.genome(args.scale)
+    ref_len = [l for _, l in contigs]
+    intervals = plan_bins_by_length(ref_len, world)[rank]
+    t0 = time.perf_counter()
+    wg, owned_R, owned_I = gen_shard(torch, dev, contigs, args.coverage, intervals, world)
+    torch.cuda.synchronize()
+    gen_s = time.perf_counter() - t0
+    R_loc, I_loc = sum(b["n_reads"] for b in wg), sum(b["n_cpg"] for b in wg)
+    tot = torch.tensor([owned_R, owned_I], device=dev, dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(tot)
+    R, I = int(tot[0]), int(tot[1])  # the whole genome's reads / calls (halo copies not counted)
+
+    def make_ctx(measures, flags, comm=False):
+        c = engine.Context(engine.default_params(measures, flags=flags), ref_len, device=local_rank)
         c.set_stream(stream.cuda_stream)
+        if comm and world > 1:  # the library's own communicator: the id travels through torch.distributed
+            idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+            if rank == 0:
+                idt.copy_(torch.frombuffer(bytearray(engine.comm_unique_id()), dtype=torch.uint8))
+            dist.broadcast(idt, 0)
+            c.comm_init_rank(world, rank, bytes(idt.cpu().numpy().tobytes()))
         return c
-
-    # The path's one exchange: LPMD's four int64 counters (NCCL sum).  It runs on a side stream behind an event, on a copy
-    # of the counters, so a rank can start its next pass while the (tiny, latency-bound) collective is in flight; the
-    # timed region ends only after the last collective has completed (the compute stream waits for it before e1).
-    ar_stream = torch.cuda.Stream(device=dev) if world > 1 else None
-    ar_buf = [torch.zeros(4, dtype=torch.int64, device=dev) for _ in range(2)] if world > 1 else None
-    ar_state = {"k": 0, "last": None}
-
-    def allreduce_lpmd(ctx):
-        if world > 1:
-            t = torch.as_tensor(_DevI64(ctx.lpmd_counters_device_ptr(), 4), device=dev)
-            buf = ar_buf[ar_state["k"] & 1]
-            ar_state["k"] += 1
-            if ar_state["last"] is not None:
-                stream.wait_event(ar_state["last"])  # the buffer's previous collective (two passes ago at the latest) is done
-            buf.copy_(t)
-            ready = torch.cuda.Event()
-            ready.record(stream)
-            with torch.cuda.stream(ar_stream):
-                ar_stream.wait_event(ready)
-                dist.all_reduce(buf)
-                done = torch.cuda.Event()
-                done.record(ar_stream)
-            ar_state["last"] = done
-            ar_state["result"] = buf
-
-    def allreduce_join():
-        if world > 1 and ar_state["last"] is not None:
-            stream.wait_event(ar_state["last"])
 
     def barrier():
         if world > 1:
@@ -411,7 +415,6 @@ def main():
         e0.record(stream)
         for _ in range(steps):
             step()
-        allreduce_join()
         e1.record(stream)
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
@@ -421,182 +424,305 @@ def main():
         barrier()
         return float(ms[0]), float(ms[1])
 
-    # ---------------- resident (value) ----------------
-    ctx = make_ctx(engine.FLAG_KEEP_ON_DEVICE)
-    rows = {}
-
-    def step_resident():
+    def resident_pass(ctx, batches, lp):
         ctx.reset()
-        ctx.submit(devb)
-        rows.update(ctx.finish())
-        allreduce_lpmd(ctx)
+        for b in batches:
+            ctx.submit(b)
+        res = ctx.finish()
+        if world > 1 and lp:
+            res["lpmd_all_ranks"] = ctx.allreduce()  # the path's one exchange: NCCL sum of 4 int64 inside the library
+        return res
 
-    for _ in range(args.warmup):
-        step_resident()
-    launches0 = ctx.stats()["kernel_launches"]
-    sampler = ClockSampler(local_rank)
+    def measure_block(measures, steps, batches=wg, n_reads=R, n_calls=I, profile=True):
+        """Resident timing + per-kernel profile of one measure set -> dict"""
+        lp = "lpmd" in measures
+        ctx = make_ctx(measures, engine.FLAG_KEEP_ON_DEVICE, comm=lp)
+        res = {}
+        def step():
+            res.update(resident_pass(ctx, batches, lp))
+        for _ in range(args.warmup):
+            step()
+        ms_dev, ms_wall = timed(step, steps)
+        st = ctx.stats()
+        dig = rows_digest(torch, dev, ctx, measures, owned=None if world == 1 else intervals)
+        ms_step = ms_dev / steps
+        blk = {"measures": list(measures), "steps": steps, "ms_per_step": ms_step, "wall_ms_per_step": ms_wall / steps,
+               "value": n_reads / (ms_step * 1e-3), "unit": "reads/s", "launches_per_step": int(st["kernel_launches"]),
+               "regions_per_step": int(st["n_regions"]), "digest": dig}
+        counts = torch.tensor([st["n_sites"]] + [dig[m][0] if m in dig else 0 for m in ALL7] + [st["fdrp_pair_ops"]], device=dev, dtype=torch.int64)
+        if world > 1:  # sites / rows / pair-ops of the whole genome (halo sites are counted by more than one rank: an upper bound)
+            dist.all_reduce(counts)
+            dt = torch.tensor([v[1] for v in dig.values()], device=dev, dtype=torch.int64)
+            dist.all_reduce(dt)
+            blk["digest"] = {m: [int(counts[1 + ALL7.index(m)]), int(x)] for m, x in zip(dig, dt)}
+        C = int(counts[0])
+        rows = {m: int(counts[1 + ALL7.index(m)]) for m in measures if m != "lpmd"}
+        blk.update(cpg_sites=C, rows=rows, cpgs_per_sec=C / (ms_step * 1e-3))
+        if "lpmd" in res:
+            l = res.get("lpmd_all_ranks") or res["lpmd"]
+            blk["lpmd"] = {k: (float(v) if k == "lpmd" else int(v)) for k, v in l.items() if k != "pairs"}
+        if st["fdrp_pair_ops"]:
+            blk["pair_ops"] = int(counts[-1])
+            blk["pair_ops_per_sec"] = int(counts[-1]) / (ms_step * 1e-3)
+        ctx.close()
+        if profile:
+            pctx = make_ctx(measures, engine.FLAG_KEEP_ON_DEVICE | engine.FLAG_PROFILE)
+            acc, PS = {}, 2
+            for it in range(1 + PS):
+                resident_pass(pctx, batches, False)
+                if it >= 1:
+                    for k, v in pctx.stats()["kernels"].items():
+                        a = acc.setdefault(k, [0, 0.0]); a[0] += v["launches"]; a[1] += v["ms"]
+            pctx.close()
+            blk["kernels"] = {k: {"launches_per_step": a[0] / PS, "ms_per_step": a[1] / PS} for k, a in acc.items()}
+        return blk
+
+    def add_roofline(blk, traffic):
+        """roofline (dominant kernel) + roofline_measure (SURVEY bytes / all kernels of the pass) for a measure block (this rank's share)."""
+        peak, peak_src = peaks()
+        measures, kern = blk["measures"], blk.get("kernels") or {}
+        Rl, Il = R_loc, I_loc
+        C = blk["cpg_sites"] // world if world > 1 else blk["cpg_sites"]
+        Q = max([v for m, v in blk["rows"].items() if m in ("pm", "me")] + [0]) // world
+        cand = {k: v for k, v in kern.items() if kernel_bytes(k, measures, Rl, Il, C, Q)}
+        if not cand:
+            return
+        hot = max(cand, key=lambda k: cand[k]["ms_per_step"])
+        nl = max(1.0, cand[hot]["launches_per_step"])
+        ab = kernel_bytes(hot, measures, Rl, Il, C, Q)
+        ach = ab / (cand[hot]["ms_per_step"] * 1e-3) / 1e9
+        tr = (traffic.get("wg", {}).get("+".join(measures), {}) or {}).get(hot)
+        blk["roofline"] = {"bound": "hbm", "kernel": hot, "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak,
+                           "traffic": (tr["dram_bytes"] / tr["launches"]) if tr else None, "launches_per_step": nl,
+                           "algorithmic_bytes_per_launch": ab / nl, "ms_per_launch": cand[hot]["ms_per_step"] / nl,
+                           "algorithmic_bytes_per_step": ab, "ms_per_step": cand[hot]["ms_per_step"]}
+        if tr:
+            blk["roofline"]["traffic_capture"] = tr
+        sb = sum(survey_bytes(m, Rl, Il, C, Q) for m in measures)
+        kms = sum(v["ms_per_step"] for v in kern.values())
+        blk["roofline_measure"] = {"algorithmic_bytes": sb, "kernel_ms_sum": kms, "kernel_ms_over_step": kms / blk["ms_per_step"],
+                                   "achieved": sb / (kms * 1e-3) / 1e9, "unit": "GB/s", "frac": sb / (kms * 1e-3) / 1e9 / peak,
+                                   "formula": "SURVEY.md 8d: " + " + ".join(measures)}
+
+    traffic = load_traffic()
+    sampler = X.ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_dev, ms_wall = timed(step_resident, args.steps)
-    st = ctx.stats()
-    n_sites = st["n_sites"]
-    n_rows = rows["pdr"]["n"]
-    ms_step = ms_dev / args.steps
-    total_reads = R * world
-    value = total_reads / (ms_step * 1e-3)
 
-    # ---------------- per-kernel times (profile flag: CUDA events around every kernel) ----------------
-    pctx = make_ctx(engine.FLAG_KEEP_ON_DEVICE | engine.FLAG_PROFILE)
-    PSTEPS = 5
-    for _ in range(3):
-        pctx.reset(); pctx.submit(devb); pctx.finish()
-    # stats are reset by reset(): collect from the LAST step only, repeated PSTEPS times for an average
-    acc = {}
-    for _ in range(PSTEPS):
-        pctx.reset(); pctx.submit(devb); pctx.finish()
-        for k, v in pctx.stats()["kernels"].items():
-            a = acc.setdefault(k, [0, 0.0])
-            a[0] += v["launches"]; a[1] += v["ms"]
-    kern = {k: {"launches_per_step": a[0] / PSTEPS, "ms_per_step": a[1] / PSTEPS} for k, a in acc.items()}
-    pctx.close()
-    C = n_sites
-    alg = {  # algorithmic bytes per launch, DESIGN.md §5
-        "k_ingest": 16 * R + 6 * I + 32,          # LPMD: meta+cpg_off+meth per read, cpg_pos+cpg_rel per CpG call, 4 counters
-        "k_pdr_scatter": 16 * R + 4 * I + 8 * C,  # PDR: per-read fields, cpg_pos per call, 2 u32 counters per site
-        "k_pdr_gather": 16 * R + 4 * I + 8 * C,
-        "k_sites_count": C * 4, "k_sites_emit": C * 4, "pdr_rows_count": C * 12, "k_pdr_emit": C * 8 + n_rows * 20,
-    }
-    hot = max((k for k in kern if k in ("k_ingest", "k_pdr_scatter", "k_pdr_gather")), key=lambda k: kern[k]["ms_per_step"])
-    peak, peak_src = peaks()
-    ach = alg[hot] / (kern[hot]["ms_per_step"] * 1e-3) / 1e9
-    step_alg = (16 * R + 4 * I + 12 * C) + (16 * R + 6 * I + 16)  # PDR + LPMD
-    kern_ms_total = sum(v["ms_per_step"] for v in kern.values())
-    traffic = None
-    try:  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get(hot, {}).get("dram_bytes")
+    # ---------------- headline: pm + me on the whole genome, resident ----------------
+    head = measure_block(HEADLINE, args.steps)
+    add_roofline(head, traffic)
+
+    # ---------------- one block per measure, and the combined passes ----------------
+    blocks, combos = {}, {}
+    for ms in SINGLE:
+        blocks[ms[0]] = measure_block(ms, args.measure_steps)
+        add_roofline(blocks[ms[0]], traffic)
+    for ms in COMBOS[1:]:
+        combos["+".join(ms)] = measure_block(ms, args.measure_steps)
+        add_roofline(combos["+".join(ms)], traffic)
+
+    # ---------------- end to end through host buffers (headline measure set) ----------------
+    e2e, eres_all = None, None
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
     except Exception:
-        pass
-    roofline = {"bound": "hbm", "kernel": hot, "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                "frac": ach / peak, "traffic": traffic, "algorithmic_bytes_per_launch": alg[hot],
-                "ms_per_launch": kern[hot]["ms_per_step"]}
-    roofline_step = {"algorithmic_bytes": step_alg, "kernel_ms_sum": kern_ms_total,
-                     "achieved": step_alg / (kern_ms_total * 1e-3) / 1e9, "unit": "GB/s",
-                     "frac": step_alg / (kern_ms_total * 1e-3) / 1e9 / peak}
+        avail = 64 << 30
+    need = sum(batch_bytes(b, False) for b in wg)
+    e_batches = wg
+    if need * 2.5 > avail:  # bounded by host memory: use the contigs that fit, say so
+        keep, acc = [], 0
+        for b in wg:
+            if (acc + batch_bytes(b, False)) * 2.5 > avail:
+                break
+            keep.append(b); acc += batch_bytes(b, False)
+        e_batches = keep
+    if e_batches:
+        host = []
+        for b in e_batches:
+            hb = {k: v for k, v in b.items() if not isinstance(v, torch.Tensor)}
+            for k in ("start", "end", "meta", "cpg_off", "cpg_pos", "meth", "meth_off"):
+                if b.get(k) is not None:
+                    hb[k] = torch.empty(b[k].shape, dtype=b[k].dtype, pin_memory=True)
+                    hb[k].copy_(b[k])
+            hb["cpg_rel"] = None
+            host.append(hb)
+        ectx = make_ctx(HEADLINE, 0)
+        eres = {}
 
-    # ---------------- end to end through host buffers ----------------
-    # The shipped host (metheor_b200/host) hands batches over in the compact wire format (mth_submit_compact) with the
-    # dense block encodings: ~7 B per read + 1.125 B per call cross PCIe and the device expands them.  `e2e` times exactly
-    # that call sequence with pinned host arrays; `e2e_compact` is the plain compact format (9 B + 2.125 B) and `e2e_soa`
-    # mth_submit with the full SoA layout (24 B + 6 B).
-    from metheor_b200 import batch as B
-
-    def pin(d):
-        d = dict(d)
-        for k, v in list(d.items()):
-            if isinstance(v, np.ndarray):
-                t = torch.from_numpy(v.view({np.dtype("uint16"): np.int16, np.dtype("uint32"): np.int32}.get(v.dtype, v.dtype)))
-                d[k] = t.pin_memory() if t.numel() else t
-        return d
-
-    hostc = pin(B.to_compact(b))
-    # dense block encodings (MTH_CENC_START16 | MTH_CENC_DELTA8), handed over like the streaming host does: a few
-    # batches of <= 2 M reads, so that the copy of one overlaps the expansion + ingest of the previous one
-    CH = 1 << 21
-    hostd = [pin(B.to_compact(B.slice_reads(b, lo, min(R, lo + CH)), dense=True)) for lo in range(0, R, CH)]
-    ectx = make_ctx(0)
-    eres = {}
-
-    def make_step(submit, payload):
-        def step():
+        def e_step():
             ectx.reset()
-            submit(payload)
-            eres.update(ectx.finish(copy=False))  # rows are read where the C ABI leaves them: the context's pinned host buffers
-            allreduce_lpmd(ectx)
-        return step
-
-    e_steps = max(3, min(args.steps, 10))
-    e2e = {}
-    def submit_dense(chunks):
-        for hc in chunks:
-            ectx.submit_compact(hc)
-
-    for name, st_fn in (("soa", make_step(ectx.submit, host)), ("compact", make_step(ectx.submit_compact, hostc)),
-                        ("dense", make_step(submit_dense, hostd))):
-        for _ in range(args.warmup):
-            st_fn()
-        _, e_wall = timed(st_fn, e_steps)
+            for hb in host:
+                ectx.submit(hb)
+            eres.update(ectx.finish(copy=False))
+        for _ in range(2):
+            e_step()
+        e_steps = max(3, min(args.steps, 5))
+        _, e_wall = timed(e_step, e_steps)
         est = ectx.stats()
-        assert eres["pdr"]["n"] == n_rows
-        assert (eres["lpmd"]["n_conc"], eres["lpmd"]["n_disc"]) == (rows["lpmd"]["n_conc"], rows["lpmd"]["n_disc"]) or world > 1
-        e2e[name] = {"value": total_reads / (e_wall / e_steps * 1e-3), "unit": "reads/s", "ms_per_step": e_wall / e_steps,
-                     "h2d_bytes_per_step": int(est["h2d_bytes"]), "d2h_bytes_per_step": int(est["d2h_bytes"]), "steps": e_steps}
-
-    # clocks / throttle reasons were sampled from the start of the resident timed region to the end of the e2e one
+        Re = sum(b["n_reads"] for b in e_batches) if len(e_batches) < len(wg) or world > 1 else R
+        if world > 1:
+            Re = R
+        e2e = {"value": Re / (e_wall / e_steps * 1e-3), "unit": "reads/s", "ms_per_step": e_wall / e_steps,
+               "h2d_bytes_per_step": int(est["h2d_bytes"]), "d2h_bytes_per_step": int(est["d2h_bytes"]), "steps": e_steps,
+               "measures": list(HEADLINE), "contigs": len(e_batches),
+               "wire_format": "SoA (mth_submit): pinned host arrays in the layout north_star names, one batch per contig; no host-side "
+                              "encoding inside or outside the timed region; rows come back into the context's pinned buffers",
+               "rows": {m: int(eres[m]["n"]) for m in HEADLINE}}
+        if world == 1 and len(e_batches) == len(wg):
+            assert all(eres[m]["n"] == head["rows"][m] for m in HEADLINE), "e2e rows differ from the resident pass"
+        ectx.close()
+        del host, eres
     clocks = sampler.stop() if rank == 0 else None
 
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rps, dt, nn = oracle_time(b, CPU_SAMPLE_READS, steps=3)
-        cpu = {"value": rps, "unit": "reads/s", "cores": 1, "kind": "port", "seconds": dt,
-               "sample": f"first {nn} reads of the workload (pdr+lpmd, defaults); C++ restatement of metheor 0.1.9, "
-                         f"single-threaded like the reference; host has {os.cpu_count()} cores"}
-
-    parity_full = None
-    if cpu is not None:
+    # ---------------- parity at full size + CPU baselines (rank 0, N = 1) ----------------
+    parity, cpu_blocks, cpu_head = None, {}, None
+    if world == 1 and not args.no_cpu_baseline:
+        n_proc = os.cpu_count() or 1
+        actx = make_ctx(ALL7, 0)
+        ares = resident_pass(actx, wg, False)  # the whole genome, all seven measures, rows to the host
+        adig = rows_digest(torch, dev, actx, ALL7)
+        nb = G.to_numpy_batch(wg[PARITY_TID])
+        parity = parity_contig(ares, nb, PARITY_TID, n_proc)
+        # LPMD is one scalar over the file: additivity over contigs (each contig alone through the engine) + the oracle on the parity contig
+        lsum = {k: 0 for k in ("n_read", "n_valid_read", "n_conc", "n_disc")}
+        lctx = make_ctx(("lpmd",), engine.FLAG_KEEP_ON_DEVICE)
+        l_par = None
+        for b in wg:
+            lctx.reset(); lctx.submit(b)
+            l = lctx.finish()["lpmd"]
+            if b["tid"] == PARITY_TID:
+                l_par = l
+            for k in lsum:
+                lsum[k] += int(l[k])
+        lctx.close()
+        import oracle_parallel as OP
+        lw, linfo = OP.run(nb, "lpmd", ORACLE_PRM["lpmd"], n_proc=n_proc)
+        la = ares["lpmd"]
+        parity["lpmd"] = {"contig": f"tid {PARITY_TID}, whole contig", "counters_identical_to_oracle": bool(all(int(l_par[k]) == int(lw[k]) for k in lsum)),
+                          "value_bit_identical_to_oracle": bool(f32bits(l_par["lpmd"]) == f32bits(lw["lpmd"])),
+                          "whole_genome_counters_equal_sum_over_contigs": bool(all(int(la[k]) == lsum[k] for k in lsum)),
+                          "oracle_wall_s": round(linfo["wall_s"], 2)}
+        # every timed pass produced the rows that were checked: digests of the single-measure / combined passes == all-seven pass
+        same = {}
+        for name, blk in list(blocks.items()) + list(combos.items()) + [("pm+me(headline)", head)]:
+            same[name] = bool(all(blk["digest"][m] == adig[m] for m in blk["digest"]))
+        parity["digests_equal_all_seven_pass"] = same
+        parity["properties"] = {
+            "rows_sorted_by_tid_pos": bool(all((np.diff(np.asarray(ares[m]["tid"], np.int64) * (1 << 32) + np.asarray(ares[m]["pos"], np.int64)) > 0).all()
+                                               for m in ("pdr", "mhl", "fdrp", "qfdrp") if ares[m]["n"] > 1)),
+            "pm_me_same_quartets": bool(ares["pm"]["n"] == ares["me"]["n"] and all(np.array_equal(ares["pm"][k], ares["me"][k]) for k in ("tid", "p1", "p2", "p3", "p4"))),
+            "qfdrp_le_fdrp_same_sites": bool(ares["fdrp"]["n"] == ares["qfdrp"]["n"] and np.array_equal(ares["fdrp"]["pos"], ares["qfdrp"]["pos"])
+                                             and bool((np.asarray(ares["qfdrp"]["value"]) <= np.asarray(ares["fdrp"]["value"]) + 1e-6).all())),
+            "values_in_unit_interval": bool(all(float(np.nanmin(ares[m]["value"])) >= -1e-7 and float(np.nanmax(ares[m]["value"])) <= 1.0 + 1e-6
+                                                for m in ("pdr", "mhl", "fdrp", "qfdrp", "pm", "me") if ares[m]["n"]))}
+        for m in blocks:
+            blocks[m]["parity_full_size"] = dict(parity.get(m, {}), digest_equals_checked_pass=same.get(m))
+        actx.close()
+        del ares
+        # CPU baselines: one thread, bounded samples of the parity contig
+        for m in ALL7:
+            try:
+                rps, dt, n = oracle_single(nb, m, CPU_SAMPLE[m])
+                cpu_blocks[m] = {"value": rps, "unit": "reads/s", "cores": 1, "kind": "port", "seconds": dt,
+                                 "sample": f"first {n} reads of contig tid {PARITY_TID} (chr21) of the workload, reference defaults; C++ restatement of "
+                                           f"metheor 0.1.9, single-threaded like the reference; host has {os.cpu_count()} cores"}
+                blocks[m]["cpu_baseline"] = cpu_blocks[m]
+            except Exception as e:
+                blocks[m]["cpu_baseline"] = {"error": repr(e)}
         try:
-            parity_full = parity_full_size(eres, R)
-        except Exception as e:  # a checker problem must never cost the bench line
-            parity_full = {"error": repr(e)}
-
-    cpu_all = None
-    if cpu is not None and (os.cpu_count() or 1) > 1:
-        try:
-            cpu_all = oracle_all_cores(b, os.cpu_count())
+            rps, dt, n = oracle_single(nb, "pm+me")
+            cpu_head = {"value": rps, "unit": "reads/s", "cores": 1, "kind": "port", "seconds": dt,
+                        "sample": f"all {n} reads of contig tid {PARITY_TID} (chr21) of the workload, pm + me (one quartet pass); C++ restatement of "
+                                  f"metheor 0.1.9, single-threaded like the reference; host has {os.cpu_count()} cores"}
         except Exception as e:
-            cpu_all = {"error": repr(e)}
+            cpu_head = {"error": repr(e)}
+        del nb
 
-    bam = None
-    if rank == 0 and world == 1 and args.bam_reads > 0 and not args.no_cpu_baseline:
-        try:
-            bam = bam_leg(b, args.bam_reads, args.length)
-        except Exception as e:  # the extra leg must never cost the bench line
-            bam = {"error": repr(e)}
+    # ---------------- N > 1: the shards together == the whole genome on one GPU ----------------
+    sharded_check = None
+    if world > 1:
+        del wg
+        torch.cuda.empty_cache()
+        if rank == 0:
+            full, _, _ = gen_shard(torch, dev, contigs, args.coverage, [(t, 0, l) for t, l in enumerate(ref_len)], 1)
+            octx = engine.Context(engine.default_params(ALL7, flags=engine.FLAG_KEEP_ON_DEVICE), ref_len, device=local_rank)
+            octx.reset()
+            for b in full:
+                octx.submit(b)
+            ol = octx.finish()["lpmd"]
+            od = rows_digest(torch, dev, octx, ALL7)
+            a7 = combos["+".join(ALL7)]
+            sharded_check = {"digests_equal_single_gpu": {m: bool(a7["digest"][m] == od[m]) for m in od},
+                             "lpmd_counters_equal_single_gpu": bool(all(int(a7["lpmd"][k]) == int(ol[k]) for k in ("n_read", "n_valid_read", "n_conc", "n_disc"))),
+                             "what": "owned rows of all ranks (row count + order-independent 64-bit digest per measure, summed over the ranks) and the "
+                                     "all-reduced LPMD counters against the same genome processed by rank 0 alone"}
+            octx.close()
+            del full
+        barrier()
+    else:
+        del wg
+    torch.cuda.empty_cache()
 
-    tag_res = None
-    if rank == 0 and world == 1 and args.tag_reads > 0 and not args.no_cpu_baseline:
+    # ---------------- secondary legs (N = 1 only) ----------------
+    extra = {}
+    if world == 1 and not args.no_extra:
+        if args.wg60 > 0:
+            try:
+                t0 = time.perf_counter()
+                w60, r60, i60 = gen_shard(torch, dev, contigs, args.wg60, [(t, 0, l) for t, l in enumerate(ref_len)], 1)
+                torch.cuda.synchronize()
+                g60 = time.perf_counter() - t0
+                R_save, I_save = R_loc, I_loc
+                R_loc, I_loc = r60, i60
+                b60 = measure_block(("fdrp", "qfdrp"), 2, batches=w60, n_reads=r60, n_calls=i60)
+                add_roofline(b60, {})
+                R_loc, I_loc = R_save, I_save
+                b60.update(workload=f"BASELINE.json configs[3] on one GPU: fdrp + qfdrp, {workload_name(args.wg60, args.scale)}", reads=r60,
+                           cpg_calls=i60, generate_seconds=g60)
+                extra["config3_wg60x_fdrp_qfdrp"] = b60
+                del w60
+                torch.cuda.empty_cache()
+            except Exception as e:
+                extra["config3_wg60x_fdrp_qfdrp"] = {"error": repr(e)}
         try:
-            tag_res = tag_leg(args.tag_reads, args.length)
+            c19, b19 = X.chr19_leg(args, torch, dev, stream, max(3, min(args.steps, 10)))
+            extra["config1_chr19_pdr_lpmd"] = c19
         except Exception as e:
-            tag_res = {"error": repr(e)}
-
-    lpmd_all = None
-    if world > 1 and ar_state.get("result") is not None:
-        torch.cuda.synchronize()
-        tot = ar_state["result"].cpu().numpy()  # n_read, n_valid_read, n_conc, n_disc summed over the ranks
-        lpmd_all = {"n_read": int(tot[0]), "n_conc": int(tot[2]), "n_disc": int(tot[3]),
-                    "lpmd": float(np.float32(tot[3]) / np.float32(tot[2] + tot[3]))}
+            extra["config1_chr19_pdr_lpmd"] = {"error": repr(e)}
+            b19 = None
+        torch.cuda.empty_cache()
+        if args.bam_reads > 0 and not args.no_cpu_baseline and b19 is not None:
+            try:
+                extra["bam_end_to_end"] = X.bam_leg(b19, args.bam_reads, X.CONTIG_LEN)
+            except Exception as e:
+                extra["bam_end_to_end"] = {"error": repr(e)}
+        if args.tag_reads > 0 and not args.no_cpu_baseline:
+            try:
+                extra["tag"] = X.tag_leg(args.tag_reads, X.CONTIG_LEN)
+            except Exception as e:
+                extra["tag"] = {"error": repr(e)}
 
     if rank == 0:
-        line = {"metric": "reads_per_sec", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "u32/u64 integer + f32 finalisation", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "measures": list(MEASURES), "reads_per_gpu": R, "cpg_calls_per_gpu": I,
-                           "cpg_sites_per_gpu": int(C), "pdr_rows_per_gpu": int(n_rows), "seed": SEED,
-                           "l2": "inputs (%.0f MB per step) larger than L2" % ((16 * R + 6 * I + 8 * R) / 1e6),
-                           "parallelism": f"genomic sharding x{world}, NCCL all-reduce of 4 LPMD counters"},
-                "cpgs_per_sec": C * world / (ms_step * 1e-3), "wall_ms_per_step": ms_wall / args.steps,
-                "e2e": dict(e2e["dense"], wire_format="compact + dense block encodings (mth_submit_compact, enc = START16 | DELTA8), "
-                                                      f"{len(hostd)} batches of <= {CH} reads"),
-                "e2e_compact": dict(e2e["compact"], wire_format="compact (mth_submit_compact, enc = 0), one batch"),
-                "e2e_soa": dict(e2e["soa"], wire_format="SoA (mth_submit), one batch"),
-                "gpu_launches": int((st["kernel_launches"] - 0) * args.steps),
-                "launches_per_step": int(st["kernel_launches"]),
-                "roofline": roofline, "roofline_step": roofline_step, "kernels": kern, "cpu_baseline": cpu, "parity_full_size": parity_full, "cpu_baseline_all_cores": cpu_all, "bam_end_to_end": bam, "tag": tag_res,
-                "clocks": clocks, "pdr_path": {1: "scatter", 2: "gather", 3: "scatter+gather(hazard sites)"}.get(st["pdr_path"]), "lpmd": float(rows["lpmd"]["lpmd"]),
-                "lpmd_all_ranks": lpmd_all}
+        ms_step = head["ms_per_step"]
+        line = {"metric": "reads_per_sec", "value": head["value"], "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+                "dtype": DTYPE, "data": "synthetic",
+                "config": {"workload": workload_name(args.coverage, args.scale), "measures": list(HEADLINE), "reads": R, "cpg_calls": I,
+                           "cpg_sites": head["cpg_sites"], "rows": head["rows"], "seed": SEED, "contigs": len(contigs),
+                           "l2": "inputs (%.1f GB per step) larger than L2" % ((16 * R + 4 * I + 8 * R) / 1e9),
+                           "parallelism": (f"one genome cut into {world} position bins (+{HALO}-bp halo), one bin per GPU; NCCL all-reduce of LPMD's 4 counters "
+                                           f"inside the library (mth_allreduce), once per pass") if world > 1 else "single GPU",
+                           "generate_seconds": gen_s},
+                "cpgs_per_sec": head["cpgs_per_sec"], "wall_ms_per_step": head["wall_ms_per_step"],
+                "e2e": e2e, "gpu_launches": int(head["launches_per_step"] * args.steps), "launches_per_step": head["launches_per_step"],
+                "roofline": head.get("roofline"), "roofline_measure": head.get("roofline_measure"), "kernels": head.get("kernels"),
+                "cpu_baseline": cpu_head, "parity_full_size": parity, "measures": blocks, "combined": combos, "sharded_check": sharded_check,
+                "clocks": clocks, "bench_wall_s": None}
+        line.update(extra)
+        line["bench_wall_s"] = time.perf_counter() - t_begin
         emit(line)
-    ctx.close(); ectx.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MTH_ABI_VERSION 1
+#define MTH_ABI_VERSION 2
 
 typedef enum {
     MTH_OK = 0,
@@ -210,6 +210,7 @@ typedef struct {
     int64_t n_reads, n_cpg, n_sites, n_regions;
     int64_t kernel_launches;      /* engine kernels launched since create/reset */
     int64_t h2d_bytes, d2h_bytes; /* bytes copied since create/reset */
+    int64_t fdrp_pair_ops;        /* read pairs compared by the FDRP / qFDRP kernels (sum over closed segments of n(n-1)/2) */
     int32_t max_ref_span;         /* longest end-start+1 seen */
     int32_t pdr_path;             /* 0 none, 1 scatter (no flush possible), 2 gather everywhere (MTH_FLAG_FORCE_GATHER), 3 scatter + gather on hazard sites */
     int32_t n_kernel_stats;
@@ -236,7 +237,7 @@ int mth_add_skipped_reads(mth_ctx* ctx, int64_t n_reads, int64_t n_reads_mapq_ok
 int mth_finish(mth_ctx* ctx, mth_results* out);
 /* Device-resident view of the last results (same struct, device pointers). */
 int mth_results_device(mth_ctx* ctx, mth_results* out);
-/* int64[4] on the device: n_read, n_valid_read, n_conc, n_disc — what a multi-GPU host all-reduces (NCCL sum). */
+/* int64[4] on the device: n_read, n_valid_read, n_conc, n_disc — what mth_allreduce sums over the ranks. */
 int mth_lpmd_counters_device(mth_ctx* ctx, void** dev_ptr);
 /* Recompute the LPMD scalar of the last results from (all-reduced) device counters. */
 int mth_lpmd_refresh(mth_ctx* ctx, mth_lpmd_result* out);
@@ -247,6 +248,25 @@ int mth_sync(mth_ctx* ctx);         /* wait for everything enqueued so far */
 int mth_sync_copies(mth_ctx* ctx);
 int mth_get_stats(mth_ctx* ctx, mth_stats* out);
 const char* mth_last_error(mth_ctx* ctx); /* ctx may be NULL: last create error */
+
+/* ---- multi-GPU (north_star: "shard by contig/position bin ... a single NCCL all-reduce at the end") ---------
+ * The reference has nothing to bind here (single process, single thread); a multi-GPU host shards the genome by contig or
+ * position bin (reads of a bin + a halo of MTH_META_HALO copies, see mth_batch), runs one context per GPU and joins the
+ * contexts with ONE collective after mth_finish: the sum of LPMD's four int64 counters (lpmd.rs:176-191 accumulates them
+ * over the whole file).  NCCL is loaded at run time (dlopen of libnccl.so.2: the copy already in the process, e.g.
+ * PyTorch's, else the system one); a host that never calls these functions does not need NCCL installed.
+ *   multi-process (one rank per GPU): rank 0 calls mth_comm_unique_id and ships the 128 bytes to the other ranks by any
+ *     means (MPI, torch.distributed, a file); every rank calls mth_comm_init_rank, then mth_allreduce after mth_finish.
+ *   single process, N contexts: mth_comm_init_all once, then mth_allreduce_group after every context has finished.
+ * After the all-reduce every context reports the global LPMD (mth_lpmd_refresh, mth_lpmd_counters_device). */
+#define MTH_COMM_ID_BYTES 128
+int mth_comm_unique_id(void* id128);                                   /* ncclGetUniqueId */
+int mth_comm_init_rank(mth_ctx* ctx, int n_ranks, int rank, const void* id128); /* ncclCommInitRank on the context's device */
+int mth_comm_init_all(mth_ctx** ctxs, int n);                          /* ncclCommInitAll over the contexts' devices */
+int mth_allreduce(mth_ctx* ctx);                                       /* ncclAllReduce(sum, int64) on the compute stream */
+int mth_allreduce_group(mth_ctx** ctxs, int n);                        /* the same for N contexts of one process (group call) */
+int mth_comm_destroy(mth_ctx* ctx);                                    /* also done by mth_ctx_destroy */
+int mth_comm_n_ranks(mth_ctx* ctx);                                    /* 0 without a communicator */
 
 void* mth_host_alloc(size_t bytes); /* pinned host memory (cudaHostAlloc) or NULL */
 void mth_host_free(void* p);

@@ -14,7 +14,7 @@ MTH_ALL = 0x7F
 MEASURE_BITS = dict(pdr=MTH_PDR, lpmd=MTH_LPMD, mhl=MTH_MHL, pm=MTH_PM, me=MTH_ME, fdrp=MTH_FDRP, qfdrp=MTH_QFDRP)
 FLAG_KEEP_ON_DEVICE, FLAG_PROFILE, FLAG_QUARTET_COUNTS, FLAG_FORCE_GATHER = 1, 2, 4, 8
 MTH_OK, ERR_INVALID, ERR_CUDA, ERR_UNSORTED, ERR_UNSUPPORTED, ERR_STATE = 0, -1, -2, -3, -4, -5
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 u32, i32, i64, u64, vp = C.c_uint32, C.c_int32, C.c_int64, C.c_uint64, C.c_void_p
 
@@ -85,7 +85,7 @@ class KernelStat(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("n_reads", i64), ("n_cpg", i64), ("n_sites", i64), ("n_regions", i64), ("kernel_launches", i64),
-                ("h2d_bytes", i64), ("d2h_bytes", i64), ("max_ref_span", i32), ("pdr_path", i32),
+                ("h2d_bytes", i64), ("d2h_bytes", i64), ("fdrp_pair_ops", i64), ("max_ref_span", i32), ("pdr_path", i32),
                 ("n_kernel_stats", i32), ("kernel", KernelStat * 48)]
 
 
@@ -102,7 +102,8 @@ EXPORTS = ["mth_params_default", "mth_ctx_create", "mth_ctx_destroy", "mth_set_s
            "mth_add_skipped_reads", "mth_finish", "mth_results_device", "mth_lpmd_counters_device", "mth_lpmd_refresh",
            "mth_reset", "mth_sync", "mth_sync_copies", "mth_get_stats", "mth_last_error", "mth_host_alloc", "mth_host_free",
            "mth_device_count", "mth_version", "mth_reservoir_draw", "mth_genome_create", "mth_genome_set_contig", "mth_tag",
-           "mth_genome_destroy", "mth_genome_last_error", "mth_genome_last_kernel_ms"]
+           "mth_genome_destroy", "mth_genome_last_error", "mth_genome_last_kernel_ms", "mth_comm_unique_id", "mth_comm_init_rank",
+           "mth_comm_init_all", "mth_allreduce", "mth_allreduce_group", "mth_comm_destroy", "mth_comm_n_ranks"]
 
 
 def build(force=False):
@@ -147,6 +148,13 @@ def lib():
     L.mth_device_count.argtypes = []; L.mth_device_count.restype = C.c_int
     L.mth_version.argtypes = []; L.mth_version.restype = C.c_char_p
     L.mth_reservoir_draw.argtypes = [u64, i32, i32, u32]; L.mth_reservoir_draw.restype = u32
+    L.mth_comm_unique_id.argtypes = [vp]; L.mth_comm_unique_id.restype = C.c_int
+    L.mth_comm_init_rank.argtypes = [vp, C.c_int, C.c_int, vp]; L.mth_comm_init_rank.restype = C.c_int
+    L.mth_comm_init_all.argtypes = [P(vp), C.c_int]; L.mth_comm_init_all.restype = C.c_int
+    L.mth_allreduce.argtypes = [vp]; L.mth_allreduce.restype = C.c_int
+    L.mth_allreduce_group.argtypes = [P(vp), C.c_int]; L.mth_allreduce_group.restype = C.c_int
+    L.mth_comm_destroy.argtypes = [vp]; L.mth_comm_destroy.restype = C.c_int
+    L.mth_comm_n_ranks.argtypes = [vp]; L.mth_comm_n_ranks.restype = C.c_int
     L.mth_genome_create.argtypes = [P(vp), C.c_int, i32, P(i64)]; L.mth_genome_create.restype = C.c_int
     L.mth_genome_set_contig.argtypes = [vp, i32, vp, i64]; L.mth_genome_set_contig.restype = C.c_int
     L.mth_tag.argtypes = [vp, P(TagBatch), P(TagResult)]; L.mth_tag.restype = C.c_int

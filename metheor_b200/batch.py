@@ -56,6 +56,21 @@ def slice_reads(b, lo, hi):
     return select_reads(b, m)
 
 
+def slice_range(b, lo, hi):
+    """Reads [lo, hi) of a batch without touching the rest of it (array slices; methylation words are per read)."""
+    off = np.asarray(b["cpg_off"], np.int64)
+    i0, i1 = int(off[lo]), int(off[hi])
+    moff = b.get("meth_off")
+    if moff is None:
+        meth, mo = b["meth"][lo:hi], None
+    else:
+        m = np.asarray(moff, np.int64)
+        meth, mo = b["meth"][int(m[lo]):int(m[hi])], (m[lo:hi + 1] - m[lo]).astype(np.uint32)
+    return dict(tid=b["tid"], n_reads=hi - lo, n_cpg=i1 - i0, start=b["start"][lo:hi], end=b["end"][lo:hi], meta=b["meta"][lo:hi],
+                cpg_off=(off[lo:hi + 1] - i0).astype(np.uint32), cpg_pos=b["cpg_pos"][i0:i1],
+                cpg_rel=None if b.get("cpg_rel") is None else b["cpg_rel"][i0:i1], meth=meth, meth_off=mo)
+
+
 def to_oracle_soa(batches):
     """Concatenate batches (in file order) into the argument dict of tests/oracle_lib.Oracle.from_soa."""
     tid, start, end, mapq, pos, rel, meth, offs = [], [], [], [], [], [], [], [np.zeros(1, np.int64)]

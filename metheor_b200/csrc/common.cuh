@@ -46,6 +46,7 @@ struct RegionScalars {
     uint32_t pad;
     unsigned long long n_sites;
     unsigned long long lpmd[4];  // n_read, n_valid_read, n_conc, n_disc
+    unsigned long long fdrp_pairs;  // read pairs compared by the FDRP / qFDRP kernels (pair-ops of SURVEY 8d)
 };
 
 struct ContigTable {       // device copy: contigs of the current region, ascending lin_off

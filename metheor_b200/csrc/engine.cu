@@ -8,8 +8,10 @@
 //   region close (contig set full, or mth_finish): bitmap -> site dictionary -> one kernel family per measure ->
 //                row counts -> exclusive scan -> row emission into device row buffers.
 //   mth_finish : D2H of the rows into pinned buffers owned by the context.
+#include <dlfcn.h>
 #include <emmintrin.h>
 #include <math.h>
+#include <nccl.h>  // types only: the library is loaded with dlopen at the first mth_comm_* call
 #include <stdio.h>
 #include <string.h>
 
@@ -56,6 +58,7 @@ struct ProfSpan {
 };
 
 constexpr int64_t COMPACT_PIECE = 1 << 21;  // reads per H2D piece of a compact host batch
+constexpr int64_t BORROWED_REGION_MIN_READS = 1 << 20;  // see place_batch
 
 enum { M_PDR = 0, M_MHL, M_FDRP, M_QFDRP, M_PM, M_ME, M_PAIRS, M_COUNT };
 
@@ -99,6 +102,9 @@ struct mth_ctx {
     PairRowsBuf rows_pairs;
     int64_t lpmd_total_host[4] = {0, 0, 0, 0};
     int me_lut_max = 0;
+
+    ncclComm_t comm = nullptr;  // multi-GPU: joins this context with its peers (mth_comm_init_*)
+    int comm_ranks = 0;
 
     mth_stats stats;
     std::vector<ProfSpan> spans;
@@ -365,6 +371,9 @@ static int place_batch(mth_ctx* c, int32_t tid, int64_t n_reads, int64_t n_cpg, 
             int64_t noff = (((int64_t)c->cur_lin_off + c->ref_len[c->last_tid] + CONTIG_GAP) + 63) & ~63ll;
             bool fits = noff + c->ref_len[tid] + 64 < (int64_t)INT32_MAX && c->I + n_cpg < (int64_t)UINT32_MAX - 64 &&
                         c->R + n_reads < (int64_t)INT32_MAX - 64 && c->W + n_words < (int64_t)UINT32_MAX - 64;
+            // A large device-resident contig that is being read in place (zero copy) closes its own region: packing the next
+            // contig behind it would first copy the whole contig into the arena, which costs more than a region boundary.
+            if (c->borrowed && c->R >= BORROWED_REGION_MIN_READS) fits = false;
             if (fits) {
                 TRY(materialize(c));
                 TRY(add_contig(c, tid, (int32_t)noff));
@@ -525,6 +534,7 @@ int mth_ctx_destroy(mth_ctx* c) {
     host_free(c->h_totals);
     for (auto& sp : c->spans) { cudaEventDestroy(sp.e0); cudaEventDestroy(sp.e1); }
     for (auto e : c->ev_pool) cudaEventDestroy(e);
+    mth_comm_destroy(c);
     if (c->ev_copy) cudaEventDestroy(c->ev_copy);
     if (c->ev_compute) cudaEventDestroy(c->ev_compute);
     if (c->own_compute) cudaStreamDestroy(c->own_compute);
@@ -950,24 +960,39 @@ static int process_region(mth_ctx* c) {
             ProfScope ps(c, "mhl_rows_count");
             ps.add(launch_exclusive_scan_u32((uint32_t*)c->rowcnt[M_MHL].p, C, scratch, d_tot + M_MHL, s));
         }
-        for (int q = 0; q < 2; q++) {
-            uint32_t bit = q ? MTH_QFDRP : MTH_FDRP;
-            int m = q ? M_QFDRP : M_FDRP;
-            if (!(M & bit)) continue;
-            mth_fdrp_params fp = q ? c->prm.qfdrp : c->prm.fdrp;
-            size_t sb = fdrp_scratch_bytes(fp, q);
-            TRY(dev_reserve(c, c->fdrp_scratch, sb, 0));
-            {
-                ProfScope ps(c, q ? "k_qfdrp" : "k_fdrp");
-                CUDA_TRY(c, cudaMemsetAsync(c->gfallback.p, 0, (size_t)C, s));
-                ps.add(launch_fdrp_tile(rv, site_pos, C, (const unsigned long long*)c->bitmap.p, n_words, (const uint32_t*)c->word_prefix.p,
-                                        d_sc, fp, q, c->prm.seed, ct, (float*)c->value[m].p, (uint32_t*)c->rowcnt[m].p,
-                                        (uint8_t*)c->gfallback.p, s));
-                ps.add(launch_fdrp(rv, site_pos, C, d_sc, fp, q, c->prm.seed, ct, c->fdrp_scratch.p, sb, (float*)c->value[m].p,
-                                   (uint32_t*)c->rowcnt[m].p, (const uint8_t*)c->gfallback.p, s));
+        {
+            // FDRP and qFDRP share the pile, the overlap test and the Hamming distance (fdrp.rs:124-145, qfdrp.rs:137-157): with
+            // equal thresholds (the reference's defaults are equal) ONE pile build + ONE pair loop emits both values.
+            const mth_fdrp_params &pf = c->prm.fdrp, &pq = c->prm.qfdrp;
+            const bool both = (M & MTH_FDRP) && (M & MTH_QFDRP) && pf.min_qual == pq.min_qual && pf.min_depth == pq.min_depth &&
+                              pf.max_depth == pq.max_depth && pf.min_overlap == pq.min_overlap;
+            for (int q = 0; q < 2; q++) {
+                uint32_t bit = q ? MTH_QFDRP : MTH_FDRP;
+                int m = q ? M_QFDRP : M_FDRP;
+                if (!(M & bit)) continue;
+                if (both && q == 1) {  // rows of qFDRP: value / rowcnt were written by the fused pass
+                    ProfScope ps(c, "qfdrp_rows_count");
+                    ps.add(launch_exclusive_scan_u32((uint32_t*)c->rowcnt[m].p, C, scratch, d_tot + m, s));
+                    continue;
+                }
+                mth_fdrp_params fp = q ? c->prm.qfdrp : c->prm.fdrp;
+                const int mode = both ? 2 : q;
+                size_t sb = fdrp_scratch_bytes(fp, q);
+                TRY(dev_reserve(c, c->fdrp_scratch, sb, 0));
+                {
+                    ProfScope ps(c, both ? "k_fdrp_qfdrp" : (q ? "k_qfdrp" : "k_fdrp"));
+                    CUDA_TRY(c, cudaMemsetAsync(c->gfallback.p, 0, (size_t)C, s));
+                    float* vq = both ? (float*)c->value[M_QFDRP].p : nullptr;
+                    uint32_t* rq = both ? (uint32_t*)c->rowcnt[M_QFDRP].p : nullptr;
+                    ps.add(launch_fdrp_tile(rv, site_pos, C, (const unsigned long long*)c->bitmap.p, n_words, (const uint32_t*)c->word_prefix.p,
+                                            d_sc, fp, mode, c->prm.seed, ct, (float*)c->value[m].p, (uint32_t*)c->rowcnt[m].p, vq, rq,
+                                            (uint8_t*)c->gfallback.p, s));
+                    ps.add(launch_fdrp(rv, site_pos, C, d_sc, fp, mode, c->prm.seed, ct, c->fdrp_scratch.p, sb, (float*)c->value[m].p,
+                                       (uint32_t*)c->rowcnt[m].p, vq, rq, (const uint8_t*)c->gfallback.p, s));
+                }
+                ProfScope ps(c, q ? "qfdrp_rows_count" : "fdrp_rows_count");
+                ps.add(launch_exclusive_scan_u32((uint32_t*)c->rowcnt[m].p, C, scratch, d_tot + m, s));
             }
-            ProfScope ps(c, q ? "qfdrp_rows_count" : "fdrp_rows_count");
-            ps.add(launch_exclusive_scan_u32((uint32_t*)c->rowcnt[m].p, C, scratch, d_tot + m, s));
         }
         int q_set[2] = {0, 1};  // which histogram / mixed-site set PM and ME use
         for (int q = 0; q < 2; q++) {
@@ -1017,6 +1042,7 @@ static int process_region(mth_ctx* c) {
         CUDA_TRY(c, cudaMemcpyAsync(c->h_scalars.p, d_sc, sizeof(RegionScalars), cudaMemcpyDeviceToHost, s));
         CUDA_TRY(c, cudaStreamSynchronize(s));
         TRY(check_scalars_err(c, ((RegionScalars*)c->h_scalars.p)->err));
+        c->stats.fdrp_pair_ops += (int64_t)((RegionScalars*)c->h_scalars.p)->fdrp_pairs;
         const unsigned long long* tot = (const unsigned long long*)c->h_totals.p;
 
         // ---------------- phase B: row emission ----------------
@@ -1072,6 +1098,10 @@ static int process_region(mth_ctx* c) {
     c->region_active = false;
     c->borrowed = false;
     c->R = c->I = c->W = 0;
+    // The emit kernels queued above still read the arena; the next region's host->device copies (copy stream) overwrite it
+    // from offset 0: order them behind this point.
+    CUDA_TRY(c, cudaEventRecord(c->ev_compute, s));
+    CUDA_TRY(c, cudaStreamWaitEvent(c->copy, c->ev_compute, 0));
     return MTH_OK;
 }
 
@@ -1222,5 +1252,155 @@ int mth_get_stats(mth_ctx* c, mth_stats* out) {
     *out = c->stats;
     return MTH_OK;
 }
+
+}  // extern "C"
+
+// ---- multi-GPU: NCCL, loaded at run time -------------------------------------------------------------------------
+namespace {
+struct NcclApi {
+    void* h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    std::string err;
+};
+NcclApi g_nccl;
+
+// The copy of NCCL already in the process wins (under PyTorch that is the one torch.distributed uses, so there is one NCCL
+// per process); otherwise the system library.
+bool nccl_load() {
+    if (g_nccl.h) return true;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+    if (!h) {
+        g_nccl.err = std::string("cannot load libnccl.so.2: ") + dlerror();
+        return false;
+    }
+    bool ok = true;
+    auto sym = [&](const char* name) {
+        void* p = dlsym(h, name);
+        if (!p) { ok = false; g_nccl.err = std::string("libnccl lacks ") + name; }
+        return p;
+    };
+    g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))sym("ncclGetUniqueId");
+    g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))sym("ncclCommInitRank");
+    g_nccl.CommInitAll = (decltype(g_nccl.CommInitAll))sym("ncclCommInitAll");
+    g_nccl.AllReduce = (decltype(g_nccl.AllReduce))sym("ncclAllReduce");
+    g_nccl.GroupStart = (decltype(g_nccl.GroupStart))sym("ncclGroupStart");
+    g_nccl.GroupEnd = (decltype(g_nccl.GroupEnd))sym("ncclGroupEnd");
+    g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))sym("ncclCommDestroy");
+    g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))sym("ncclGetErrorString");
+    if (!ok) return false;
+    g_nccl.h = h;
+    return true;
+}
+int nccl_fail(mth_ctx* c, const char* what, ncclResult_t r) {
+    std::string m = std::string(what) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "NCCL error");
+    if (c) c->err = m; else g_create_err = m;
+    return MTH_ERR_CUDA;
+}
+// enqueue the sum of the context's device-side LPMD totals (int64[4]) on its compute stream
+int enqueue_allreduce(mth_ctx* c) {
+    if (!c->comm) return fail(c, MTH_ERR_STATE, "mth_allreduce without a communicator (mth_comm_init_rank / mth_comm_init_all)");
+    if (!c->finished) return fail(c, MTH_ERR_STATE, "mth_allreduce before mth_finish");
+    ncclResult_t r = g_nccl.AllReduce(c->lpmd_total.p, c->lpmd_total.p, 4, ncclInt64, ncclSum, c->comm, c->compute);
+    if (r != ncclSuccess) return nccl_fail(c, "ncclAllReduce", r);
+    c->stats.kernel_launches += 1;
+    return MTH_OK;
+}
+int fetch_allreduced(mth_ctx* c) {
+    CUDA_TRY(c, cudaMemcpyAsync(c->lpmd_total_host, c->lpmd_total.p, 32, cudaMemcpyDeviceToHost, c->compute));
+    CUDA_TRY(c, cudaStreamSynchronize(c->compute));
+    return MTH_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int mth_comm_unique_id(void* id128) {
+    if (!id128) return MTH_ERR_INVALID;
+    if (!nccl_load()) { g_create_err = g_nccl.err; return MTH_ERR_CUDA; }
+    ncclUniqueId id;
+    ncclResult_t r = g_nccl.GetUniqueId(&id);
+    if (r != ncclSuccess) return nccl_fail(nullptr, "ncclGetUniqueId", r);
+    static_assert(sizeof(id) == MTH_COMM_ID_BYTES, "ncclUniqueId size");
+    memcpy(id128, &id, sizeof(id));
+    return MTH_OK;
+}
+
+int mth_comm_init_rank(mth_ctx* c, int n_ranks, int rank, const void* id128) {
+    if (!c || !id128 || n_ranks < 1 || rank < 0 || rank >= n_ranks) return MTH_ERR_INVALID;
+    if (c->comm) return fail(c, MTH_ERR_STATE, "context already has a communicator");
+    if (!nccl_load()) return fail(c, MTH_ERR_CUDA, g_nccl.err);
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    ncclResult_t r = g_nccl.CommInitRank(&c->comm, n_ranks, id, rank);
+    if (r != ncclSuccess) { c->comm = nullptr; return nccl_fail(c, "ncclCommInitRank", r); }
+    c->comm_ranks = n_ranks;
+    return MTH_OK;
+}
+
+int mth_comm_init_all(mth_ctx** ctxs, int n) {
+    if (!ctxs || n < 1) return MTH_ERR_INVALID;
+    for (int i = 0; i < n; i++)
+        if (!ctxs[i] || ctxs[i]->comm) return MTH_ERR_INVALID;
+    if (!nccl_load()) return fail(ctxs[0], MTH_ERR_CUDA, g_nccl.err);
+    std::vector<int> devs(n);
+    std::vector<ncclComm_t> comms(n, nullptr);
+    for (int i = 0; i < n; i++) devs[i] = ctxs[i]->device;
+    ncclResult_t r = g_nccl.CommInitAll(comms.data(), n, devs.data());
+    if (r != ncclSuccess) return nccl_fail(ctxs[0], "ncclCommInitAll", r);
+    for (int i = 0; i < n; i++) { ctxs[i]->comm = comms[i]; ctxs[i]->comm_ranks = n; }
+    return MTH_OK;
+}
+
+int mth_allreduce(mth_ctx* c) {
+    if (!c) return MTH_ERR_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    TRY(enqueue_allreduce(c));
+    return fetch_allreduced(c);
+}
+
+int mth_allreduce_group(mth_ctx** ctxs, int n) {
+    if (!ctxs || n < 1) return MTH_ERR_INVALID;
+    for (int i = 0; i < n; i++)
+        if (!ctxs[i]) return MTH_ERR_INVALID;
+    if (!g_nccl.h) return fail(ctxs[0], MTH_ERR_STATE, "mth_allreduce_group without a communicator");
+    ncclResult_t r = g_nccl.GroupStart();
+    if (r != ncclSuccess) return nccl_fail(ctxs[0], "ncclGroupStart", r);
+    int rc = MTH_OK;
+    for (int i = 0; i < n && rc == MTH_OK; i++) {
+        cudaSetDevice(ctxs[i]->device);
+        rc = enqueue_allreduce(ctxs[i]);
+    }
+    r = g_nccl.GroupEnd();
+    if (rc != MTH_OK) return rc;
+    if (r != ncclSuccess) return nccl_fail(ctxs[0], "ncclGroupEnd", r);
+    for (int i = 0; i < n; i++) {
+        CUDA_TRY(ctxs[i], cudaSetDevice(ctxs[i]->device));
+        TRY(fetch_allreduced(ctxs[i]));
+    }
+    return MTH_OK;
+}
+
+int mth_comm_destroy(mth_ctx* c) {
+    if (!c) return MTH_ERR_INVALID;
+    if (c->comm && g_nccl.CommDestroy) {
+        cudaSetDevice(c->device);
+        g_nccl.CommDestroy(c->comm);
+    }
+    c->comm = nullptr;
+    c->comm_ranks = 0;
+    return MTH_OK;
+}
+
+int mth_comm_n_ranks(mth_ctx* c) { return c ? c->comm_ranks : 0; }
 
 }  // extern "C"

@@ -45,27 +45,31 @@ struct FdrpPolicy {
     static constexpr int SLACK = 0;  // fdrp.rs:214 strict cpg < first
     const ReadsView& rv;
     mth_fdrp_params prm;
-    bool quant;
+    int quant;  // 0 FDRP, 1 qFDRP, 2 both from one pair loop (value = FDRP, value_q = qFDRP)
     uint64_t seed;
     ContigTable ct;
     float* value;
     uint32_t* rowcnt;
+    float* value_q;
+    uint32_t* rowcnt_q;
     FdrpScratch sc;
     uint32_t D;        // max_depth
     uint32_t* U;       // shared: union bitmap [13]
     uint32_t* UP;      // shared: prefix [13]
     int32_t p;
     uint32_t total, depth;
-    float best;
+    float best, best_q;
     bool have;
+    unsigned long long pair_ops = 0;
 
-    __device__ FdrpPolicy(const ReadsView& rv_, mth_fdrp_params prm_, bool q, uint64_t seed_, ContigTable ct_, float* v,
-                          uint32_t* rc, FdrpScratch sc_, uint32_t* U_, uint32_t* UP_)
-        : rv(rv_), prm(prm_), quant(q), seed(seed_), ct(ct_), value(v), rowcnt(rc), sc(sc_), D(prm_.max_depth), U(U_), UP(UP_) {}
+    __device__ FdrpPolicy(const ReadsView& rv_, mth_fdrp_params prm_, int q, uint64_t seed_, ContigTable ct_, float* v,
+                          uint32_t* rc, float* vq, uint32_t* rcq, FdrpScratch sc_, uint32_t* U_, uint32_t* UP_)
+        : rv(rv_), prm(prm_), quant(q), seed(seed_), ct(ct_), value(v), rowcnt(rc), value_q(vq), rowcnt_q(rcq), sc(sc_),
+          D(prm_.max_depth), U(U_), UP(UP_) {}
     // fdrp.rs:205 mapq, :208 no CpGs
     __device__ __forceinline__ bool contrib_ok(uint32_t mapq, uint32_t n) const { return mapq >= prm.min_qual && n > 0; }
     __device__ __forceinline__ bool trigger_ok(uint32_t mapq, uint32_t n) const { return mapq >= prm.min_qual && n > 0; }
-    __device__ __forceinline__ void begin_site(int32_t p_) { p = p_; total = depth = 0; have = false; best = 0.f; }
+    __device__ __forceinline__ void begin_site(int32_t p_) { p = p_; total = depth = 0; have = false; best = best_q = 0.f; }
 
     __device__ __forceinline__ void add(uint32_t mask, const LaneRead& lr) {
         const int lane = lane_id();
@@ -100,8 +104,9 @@ struct FdrpPolicy {
         __syncwarp();
     }
 
-    __device__ float evaluate() {
+    __device__ void evaluate() {
         const int lane = lane_id();
+        const bool want_q = quant != 0, want_d = quant != 1;
         const uint32_t n = depth;
         const size_t Dp = ((size_t)D + 3) & ~(size_t)3;
         // ---- union of CpG positions of the pile, in window coordinates ----
@@ -146,6 +151,7 @@ struct FdrpPolicy {
         __syncwarp();
         // ---- all pairs (i<j) in lexicographic order ----
         const uint64_t P = (uint64_t)n * (n - 1) / 2;
+        pair_ops += P;
         uint32_t i = 0, jj = 1 + lane;  // pair index t = lane maps to (0, 1+lane) before normalisation
         while (i < n && jj >= n) { jj = jj - n + i + 2; i++; }  // row i holds n-1-i pairs
         float acc = 0.f;
@@ -166,11 +172,11 @@ struct FdrpPolicy {
                         shared += __popcll(both);
                         ham += __popcll(both & sc.vm[w * Dp + i] & sc.vm[w * Dp + jj] & (sc.mm[w * Dp + i] ^ sc.mm[w * Dp + jj]));
                     }
-                    if (quant) { if (ham) term = __fdiv_rn((float)ham, (float)shared); }  // qfdrp.rs:152 (0 / shared adds nothing)
-                    else disc += (ham > 0) ? 1u : 0u;                                      // fdrp.rs:138-140
+                    if (want_q && ham) term = __fdiv_rn((float)ham, (float)shared);  // qfdrp.rs:152 (0 / shared adds nothing)
+                    if (want_d) disc += (ham > 0) ? 1u : 0u;                         // fdrp.rs:138-140
                 }
             }
-            if (quant) {  // sequential f32 accumulation in pair order
+            if (want_q) {  // sequential f32 accumulation in pair order
                 uint32_t nz = __ballot_sync(FULL, term != 0.f);
                 if (__popc(nz) > 8) {
                     // dense step: fold all 32 lanes in order, branch-free (x + 0.0f == x exactly, acc >= 0)
@@ -190,20 +196,17 @@ struct FdrpPolicy {
                 while (i < n && jj >= n) { jj = jj - n + i + 2; i++; }
             }
         }
-        float num;
-        if (quant) {
-            num = acc;
-        } else {
-            uint32_t tot = __reduce_add_sync(FULL, disc);
-            num = (float)tot;  // fdrp += 1.0 per discordant pair: exact in f32 below 2^24
+        const float den = __fdiv_rn((float)((unsigned long long)n * (unsigned long long)(n - 1)), 2.0f);  // fdrp.rs:143
+        if (want_d) best = __fdiv_rn((float)__reduce_add_sync(FULL, disc), den);  // += 1.0 per discordant pair: exact in f32 below 2^24
+        if (want_q) {
+            const float v = __fdiv_rn(acc, den);
+            if (quant == 2) best_q = v; else best = v;
         }
-        float den = __fdiv_rn((float)((unsigned long long)n * (unsigned long long)(n - 1)), 2.0f);  // fdrp.rs:143
-        return __fdiv_rn(num, den);
     }
 
     __device__ __forceinline__ void close() {
         if (depth > 0 && depth >= prm.min_depth) {  // fdrp.rs:215
-            best = evaluate();
+            evaluate();
             have = true;
         }
         total = depth = 0;
@@ -212,14 +215,19 @@ struct FdrpPolicy {
         if (lane_id() == 0) {
             value[s] = best;
             rowcnt[s] = have ? 1u : 0u;
+            if (quant == 2) {
+                value_q[s] = best_q;
+                rowcnt_q[s] = have ? 1u : 0u;
+            }
         }
     }
 };
 
 __global__ void __launch_bounds__(GATHER_BLOCK, 4) k_fdrp(ReadsView rv, const int32_t* __restrict__ site_pos, int64_t C,
-                                                       const RegionScalars* __restrict__ scal, mth_fdrp_params prm, int quant,
+                                                       RegionScalars* __restrict__ scal, mth_fdrp_params prm, int quant,
                                                        uint64_t seed, ContigTable ct, char* scratch, float* __restrict__ value,
-                                                       uint32_t* __restrict__ rowcnt, const uint8_t* __restrict__ only) {
+                                                       uint32_t* __restrict__ rowcnt, float* __restrict__ value_q,
+                                                       uint32_t* __restrict__ rowcnt_q, const uint8_t* __restrict__ only) {
     __shared__ uint32_t sU[FDRP_WARPS][FDRP_UWORDS + 1];
     __shared__ uint32_t sP[FDRP_WARPS][FDRP_UWORDS + 1];
     const int warp = threadIdx.x >> 5;
@@ -234,8 +242,9 @@ __global__ void __launch_bounds__(GATHER_BLOCK, 4) k_fdrp(ReadsView rv, const in
     fs.cm = (unsigned long long*)(base + Dp * 12);
     fs.mm = fs.cm + Dp * FDRP_MAXW;
     fs.vm = fs.mm + Dp * FDRP_MAXW;
-    FdrpPolicy pol(rv, prm, quant != 0, seed, ct, value, rowcnt, fs, sU[warp], sP[warp]);
+    FdrpPolicy pol(rv, prm, quant, seed, ct, value, rowcnt, value_q, rowcnt_q, fs, sU[warp], sP[warp]);
     gather_sites(rv, site_pos, C, scal->lmax, pol, only);
+    if (lane_id() == 0 && pol.pair_ops) atomicAdd(&scal->fdrp_pairs, pol.pair_ops);
 }
 
 // grid is bounded so that the per-warp scratch stays below ~2 GB even for very large max_depth
@@ -257,13 +266,13 @@ size_t fdrp_scratch_bytes(mth_fdrp_params prm, int) {
     return blocks * per_block;
 }
 
-int launch_fdrp(const ReadsView& rv, const int32_t* site_pos, int64_t C, const RegionScalars* sc, mth_fdrp_params prm,
+int launch_fdrp(const ReadsView& rv, const int32_t* site_pos, int64_t C, RegionScalars* sc, mth_fdrp_params prm,
                 int quantitative, uint64_t seed, ContigTable ct, void* scratch, size_t scratch_bytes, float* value,
-                uint32_t* rowcnt, const uint8_t* only, cudaStream_t s) {
+                uint32_t* rowcnt, float* value_q, uint32_t* rowcnt_q, const uint8_t* only, cudaStream_t s) {
     if (C <= 0) return 0;
     int g = fdrp_grid(C, prm.max_depth);
     if ((size_t)g * fdrp_per_warp_bytes(prm.max_depth) * FDRP_WARPS > scratch_bytes) return 0;
-    k_fdrp<<<g, GATHER_BLOCK, 0, s>>>(rv, site_pos, C, sc, prm, quantitative, seed, ct, (char*)scratch, value, rowcnt, only);
+    k_fdrp<<<g, GATHER_BLOCK, 0, s>>>(rv, site_pos, C, sc, prm, quantitative, seed, ct, (char*)scratch, value, rowcnt, value_q, rowcnt_q, only);
     return 1;
 }
 

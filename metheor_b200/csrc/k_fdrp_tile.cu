@@ -41,9 +41,10 @@ struct FtSmem {
 __global__ void __launch_bounds__(FT_THREADS, 3) k_fdrp_tile(ReadsView rv, const int32_t* __restrict__ site_pos, int64_t C,
                                                              const unsigned long long* __restrict__ bitmap, int64_t n_words,
                                                              const uint32_t* __restrict__ word_prefix,
-                                                             const RegionScalars* __restrict__ scal, mth_fdrp_params prm, int quant,
+                                                             RegionScalars* __restrict__ scal, mth_fdrp_params prm, int quant,
                                                              uint64_t seed, ContigTable ct, float* __restrict__ value,
-                                                             uint32_t* __restrict__ rowcnt, uint8_t* __restrict__ fallback) {
+                                                             uint32_t* __restrict__ rowcnt, float* __restrict__ value_q,
+                                                             uint32_t* __restrict__ rowcnt_q, uint8_t* __restrict__ fallback) {
     extern __shared__ __align__(16) unsigned char ft_raw[];
     FtSmem& sh = *reinterpret_cast<FtSmem*>(ft_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -51,6 +52,7 @@ __global__ void __launch_bounds__(FT_THREADS, 3) k_fdrp_tile(ReadsView rv, const
     const uint32_t D = prm.max_depth;
     const int64_t n_tiles = (C + FT_SITES - 1) / FT_SITES;
     uint16_t* pile = sh.pile[warp];
+    unsigned long long pair_ops = 0;  // per warp, flushed with one atomic at the end
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t s0 = tile * FT_SITES;
@@ -134,11 +136,13 @@ __global__ void __launch_bounds__(FT_THREADS, 3) k_fdrp_tile(ReadsView rv, const
             int lo = 0, hi = nreads;  // first read with start >= p - lmax + 1 (all lanes compute the same)
             while (lo < hi) { int m = (lo + hi) >> 1; if (sh.start[m] < p - lmax + 1) lo = m + 1; else hi = m; }
             uint32_t total = 0;
-            float best = 0.f;
+            float best = 0.f, best_q = 0.f;  // quant == 2 (both measures from one pair loop): best = FDRP, best_q = qFDRP
             bool have = false;
+            const bool want_q = quant != 0, want_d = quant != 1;
 
-            auto evaluate = [&](uint32_t n) -> float {
+            auto evaluate = [&](uint32_t n) {
                 const uint64_t P = (uint64_t)n * (n - 1) / 2;
+                pair_ops += P;
                 uint32_t i = 0, jj = 1 + lane;  // this lane's pair (i, jj): pair index = lane, then += 32
                 while (i < n && jj >= n) { jj = jj - n + i + 2; i++; }
                 float acc = 0.f;
@@ -156,13 +160,13 @@ __global__ void __launch_bounds__(FT_THREADS, 3) k_fdrp_tile(ReadsView rv, const
                             if (uj < 64u) v0 &= ~(1ull << uj); else if (uj < 128u) v1 &= ~(1ull << (uj - 64u));
                             const uint32_t ham = (uint32_t)__popcll(v0 & (sh.mm[ri][0] ^ sh.mm[rj][0])) +
                                                  (uint32_t)__popcll(v1 & (sh.mm[ri][1] ^ sh.mm[rj][1]));  // fdrp.rs:109-122
-                            if (quant) { if (ham) term = __fdiv_rn((float)ham, (float)(__popcll(b0) + __popcll(b1))); }  // qfdrp.rs:152
-                            else disc += ham ? 1u : 0u;                                                                // fdrp.rs:138-140
+                            if (want_q && ham) term = __fdiv_rn((float)ham, (float)(__popcll(b0) + __popcll(b1)));  // qfdrp.rs:152
+                            if (want_d) disc += ham ? 1u : 0u;                                                       // fdrp.rs:138-140
                         }
                         jj += 32;
                         while (i < n && jj >= n) { jj = jj - n + i + 2; i++; }
                     }
-                    if (quant) {  // sequential f32 accumulation in pair order
+                    if (want_q) {  // sequential f32 accumulation in pair order
                         uint32_t nz = __ballot_sync(FULL, term != 0.f);
                         if (__popc(nz) > 8) {
                             // dense step: fold all 32 lanes in order, branch-free (x + 0.0f == x exactly, acc >= 0)
@@ -177,15 +181,21 @@ __global__ void __launch_bounds__(FT_THREADS, 3) k_fdrp_tile(ReadsView rv, const
                         }
                     }
                 }
-                const float num = quant ? acc : (float)__reduce_add_sync(FULL, disc);
                 const float den = __fdiv_rn((float)((unsigned long long)n * (unsigned long long)(n - 1)), 2.0f);  // fdrp.rs:143
-                return __fdiv_rn(num, den);
+                if (want_d) {
+                    const float v = __fdiv_rn((float)__reduce_add_sync(FULL, disc), den);
+                    best = v;
+                }
+                if (want_q) {
+                    const float v = __fdiv_rn(acc, den);
+                    if (quant == 2) best_q = v; else best = v;
+                }
             };
             auto close = [&]() {
                 const uint32_t depth = min(total, D);
                 if (depth > 0 && depth >= prm.min_depth) {  // fdrp.rs:215
                     __syncwarp();
-                    best = evaluate(depth);
+                    evaluate(depth);
                     have = true;
                 }
                 total = 0;
@@ -241,14 +251,20 @@ __global__ void __launch_bounds__(FT_THREADS, 3) k_fdrp_tile(ReadsView rv, const
             if (lane == 0) {
                 value[s0 + ls] = best;
                 rowcnt[s0 + ls] = have ? 1u : 0u;
+                if (quant == 2) {
+                    value_q[s0 + ls] = best_q;
+                    rowcnt_q[s0 + ls] = have ? 1u : 0u;
+                }
             }
         }
     }
+    if (lane == 0 && pair_ops) atomicAdd(&scal->fdrp_pairs, pair_ops);
 }
 
 int launch_fdrp_tile(const ReadsView& rv, const int32_t* site_pos, int64_t C, const unsigned long long* bitmap, int64_t n_words,
-                     const uint32_t* word_prefix, const RegionScalars* sc, mth_fdrp_params prm, int quantitative, uint64_t seed,
-                     ContigTable ct, float* value, uint32_t* rowcnt, uint8_t* fallback, cudaStream_t s) {
+                     const uint32_t* word_prefix, RegionScalars* sc, mth_fdrp_params prm, int quantitative, uint64_t seed,
+                     ContigTable ct, float* value, uint32_t* rowcnt, float* value_q, uint32_t* rowcnt_q, uint8_t* fallback,
+                     cudaStream_t s) {
     if (C <= 0) return 0;
     static bool attr_set = false;
     if (!attr_set) {
@@ -258,7 +274,7 @@ int launch_fdrp_tile(const ReadsView& rv, const int32_t* site_pos, int64_t C, co
     int64_t tiles = (C + FT_SITES - 1) / FT_SITES;
     if (tiles > 148 * 48) tiles = 148 * 48;
     k_fdrp_tile<<<(unsigned)tiles, FT_THREADS, sizeof(FtSmem), s>>>(rv, site_pos, C, bitmap, n_words, word_prefix, sc, prm, quantitative,
-                                                                   seed, ct, value, rowcnt, fallback);
+                                                                   seed, ct, value, rowcnt, value_q, rowcnt_q, fallback);
     return 1;
 }
 

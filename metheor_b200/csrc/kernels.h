@@ -119,14 +119,17 @@ int launch_lpmd_pairs_emit(const ReadsView& rv, const uint16_t* rel, const int32
                            PairRowsDev rows, int64_t row_base, cudaStream_t s);
 
 // ---- FDRP / qFDRP (k_fdrp.cu) ---------------------------------------------------------------
-int launch_fdrp(const ReadsView& rv, const int32_t* site_pos, int64_t C, const RegionScalars* sc, mth_fdrp_params prm,
+int launch_fdrp(const ReadsView& rv, const int32_t* site_pos, int64_t C, RegionScalars* sc, mth_fdrp_params prm,
                 int quantitative, uint64_t seed, ContigTable ct, void* scratch, size_t scratch_bytes, float* value,
-                uint32_t* rowcnt, const uint8_t* only, cudaStream_t s);  // only != nullptr: just the flagged sites
+                uint32_t* rowcnt, float* value_q, uint32_t* rowcnt_q, const uint8_t* only, cudaStream_t s);  // only != nullptr: just the flagged sites
+// quantitative: 0 = FDRP, 1 = qFDRP, 2 = BOTH from one pile + one pair loop (fdrp.rs:124-145 and qfdrp.rs:137-157 share the
+// pile, the overlap test and the Hamming distance): FDRP -> value / rowcnt, qFDRP -> value_q / rowcnt_q
 // tile form (k_fdrp_tile.cu): takes every site whose tile fits shared memory, flags the rest in fallback[] (C bytes, zeroed by
 // the caller) for launch_fdrp(..., only = fallback)
 int launch_fdrp_tile(const ReadsView& rv, const int32_t* site_pos, int64_t C, const unsigned long long* bitmap, int64_t n_words,
-                     const uint32_t* word_prefix, const RegionScalars* sc, mth_fdrp_params prm, int quantitative, uint64_t seed,
-                     ContigTable ct, float* value, uint32_t* rowcnt, uint8_t* fallback, cudaStream_t s);
+                     const uint32_t* word_prefix, RegionScalars* sc, mth_fdrp_params prm, int quantitative, uint64_t seed,
+                     ContigTable ct, float* value, uint32_t* rowcnt, float* value_q, uint32_t* rowcnt_q, uint8_t* fallback,
+                     cudaStream_t s);
 size_t fdrp_scratch_bytes(mth_fdrp_params prm, int quantitative);
 
 }  // namespace mth

@@ -195,6 +195,20 @@ class Context:
         self._check(self._L.mth_lpmd_refresh(self._h, C.byref(r)))
         return dict(n_read=r.n_read, n_valid_read=r.n_valid_read, n_conc=r.n_conc, n_disc=r.n_disc, lpmd=np.float32(r.lpmd))
 
+    # ---- multi-GPU: one context per rank, joined by NCCL inside the library (mth_comm_*, mth_allreduce) ----
+    def comm_init_rank(self, n_ranks, rank, unique_id):
+        """unique_id: the 128 bytes rank 0 got from `comm_unique_id()` (shipped to the ranks by the caller)."""
+        buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
+        self._check(self._L.mth_comm_init_rank(self._h, n_ranks, rank, C.cast(buf, C.c_void_p)))
+
+    def allreduce(self):
+        """Sum LPMD's counters over the ranks (after finish()); -> the global LPMD result."""
+        self._check(self._L.mth_allreduce(self._h))
+        return self.lpmd_refresh()
+
+    def comm_n_ranks(self):
+        return int(self._L.mth_comm_n_ranks(self._h))
+
     def reset(self):
         self._check(self._L.mth_reset(self._h))
         self._keep.clear()
@@ -206,10 +220,34 @@ class Context:
         s = Stats()
         self._check(self._L.mth_get_stats(self._h, C.byref(s)))
         d = {k: getattr(s, k) for k in ("n_reads", "n_cpg", "n_sites", "n_regions", "kernel_launches", "h2d_bytes",
-                                         "d2h_bytes", "max_ref_span", "pdr_path")}
+                                         "d2h_bytes", "fdrp_pair_ops", "max_ref_span", "pdr_path")}
         d["kernels"] = {s.kernel[i].name.decode(): dict(launches=s.kernel[i].launches, ms=s.kernel[i].ms)
                         for i in range(s.n_kernel_stats)}
         return d
+
+
+def comm_unique_id():
+    buf = (C.c_char * 128)()
+    rc = _lib.lib().mth_comm_unique_id(C.cast(buf, C.c_void_p))
+    if rc != 0:
+        raise EngineError(rc, _lib.lib().mth_last_error(None).decode())
+    return bytes(buf)
+
+
+def comm_init_all(contexts):
+    """Single process, several contexts (one per GPU): ncclCommInitAll."""
+    arr = (C.c_void_p * len(contexts))(*[c._h for c in contexts])
+    rc = _lib.lib().mth_comm_init_all(arr, len(contexts))
+    if rc != 0:
+        raise EngineError(rc, _lib.lib().mth_last_error(contexts[0]._h).decode())
+
+
+def allreduce_group(contexts):
+    arr = (C.c_void_p * len(contexts))(*[c._h for c in contexts])
+    rc = _lib.lib().mth_allreduce_group(arr, len(contexts))
+    if rc != 0:
+        raise EngineError(rc, _lib.lib().mth_last_error(contexts[0]._h).decode())
+    return [c.lpmd_refresh() for c in contexts]
 
 
 def run_batches(batches, ref_len, measures, device=0, flags=0, seed=0, compact=False, **overrides):

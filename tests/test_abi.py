@@ -47,7 +47,7 @@ def test_calls_that_need_no_device():
     assert b"sm_100a" in L.mth_version()
     p = _lib.Params()
     L.mth_params_default(C.byref(p))
-    assert p.abi_version == 1 and p.pdr.min_depth == 10 and p.pdr.min_cpgs == 4 and p.lpmd.max_distance == 16
+    assert p.abi_version == 2 and p.pdr.min_depth == 10 and p.pdr.min_cpgs == 4 and p.lpmd.max_distance == 16
     a = L.mth_reservoir_draw(7, 0, 1234, 100)
     assert 1 <= a <= 100 and a == L.mth_reservoir_draw(7, 0, 1234, 100)
 
