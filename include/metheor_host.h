@@ -40,7 +40,8 @@ typedef struct {
     int32_t max_distance;   /* -M (lpmd) */
     /* engine options (not in the reference; long flags only, no collision with -i -o -d -p -q -c -D -l -m -M -g) */
     int32_t device;         /* --device N : first GPU to use (default 0) */
-    int32_t n_gpus;         /* --gpus N   : contigs are sharded over N GPUs of this node (default 1) */
+    int32_t n_gpus;         /* --gpus N   : the genome is sharded over N GPUs of this node (default 1): position bins + halo */
+    int32_t shard_contigs;  /* --shard contigs : shard whole contigs instead of position bins (default 0 = bins) */
     int32_t threads;        /* --threads N: decode threads, 0 = all cores */
     uint64_t seed;          /* --seed     : reservoir sampling seed once a pile exceeds max_depth */
     const char* stats_json; /* --stats F  : write reads/s, per-stage seconds and kernel stats as JSON, or NULL */
@@ -80,6 +81,12 @@ void mthh_decoded_free(mthh_decoded* d);
  * 0 on success, otherwise the exit status (101 where the reference panics) with the message in `err`. */
 int mthh_tag(const char* input, const char* output, const char* genome, int32_t device, int32_t threads,
              const char* stats_json, char* err, size_t errcap);
+
+/* The multi-GPU sharding plan `metheor --gpus N` uses: the linearised genome cut into `world` position bins of
+ * equal length (by_contig = 0) or whole contigs, longest first onto the least loaded rank (by_contig = 1).  Writes up to `cap`
+ * intervals (rank, tid, lo, hi — hi exclusive) ordered by rank; returns the number of intervals. */
+typedef struct { int32_t rank, tid; int64_t lo, hi; } mthh_interval;
+int mthh_plan_shards(int32_t n_ref, const int64_t* ref_len, int32_t world, int32_t by_contig, mthh_interval* out, int32_t cap);
 
 /* Rust `{}` formatting of an f32 (shortest round-trip digits, positional, "NaN", "inf", "-0"); returns length. */
 int mthh_format_f32(float v, char* buf, int cap);

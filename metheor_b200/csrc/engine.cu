@@ -88,7 +88,9 @@ struct mth_ctx {
     DevBuf bitmap, word_prefix, block_sums, site_pos, scalars, totals, ct_lin, ct_tid;
     DevBuf cnt2, scan_scratch, fdrp_scratch, me_lut, lpmd_total;
     DevBuf gfallback;            // sites the thread-per-site gather kernels hand to the warp-per-site form
-    DevBuf qhist[2], qmixed[2];  // PM / ME: per-site 16-pattern histograms of canonical quartets + mixed-site flags
+    // PM / ME: per-(site, slot) observation counts, mixed-site flags, the observation list (site / slot+pattern / length) and
+    // the 16-bin histograms of the output rows (k_quartet.cu)
+    DevBuf qcnt[2], qmixed[2], qobs_site[2], qobs_vp[2], qobs_n, qhrows[2];
     DevBuf stage[2][13], exp_blocks, exp_tot;  // compact wire format: two staging sets + scan scratch
     cudaEvent_t ev_stage_free[2] = {nullptr, nullptr};
     bool stage_busy[2] = {false, false};
@@ -511,7 +513,8 @@ int mth_ctx_destroy(mth_ctx* c) {
         for (DevBuf& b : set) dev_free(b);
     dev_free(c->exp_blocks);
     dev_free(c->exp_tot);
-    for (int q = 0; q < 2; q++) { dev_free(c->qhist[q]); dev_free(c->qmixed[q]); }
+    for (int q = 0; q < 2; q++) { dev_free(c->qcnt[q]); dev_free(c->qmixed[q]); dev_free(c->qobs_site[q]); dev_free(c->qobs_vp[q]); dev_free(c->qhrows[q]); }
+    dev_free(c->qobs_n);
     dev_free(c->gfallback);
     for (cudaEvent_t e : c->ev_stage_free)
         if (e) cudaEventDestroy(e);
@@ -1008,19 +1011,24 @@ static int process_region(mth_ctx* c) {
                 continue;
             }
             q_set[q] = q;
-            TRY(dev_reserve(c, c->qhist[q], (size_t)(C + 4) * 256, 0));  // [site][4 key variants][16 patterns] u32
+            TRY(dev_reserve(c, c->qcnt[q], (size_t)(C + 4) * 16, 0));  // [site][4 slots] u32
             TRY(dev_reserve(c, c->qmixed[q], (size_t)C + 64, 0));
-            CUDA_TRY(c, cudaMemsetAsync(c->qhist[q].p, 0, (size_t)(C + 4) * 256, s));
+            TRY(dev_reserve(c, c->qobs_site[q], (size_t)rv.I * 4 + 64, 0));  // at most one observation per call
+            TRY(dev_reserve(c, c->qobs_vp[q], (size_t)rv.I + 64, 0));
+            TRY(dev_reserve(c, c->qobs_n, 16, 0));
+            CUDA_TRY(c, cudaMemsetAsync(c->qcnt[q].p, 0, (size_t)(C + 4) * 16, s));
             CUDA_TRY(c, cudaMemsetAsync(c->qmixed[q].p, 0, (size_t)C + 64, s));
+            CUDA_TRY(c, cudaMemsetAsync((unsigned long long*)c->qobs_n.p + q, 0, 8, s));
             {
                 ProfScope ps(c, q ? "k_me_scatter" : "k_pm_scatter");
                 ps.add(launch_quartet_scatter(rv.cpg_pos, (const uint8_t*)c->a_flags.p, rv.I, (const unsigned long long*)c->bitmap.p, n_words,
-                                              (const uint32_t*)c->word_prefix.p, d_sc, q ? CF_ME_OK : CF_PM_OK, (uint32_t*)c->qhist[q].p,
-                                              (uint8_t*)c->qmixed[q].p, s));
+                                              (const uint32_t*)c->word_prefix.p, d_sc, q ? CF_ME_OK : CF_PM_OK, (uint32_t*)c->qcnt[q].p,
+                                              (uint8_t*)c->qmixed[q].p, (uint32_t*)c->qobs_site[q].p, (uint8_t*)c->qobs_vp[q].p,
+                                              (unsigned long long*)c->qobs_n.p + q, s));
             }
             {
                 ProfScope ps(c, q ? "k_me_count" : "k_pm_count");
-                ps.add(launch_quartet_canon_count((const uint32_t*)c->qhist[q].p, (const uint8_t*)c->qmixed[q].p, C, qp.min_depth,
+                ps.add(launch_quartet_canon_count((const uint32_t*)c->qcnt[q].p, (const uint8_t*)c->qmixed[q].p, C, qp.min_depth,
                                                   (uint32_t*)c->rowcnt[m].p, s));
                 ps.add(launch_quartet_count(rv, site_pos, C, d_sc, qp, (const uint8_t*)c->qmixed[q].p, (uint32_t*)c->rowcnt[m].p, s));
             }
@@ -1064,24 +1072,50 @@ static int process_region(mth_ctx* c) {
                                     site_rows_dev(*e.r), e.r->n, s));
             e.r->n += (int64_t)tot[e.m];
         }
-        for (int q = 0; q < 2; q++) {
-            uint32_t bit = q ? MTH_ME : MTH_PM;
-            int m = q ? M_ME : M_PM;
-            if (!(M & bit)) continue;
-            QuartetRowsBuf& r = q ? c->rows_me : c->rows_pm;
-            bool counts = (c->prm.flags & MTH_FLAG_QUARTET_COUNTS) != 0;
-            TRY(reserve_quartet_rows(c, r, r.n + (int64_t)tot[m], counts));
-            QuartetRowsDev rd = quartet_rows_dev(r);
-            if (!counts) rd.counts = nullptr;
-            ProfScope ps(c, q ? "k_me_emit" : "k_pm_emit");
-            const mth_quartet_params qp = q ? c->prm.me : c->prm.pm;
-            const uint32_t* qh = (const uint32_t*)c->qhist[q_set[q]].p;
-            const uint8_t* qm = (const uint8_t*)c->qmixed[q_set[q]].p;
-            ps.add(launch_quartet_canon_emit(qh, qm, site_pos, C, qp.min_depth, q, (const uint32_t*)c->rowcnt[m].p, (const float*)c->me_lut.p,
-                                             c->me_lut_max, ct, rd, r.n, s));
-            ps.add(launch_quartet_emit(rv, site_pos, C, d_sc, qp, q, qm, (const uint32_t*)c->rowcnt[m].p, (const float*)c->me_lut.p,
-                                       c->me_lut_max, ct, rd, r.n, s));
-            r.n += (int64_t)tot[m];
+        {
+            const bool counts = (c->prm.flags & MTH_FLAG_QUARTET_COUNTS) != 0;
+            const bool shared = (M & MTH_PM) && (M & MTH_ME) && q_set[1] == 0;  // identical thresholds: one histogram, identical rows
+            for (int q = 0; q < 2; q++) {
+                uint32_t bit = q ? MTH_ME : MTH_PM;
+                int m = q ? M_ME : M_PM;
+                if (!(M & bit)) continue;
+                QuartetRowsBuf& r = q ? c->rows_me : c->rows_pm;
+                TRY(reserve_quartet_rows(c, r, r.n + (int64_t)tot[m], counts));
+            }
+            for (int q = 0; q < 2; q++) {
+                uint32_t bit = q ? MTH_ME : MTH_PM;
+                int m = q ? M_ME : M_PM;
+                if (!(M & bit)) continue;
+                QuartetRowsBuf& r = q ? c->rows_me : c->rows_pm;
+                QuartetRowsDev rd = quartet_rows_dev(r);
+                if (!counts) rd.counts = nullptr;
+                const mth_quartet_params qp = q ? c->prm.me : c->prm.pm;
+                const int qs = q_set[q];
+                const uint8_t* qm = (const uint8_t*)c->qmixed[qs].p;
+                if (!(shared && q == 1)) {  // row histograms from the observation list (once per histogram set)
+                    ProfScope ps(c, q ? "k_me_hist" : "k_pm_hist");
+                    TRY(dev_reserve(c, c->qhrows[qs], (size_t)(tot[m] + 1) * 64, 0));
+                    CUDA_TRY(c, cudaMemsetAsync(c->qhrows[qs].p, 0, (size_t)(tot[m] + 1) * 64, s));
+                    ps.add(launch_quartet_hist((const uint32_t*)c->qobs_site[qs].p, (const uint8_t*)c->qobs_vp[qs].p,
+                                               (const unsigned long long*)c->qobs_n.p + qs, rv.I, (const uint32_t*)c->qcnt[qs].p, qm,
+                                               (const uint32_t*)c->rowcnt[m].p, qp.min_depth, (uint32_t*)c->qhrows[qs].p, s));
+                }
+                ProfScope ps(c, q ? "k_me_emit" : "k_pm_emit");
+                if (shared && q == 0) {  // PM and ME rows from one read of the histograms
+                    QuartetRowsDev rd2 = quartet_rows_dev(c->rows_me);
+                    if (!counts) rd2.counts = nullptr;
+                    ps.add(launch_quartet_canon_emit((const uint32_t*)c->qcnt[qs].p, qm, (const uint32_t*)c->qhrows[qs].p, site_pos, C, qp.min_depth, 2,
+                                                     (const uint32_t*)c->rowcnt[m].p, (const float*)c->me_lut.p, c->me_lut_max, ct, rd, r.n, rd2,
+                                                     c->rows_me.n, s));
+                } else if (!(shared && q == 1)) {
+                    ps.add(launch_quartet_canon_emit((const uint32_t*)c->qcnt[qs].p, qm, (const uint32_t*)c->qhrows[qs].p, site_pos, C, qp.min_depth, q,
+                                                     (const uint32_t*)c->rowcnt[m].p, (const float*)c->me_lut.p, c->me_lut_max, ct, rd, r.n, rd, r.n, s));
+                }
+                ps.add(launch_quartet_emit(rv, site_pos, C, d_sc, qp, q, qm, (const uint32_t*)c->rowcnt[m].p, (const float*)c->me_lut.p,
+                                           c->me_lut_max, ct, rd, r.n, s));
+            }
+            if (M & MTH_PM) c->rows_pm.n += (int64_t)tot[M_PM];
+            if (M & MTH_ME) c->rows_me.n += (int64_t)tot[M_ME];
         }
         if (want_pairs) {
             PairRowsBuf& r = c->rows_pairs;

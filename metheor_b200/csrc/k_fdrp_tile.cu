@@ -10,7 +10,8 @@
 // (32 pairs per step, lexicographic order, qFDRP's ordered f32 sum) ANDs two staged masks per pair.
 //
 // What does not fit — tiles with more than FT_RCAP reads, calls further than 32 sites from the tile (dense islands),
-// max_depth > 64 — is flagged in `fallback` and done by k_fdrp afterwards (same results).
+// max_depth > 64 — is flagged in `fallback` and done by k_fdrp afterwards (same results).  Two instances differ only in how
+// many reads a tile may stage: CpG-dense contigs (chr19-like) need ~700 per 64 sites at 30x, whole-genome density ~1500.
 #include "gather.cuh"
 #include "kernels.h"
 
@@ -19,17 +20,19 @@ namespace mth {
 constexpr int FT_SITES = 64;       // sites per CTA
 constexpr int FT_THREADS = 256;
 constexpr int FT_WARPS = FT_THREADS / 32;
-constexpr int FT_RCAP = 1024;      // reads staged per tile
+constexpr int FT_RCAP = 1024;      // reads staged per tile (dense instance: chr19-like CpG density, ~700 reads per 64 sites at 30x)
+constexpr int FT_RCAP_SPARSE = 2048;  // sparse instance: whole-genome density (a 64-site tile spans ~7 kb: ~1500 reads at 30x)
 constexpr int FT_MARGIN = 32;      // site ranks representable before / after the tile
 constexpr int FT_WIN = 256;        // 64-bit words of the site bitmap staged for rank lookups (16 384 positions)
 constexpr int FT_MAXD = 64;        // pile slots per warp
 constexpr int FT_MAX_READ_LEN = 201;  // fdrp.rs:10
 
+template <int RCAP>
 struct FtSmem {
-    unsigned long long cm[FT_RCAP][2], mm[FT_RCAP][2];
-    int32_t start[FT_RCAP], end[FT_RCAP], first[FT_RCAP];
-    uint8_t flag[FT_RCAP];       // 1: eligible (mapq >= min_qual, >= 1 call)
-    uint8_t ub[FT_RCAP];         // mask bit of the call outside [start, end] (reverse-strand call at start-1), 255 = none
+    unsigned long long cm[RCAP][2], mm[RCAP][2];
+    int32_t start[RCAP], end[RCAP], first[RCAP];
+    uint8_t flag[RCAP];       // 1: eligible (mapq >= min_qual, >= 1 call)
+    uint8_t ub[RCAP];         // mask bit of the call outside [start, end] (reverse-strand call at start-1), 255 = none
     uint16_t pile[FT_WARPS][FT_MAXD];
     unsigned long long bmw[FT_WIN];
     uint32_t pref[FT_WIN];
@@ -38,7 +41,8 @@ struct FtSmem {
     int nreads, bad;
 };
 
-__global__ void __launch_bounds__(FT_THREADS, 3) k_fdrp_tile(ReadsView rv, const int32_t* __restrict__ site_pos, int64_t C,
+template <int RCAP>
+__global__ void __launch_bounds__(FT_THREADS, RCAP <= 1024 ? 3 : 2) k_fdrp_tile(ReadsView rv, const int32_t* __restrict__ site_pos, int64_t C,
                                                              const unsigned long long* __restrict__ bitmap, int64_t n_words,
                                                              const uint32_t* __restrict__ word_prefix,
                                                              RegionScalars* __restrict__ scal, mth_fdrp_params prm, int quant,
@@ -46,7 +50,7 @@ __global__ void __launch_bounds__(FT_THREADS, 3) k_fdrp_tile(ReadsView rv, const
                                                              uint32_t* __restrict__ rowcnt, float* __restrict__ value_q,
                                                              uint32_t* __restrict__ rowcnt_q, uint8_t* __restrict__ fallback) {
     extern __shared__ __align__(16) unsigned char ft_raw[];
-    FtSmem& sh = *reinterpret_cast<FtSmem*>(ft_raw);
+    FtSmem<RCAP>& sh = *reinterpret_cast<FtSmem<RCAP>*>(ft_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int32_t lmax = scal->lmax;
     const uint32_t D = prm.max_depth;
@@ -66,7 +70,7 @@ __global__ void __launch_bounds__(FT_THREADS, 3) k_fdrp_tile(ReadsView rv, const
             const int64_t rb = warp_lower_bound(rv.start, rv.R, p_last + 2);
             if (lane == 0) {
                 sh.ra = ra;
-                sh.nreads = (int)min(rb - ra, (int64_t)FT_RCAP + 1);
+                sh.nreads = (int)min(rb - ra, (int64_t)RCAP + 1);
                 sh.bad = (D > (uint32_t)FT_MAXD || ((uint32_t)(p_last + lmax + 1) >> 6) - w0 >= (uint32_t)FT_WIN) ? 1 : 0;
             }
         }
@@ -91,7 +95,7 @@ __global__ void __launch_bounds__(FT_THREADS, 3) k_fdrp_tile(ReadsView rv, const
         __syncthreads();
         const int64_t ra = sh.ra;
         const int nreads = sh.nreads;
-        if (nreads > FT_RCAP || sh.bad) {
+        if (nreads > RCAP || sh.bad) {
             if (tid < ns) fallback[s0 + tid] = 1;
             continue;
         }
@@ -268,13 +272,20 @@ int launch_fdrp_tile(const ReadsView& rv, const int32_t* site_pos, int64_t C, co
     if (C <= 0) return 0;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(k_fdrp_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FtSmem));
+        cudaFuncSetAttribute(k_fdrp_tile<FT_RCAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FtSmem<FT_RCAP>));
+        cudaFuncSetAttribute(k_fdrp_tile<FT_RCAP_SPARSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FtSmem<FT_RCAP_SPARSE>));
         attr_set = true;
     }
     int64_t tiles = (C + FT_SITES - 1) / FT_SITES;
     if (tiles > 148 * 48) tiles = 148 * 48;
-    k_fdrp_tile<<<(unsigned)tiles, FT_THREADS, sizeof(FtSmem), s>>>(rv, site_pos, C, bitmap, n_words, word_prefix, sc, prm, quantitative,
-                                                                   seed, ct, value, rowcnt, value_q, rowcnt_q, fallback);
+    // reads a tile has to stage ~ FT_SITES x reads per site gap: pick the instance whose capacity covers it with some room
+    const double est = (double)FT_SITES * (double)rv.R / (double)C;
+    if (est * 1.3 <= (double)FT_RCAP)
+        k_fdrp_tile<FT_RCAP><<<(unsigned)tiles, FT_THREADS, sizeof(FtSmem<FT_RCAP>), s>>>(rv, site_pos, C, bitmap, n_words, word_prefix, sc, prm,
+                                                                                       quantitative, seed, ct, value, rowcnt, value_q, rowcnt_q, fallback);
+    else
+        k_fdrp_tile<FT_RCAP_SPARSE><<<(unsigned)tiles, FT_THREADS, sizeof(FtSmem<FT_RCAP_SPARSE>), s>>>(
+            rv, site_pos, C, bitmap, n_words, word_prefix, sc, prm, quantitative, seed, ct, value, rowcnt, value_q, rowcnt_q, fallback);
     return 1;
 }
 

@@ -17,19 +17,22 @@
 namespace mth {
 
 constexpr int MS_SITES = 128;    // sites (= threads) per CTA
-constexpr int MS_RCAP = 2048;    // reads staged per tile
+constexpr int MS_RCAP = 2048;    // reads staged per tile (dense instance: chr19-like density, ~1400 reads per 128 sites at 30x)
 constexpr int MS_CCAP = 6144;    // calls staged per tile
+constexpr int MS_RCAP_SPARSE = 4608;  // sparse instance: whole-genome density (a 128-site tile spans ~14 kb: ~3000 reads at 30x)
+constexpr int MS_CCAP_SPARSE = 8192;
 constexpr int MS_L = 16;         // longest read (in calls) the per-thread accumulators hold
 constexpr int MS_SPAN = 60000;   // positions a tile may span (calls are staged as 16-bit offsets)
 
 // Shared-memory footprint decides how many sites are in flight per SM, so everything is packed: 10 bytes per read,
 // 2 bytes per call, 16-bit accumulators (a segment deeper than 65 535 reads goes to the per-site kernel).
+template <int RCAP, int CCAP>
 struct MsSmem {
-    int32_t start[MS_RCAP];
-    uint16_t meta[MS_RCAP];      // mapq | n << 8   (n <= MS_L)
-    uint16_t o0[MS_RCAP];        // first call of the read, tile-relative
-    uint16_t first[MS_RCAP];     // first call, as offset from the tile base (0xFFFF: no call)
-    uint16_t pos[MS_CCAP];       // calls, as offsets from the tile base
+    int32_t start[RCAP];
+    uint16_t meta[RCAP];      // mapq | n << 8   (n <= MS_L)
+    uint16_t o0[RCAP];        // first call of the read, tile-relative
+    uint16_t first[RCAP];     // first call, as offset from the tile base (0xFFFF: no call)
+    uint16_t pos[CCAP];       // calls, as offsets from the tile base
     uint16_t S[MS_L + 1][MS_SITES];   // [l][thread]: bank-conflict-free
     uint16_t N[MS_L + 1][MS_SITES];
     long long ra;
@@ -37,12 +40,13 @@ struct MsSmem {
     int nreads, ncalls, bad;
 };
 
+template <int RCAP, int CCAP>
 __global__ void __launch_bounds__(MS_SITES) k_mhl_site(ReadsView rv, const int32_t* __restrict__ site_pos, int64_t C,
                                                        const RegionScalars* __restrict__ sc, mth_mhl_params prm,
                                                        float* __restrict__ value, uint32_t* __restrict__ rowcnt,
                                                        uint8_t* __restrict__ fallback) {
     extern __shared__ __align__(16) unsigned char ms_raw[];
-    MsSmem& sh = *reinterpret_cast<MsSmem*>(ms_raw);
+    MsSmem<RCAP, CCAP>& sh = *reinterpret_cast<MsSmem<RCAP, CCAP>*>(ms_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int32_t lmax = sc->lmax;
     const int64_t n_tiles = (C + MS_SITES - 1) / MS_SITES;
@@ -58,8 +62,8 @@ __global__ void __launch_bounds__(MS_SITES) k_mhl_site(ReadsView rv, const int32
                 const unsigned int c0 = rv.cpg_off[ra], c1 = rv.cpg_off[rb];
                 sh.ra = ra;
                 sh.c0 = c0;
-                sh.nreads = (int)min(rb - ra, (int64_t)MS_RCAP + 1);
-                sh.ncalls = (int)min(c1 - c0, (unsigned int)MS_CCAP + 1u);
+                sh.nreads = (int)min(rb - ra, (int64_t)RCAP + 1);
+                sh.ncalls = (int)min(c1 - c0, (unsigned int)CCAP + 1u);
                 // multi-word reads or a tile too wide for 16-bit offsets: per-site kernel
                 sh.bad = (rv.meth_off != nullptr || site_pos[s0 + ns - 1] - site_pos[s0] + 2 * lmax > MS_SPAN) ? 1 : 0;
             }
@@ -68,7 +72,7 @@ __global__ void __launch_bounds__(MS_SITES) k_mhl_site(ReadsView rv, const int32
         const int64_t ra = sh.ra;
         const uint32_t c0 = sh.c0;
         const int nreads = sh.nreads, ncalls = sh.ncalls;
-        if (nreads > MS_RCAP || ncalls > MS_CCAP || sh.bad) {
+        if (nreads > RCAP || ncalls > CCAP || sh.bad) {
             if (tid < ns) fallback[s0 + tid] = 1;
             continue;
         }
@@ -160,14 +164,22 @@ __global__ void __launch_bounds__(MS_SITES) k_mhl_site(ReadsView rv, const int32
 int launch_mhl_site(const ReadsView& rv, const int32_t* site_pos, int64_t C, const RegionScalars* sc, mth_mhl_params prm,
                     float* value, uint32_t* rowcnt, uint8_t* fallback, cudaStream_t s) {
     if (C <= 0) return 0;
+    using Dense = MsSmem<MS_RCAP, MS_CCAP>;
+    using Sparse = MsSmem<MS_RCAP_SPARSE, MS_CCAP_SPARSE>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(k_mhl_site, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MsSmem));
+        cudaFuncSetAttribute(k_mhl_site<MS_RCAP, MS_CCAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Dense));
+        cudaFuncSetAttribute(k_mhl_site<MS_RCAP_SPARSE, MS_CCAP_SPARSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Sparse));
         attr_set = true;
     }
     int64_t tiles = (C + MS_SITES - 1) / MS_SITES;
     if (tiles > 148 * 64) tiles = 148 * 64;
-    k_mhl_site<<<(unsigned)tiles, MS_SITES, sizeof(MsSmem), s>>>(rv, site_pos, C, sc, prm, value, rowcnt, fallback);
+    // reads a tile has to stage ~ MS_SITES x reads per site gap: pick the instance whose capacity covers it with some room
+    const double est = (double)MS_SITES * (double)rv.R / (double)C;
+    if (est * 1.3 <= (double)MS_RCAP)
+        k_mhl_site<MS_RCAP, MS_CCAP><<<(unsigned)tiles, MS_SITES, sizeof(Dense), s>>>(rv, site_pos, C, sc, prm, value, rowcnt, fallback);
+    else
+        k_mhl_site<MS_RCAP_SPARSE, MS_CCAP_SPARSE><<<(unsigned)tiles, MS_SITES, sizeof(Sparse), s>>>(rv, site_pos, C, sc, prm, value, rowcnt, fallback);
     return 1;
 }
 

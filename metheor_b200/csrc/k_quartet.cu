@@ -237,13 +237,19 @@ __global__ void __launch_bounds__(GATHER_BLOCK) k_quartet(QuartetArgs a) {
 // ---- streaming path: canonical quartets --------------------------------------------------------------------
 // A quartet observation is a call x with three more calls of the same read behind it (readutil.rs:97-132); its key is
 // (pos[x], pos[x+1], pos[x+2], pos[x+3]).  When those are four CONSECUTIVE sites of the dictionary — rank(pos[x+3]) ==
-// rank(pos[x]) + 3, true unless a read skipped a site (no-call, deletion) — the key is implied by the first site and the
-// observation is one atomic add into hist[rank][0][pattern].  A read that skipped exactly ONE of the next four sites (a
-// no-call) gives one of three other keys — (r+1,r+2,r+4), (r+1,r+3,r+4), (r+2,r+3,r+4) — which get the slots 1..3; in
-// that order the four keys are already sorted the way the rows must be.  Anything else (two skips, deletions) flags the
-// site as mixed and leaves it to the gather kernel.  Everything needed is in cpg_pos[] and call_flags[] (5 B per call):
-// methylation bits, read boundaries (CF_FIRST) and the mapq verdict; no per-read data is touched.
-constexpr int QV = 4;  // key variants with a histogram slot per site
+// rank(pos[x]) + 3, true unless a read skipped a site (no-call, deletion) — the key is implied by the first site: slot 0 of
+// that site.  A read that skipped exactly ONE of the next four sites (a no-call) gives one of three other keys —
+// (r+1,r+2,r+4), (r+1,r+3,r+4), (r+2,r+3,r+4) — the slots 1..3; in that order the four keys are already sorted the way the
+// rows must be.  Anything else (two skips, deletions) flags the site as mixed and leaves it to the gather kernel.
+// Everything needed is in cpg_pos[] and call_flags[] (5 B per call): methylation bits, read boundaries (CF_FIRST) and the
+// mapq verdict; no per-read data is touched.
+//
+// Most sites never start a quartet (at whole-genome density 87 % of them have no row), so there is no per-site
+// 16-pattern histogram.  Pass 1 (k_quartet_scatter) counts the observations per (site, slot) — 16 B per site — and
+// appends every observation (site, slot, pattern) to a compact list; the row counts and the scan follow from the counts;
+// pass 2 (k_quartet_hist) walks the LIST (not the calls) and adds each observation of a slot that reached min_depth into
+// the 16-bin histogram of its output ROW (64 B per row, rows << sites); the emit kernel turns row histograms into PM / ME.
+constexpr int QV = 4;  // key variants (slots) per site
 constexpr int QS_THREADS = 256;
 constexpr int QS_CPT = 8;
 constexpr int QS_TILE = QS_THREADS * QS_CPT;
@@ -253,16 +259,21 @@ __global__ void __launch_bounds__(QS_THREADS) k_quartet_scatter(const int32_t* _
                                                                 int64_t n_calls, const unsigned long long* __restrict__ bitmap,
                                                                 int64_t n_words, const uint32_t* __restrict__ word_prefix,
                                                                 const RegionScalars* __restrict__ sc, uint32_t ok_bit,
-                                                                uint32_t* __restrict__ hist, uint8_t* __restrict__ mixed) {
+                                                                uint32_t* __restrict__ qcnt, uint8_t* __restrict__ mixed,
+                                                                uint32_t* __restrict__ obs_site, uint8_t* __restrict__ obs_vp,
+                                                                unsigned long long* __restrict__ obs_n) {
     __shared__ int32_t s_pos[QS_TILE + 4];
     __shared__ uint8_t s_fl[QS_TILE + 4];
     __shared__ unsigned long long s_bmw[QS_WIN];
     __shared__ uint32_t s_pref[QS_WIN];
     __shared__ uint32_t s_wsum[QS_THREADS / 32];
+    __shared__ uint32_t s_nobs;
+    __shared__ unsigned long long s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t x0 = (int64_t)blockIdx.x * QS_TILE;
     const int nt = (int)min((int64_t)QS_TILE, n_calls - x0);
     const int nh = (int)min((int64_t)QS_TILE + 3, n_calls - x0);  // with the 3-call halo
+    if (tid == 0) s_nobs = 0;
     for (int y = tid; y < nh; y += QS_THREADS) {
         s_pos[y] = cpg_pos[x0 + y];
         s_fl[y] = call_flags[x0 + y];
@@ -295,15 +306,22 @@ __global__ void __launch_bounds__(QS_THREADS) k_quartet_scatter(const int32_t* _
         const uint32_t gw = bit >> 6;
         return __ldg(word_prefix + gw) + (uint32_t)__popcll(__ldg(bitmap + gw) & ((1ull << (bit & 63)) - 1ull));
     };
-    for (int y = tid; y < nt; y += QS_THREADS) {
+    uint32_t o_site[QS_CPT], o_slot[QS_CPT];  // this thread's observations: site rank, (list index << 8) | slot << 4 | pattern
+    int n_mine = 0;
+#pragma unroll
+    for (int it = 0; it < QS_CPT; it++) {
+        const int y = it * QS_THREADS + tid;
+        o_site[it] = 0xffffffffu;
+        o_slot[it] = 0;
+        if (y >= nt || y + 3 >= nh) continue;
         const uint32_t f0 = s_fl[y];
-        if (!(f0 & ok_bit) || y + 3 >= nh) continue;
+        if (!(f0 & ok_bit)) continue;
         const uint32_t f1 = s_fl[y + 1], f2 = s_fl[y + 2], f3 = s_fl[y + 3];
         if ((f1 | f2 | f3) & CF_FIRST) continue;  // fewer than four calls left in this read
         const uint32_t pat = ((f0 & CF_METH) << 3) | ((f1 & CF_METH) << 2) | ((f2 & CF_METH) << 1) | (f3 & CF_METH);
         const uint32_t r = rank_of(s_pos[y]);
         const uint32_t g3 = rank_of(s_pos[y + 3]) - r;
-        int v = -1;  // variant slot: which of the dictionary's next sites the read called
+        int v = -1;  // slot: which of the dictionary's next sites the read called
         if (g3 == 3) {
             v = 0;                                             // (r+1, r+2, r+3)
         } else if (g3 == 4) {
@@ -311,84 +329,151 @@ __global__ void __launch_bounds__(QS_THREADS) k_quartet_scatter(const int32_t* _
             if (g1 == 1) v = g2 == 2 ? 1 : 2;                  // (r+1, r+2, r+4) / (r+1, r+3, r+4)
             else v = 3;                                        // (r+2, r+3, r+4)
         }
-        if (v >= 0) atomicAdd(&hist[((size_t)r * QV + v) * 16 + pat], 1u);
-        else mixed[r] = 1;
+        if (v >= 0) {
+            atomicAdd(&qcnt[(size_t)r * QV + v], 1u);
+            o_site[it] = r;
+            o_slot[it] = ((uint32_t)v << 4) | pat;
+            n_mine++;
+        } else {
+            mixed[r] = 1;
+        }
+    }
+    // append this CTA's observations to the list: one shared counter, ONE global atomic per CTA
+    const uint32_t my0 = n_mine ? atomicAdd(&s_nobs, (uint32_t)n_mine) : 0u;
+    __syncthreads();
+    if (tid == 0) s_base = s_nobs ? atomicAdd(obs_n, (unsigned long long)s_nobs) : 0ull;
+    __syncthreads();
+    unsigned long long at = s_base + my0;
+#pragma unroll
+    for (int it = 0; it < QS_CPT; it++) {
+        if (o_site[it] != 0xffffffffu) {
+            obs_site[at] = o_site[it];
+            obs_vp[at] = (uint8_t)o_slot[it];
+            at++;
+        }
     }
 }
 
-template <bool EMIT>
-__global__ void __launch_bounds__(256) k_quartet_canon(const uint32_t* __restrict__ hist, const uint8_t* __restrict__ mixed,
-                                                       const int32_t* __restrict__ site_pos, int64_t C, uint32_t min_depth, int kind,
-                                                       uint32_t* __restrict__ rowcnt, const uint32_t* __restrict__ rowoff,
-                                                       const float* __restrict__ me_lut, int me_lut_max, ContigTable ct,
-                                                       QuartetRowsDev rows, int64_t row_base) {
+// rows per site from the slot counts: slots that reached min_depth (pm.rs:77 / me.rs:82), in slot order
+__global__ void __launch_bounds__(256) k_quartet_canon_count(const uint32_t* __restrict__ qcnt, const uint8_t* __restrict__ mixed, int64_t C,
+                                                             uint32_t min_depth, uint32_t* __restrict__ rowcnt) {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= C) return;
-    if (mixed[s]) {
-        if (!EMIT) rowcnt[s] = 0;  // overwritten by the gather pass
-        return;
+    if (mixed[s]) { rowcnt[s] = 0; return; }  // overwritten by the gather pass
+    const uint4 q = reinterpret_cast<const uint4*>(qcnt)[s];
+    const uint32_t md = max(min_depth, 1u);
+    rowcnt[s] = (q.x >= md) + (q.y >= md) + (q.z >= md) + (q.w >= md);
+}
+
+// pass 2: every listed observation whose (site, slot) reached min_depth goes into the histogram of its row
+__global__ void __launch_bounds__(256) k_quartet_hist(const uint32_t* __restrict__ obs_site, const uint8_t* __restrict__ obs_vp,
+                                                      const unsigned long long* __restrict__ obs_n, const uint32_t* __restrict__ qcnt,
+                                                      const uint8_t* __restrict__ mixed, const uint32_t* __restrict__ rowoff,
+                                                      uint32_t min_depth, uint32_t* __restrict__ hrows) {
+    const unsigned long long n = *obs_n;
+    const uint32_t md = max(min_depth, 1u);
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t s = obs_site[i];
+        if (mixed[s]) continue;
+        const uint32_t vp = obs_vp[i], v = vp >> 4, pat = vp & 15u;
+        const uint4 q = reinterpret_cast<const uint4*>(qcnt)[s];
+        const uint32_t c[4] = {q.x, q.y, q.z, q.w};
+        if (c[v] < md) continue;
+        uint32_t before = 0;
+#pragma unroll
+        for (int k = 0; k < 3; k++) before += (k < (int)v && c[k] >= md) ? 1u : 0u;
+        atomicAdd(&hrows[((size_t)rowoff[s] + before) * 16 + pat], 1u);
     }
-    uint32_t n_rows = 0;
-    int64_t r = 0;
-    int32_t tid = 0, pos = 0, off = 0;
-    if (EMIT) {
-        r = row_base + rowoff[s];
-        delinearize(ct, site_pos[s], &tid, &pos);
-        off = site_pos[s] - pos;
-    }
+}
+
+// rows of the canonical sites from the row histograms (thread per site); mixed sites are skipped (gather kernels).
+// BOTH: PM into rows_a and ME into rows_b from one read of the histograms (same thresholds: same rows).
+template <int KIND>  // 0 PM, 1 ME, 2 both
+__global__ void __launch_bounds__(256) k_quartet_canon_emit(const uint32_t* __restrict__ qcnt, const uint8_t* __restrict__ mixed,
+                                                            const uint32_t* __restrict__ hrows, const int32_t* __restrict__ site_pos,
+                                                            int64_t C, uint32_t min_depth, const uint32_t* __restrict__ rowoff,
+                                                            const float* __restrict__ me_lut, int me_lut_max, ContigTable ct,
+                                                            QuartetRowsDev rows_a, int64_t base_a, QuartetRowsDev rows_b, int64_t base_b) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= C || mixed[s]) return;
+    const uint4 q = reinterpret_cast<const uint4*>(qcnt)[s];
+    const uint32_t c[4] = {q.x, q.y, q.z, q.w};
+    const uint32_t md = max(min_depth, 1u);
+    if (!(c[0] >= md || c[1] >= md || c[2] >= md || c[3] >= md)) return;
+    int32_t tid, pos;
+    delinearize(ct, site_pos[s], &tid, &pos);
+    const int32_t off = site_pos[s] - pos;
+    int64_t r = rowoff[s];
 #pragma unroll
     for (int v = 0; v < QV; v++) {
+        if (c[v] < md) continue;
         uint32_t cnt[16];
-        const uint4* h = reinterpret_cast<const uint4*>(hist + ((size_t)s * QV + v) * 16);
+        const uint4* h = reinterpret_cast<const uint4*>(hrows + (size_t)r * 16);
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const uint4 x = h[q];
-            cnt[4 * q] = x.x; cnt[4 * q + 1] = x.y; cnt[4 * q + 2] = x.z; cnt[4 * q + 3] = x.w;
+        for (int k = 0; k < 4; k++) {
+            const uint4 x = h[k];
+            cnt[4 * k] = x.x; cnt[4 * k + 1] = x.y; cnt[4 * k + 2] = x.z; cnt[4 * k + 3] = x.w;
         }
-        uint32_t total = 0;
-#pragma unroll
-        for (int k = 0; k < 16; k++) total += cnt[k];
-        if (!(total > 0 && total >= min_depth)) continue;  // pm.rs:77 / me.rs:82
-        if (EMIT) {
-            // the key of slot v: sites s+1..s+4 of the dictionary minus the one the reads skipped
-            const int d2 = v == 3 ? 2 : 1, d3 = v >= 2 ? 3 : 2, d4 = v >= 1 ? 4 : 3;
-            const int64_t o = r + n_rows;
-            rows.tid[o] = tid;
-            rows.p1[o] = pos;
-            rows.p2[o] = site_pos[s + d2] - off;
-            rows.p3[o] = site_pos[s + d3] - off;
-            rows.p4[o] = site_pos[s + d4] - off;
-            rows.value[o] = kind == 0 ? pm_value(cnt, total) : me_value(cnt, total, me_lut, me_lut_max);
-            if (rows.counts)
-                for (int k = 0; k < 16; k++) rows.counts[(size_t)o * 16 + k] = cnt[k];
+        const uint32_t total = c[v];
+        // the key of slot v: sites s+1..s+4 of the dictionary minus the one the reads skipped
+        const int d2 = v == 3 ? 2 : 1, d3 = v >= 2 ? 3 : 2, d4 = v >= 1 ? 4 : 3;
+        const int32_t p2 = site_pos[s + d2] - off, p3 = site_pos[s + d3] - off, p4 = site_pos[s + d4] - off;
+        if (KIND == 0 || KIND == 2) {
+            const int64_t o = base_a + r;
+            rows_a.tid[o] = tid; rows_a.p1[o] = pos; rows_a.p2[o] = p2; rows_a.p3[o] = p3; rows_a.p4[o] = p4;
+            rows_a.value[o] = pm_value(cnt, total);
+            if (rows_a.counts)
+                for (int k = 0; k < 16; k++) rows_a.counts[(size_t)o * 16 + k] = cnt[k];
         }
-        n_rows++;
+        if (KIND == 1 || KIND == 2) {
+            QuartetRowsDev& rw = KIND == 1 ? rows_a : rows_b;
+            const int64_t o = (KIND == 1 ? base_a : base_b) + r;
+            rw.tid[o] = tid; rw.p1[o] = pos; rw.p2[o] = p2; rw.p3[o] = p3; rw.p4[o] = p4;
+            rw.value[o] = me_value(cnt, total, me_lut, me_lut_max);
+            if (rw.counts)
+                for (int k = 0; k < 16; k++) rw.counts[(size_t)o * 16 + k] = cnt[k];
+        }
+        r++;
     }
-    if (!EMIT) rowcnt[s] = n_rows;
 }
 
 int launch_quartet_scatter(const int32_t* cpg_pos, const uint8_t* call_flags, int64_t n_calls, const unsigned long long* bitmap,
-                           int64_t n_words, const uint32_t* word_prefix, const RegionScalars* sc, uint32_t ok_bit, uint32_t* hist,
-                           uint8_t* mixed, cudaStream_t s) {
+                           int64_t n_words, const uint32_t* word_prefix, const RegionScalars* sc, uint32_t ok_bit, uint32_t* qcnt,
+                           uint8_t* mixed, uint32_t* obs_site, uint8_t* obs_vp, unsigned long long* obs_n, cudaStream_t s) {
     if (n_calls <= 0) return 0;
     k_quartet_scatter<<<(unsigned)((n_calls + QS_TILE - 1) / QS_TILE), QS_THREADS, 0, s>>>(cpg_pos, call_flags, n_calls, bitmap, n_words,
-                                                                                          word_prefix, sc, ok_bit, hist, mixed);
+                                                                                          word_prefix, sc, ok_bit, qcnt, mixed, obs_site,
+                                                                                          obs_vp, obs_n);
     return 1;
 }
 
-int launch_quartet_canon_count(const uint32_t* hist, const uint8_t* mixed, int64_t C, uint32_t min_depth, uint32_t* rowcnt, cudaStream_t s) {
+int launch_quartet_canon_count(const uint32_t* qcnt, const uint8_t* mixed, int64_t C, uint32_t min_depth, uint32_t* rowcnt, cudaStream_t s) {
     if (C <= 0) return 0;
-    k_quartet_canon<false><<<(unsigned)((C + 255) / 256), 256, 0, s>>>(hist, mixed, nullptr, C, min_depth, 0, rowcnt, nullptr, nullptr, 0,
-                                                                       ContigTable{0, nullptr, nullptr}, QuartetRowsDev{}, 0);
+    k_quartet_canon_count<<<(unsigned)((C + 255) / 256), 256, 0, s>>>(qcnt, mixed, C, min_depth, rowcnt);
     return 1;
 }
 
-int launch_quartet_canon_emit(const uint32_t* hist, const uint8_t* mixed, const int32_t* site_pos, int64_t C, uint32_t min_depth, int kind,
-                              const uint32_t* rowoff, const float* me_lut, int me_lut_max, ContigTable ct, QuartetRowsDev rows,
-                              int64_t row_base, cudaStream_t s) {
+int launch_quartet_hist(const uint32_t* obs_site, const uint8_t* obs_vp, const unsigned long long* obs_n, int64_t n_obs_max,
+                        const uint32_t* qcnt, const uint8_t* mixed, const uint32_t* rowoff, uint32_t min_depth, uint32_t* hrows,
+                        cudaStream_t s) {
+    if (n_obs_max <= 0) return 0;
+    int64_t blocks = (n_obs_max + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    k_quartet_hist<<<(unsigned)blocks, 256, 0, s>>>(obs_site, obs_vp, obs_n, qcnt, mixed, rowoff, min_depth, hrows);
+    return 1;
+}
+
+int launch_quartet_canon_emit(const uint32_t* qcnt, const uint8_t* mixed, const uint32_t* hrows, const int32_t* site_pos, int64_t C,
+                              uint32_t min_depth, int kind, const uint32_t* rowoff, const float* me_lut, int me_lut_max, ContigTable ct,
+                              QuartetRowsDev rows_a, int64_t base_a, QuartetRowsDev rows_b, int64_t base_b, cudaStream_t s) {
     if (C <= 0) return 0;
-    k_quartet_canon<true><<<(unsigned)((C + 255) / 256), 256, 0, s>>>(hist, mixed, site_pos, C, min_depth, kind, nullptr, rowoff, me_lut,
-                                                                      me_lut_max, ct, rows, row_base);
+    const unsigned g = (unsigned)((C + 255) / 256);
+    if (kind == 0)
+        k_quartet_canon_emit<0><<<g, 256, 0, s>>>(qcnt, mixed, hrows, site_pos, C, min_depth, rowoff, me_lut, me_lut_max, ct, rows_a, base_a, rows_b, base_b);
+    else if (kind == 1)
+        k_quartet_canon_emit<1><<<g, 256, 0, s>>>(qcnt, mixed, hrows, site_pos, C, min_depth, rowoff, me_lut, me_lut_max, ct, rows_a, base_a, rows_b, base_b);
+    else
+        k_quartet_canon_emit<2><<<g, 256, 0, s>>>(qcnt, mixed, hrows, site_pos, C, min_depth, rowoff, me_lut, me_lut_max, ct, rows_a, base_a, rows_b, base_b);
     return 1;
 }
 

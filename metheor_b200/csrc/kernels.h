@@ -90,17 +90,24 @@ int gather_grid(int64_t C);  // grid size for the warp-per-site kernels
 
 // ---- PM / ME (k_quartet.cu) -----------------------------------------------------------------
 struct QuartetRowsDev { int32_t* tid; int32_t* p1; int32_t* p2; int32_t* p3; int32_t* p4; float* value; uint32_t* counts; };
-// Streaming per-call pass: every call that starts a quartet inside its read adds its pattern to hist[rank][16] when the
-// quartet is CANONICAL (its four calls are four consecutive sites of the dictionary); otherwise mixed[rank] is set and
-// the site is left to the gather kernels below.  ok_bit = CF_PM_OK or CF_ME_OK.
+// Streaming per-call pass (k_quartet.cu): every call that starts a quartet inside its read is an observation (site, slot,
+// pattern) when the quartet is CANONICAL or skips exactly one dictionary site (4 slots per site); it is counted in
+// qcnt[site][slot] and appended to the observation list.  Anything else sets mixed[site] and the site is left to the gather
+// kernels below.  ok_bit = CF_PM_OK or CF_ME_OK.
 int launch_quartet_scatter(const int32_t* cpg_pos, const uint8_t* call_flags, int64_t n_calls, const unsigned long long* bitmap,
-                           int64_t n_words, const uint32_t* word_prefix, const RegionScalars* sc, uint32_t ok_bit, uint32_t* hist,
-                           uint8_t* mixed, cudaStream_t s);
-// rows of the canonical sites straight from the histogram (thread per site); mixed sites are skipped
-int launch_quartet_canon_count(const uint32_t* hist, const uint8_t* mixed, int64_t C, uint32_t min_depth, uint32_t* rowcnt, cudaStream_t s);
-int launch_quartet_canon_emit(const uint32_t* hist, const uint8_t* mixed, const int32_t* site_pos, int64_t C, uint32_t min_depth, int kind,
-                              const uint32_t* rowoff, const float* me_lut, int me_lut_max, ContigTable ct, QuartetRowsDev rows,
-                              int64_t row_base, cudaStream_t s);
+                           int64_t n_words, const uint32_t* word_prefix, const RegionScalars* sc, uint32_t ok_bit, uint32_t* qcnt,
+                           uint8_t* mixed, uint32_t* obs_site, uint8_t* obs_vp, unsigned long long* obs_n, cudaStream_t s);
+// rows per canonical site = slots with count >= min_depth; mixed sites get 0 (overwritten by the gather count)
+int launch_quartet_canon_count(const uint32_t* qcnt, const uint8_t* mixed, int64_t C, uint32_t min_depth, uint32_t* rowcnt, cudaStream_t s);
+// observation list -> 16-bin histogram per output row (hrows[row][16], zeroed by the caller; row = rowoff[site] + slot rank)
+int launch_quartet_hist(const uint32_t* obs_site, const uint8_t* obs_vp, const unsigned long long* obs_n, int64_t n_obs_max,
+                        const uint32_t* qcnt, const uint8_t* mixed, const uint32_t* rowoff, uint32_t min_depth, uint32_t* hrows,
+                        cudaStream_t s);
+// rows of the canonical sites from the row histograms; kind 0 = PM into rows_a, 1 = ME into rows_a, 2 = PM into rows_a AND ME
+// into rows_b (identical thresholds: identical rows)
+int launch_quartet_canon_emit(const uint32_t* qcnt, const uint8_t* mixed, const uint32_t* hrows, const int32_t* site_pos, int64_t C,
+                              uint32_t min_depth, int kind, const uint32_t* rowoff, const float* me_lut, int me_lut_max, ContigTable ct,
+                              QuartetRowsDev rows_a, int64_t base_a, QuartetRowsDev rows_b, int64_t base_b, cudaStream_t s);
 // gather pass 1: rowcnt[s] = number of quartets starting at site s whose depth >= min_depth.  `mixed` != nullptr restricts
 // both gather passes to the sites it flags (the others keep what the canonical kernels wrote).
 int launch_quartet_count(const ReadsView& rv, const int32_t* site_pos, int64_t C, const RegionScalars* sc,

@@ -17,7 +17,7 @@ class Options(C.Structure):
     _fields_ = [("measure", C.c_int32), ("input", C.c_char_p), ("output", C.c_char_p), ("cpg_set", C.c_char_p),
                 ("pairs", C.c_char_p), ("min_depth", C.c_uint32), ("min_cpgs", C.c_uint32), ("min_qual", C.c_uint32),
                 ("max_depth", C.c_uint32), ("min_overlap", C.c_int32), ("min_distance", C.c_int32),
-                ("max_distance", C.c_int32), ("device", C.c_int32), ("n_gpus", C.c_int32), ("threads", C.c_int32),
+                ("max_distance", C.c_int32), ("device", C.c_int32), ("n_gpus", C.c_int32), ("shard_contigs", C.c_int32), ("threads", C.c_int32),
                 ("seed", C.c_uint64), ("stats_json", C.c_char_p)]
 
 
@@ -29,7 +29,11 @@ class Decoded(C.Structure):
 
 
 EXPORTS = ["mthh_options_default", "mthh_run", "mthh_main", "mthh_decode_file", "mthh_decoded_free", "mthh_format_f32", "mthh_inflate_raw",
-           "mthh_zlib_fallbacks", "mthh_tag", "mthh_crc32"]
+           "mthh_zlib_fallbacks", "mthh_tag", "mthh_crc32", "mthh_plan_shards"]
+
+
+class Interval(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("tid", C.c_int32), ("lo", C.c_int64), ("hi", C.c_int64)]
 
 
 class HostError(RuntimeError):
@@ -108,6 +112,21 @@ def run(measure, input, output, **kw):
     rc = L.mthh_run(C.byref(o), err, 4096)
     if rc != 0:
         raise HostError(rc, err.value.decode())
+
+
+def plan_shards(ref_len, world, by_contig=False):
+    """The multi-GPU plan of `metheor --gpus N` -> list (per rank) of (tid, lo, hi); same result as shard.plan_bins / plan_contigs."""
+    L = lib()
+    L.mthh_plan_shards.argtypes = [C.c_int32, C.POINTER(C.c_int64), C.c_int32, C.c_int32, C.POINTER(Interval), C.c_int32]
+    L.mthh_plan_shards.restype = C.c_int32
+    arr = (C.c_int64 * len(ref_len))(*[int(x) for x in ref_len])
+    cap = len(ref_len) + 2 * world + 4
+    out = (Interval * cap)()
+    n = L.mthh_plan_shards(len(ref_len), arr, world, int(by_contig), out, cap)
+    res = [[] for _ in range(world)]
+    for k in range(n):
+        res[out[k].rank].append((out[k].tid, out[k].lo, out[k].hi))
+    return res
 
 
 def format_f32(v):

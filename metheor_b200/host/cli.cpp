@@ -48,7 +48,8 @@ const ArgSpec IN2 = {'i', "input", A_STR, true, nullptr, "Path to input BAM file
 const ArgSpec CPGSET = {'c', "cpg-set", A_STR, false, nullptr, "(Optional) Specify a predefined set of CpGs (in BED file) to be analyzed", "CPG_SET"};
 // engine options: long flags only, none collides with the reference's -i -o -d -p -q -c -D -l -m -M -g
 const ArgSpec E_DEVICE = {0, "device", A_I32, false, "0", "[engine] first CUDA device to use", "DEVICE"};
-const ArgSpec E_GPUS = {0, "gpus", A_I32, false, "1", "[engine] shard contigs over this many GPUs", "GPUS"};
+const ArgSpec E_GPUS = {0, "gpus", A_I32, false, "1", "[engine] shard the genome over this many GPUs (position bins + halo reads)", "GPUS"};
+const ArgSpec E_SHARD = {0, "shard", A_STR, false, "bins", "[engine] multi-GPU sharding: bins (equal position ranges) or contigs (whole contigs)", "SHARD"};
 const ArgSpec E_THREADS = {0, "threads", A_I32, false, "0", "[engine] host decode threads (0 = all cores)", "THREADS"};
 const ArgSpec E_SEED = {0, "seed", A_U64, false, "0", "[engine] reservoir-sampling seed once a pile exceeds --max-depth", "SEED"};
 const ArgSpec E_STATS = {0, "stats", A_STR, false, nullptr, "[engine] write timing / throughput statistics as JSON", "STATS"};
@@ -92,7 +93,7 @@ std::vector<CmdSpec> commands() {
                   {'g', "genome", A_STR, true, nullptr, "", "GENOME"}, E_DEVICE, E_THREADS, E_STATS}});
     for (auto& cmd : c)
         if (cmd.measure >= 0) {
-            cmd.args.push_back(E_DEVICE); cmd.args.push_back(E_GPUS); cmd.args.push_back(E_THREADS); cmd.args.push_back(E_STATS);
+            cmd.args.push_back(E_DEVICE); cmd.args.push_back(E_GPUS); cmd.args.push_back(E_SHARD); cmd.args.push_back(E_THREADS); cmd.args.push_back(E_STATS);
             if (cmd.measure == MTHH_FDRP || cmd.measure == MTHH_QFDRP) cmd.args.push_back(E_SEED);
         }
     return c;
@@ -167,6 +168,7 @@ void mthh_options_default(mthh_options* o, int32_t measure) {
     o->min_distance = 2; // lib.rs:215
     o->max_distance = 16;
     o->n_gpus = 1;
+    o->shard_contigs = 0;
 }
 
 int mthh_run(const mthh_options* o, char* err, size_t errcap) {
@@ -198,6 +200,19 @@ int mthh_tag(const char* input, const char* output, const char* genome, int32_t 
 }
 
 int mthh_format_f32(float v, char* buf, int cap) { return mthh::format_f32(v, buf, cap); }
+
+int mthh_plan_shards(int32_t n_ref, const int64_t* ref_len, int32_t world, int32_t by_contig, mthh_interval* out, int32_t cap) {
+    if (n_ref < 0 || world < 1 || (n_ref && !ref_len)) return -1;
+    std::vector<int64_t> rl(ref_len, ref_len + n_ref);
+    auto plan = by_contig ? mthh::plan_contigs(rl, world) : mthh::plan_bins(rl, world);
+    int32_t n = 0;
+    for (int r = 0; r < world; r++)
+        for (const auto& iv : plan[(size_t)r]) {
+            if (out && n < cap) out[n] = mthh_interval{r, iv.tid, iv.lo, iv.hi};
+            n++;
+        }
+    return n;
+}
 
 int mthh_inflate_raw(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_len) {
     return mthh::inflate_fast(in, in_len, out, out_len) ? 1 : 0;
@@ -298,6 +313,11 @@ int mthh_main(int argc, char** argv) {
         else if (n == "max-distance") o.max_distance = (int32_t)s;
         else if (n == "device") o.device = (int32_t)s;
         else if (n == "gpus") o.n_gpus = (int32_t)s;
+        else if (n == "shard") {
+            if (!strcmp(v, "contigs")) o.shard_contigs = 1;
+            else if (!strcmp(v, "bins")) o.shard_contigs = 0;
+            else return usage_error(cmd, std::string("invalid value '") + v + "' for '--shard <SHARD>': expected bins or contigs");
+        }
         else if (n == "threads") o.threads = (int32_t)s;
         else if (n == "seed") o.seed = u;
         else if (n == "stats") o.stats_json = v;

@@ -182,13 +182,15 @@ void decode_bam(const RecordRef& rec, const DecodeOptions& opt, SoaChunk* out, D
             case 'A': case 'c': case 'C': len = 1; break;
             case 's': case 'S': len = 2; break;
             case 'i': case 'I': case 'f': len = 4; break;
+            case 'd': len = 8; break;  // double: htslib accepts it
             case 'Z': case 'H': {
                 const void* z = memchr(p + q, 0, bs - q);
-                len = z ? (size_t)((const uint8_t*)z - (p + q)) + 1 : bs - q;
+                if (!z) throw HostError{101, "Error opening BAM file. corrupt BAM record (unterminated string in an auxiliary field)"};
+                len = (size_t)((const uint8_t*)z - (p + q)) + 1;
                 break;
             }
             case 'B': {
-                if (q + 5 > bs) { len = bs - q; break; }
+                if (q + 5 > bs) throw HostError{101, "Error opening BAM file. corrupt BAM record (truncated array in an auxiliary field)"};
                 const uint8_t st = p[q];
                 const size_t es = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : 4;
                 len = 5 + es * (size_t)(uint32_t)le32(p + q + 1);
@@ -196,6 +198,7 @@ void decode_bam(const RecordRef& rec, const DecodeOptions& opt, SoaChunk* out, D
             }
             default: throw HostError{101, "Error opening BAM file. unknown auxiliary field type in BAM record"};
         }
+        if (len > bs - q) throw HostError{101, "Error opening BAM file. corrupt BAM record (auxiliary field runs past the record)"};
         if (t0 == 'X' && t1 == 'M') {
             if (ty == 'Z') { r.xm = (const char*)p + q; r.xm_len = len ? len - 1 : 0; }
             break;  // a non-string XM panics like a missing one (readutil.rs:45-47)

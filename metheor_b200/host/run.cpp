@@ -36,6 +36,7 @@ int format_f32(float v, char* buf, int cap) {
 namespace {
 
 const size_t WINDOW_BYTES = 64u << 20;
+const int64_t SHARD_HALO = 65536;  // >= the engine's longest accepted reference span (65 024) + 2
 const size_t TASK_RECORDS = 4096;
 const int RING = 3;
 
@@ -57,8 +58,11 @@ struct PinnedBatch {
     }
 };
 
+using Interval = ShardInterval;  // sites [lo, hi) of contig tid are OWNED by one GPU
+
 struct Gpu {
     mth_ctx* ctx = nullptr;
+    std::vector<Interval> own;  // ascending (tid, lo)
     PinnedBatch ring[RING];
     int next_slot = 0;
     int64_t submitted = 0;
@@ -80,8 +84,9 @@ uint32_t measure_bit(int m) {
 }
 
 // Gathers the decoded chunks [c0, c1) (all of one contig) into the pinned arrays of `pb` and fills `b`.
+// own_lo / own_hi: reads starting outside [own_lo, own_hi) are halo copies for this GPU (MTH_META_HALO).
 void assemble(ThreadPool& pool, std::vector<SoaChunk>& chunks, size_t c0, size_t c1, int32_t tid, bool want_rel, int max_cpgs,
-              PinnedBatch& pb, mth_batch* b) {
+              int64_t own_lo, int64_t own_hi, PinnedBatch& pb, mth_batch* b) {
     const size_t nc = c1 - c0;
     std::vector<size_t> r_off(nc + 1, 0), i_off(nc + 1, 0), w_off(nc + 1, 0);
     const bool multiword = max_cpgs > 64;
@@ -116,7 +121,8 @@ void assemble(ThreadPool& pool, std::vector<SoaChunk>& chunks, size_t c0, size_t
         if (!n) return;
         memcpy(start + r0, ch.start.data(), n * 4);
         memcpy(end + r0, ch.end.data(), n * 4);
-        for (size_t r = 0; r < n; r++) meta[r0 + r] = ch.meta[r] & ~SOA_META_COMPLEX;
+        for (size_t r = 0; r < n; r++)
+            meta[r0 + r] = (ch.meta[r] & ~SOA_META_COMPLEX) | ((ch.start[r] < own_lo || ch.start[r] >= own_hi) ? (uint32_t)MTH_META_HALO : 0u);
         memcpy(pos + i0, ch.cpg_pos.data(), ch.cpg_pos.size() * 4);
         if (want_rel) memcpy(rel + i0, ch.cpg_rel.data(), ch.cpg_rel.size() * 2);
         size_t io = i0, wo = w_off[(size_t)k];
@@ -153,8 +159,10 @@ void assemble(ThreadPool& pool, std::vector<SoaChunk>& chunks, size_t c0, size_t
 
 // Same reads in the compact wire format (mth_batch_compact): 9 B per read + 2.125 B per call over PCIe instead of 24 + 6.
 // dense = also the block encodings MTH_CENC_START16 | MTH_CENC_DELTA8 (7 B per read + 1.125 B per call on short-read data).
-void assemble_compact(ThreadPool& pool, std::vector<SoaChunk>& chunks, size_t nc, int32_t tid, bool want_rel, bool dense,
-                      PinnedBatch& pb, mth_batch_compact* b) {
+void assemble_compact(ThreadPool& pool, std::vector<SoaChunk>& all_chunks, size_t c0, size_t c1, int32_t tid, bool want_rel, bool dense,
+                      int64_t own_lo, int64_t own_hi, PinnedBatch& pb, mth_batch_compact* b) {
+    const size_t nc = c1 - c0;
+    SoaChunk* chunks = all_chunks.data() + c0;
     std::vector<size_t> r_off(nc + 1, 0), i_off(nc + 1, 0), e_off(nc + 1, 0);
     for (size_t k = 0; k < nc; k++) {
         const SoaChunk& ch = chunks[k];
@@ -196,7 +204,7 @@ void assemble_compact(ThreadPool& pool, std::vector<SoaChunk>& chunks, size_t nc
             mapq[r0 + r] = (uint8_t)(m & 0xFFu);
             ncpg[r0 + r] = (uint8_t)nr;
             const bool cx = want_rel && (m & SOA_META_COMPLEX);
-            flags[r0 + r] = (uint8_t)(((m >> 8) & 1u) | (cx ? MTH_CFLAG_REL_EXPLICIT : 0u));
+            flags[r0 + r] = (uint8_t)(((m >> 8) & 1u) | (cx ? MTH_CFLAG_REL_EXPLICIT : 0u) | ((s < own_lo || s >= own_hi) ? MTH_CFLAG_HALO : 0u));
             int32_t prev = s - 1;
             for (uint32_t q = 0; q < nr; q++, c++, x++) {
                 // dense: delta from the previous call of the read (MTH_CENC_DELTA8); plain: offset from start - 1
@@ -334,29 +342,30 @@ void write_rows(ThreadPool& pool, OutFile& out, int64_t n, RowFn&& row) {
     }
 }
 
-// Row sources of several GPUs merged by contig: each contig lives on exactly one GPU and rows are sorted by
-// (tid, pos) within a GPU, so the global order is "for tid ascending: that GPU's run of rows with this tid".
-struct Run { int gpu; int64_t lo, hi; };
-template <class TidOf>
-std::vector<Run> merge_runs(int n_gpus, const std::vector<int64_t>& n_rows, TidOf&& tid_of) {
-    struct Item { int32_t tid; Run r; };
-    std::vector<Item> items;
-    for (int g = 0; g < n_gpus; g++) {
-        int64_t i = 0, n = n_rows[(size_t)g];
-        while (i < n) {
-            const int32_t t = tid_of(g, i);
-            int64_t lo = i, a = i, b = n;  // first index with tid > t
+// Row sources of several GPUs merged by ownership: a GPU's rows are sorted by (tid, first position); the rows it OWNS are
+// those whose first position lies in one of its intervals, i.e. one contiguous sub-run per interval, and the global order
+// is the order of the intervals.
+struct Run { int gpu; int64_t lo, hi; int32_t tid; int64_t pos_lo; };
+template <class TidOf, class PosOf>
+std::vector<Run> owned_runs(const std::vector<std::unique_ptr<Gpu>>& gpus, const std::vector<int64_t>& n_rows, TidOf&& tid_of, PosOf&& pos_of) {
+    std::vector<Run> runs;
+    for (int g = 0; g < (int)gpus.size(); g++) {
+        const int64_t n = n_rows[(size_t)g];
+        auto lower = [&](int32_t t, int64_t x) {  // first row with (tid, pos) >= (t, x)
+            int64_t a = 0, b = n;
             while (a < b) {
-                int64_t m = (a + b) / 2;
-                if (tid_of(g, m) <= t) a = m + 1; else b = m;
+                const int64_t m = (a + b) / 2;
+                const int32_t tm = tid_of(g, m);
+                if (tm < t || (tm == t && (int64_t)pos_of(g, m) < x)) a = m + 1; else b = m;
             }
-            items.push_back(Item{t, Run{g, lo, a}});
-            i = a;
+            return a;
+        };
+        for (const Interval& iv : gpus[(size_t)g]->own) {
+            const int64_t a = lower(iv.tid, iv.lo), b = lower(iv.tid, iv.hi);
+            if (b > a) runs.push_back(Run{g, a, b, iv.tid, iv.lo});
         }
     }
-    std::stable_sort(items.begin(), items.end(), [](const Item& x, const Item& y) { return x.tid < y.tid; });
-    std::vector<Run> runs;
-    for (auto& it : items) runs.push_back(it.r);
+    std::stable_sort(runs.begin(), runs.end(), [](const Run& x, const Run& y) { return x.tid != y.tid ? x.tid < y.tid : x.pos_lo < y.pos_lo; });
     return runs;
 }
 
@@ -368,6 +377,49 @@ void json_escape(FILE* f, const char* s) {
 }
 
 }  // namespace
+
+// ---- multi-GPU sharding plans (mirrors metheor_b200/shard.py) ------------------------------------------
+// bins: the linearised genome is cut into `world` contiguous ranges of equal length; rank r owns the sites in its range.
+std::vector<std::vector<ShardInterval>> plan_bins(const std::vector<int64_t>& ref_len, int world) {
+    std::vector<std::vector<ShardInterval>> out((size_t)world);
+    const int n_ref = (int)ref_len.size();
+    if (n_ref == 0) return out;
+    std::vector<int64_t> base((size_t)n_ref + 1, 0);
+    for (int t = 0; t < n_ref; t++) base[(size_t)t + 1] = base[(size_t)t] + ref_len[(size_t)t];
+    const int64_t total = base[(size_t)n_ref];
+    std::vector<std::pair<int, int64_t>> cuts;  // rank r covers [cuts[r], cuts[r+1]) in (tid, pos) order
+    cuts.push_back({0, 0});
+    for (int r = 1; r < world; r++) {
+        const int64_t x = (int64_t)((__int128)total * r / world);
+        int tid = (int)(std::upper_bound(base.begin(), base.end(), x) - base.begin()) - 1;
+        if (tid > n_ref - 1) tid = n_ref - 1;
+        cuts.push_back({tid, x - base[(size_t)tid]});
+    }
+    cuts.push_back({n_ref - 1, ref_len[(size_t)n_ref - 1]});
+    for (int r = 0; r < world; r++) {
+        const auto a = cuts[(size_t)r], b = cuts[(size_t)r + 1];
+        for (int tid = a.first; tid <= b.first; tid++) {
+            const int64_t lo = tid == a.first ? a.second : 0, hi = tid == b.first ? b.second : ref_len[(size_t)tid];
+            if (hi > lo) out[(size_t)r].push_back(ShardInterval{tid, lo, hi});
+        }
+    }
+    return out;
+}
+// contigs: whole contigs, longest first onto the least loaded rank
+std::vector<std::vector<ShardInterval>> plan_contigs(const std::vector<int64_t>& ref_len, int world) {
+    std::vector<std::vector<ShardInterval>> out((size_t)world);
+    std::vector<size_t> order(ref_len.size());
+    for (size_t i = 0; i < order.size(); i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return ref_len[a] > ref_len[b]; });
+    std::vector<int64_t> load((size_t)world, 0);
+    for (size_t t : order) {
+        const size_t g = (size_t)(std::min_element(load.begin(), load.end()) - load.begin());
+        out[g].push_back(ShardInterval{(int32_t)t, 0, ref_len[t]});
+        load[g] += ref_len[t];
+    }
+    for (auto& v : out) std::sort(v.begin(), v.end(), [](const ShardInterval& a, const ShardInterval& b) { return a.tid < b.tid; });
+    return out;
+}
 
 void run(const mthh_options& o) {
     const double t_begin = now_s();
@@ -406,7 +458,7 @@ void run(const mthh_options& o) {
     if ((o.measure == MTHH_FDRP || o.measure == MTHH_QFDRP) && o.max_depth == 0)
         throw HostError{1, "metheor_b200: --max-depth must be at least 1"};
 
-    std::vector<int64_t> ref_len = hdr.lengths;
+    const std::vector<int64_t>& ref_len = hdr.lengths;
     std::vector<std::unique_ptr<Gpu>> gpus;
     for (int g = 0; g < n_gpus; g++) {
         gpus.emplace_back(new Gpu());
@@ -420,17 +472,18 @@ void run(const mthh_options& o) {
         }
     } guard{gpus};
 
-    // contig -> GPU: longest-first onto the least loaded GPU
-    std::vector<int> gpu_of(ref_len.size(), 0);
-    if (n_gpus > 1) {
-        std::vector<size_t> order(ref_len.size());
-        for (size_t i = 0; i < order.size(); i++) order[i] = i;
-        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return ref_len[a] > ref_len[b]; });
-        std::vector<int64_t> load((size_t)n_gpus, 0);
-        for (size_t t : order) {
-            int g = (int)(std::min_element(load.begin(), load.end()) - load.begin());
-            gpu_of[t] = g;
-            load[(size_t)g] += ref_len[t];
+    // Sharding: position bins of the linearised genome (default) or whole contigs.  A GPU receives the reads
+    // that start in its interval plus a halo (reads starting up to SHARD_HALO before it, or exactly at its end); it OWNS the
+    // sites inside the interval: every contributor and every flush trigger of an owned site is among its reads, so the rows
+    // it reports for them are final.  Halo copies carry MTH_META_HALO so that LPMD counts each read once.
+    {
+        auto plan = (n_gpus > 1 && o.shard_contigs) ? plan_contigs(ref_len, n_gpus) : plan_bins(ref_len, n_gpus);
+        for (int g = 0; g < n_gpus; g++) gpus[(size_t)g]->own = plan[(size_t)g];
+        if (n_gpus > 1) {  // the contexts are joined by one NCCL communicator: LPMD's counters are summed at the end
+            std::vector<mth_ctx*> cs;
+            for (auto& gp : gpus) cs.push_back(gp->ctx);
+            int rc = mth_comm_init_all(cs.data(), n_gpus);
+            if (rc != MTH_OK) engine_fail(cs[0], rc, "mth_comm_init_all");
         }
     }
 
@@ -501,39 +554,66 @@ void run(const mthh_options& o) {
                 if (scale > 1.5) mth_reserve(gpus[0]->ctx, (int64_t)((double)kept * scale) + 4096, (int64_t)((double)kept_calls * scale) + 4096);
                 reserved = true;
             }
-            if (kept && tid >= 0 && (size_t)tid < ref_len.size()) {
-                Gpu& G = *gpus[(size_t)gpu_of[(size_t)tid]];
-                t0 = now_s();
-                // the slot was last used RING submits ago: its copy has long been issued, wait for it to have completed
-                if (G.submitted >= RING) {
-                    int rc = mth_sync_copies(G.ctx);
-                    if (rc != MTH_OK) engine_fail(G.ctx, rc, "mth_sync_copies");
+            if (kept && (tid < 0 || (size_t)tid >= ref_len.size()))
+                throw HostError{101, "metheor_b200: a read with CpG calls has no valid reference id (tid " + std::to_string(tid) + ")"};
+            // coordinate order within the contig (the engine checks it again on the device; chunk routing below relies on it)
+            {
+                int32_t prev = INT32_MIN;
+                for (size_t k = 0; k < n_tasks; k++) {
+                    const auto& st = chunks[k].start;
+                    for (size_t r = 0; r < st.size(); r++) {
+                        if (st[r] < prev) throw HostError{1, "metheor_b200: input is not coordinate-sorted; sort it with samtools sort"};
+                        prev = st[r];
+                    }
                 }
-                PinnedBatch& pb = G.ring[G.next_slot];
-                G.next_slot = (G.next_slot + 1) % RING;
-                int64_t nr_b, nc_b;
-                int rc;
-                if (seg.max_cpgs <= 64 && seg.max_span <= 65024) {  // compact wire format: ~1/3 of the PCIe bytes
-                    mth_batch_compact b;
-                    assemble_compact(pool, chunks, n_tasks, tid, want_rel, /*dense=*/true, pb, &b);
-                    s_assemble += now_s() - t0;
+            }
+            for (int g = 0; kept && g < n_gpus; g++) {
+                Gpu& G = *gpus[(size_t)g];
+                for (const Interval& iv : G.own) {
+                    if (iv.tid != tid) continue;
+                    // chunks (ascending starts) that hold a read starting in [lo - halo, hi]
+                    size_t c0 = n_tasks, c1 = 0;
+                    const int64_t need_lo = n_gpus > 1 ? iv.lo - SHARD_HALO : INT64_MIN, need_hi = n_gpus > 1 ? iv.hi : INT64_MAX;
+                    for (size_t k = 0; k < n_tasks; k++) {
+                        const auto& st = chunks[k].start;
+                        if (st.empty() || (int64_t)st.back() < need_lo || (int64_t)st.front() > need_hi) continue;
+                        c0 = std::min(c0, k);
+                        c1 = std::max(c1, k + 1);
+                    }
+                    if (c0 >= c1) continue;
+                    const int64_t own_lo = n_gpus > 1 ? iv.lo : INT64_MIN, own_hi = n_gpus > 1 ? iv.hi : INT64_MAX;
                     t0 = now_s();
-                    rc = mth_submit_compact(G.ctx, &b);
-                    nr_b = b.n_reads; nc_b = b.n_cpg;
-                } else {
-                    mth_batch b;
-                    assemble(pool, chunks, 0, n_tasks, tid, want_rel, seg.max_cpgs, pb, &b);
-                    s_assemble += now_s() - t0;
-                    t0 = now_s();
-                    rc = mth_submit(G.ctx, &b);
-                    nr_b = b.n_reads; nc_b = b.n_cpg;
+                    // the slot was last used RING submits ago: its copy has long been issued, wait for it to have completed
+                    if (G.submitted >= RING) {
+                        int rc = mth_sync_copies(G.ctx);
+                        if (rc != MTH_OK) engine_fail(G.ctx, rc, "mth_sync_copies");
+                    }
+                    PinnedBatch& pb = G.ring[G.next_slot];
+                    G.next_slot = (G.next_slot + 1) % RING;
+                    int64_t nr_b, nc_b;
+                    int rc;
+                    if (seg.max_cpgs <= 64 && seg.max_span <= 65024) {  // compact wire format: ~1/3 of the PCIe bytes
+                        mth_batch_compact b;
+                        assemble_compact(pool, chunks, c0, c1, tid, want_rel, /*dense=*/true, own_lo, own_hi, pb, &b);
+                        s_assemble += now_s() - t0;
+                        t0 = now_s();
+                        rc = mth_submit_compact(G.ctx, &b);
+                        nr_b = b.n_reads; nc_b = b.n_cpg;
+                    } else {
+                        mth_batch b;
+                        assemble(pool, chunks, c0, c1, tid, want_rel, seg.max_cpgs, own_lo, own_hi, pb, &b);
+                        s_assemble += now_s() - t0;
+                        t0 = now_s();
+                        rc = mth_submit(G.ctx, &b);
+                        nr_b = b.n_reads; nc_b = b.n_cpg;
+                    }
+                    if (rc != MTH_OK) engine_fail(G.ctx, rc, "mth_submit");
+                    G.submitted++;
+                    s_submit += now_s() - t0;
+                    n_batches++;
+                    n_shipped_reads += nr_b;
+                    n_shipped_cpg += nc_b;
                 }
-                if (rc != MTH_OK) engine_fail(G.ctx, rc, "mth_submit");
-                G.submitted++;
-                s_submit += now_s() - t0;
-                n_batches++;
-                n_shipped_reads += nr_b;
-                n_shipped_cpg += nc_b;
             }
             seg0 = seg1;
         }
@@ -563,13 +643,18 @@ void run(const mthh_options& o) {
     auto chrom = [&](int32_t tid) -> const std::string& { return hdr.names[(size_t)tid]; };
     int64_t n_rows_total = 0;
     if (o.measure == MTHH_LPMD) {
-        int64_t t[4] = {0, 0, 0, 0};
-        for (auto& gp : gpus) {
-            t[0] += gp->res.lpmd.n_read; t[1] += gp->res.lpmd.n_valid_read; t[2] += gp->res.lpmd.n_conc; t[3] += gp->res.lpmd.n_disc;
+        // lpmd.rs:190-191 sums over the whole file: with several GPUs that is the path's ONE collective — an NCCL all-reduce
+        // of the four int64 counters inside the library; afterwards every context holds the global result.
+        mth_lpmd_result lr = gpus[0]->res.lpmd;
+        if (n_gpus > 1) {
+            std::vector<mth_ctx*> cs;
+            for (auto& gp : gpus) cs.push_back(gp->ctx);
+            int rc = mth_allreduce_group(cs.data(), n_gpus);
+            if (rc != MTH_OK) engine_fail(cs[0], rc, "mth_allreduce_group");
+            rc = mth_lpmd_refresh(gpus[0]->ctx, &lr);
+            if (rc != MTH_OK) engine_fail(gpus[0]->ctx, rc, "mth_lpmd_refresh");
         }
-        // lpmd.rs:51-55: n_discordant as f32 / (n_concordant + n_discordant) as f32
-        volatile float num = (float)t[3], den = (float)(t[2] + t[3]);
-        float lpmd = num / den;
+        const float lpmd = lr.lpmd;
         std::string s = "name\tlpmd\n";  // lpmd.rs:145-147
         s += o.input;
         s += '\t';
@@ -581,7 +666,8 @@ void run(const mthh_options& o) {
             pf.write("chrom\tcpg1\tcpg2\tlpmd\tn_concordant\tn_discordant\n");  // lpmd.rs:104
             std::vector<int64_t> nr;
             for (auto& gp : gpus) nr.push_back(gp->res.lpmd_pairs.n);
-            auto runs = merge_runs(n_gpus, nr, [&](int g, int64_t i) { return gpus[(size_t)g]->res.lpmd_pairs.tid[i]; });
+            auto runs = owned_runs(gpus, nr, [&](int g, int64_t i) { return gpus[(size_t)g]->res.lpmd_pairs.tid[i]; },
+                                   [&](int g, int64_t i) { return gpus[(size_t)g]->res.lpmd_pairs.pos1[i]; });
             for (const Run& r : runs) {
                 const mth_pair_rows& R = gpus[(size_t)r.gpu]->res.lpmd_pairs;
                 write_rows(pool, pf, r.hi - r.lo, [&](int64_t k, std::string& s2) {
@@ -596,7 +682,8 @@ void run(const mthh_options& o) {
         auto rows_of = [&](Gpu& G) -> const mth_quartet_rows& { return o.measure == MTHH_PM ? G.res.pm : G.res.me; };
         std::vector<int64_t> nr;
         for (auto& gp : gpus) nr.push_back(rows_of(*gp).n);
-        auto runs = merge_runs(n_gpus, nr, [&](int g, int64_t i) { return rows_of(*gpus[(size_t)g]).tid[i]; });
+        auto runs = owned_runs(gpus, nr, [&](int g, int64_t i) { return rows_of(*gpus[(size_t)g]).tid[i]; },
+                               [&](int g, int64_t i) { return rows_of(*gpus[(size_t)g]).p1[i]; });
         for (const Run& r : runs) {
             const mth_quartet_rows& R = rows_of(*gpus[(size_t)r.gpu]);
             write_rows(pool, out, r.hi - r.lo, [&](int64_t k, std::string& s) {  // pm.rs:56-59, me.rs:61-64
@@ -618,7 +705,8 @@ void run(const mthh_options& o) {
         const bool counts = o.measure == MTHH_PDR;
         std::vector<int64_t> nr;
         for (auto& gp : gpus) nr.push_back(rows_of(*gp).n);
-        auto runs = merge_runs(n_gpus, nr, [&](int g, int64_t i) { return rows_of(*gpus[(size_t)g]).tid[i]; });
+        auto runs = owned_runs(gpus, nr, [&](int g, int64_t i) { return rows_of(*gpus[(size_t)g]).tid[i]; },
+                               [&](int g, int64_t i) { return rows_of(*gpus[(size_t)g]).pos[i]; });
         for (const Run& r : runs) {
             const mth_site_rows& R = rows_of(*gpus[(size_t)r.gpu]);
             write_rows(pool, out, r.hi - r.lo, [&](int64_t k, std::string& s) {  // pdr.rs:105-114, mhl.rs:123-130, fdrp.rs:171

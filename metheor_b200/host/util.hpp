@@ -20,6 +20,14 @@ struct HostError {
     std::string msg;
 };
 
+// multi-GPU sharding (run.cpp): the sites [lo, hi) of contig tid are owned by one rank
+struct ShardInterval {
+    int32_t tid;
+    int64_t lo, hi;
+};
+std::vector<std::vector<ShardInterval>> plan_bins(const std::vector<int64_t>& ref_len, int world);
+std::vector<std::vector<ShardInterval>> plan_contigs(const std::vector<int64_t>& ref_len, int world);
+
 inline double now_s() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }

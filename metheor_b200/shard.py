@@ -38,12 +38,14 @@ def plan_bins(ref_len, world, weights=None):
     n_ref = len(ref_len)
     cuts = [(0, 0)]  # rank r covers [cuts[r], cuts[r+1]) in (tid, pos) order
     if weights is None:
-        total = float(sum(ref_len))
-        base = np.concatenate([[0.0], np.cumsum(np.asarray(ref_len, np.float64))])
-        for r in range(1, world):
-            x = total * r / world
-            tid = min(int(np.searchsorted(base, x, "right")) - 1, n_ref - 1)
-            cuts.append((tid, int(round(x - base[tid]))))
+        base = [0]
+        for l in ref_len:
+            base.append(base[-1] + int(l))
+        total = base[-1]
+        for r in range(1, world):  # integer arithmetic: host/run.cpp plan_bins computes the same cuts
+            x = total * r // world
+            tid = min(int(np.searchsorted(np.asarray(base, np.int64), x, "right")) - 1, n_ref - 1)
+            cuts.append((tid, x - base[tid]))
     else:
         counts = np.array([len(w) for w in weights], np.int64)
         base = np.concatenate([[0], np.cumsum(counts)])

@@ -166,3 +166,35 @@ def test_reads_with_more_than_64_calls_take_the_soa_batch(tmp_path):
     for m in MEASURES:
         t = _both(tmp_path, m, bam, *(() if m == "lpmd" else ("-d", 5)))
         assert t.count("\n") > (1 if m == "lpmd" else 50), m
+
+
+def test_multi_gpu_position_bins_and_contigs(tmp_path):
+    """`metheor --gpus N` (one process, N engine contexts): the genome cut into position bins with halo reads (default) or into
+    whole contigs; LPMD's counters joined by the library's NCCL all-reduce.  TSVs must equal the oracle CLI byte for byte."""
+    from metheor_b200 import _lib
+    n_dev = _lib.lib().mth_device_count()
+    if n_dev < 2:
+        pytest.skip("needs at least 2 GPUs")
+    n = min(n_dev, 4)
+    refs = [("chrA", 150_000), ("chrB", 60_000), ("chrC", 90_000)]
+    recs = []
+    for tid, (_, length) in enumerate(refs):
+        sites = synth.make_sites(90 + tid, length)
+        b = synth.make_reads(190 + tid, sites, length, 25.0, tid=tid, del_frac=0.05)
+        recs += recgen.batch_to_records(b)
+    bam = str(tmp_path / "mg.bam")
+    bamio.write_bam(bam, refs, recs, block=5000)
+    for shard in ("bins", "contigs"):
+        for m in MEASURES:
+            a, b_ = str(tmp_path / f"{m}.{shard}.tsv"), str(tmp_path / f"{m}.oracle.tsv")
+            r = host.cli(m, "-i", bam, "-o", a, "--gpus", n, "--shard", shard)
+            assert r.returncode == 0, r.stderr
+            if not os.path.exists(b_):
+                o = _oracle_cli(m, "-i", bam, "-o", b_)
+                assert o.returncode == 0, o.stderr
+            assert open(a).read() == open(b_).read(), (m, shard)
+            assert open(a).read().count("\n") > (1 if m == "lpmd" else 100)
+    pa, pb = str(tmp_path / "pairs.mg.tsv"), str(tmp_path / "pairs.oracle.tsv")
+    assert host.cli("lpmd", "-i", bam, "-o", str(tmp_path / "l.tsv"), "-p", pa, "--gpus", n).returncode == 0
+    assert _oracle_cli("lpmd", "-i", bam, "-o", str(tmp_path / "l2.tsv"), "-p", pb).returncode == 0
+    assert open(pa).read() == open(pb).read()

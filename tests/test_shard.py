@@ -122,3 +122,22 @@ def test_plans_cover_the_genome_exactly():
             assert (cover == 1).all()
         c = shard.plan_contigs(LENS, world)
         assert sorted(t for r in c for t in r) == list(range(len(LENS)))
+
+
+def test_cpp_host_plans_equal_the_python_planner():
+    """`metheor --gpus N` (host/run.cpp plan_bins / plan_contigs, through mthh_plan_shards) and shard.py agree."""
+    from metheor_b200 import host, synth_gpu
+    rng = np.random.default_rng(3)
+    cases = [[l for _, l in synth_gpu.HG38], [1000], [5, 7, 11, 13], list(rng.integers(1, 10_000_000, 40))]
+    for rl in cases:
+        for w in (1, 2, 3, 4, 8, 16):
+            a = host.plan_shards(rl, w)
+            b = shard.plan_bins([int(x) for x in rl], w)
+            assert [[tuple(int(v) for v in x) for x in r] for r in a] == [[tuple(int(v) for v in x) for x in r] for r in b], (rl, w)
+            # the intervals of all ranks tile the genome exactly
+            cover = sorted(x for r in a for x in r)
+            for t, l in enumerate(rl):
+                iv = [(lo, hi) for tt, lo, hi in cover if tt == t]
+                assert iv[0][0] == 0 and iv[-1][1] == l and all(iv[k][1] == iv[k + 1][0] for k in range(len(iv) - 1)), (rl, w, t)
+            c = host.plan_shards(rl, w, True)
+            assert [[t for t, _, _ in r] for r in c] == shard.plan_contigs([int(x) for x in rl], w)
