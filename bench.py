@@ -154,7 +154,7 @@ def rows_digest(torch, dev, ctx, measures, owned=None):
             return None
         m = torch.zeros_like(tid, dtype=torch.bool)
         for t, lo, hi in owned:
-            m |= (tid == t) & (pos >= lo) & (pos < hi)
+            m |= (tid == t) & (pos >= (lo if lo > 0 else -1)) & (pos < hi)
         return m
 
     for name in ("pdr", "mhl", "fdrp", "qfdrp"):
@@ -473,8 +473,14 @@ def main():
                 if it >= 1:
                     for k, v in pctx.stats()["kernels"].items():
                         a = acc.setdefault(k, [0, 0.0]); a[0] += v["launches"]; a[1] += v["ms"]
+            pst = pctx.stats()
             pctx.close()
-            blk["kernels"] = {k: {"launches_per_step": a[0] / PS, "ms_per_step": a[1] / PS} for k, a in acc.items()}
+            blk["kernels"] = {k: {"launches_per_step": a[0] / PS, "ms_per_step": a[1] / PS} for k, a in acc.items() if not k.startswith("~")}
+            det = {k[1:]: round(a[1] / PS, 3) for k, a in acc.items() if k.startswith("~")}  # tile kernel vs per-site fall-back, inside k_mhl / k_fdrp*
+            if det:
+                blk["kernel_detail_ms"] = det
+            if pst["fallback_sites_mhl"] or pst["fallback_sites_fdrp"]:
+                blk["fallback_sites"] = {"mhl": int(pst["fallback_sites_mhl"]), "fdrp": int(pst["fallback_sites_fdrp"])}
         return blk
 
     def add_roofline(blk, traffic):

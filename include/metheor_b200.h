@@ -211,6 +211,7 @@ typedef struct {
     int64_t kernel_launches;      /* engine kernels launched since create/reset */
     int64_t h2d_bytes, d2h_bytes; /* bytes copied since create/reset */
     int64_t fdrp_pair_ops;        /* read pairs compared by the FDRP / qFDRP kernels (sum over closed segments of n(n-1)/2) */
+    int64_t fallback_sites_mhl, fallback_sites_fdrp; /* MTH_FLAG_PROFILE: sites the tile kernels handed to the per-site kernels */
     int32_t max_ref_span;         /* longest end-start+1 seen */
     int32_t pdr_path;             /* 0 none, 1 scatter (no flush possible), 2 gather everywhere (MTH_FLAG_FORCE_GATHER), 3 scatter + gather on hazard sites */
     int32_t n_kernel_stats;

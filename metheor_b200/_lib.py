@@ -85,7 +85,7 @@ class KernelStat(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("n_reads", i64), ("n_cpg", i64), ("n_sites", i64), ("n_regions", i64), ("kernel_launches", i64),
-                ("h2d_bytes", i64), ("d2h_bytes", i64), ("fdrp_pair_ops", i64), ("max_ref_span", i32), ("pdr_path", i32),
+                ("h2d_bytes", i64), ("d2h_bytes", i64), ("fdrp_pair_ops", i64), ("fallback_sites_mhl", i64), ("fallback_sites_fdrp", i64), ("max_ref_span", i32), ("pdr_path", i32),
                 ("n_kernel_stats", i32), ("kernel", KernelStat * 48)]
 
 

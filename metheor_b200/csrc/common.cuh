@@ -47,6 +47,7 @@ struct RegionScalars {
     unsigned long long n_sites;
     unsigned long long lpmd[4];  // n_read, n_valid_read, n_conc, n_disc
     unsigned long long fdrp_pairs;  // read pairs compared by the FDRP / qFDRP kernels (pair-ops of SURVEY 8d)
+    unsigned long long fallback_sites[2];  // MTH_FLAG_PROFILE: sites the MHL / FDRP tile kernels handed to the per-site kernels
 };
 
 struct ContigTable {       // device copy: contigs of the current region, ascending lin_off

@@ -204,6 +204,7 @@ struct ProfScope {
         sp.launches += n;
         c->stats.kernel_launches += n;
     }
+    void add0(int n) { sp.launches += n; }  // nested detail scope ("~name"): the launch is counted by the enclosing scope
     ~ProfScope() {
         if (on) {
             cudaEventRecord(sp.e1, c->compute);
@@ -955,10 +956,19 @@ static int process_region(mth_ctx* c) {
             {
                 ProfScope ps(c, "k_mhl");
                 CUDA_TRY(c, cudaMemsetAsync(c->gfallback.p, 0, (size_t)C, s));
-                ps.add(launch_mhl_site(rv, site_pos, C, d_sc, c->prm.mhl, (float*)c->value[M_MHL].p, (uint32_t*)c->rowcnt[M_MHL].p,
-                                       (uint8_t*)c->gfallback.p, s));
-                ps.add(launch_mhl(rv, site_pos, C, d_sc, c->prm.mhl, (float*)c->value[M_MHL].p, (uint32_t*)c->rowcnt[M_MHL].p,
-                                  (const uint8_t*)c->gfallback.p, s));
+                {
+                    ProfScope p2(c, "~mhl_tile");
+                    p2.add0(launch_mhl_site(rv, site_pos, C, d_sc, c->prm.mhl, (float*)c->value[M_MHL].p, (uint32_t*)c->rowcnt[M_MHL].p,
+                                            (uint8_t*)c->gfallback.p, s));
+                }
+                ps.add(1);
+                if (c->prm.flags & MTH_FLAG_PROFILE) ps.add(launch_count_flags((const uint8_t*)c->gfallback.p, C, &d_sc->fallback_sites[0], s));
+                {
+                    ProfScope p2(c, "~mhl_fallback");
+                    p2.add0(launch_mhl(rv, site_pos, C, d_sc, c->prm.mhl, (float*)c->value[M_MHL].p, (uint32_t*)c->rowcnt[M_MHL].p,
+                                       (const uint8_t*)c->gfallback.p, s));
+                }
+                ps.add(1);
             }
             ProfScope ps(c, "mhl_rows_count");
             ps.add(launch_exclusive_scan_u32((uint32_t*)c->rowcnt[M_MHL].p, C, scratch, d_tot + M_MHL, s));
@@ -987,11 +997,20 @@ static int process_region(mth_ctx* c) {
                     CUDA_TRY(c, cudaMemsetAsync(c->gfallback.p, 0, (size_t)C, s));
                     float* vq = both ? (float*)c->value[M_QFDRP].p : nullptr;
                     uint32_t* rq = both ? (uint32_t*)c->rowcnt[M_QFDRP].p : nullptr;
-                    ps.add(launch_fdrp_tile(rv, site_pos, C, (const unsigned long long*)c->bitmap.p, n_words, (const uint32_t*)c->word_prefix.p,
-                                            d_sc, fp, mode, c->prm.seed, ct, (float*)c->value[m].p, (uint32_t*)c->rowcnt[m].p, vq, rq,
-                                            (uint8_t*)c->gfallback.p, s));
-                    ps.add(launch_fdrp(rv, site_pos, C, d_sc, fp, mode, c->prm.seed, ct, c->fdrp_scratch.p, sb, (float*)c->value[m].p,
-                                       (uint32_t*)c->rowcnt[m].p, vq, rq, (const uint8_t*)c->gfallback.p, s));
+                    {
+                        ProfScope p2(c, "~fdrp_tile");
+                        p2.add0(launch_fdrp_tile(rv, site_pos, C, (const unsigned long long*)c->bitmap.p, n_words, (const uint32_t*)c->word_prefix.p,
+                                                 d_sc, fp, mode, c->prm.seed, ct, (float*)c->value[m].p, (uint32_t*)c->rowcnt[m].p, vq, rq,
+                                                 (uint8_t*)c->gfallback.p, s));
+                    }
+                    ps.add(1);
+                    if (c->prm.flags & MTH_FLAG_PROFILE) ps.add(launch_count_flags((const uint8_t*)c->gfallback.p, C, &d_sc->fallback_sites[1], s));
+                    {
+                        ProfScope p2(c, "~fdrp_fallback");
+                        p2.add0(launch_fdrp(rv, site_pos, C, d_sc, fp, mode, c->prm.seed, ct, c->fdrp_scratch.p, sb, (float*)c->value[m].p,
+                                            (uint32_t*)c->rowcnt[m].p, vq, rq, (const uint8_t*)c->gfallback.p, s));
+                    }
+                    ps.add(1);
                 }
                 ProfScope ps(c, q ? "qfdrp_rows_count" : "fdrp_rows_count");
                 ps.add(launch_exclusive_scan_u32((uint32_t*)c->rowcnt[m].p, C, scratch, d_tot + m, s));
@@ -1051,6 +1070,8 @@ static int process_region(mth_ctx* c) {
         CUDA_TRY(c, cudaStreamSynchronize(s));
         TRY(check_scalars_err(c, ((RegionScalars*)c->h_scalars.p)->err));
         c->stats.fdrp_pair_ops += (int64_t)((RegionScalars*)c->h_scalars.p)->fdrp_pairs;
+        c->stats.fallback_sites_mhl += (int64_t)((RegionScalars*)c->h_scalars.p)->fallback_sites[0];
+        c->stats.fallback_sites_fdrp += (int64_t)((RegionScalars*)c->h_scalars.p)->fallback_sites[1];
         const unsigned long long* tot = (const unsigned long long*)c->h_totals.p;
 
         // ---------------- phase B: row emission ----------------
@@ -1100,19 +1121,22 @@ static int process_region(mth_ctx* c) {
                                                (const unsigned long long*)c->qobs_n.p + qs, rv.I, (const uint32_t*)c->qcnt[qs].p, qm,
                                                (const uint32_t*)c->rowcnt[m].p, qp.min_depth, (uint32_t*)c->qhrows[qs].p, s));
                 }
-                ProfScope ps(c, q ? "k_me_emit" : "k_pm_emit");
-                if (shared && q == 0) {  // PM and ME rows from one read of the histograms
+                if (shared && q == 1) continue;  // written together with the PM rows
+                ProfScope ps(c, shared ? "k_pm_me_emit" : (q ? "k_me_emit" : "k_pm_emit"));
+                if (shared) {  // PM and ME rows from one read of the histograms / one gather pass over the mixed sites
                     QuartetRowsDev rd2 = quartet_rows_dev(c->rows_me);
                     if (!counts) rd2.counts = nullptr;
                     ps.add(launch_quartet_canon_emit((const uint32_t*)c->qcnt[qs].p, qm, (const uint32_t*)c->qhrows[qs].p, site_pos, C, qp.min_depth, 2,
                                                      (const uint32_t*)c->rowcnt[m].p, (const float*)c->me_lut.p, c->me_lut_max, ct, rd, r.n, rd2,
                                                      c->rows_me.n, s));
-                } else if (!(shared && q == 1)) {
+                    ps.add(launch_quartet_emit(rv, site_pos, C, d_sc, qp, 2, qm, (const uint32_t*)c->rowcnt[m].p, (const float*)c->me_lut.p,
+                                               c->me_lut_max, ct, rd, r.n, rd2, c->rows_me.n, s));
+                } else {
                     ps.add(launch_quartet_canon_emit((const uint32_t*)c->qcnt[qs].p, qm, (const uint32_t*)c->qhrows[qs].p, site_pos, C, qp.min_depth, q,
                                                      (const uint32_t*)c->rowcnt[m].p, (const float*)c->me_lut.p, c->me_lut_max, ct, rd, r.n, rd, r.n, s));
+                    ps.add(launch_quartet_emit(rv, site_pos, C, d_sc, qp, q, qm, (const uint32_t*)c->rowcnt[m].p, (const float*)c->me_lut.p,
+                                               c->me_lut_max, ct, rd, r.n, rd, r.n, s));
                 }
-                ps.add(launch_quartet_emit(rv, site_pos, C, d_sc, qp, q, qm, (const uint32_t*)c->rowcnt[m].p, (const float*)c->me_lut.p,
-                                           c->me_lut_max, ct, rd, r.n, s));
             }
             if (M & MTH_PM) c->rows_pm.n += (int64_t)tot[M_PM];
             if (M & MTH_ME) c->rows_me.n += (int64_t)tot[M_ME];

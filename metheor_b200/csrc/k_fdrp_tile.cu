@@ -144,43 +144,64 @@ __global__ void __launch_bounds__(FT_THREADS, RCAP <= 1024 ? 3 : 2) k_fdrp_tile(
             bool have = false;
             const bool want_q = quant != 0, want_d = quant != 1;
 
+            // All pairs (i < j) of the pile in lexicographic order (itertools combinations(2), fdrp.rs:128), ROW-WISE: every lane
+            // keeps the masks of "its" pile read j = lane (and lane + 32 for piles deeper than 32) in registers; row i is
+            // broadcast from shared memory (uniform addresses: no bank conflicts) and lane j evaluates the pair (i, j) when
+            // j > i.  Within row i the lanes ARE in ascending j, so qFDRP's ordered f32 sum is a fold over the lanes of the
+            // row's ballot — the same order of additions as the reference (qfdrp.rs:141-153).
             auto evaluate = [&](uint32_t n) {
-                const uint64_t P = (uint64_t)n * (n - 1) / 2;
-                pair_ops += P;
-                uint32_t i = 0, jj = 1 + lane;  // this lane's pair (i, jj): pair index = lane, then += 32
-                while (i < n && jj >= n) { jj = jj - n + i + 2; i++; }
+                pair_ops += (uint64_t)n * (n - 1) / 2;
+                unsigned long long jc0[2], jc1[2], jm0[2], jm1[2];
+                int32_t js[2], je[2];
+                uint32_t ju[2];
+#pragma unroll
+                for (int b = 0; b < 2; b++) {
+                    const uint32_t j = (uint32_t)(b * 32 + lane);
+                    jc0[b] = jc1[b] = jm0[b] = jm1[b] = 0ull;
+                    js[b] = 0x3fffffff; je[b] = -0x3fffffff; ju[b] = 255u;  // lanes beyond the pile: overlap far below zero
+                    if (j < n) {
+                        const int rj = pile[j];
+                        jc0[b] = sh.cm[rj][0]; jc1[b] = sh.cm[rj][1]; jm0[b] = sh.mm[rj][0]; jm1[b] = sh.mm[rj][1];
+                        js[b] = sh.start[rj]; je[b] = sh.end[rj]; ju[b] = sh.ub[rj];
+                    }
+                }
                 float acc = 0.f;
                 uint32_t disc = 0;
-                for (uint64_t t0 = 0; t0 < P; t0 += 32) {
-                    float term = 0.f;
-                    if (t0 + lane < P) {
-                        const int ri = pile[i], rj = pile[jj];
-                        const int32_t ov = min(sh.end[ri], sh.end[rj]) - max(sh.start[ri], sh.start[rj]) + 1;  // fdrp.rs:97-107
-                        if (ov >= prm.min_overlap && ov > 0) {  // fdrp.rs:133-136 (without overlap: ham = 0, adds nothing)
-                            unsigned long long b0 = sh.cm[ri][0] & sh.cm[rj][0], b1 = sh.cm[ri][1] & sh.cm[rj][1];
+                for (uint32_t i = 0; i + 1 < n; i++) {
+                    const int ri = pile[i];
+                    const unsigned long long ic0 = sh.cm[ri][0], ic1 = sh.cm[ri][1], im0 = sh.mm[ri][0], im1 = sh.mm[ri][1];
+                    const int32_t is = sh.start[ri], ie = sh.end[ri];
+                    const uint32_t iu = sh.ub[ri];
+#pragma unroll
+                    for (int b = 0; b < 2; b++) {
+                        if (b * 32 + 31 <= (int)i || (uint32_t)(b * 32) >= n) continue;  // warp-uniform: no j > i in this half
+                        const uint32_t j = (uint32_t)(b * 32 + lane);
+                        const int32_t ov = min(ie, je[b]) - max(is, js[b]) + 1;  // fdrp.rs:97-107 (lanes beyond the pile: negative)
+                        float term = 0.f;
+                        if (j > i && j < n && ov >= prm.min_overlap && ov > 0) {  // fdrp.rs:133-136 (without overlap: ham = 0, adds nothing)
+                            const unsigned long long b0 = ic0 & jc0[b], b1 = ic1 & jc1[b];
                             unsigned long long v0 = b0, v1 = b1;  // both called AND both covered: drop the uncovered calls
-                            const uint32_t ui = sh.ub[ri], uj = sh.ub[rj];
-                            if (ui < 64u) v0 &= ~(1ull << ui); else if (ui < 128u) v1 &= ~(1ull << (ui - 64u));
-                            if (uj < 64u) v0 &= ~(1ull << uj); else if (uj < 128u) v1 &= ~(1ull << (uj - 64u));
-                            const uint32_t ham = (uint32_t)__popcll(v0 & (sh.mm[ri][0] ^ sh.mm[rj][0])) +
-                                                 (uint32_t)__popcll(v1 & (sh.mm[ri][1] ^ sh.mm[rj][1]));  // fdrp.rs:109-122
+                            if ((iu & ju[b]) != 255u) {           // rare: a reverse-strand call at start - 1 (fdrp.rs:65-72)
+                                const uint32_t uj = ju[b];
+                                if (iu < 64u) v0 &= ~(1ull << iu); else if (iu < 128u) v1 &= ~(1ull << (iu - 64u));
+                                if (uj < 64u) v0 &= ~(1ull << uj); else if (uj < 128u) v1 &= ~(1ull << (uj - 64u));
+                            }
+                            const uint32_t ham = (uint32_t)__popcll(v0 & (im0 ^ jm0[b])) + (uint32_t)__popcll(v1 & (im1 ^ jm1[b]));  // fdrp.rs:109-122
                             if (want_q && ham) term = __fdiv_rn((float)ham, (float)(__popcll(b0) + __popcll(b1)));  // qfdrp.rs:152
                             if (want_d) disc += ham ? 1u : 0u;                                                       // fdrp.rs:138-140
                         }
-                        jj += 32;
-                        while (i < n && jj >= n) { jj = jj - n + i + 2; i++; }
-                    }
-                    if (want_q) {  // sequential f32 accumulation in pair order
-                        uint32_t nz = __ballot_sync(FULL, term != 0.f);
-                        if (__popc(nz) > 8) {
-                            // dense step: fold all 32 lanes in order, branch-free (x + 0.0f == x exactly, acc >= 0)
+                        if (want_q) {  // sequential f32 accumulation in pair order: lanes ascending = j ascending
+                            uint32_t nz = __ballot_sync(FULL, term != 0.f);
+                            if (__popc(nz) > 10) {
+                                // dense row: fold all 32 lanes in order, branch-free (x + 0.0f == x exactly, acc >= 0)
 #pragma unroll
-                            for (int src = 0; src < 32; src++) acc = __fadd_rn(acc, __shfl_sync(FULL, term, src));
-                        } else {
-                            while (nz) {
-                                const int src = __ffs(nz) - 1;
-                                acc = __fadd_rn(acc, __shfl_sync(FULL, term, src));
-                                nz &= nz - 1;
+                                for (int src = 0; src < 32; src++) acc = __fadd_rn(acc, __shfl_sync(FULL, term, src));
+                            } else {
+                                while (nz) {
+                                    const int src = __ffs(nz) - 1;
+                                    acc = __fadd_rn(acc, __shfl_sync(FULL, term, src));
+                                    nz &= nz - 1;
+                                }
                             }
                         }
                     }

@@ -106,7 +106,7 @@ struct QuartetArgs {
     int64_t C;
     const RegionScalars* sc;
     mth_quartet_params prm;
-    int kind;                 // 0 PM, 1 ME (EMIT only)
+    int kind;                 // 0 PM, 1 ME, 2 PM into rows and ME into rows_b (EMIT only)
     const uint8_t* mixed;     // nullptr: every site; else only the sites flagged by k_quartet_scatter
     uint32_t* rowcnt;         // COUNT: out
     const uint32_t* rowoff;   // EMIT: in
@@ -115,6 +115,8 @@ struct QuartetArgs {
     ContigTable ct;
     QuartetRowsDev rows;
     int64_t row_base;
+    QuartetRowsDev rows_b;    // kind 2: the ME rows
+    int64_t row_base_b;
 };
 
 template <bool EMIT>
@@ -128,6 +130,7 @@ __global__ void __launch_bounds__(GATHER_BLOCK) k_quartet(QuartetArgs a) {
     for_each_site(rv, a.site_pos, a.C, a.sc->lmax, [&](int64_t s, int32_t p, int64_t lo, int32_t target) {
         uint32_t n_rows = 0;
         const int64_t out0 = EMIT ? (a.row_base + a.rowoff[s]) : 0;
+        const int64_t out0b = EMIT ? (a.row_base_b + a.rowoff[s]) : 0;
 
         auto lane_quartet = [&](const LaneRead& lr, QKey* key, uint32_t* pat) -> bool {
             // pm.rs:111 / me.rs:115 mapq filter; readutil.rs:101-105 needs 4 CpGs from the site onwards
@@ -154,9 +157,20 @@ __global__ void __launch_bounds__(GATHER_BLOCK) k_quartet(QuartetArgs a) {
                     a.rows.p2[r] = key.a - off;
                     a.rows.p3[r] = key.b - off;
                     a.rows.p4[r] = key.c - off;
-                    a.rows.value[r] = a.kind == 0 ? pm_value(cnt, total) : me_value(cnt, total, a.me_lut, a.me_lut_max);
+                    a.rows.value[r] = a.kind == 1 ? me_value(cnt, total, a.me_lut, a.me_lut_max) : pm_value(cnt, total);
                     if (a.rows.counts)
                         for (int k = 0; k < 16; k++) a.rows.counts[(size_t)r * 16 + k] = cnt[k];
+                    if (a.kind == 2) {
+                        const int64_t r2 = out0b + n_rows;
+                        a.rows_b.tid[r2] = tid;
+                        a.rows_b.p1[r2] = pos;
+                        a.rows_b.p2[r2] = key.a - off;
+                        a.rows_b.p3[r2] = key.b - off;
+                        a.rows_b.p4[r2] = key.c - off;
+                        a.rows_b.value[r2] = me_value(cnt, total, a.me_lut, a.me_lut_max);
+                        if (a.rows_b.counts)
+                            for (int k = 0; k < 16; k++) a.rows_b.counts[(size_t)r2 * 16 + k] = cnt[k];
+                    }
                 }
                 n_rows++;
             }
@@ -489,12 +503,13 @@ int launch_quartet_count(const ReadsView& rv, const int32_t* site_pos, int64_t C
 
 int launch_quartet_emit(const ReadsView& rv, const int32_t* site_pos, int64_t C, const RegionScalars* sc,
                         mth_quartet_params prm, int kind, const uint8_t* mixed, const uint32_t* rowoff, const float* me_lut,
-                        int me_lut_max, ContigTable ct, QuartetRowsDev rows, int64_t row_base, cudaStream_t s) {
+                        int me_lut_max, ContigTable ct, QuartetRowsDev rows, int64_t row_base, QuartetRowsDev rows_b, int64_t row_base_b,
+                        cudaStream_t s) {
     if (C <= 0) return 0;
     QuartetArgs a;
     memset(&a, 0, sizeof(a));
     a.rv = rv; a.site_pos = site_pos; a.C = C; a.sc = sc; a.prm = prm; a.kind = kind; a.rowoff = rowoff; a.mixed = mixed;
-    a.me_lut = me_lut; a.me_lut_max = me_lut_max; a.ct = ct; a.rows = rows; a.row_base = row_base;
+    a.me_lut = me_lut; a.me_lut_max = me_lut_max; a.ct = ct; a.rows = rows; a.row_base = row_base; a.rows_b = rows_b; a.row_base_b = row_base_b;
     k_quartet<true><<<gather_grid(C), GATHER_BLOCK, 0, s>>>(a);
     return 1;
 }

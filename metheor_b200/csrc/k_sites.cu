@@ -164,4 +164,18 @@ int launch_exclusive_scan_u32(uint32_t* a, int64_t n, uint32_t* scratch, unsigne
     return 3;
 }
 
+__global__ void k_count_flags(const uint8_t* __restrict__ flags, int64_t n, unsigned long long* __restrict__ total) {
+    unsigned int c = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) c += flags[i] ? 1u : 0u;
+    c = __reduce_add_sync(FULL, c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(total, (unsigned long long)c);
+}
+int launch_count_flags(const uint8_t* flags, int64_t n, unsigned long long* total, cudaStream_t s) {
+    if (n <= 0) return 0;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_count_flags<<<(unsigned)blocks, 256, 0, s>>>(flags, n, total);
+    return 1;
+}
+
 }  // namespace mth

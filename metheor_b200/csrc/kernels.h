@@ -87,6 +87,7 @@ int launch_mhl_site(const ReadsView& rv, const int32_t* site_pos, int64_t C, con
 int launch_site_emit(const float* value, const uint32_t* rowoff, uint64_t n_rows_region, const int32_t* site_pos,
                      int64_t C, ContigTable ct, SiteRowsDev rows, int64_t row_base, cudaStream_t s);
 int gather_grid(int64_t C);  // grid size for the warp-per-site kernels
+int launch_count_flags(const uint8_t* flags, int64_t n, unsigned long long* total, cudaStream_t s);  // *total += #non-zero bytes
 
 // ---- PM / ME (k_quartet.cu) -----------------------------------------------------------------
 struct QuartetRowsDev { int32_t* tid; int32_t* p1; int32_t* p2; int32_t* p3; int32_t* p4; float* value; uint32_t* counts; };
@@ -112,10 +113,11 @@ int launch_quartet_canon_emit(const uint32_t* qcnt, const uint8_t* mixed, const 
 // both gather passes to the sites it flags (the others keep what the canonical kernels wrote).
 int launch_quartet_count(const ReadsView& rv, const int32_t* site_pos, int64_t C, const RegionScalars* sc,
                          mth_quartet_params prm, const uint8_t* mixed, uint32_t* rowcnt, cudaStream_t s);
-// pass 2: write the rows (sorted by key within a site) at rowoff[s]; kind 0 = PM, 1 = ME
+// pass 2: write the rows (sorted by key within a site) at rowoff[s]; kind 0 = PM, 1 = ME, 2 = PM into rows AND ME into rows_b
 int launch_quartet_emit(const ReadsView& rv, const int32_t* site_pos, int64_t C, const RegionScalars* sc,
                         mth_quartet_params prm, int kind, const uint8_t* mixed, const uint32_t* rowoff, const float* me_lut,
-                        int me_lut_max, ContigTable ct, QuartetRowsDev rows, int64_t row_base, cudaStream_t s);
+                        int me_lut_max, ContigTable ct, QuartetRowsDev rows, int64_t row_base, QuartetRowsDev rows_b, int64_t row_base_b,
+                        cudaStream_t s);
 
 // ---- LPMD --pairs (k_pairs.cu) ----------------------------------------------------------------
 struct PairRowsDev { int32_t* tid; int32_t* pos1; int32_t* pos2; float* lpmd; int32_t* n_conc; int32_t* n_disc; };

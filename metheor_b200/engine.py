@@ -220,7 +220,7 @@ class Context:
         s = Stats()
         self._check(self._L.mth_get_stats(self._h, C.byref(s)))
         d = {k: getattr(s, k) for k in ("n_reads", "n_cpg", "n_sites", "n_regions", "kernel_launches", "h2d_bytes",
-                                         "d2h_bytes", "fdrp_pair_ops", "max_ref_span", "pdr_path")}
+                                         "d2h_bytes", "fdrp_pair_ops", "fallback_sites_mhl", "fallback_sites_fdrp", "max_ref_span", "pdr_path")}
         d["kernels"] = {s.kernel[i].name.decode(): dict(launches=s.kernel[i].launches, ms=s.kernel[i].ms)
                         for i in range(s.n_kernel_stats)}
         return d

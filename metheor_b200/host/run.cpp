@@ -361,7 +361,8 @@ std::vector<Run> owned_runs(const std::vector<std::unique_ptr<Gpu>>& gpus, const
             return a;
         };
         for (const Interval& iv : gpus[(size_t)g]->own) {
-            const int64_t a = lower(iv.tid, iv.lo), b = lower(iv.tid, iv.hi);
+            // a reverse-strand read at position 0 calls the site at -1 (readutil.rs:338): it belongs to the contig's first interval
+            const int64_t a = lower(iv.tid, iv.lo == 0 ? -1 : iv.lo), b = lower(iv.tid, iv.hi);
             if (b > a) runs.push_back(Run{g, a, b, iv.tid, iv.lo});
         }
     }

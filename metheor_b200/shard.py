@@ -93,7 +93,7 @@ def owned_rows(rows, intervals, pos_key="pos"):
     tid, pos = np.asarray(rows["tid"]), np.asarray(rows[pos_key])
     keep = np.zeros(len(tid), bool)
     for t, lo, hi in intervals:
-        keep |= (tid == t) & (pos >= lo) & (pos < hi)
+        keep |= (tid == t) & (pos >= (lo if lo > 0 else -1)) & (pos < hi)  # a reverse read at 0 calls site -1 (readutil.rs:338)
     out = {}
     for k, v in rows.items():
         out[k] = v[keep] if isinstance(v, np.ndarray) and len(v) == len(keep) else v
