@@ -210,7 +210,7 @@ def kernel_bytes(k, measures, R, I, C, Q):
         return 24 * R + 4 * I + 16 * C
     if k in ("k_pm_scatter", "k_me_scatter"):
         return 5 * I + 64 * C                     # cpg_pos + flag byte per call, one 16-bin u32 histogram per site
-    if k in ("k_pm_count", "k_me_count", "k_pm_emit", "k_me_emit"):
+    if k in ("k_pm_count", "k_me_count", "k_pm_emit", "k_me_emit", "k_pm_me_emit", "k_pm_hist", "k_me_hist"):
         return 64 * C + 24 * Q
     return None
 

@@ -12,12 +12,15 @@
 // What does not fit — tiles with more than FT_RCAP reads, calls further than 32 sites from the tile (dense islands),
 // max_depth > 64 — is flagged in `fallback` and done by k_fdrp afterwards (same results).  Two instances differ only in how
 // many reads a tile may stage: CpG-dense contigs (chr19-like) need ~700 per 64 sites at 30x, whole-genome density ~1500.
+#include <stdlib.h>
+#include <string.h>
+
 #include "gather.cuh"
 #include "kernels.h"
 
 namespace mth {
 
-constexpr int FT_SITES = 64;       // sites per CTA
+constexpr int FT_SITES = 64;       // sites per CTA (dense instance); the sparse instances take 32 or 64
 constexpr int FT_THREADS = 256;
 constexpr int FT_WARPS = FT_THREADS / 32;
 constexpr int FT_RCAP = 1024;      // reads staged per tile (dense instance: chr19-like CpG density, ~700 reads per 64 sites at 30x)
@@ -41,7 +44,7 @@ struct FtSmem {
     int nreads, bad;
 };
 
-template <int RCAP>
+template <int SITES, int RCAP>
 __global__ void __launch_bounds__(FT_THREADS, RCAP <= 1024 ? 3 : 2) k_fdrp_tile(ReadsView rv, const int32_t* __restrict__ site_pos, int64_t C,
                                                              const unsigned long long* __restrict__ bitmap, int64_t n_words,
                                                              const uint32_t* __restrict__ word_prefix,
@@ -54,13 +57,13 @@ __global__ void __launch_bounds__(FT_THREADS, RCAP <= 1024 ? 3 : 2) k_fdrp_tile(
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int32_t lmax = scal->lmax;
     const uint32_t D = prm.max_depth;
-    const int64_t n_tiles = (C + FT_SITES - 1) / FT_SITES;
+    const int64_t n_tiles = (C + SITES - 1) / SITES;
     uint16_t* pile = sh.pile[warp];
     unsigned long long pair_ops = 0;  // per warp, flushed with one atomic at the end
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t s0 = tile * FT_SITES;
-        const int ns = (int)min((int64_t)FT_SITES, C - s0);
+        const int64_t s0 = tile * SITES;
+        const int ns = (int)min((int64_t)SITES, C - s0);
         __syncthreads();  // previous tile fully consumed
         const int32_t p_first = site_pos[s0], p_last = site_pos[s0 + ns - 1];
         // window of the site bitmap for rank lookups: every call of a tile read lies in [p_first - lmax, p_last + lmax]
@@ -144,64 +147,49 @@ __global__ void __launch_bounds__(FT_THREADS, RCAP <= 1024 ? 3 : 2) k_fdrp_tile(
             bool have = false;
             const bool want_q = quant != 0, want_d = quant != 1;
 
-            // All pairs (i < j) of the pile in lexicographic order (itertools combinations(2), fdrp.rs:128), ROW-WISE: every lane
-            // keeps the masks of "its" pile read j = lane (and lane + 32 for piles deeper than 32) in registers; row i is
-            // broadcast from shared memory (uniform addresses: no bank conflicts) and lane j evaluates the pair (i, j) when
-            // j > i.  Within row i the lanes ARE in ascending j, so qFDRP's ordered f32 sum is a fold over the lanes of the
-            // row's ballot — the same order of additions as the reference (qfdrp.rs:141-153).
+            // All pairs (i < j) of the pile, 32 per step in lexicographic order (itertools combinations(2), fdrp.rs:128).
+            // (A row-wise form — pile reads in registers, row i broadcast from shared memory — was measured slower: 143 ms
+            // against 119 ms for FDRP on the whole-genome workload, twice as slow for qFDRP: 30 short rows instead of 12 full
+            // steps; profiles/R2_summary.md.)
             auto evaluate = [&](uint32_t n) {
-                pair_ops += (uint64_t)n * (n - 1) / 2;
-                unsigned long long jc0[2], jc1[2], jm0[2], jm1[2];
-                int32_t js[2], je[2];
-                uint32_t ju[2];
-#pragma unroll
-                for (int b = 0; b < 2; b++) {
-                    const uint32_t j = (uint32_t)(b * 32 + lane);
-                    jc0[b] = jc1[b] = jm0[b] = jm1[b] = 0ull;
-                    js[b] = 0x3fffffff; je[b] = -0x3fffffff; ju[b] = 255u;  // lanes beyond the pile: overlap far below zero
-                    if (j < n) {
-                        const int rj = pile[j];
-                        jc0[b] = sh.cm[rj][0]; jc1[b] = sh.cm[rj][1]; jm0[b] = sh.mm[rj][0]; jm1[b] = sh.mm[rj][1];
-                        js[b] = sh.start[rj]; je[b] = sh.end[rj]; ju[b] = sh.ub[rj];
-                    }
-                }
+                const uint64_t P = (uint64_t)n * (n - 1) / 2;
+                pair_ops += P;
+                uint32_t i = 0, jj = 1 + lane;  // this lane's pair (i, jj): pair index = lane, then += 32
+                while (i < n && jj >= n) { jj = jj - n + i + 2; i++; }
                 float acc = 0.f;
                 uint32_t disc = 0;
-                for (uint32_t i = 0; i + 1 < n; i++) {
-                    const int ri = pile[i];
-                    const unsigned long long ic0 = sh.cm[ri][0], ic1 = sh.cm[ri][1], im0 = sh.mm[ri][0], im1 = sh.mm[ri][1];
-                    const int32_t is = sh.start[ri], ie = sh.end[ri];
-                    const uint32_t iu = sh.ub[ri];
-#pragma unroll
-                    for (int b = 0; b < 2; b++) {
-                        if (b * 32 + 31 <= (int)i || (uint32_t)(b * 32) >= n) continue;  // warp-uniform: no j > i in this half
-                        const uint32_t j = (uint32_t)(b * 32 + lane);
-                        const int32_t ov = min(ie, je[b]) - max(is, js[b]) + 1;  // fdrp.rs:97-107 (lanes beyond the pile: negative)
-                        float term = 0.f;
-                        if (j > i && j < n && ov >= prm.min_overlap && ov > 0) {  // fdrp.rs:133-136 (without overlap: ham = 0, adds nothing)
-                            const unsigned long long b0 = ic0 & jc0[b], b1 = ic1 & jc1[b];
+                for (uint64_t t0 = 0; t0 < P; t0 += 32) {
+                    float term = 0.f;
+                    if (t0 + lane < P) {
+                        const int ri = pile[i], rj = pile[jj];
+                        const int32_t ov = min(sh.end[ri], sh.end[rj]) - max(sh.start[ri], sh.start[rj]) + 1;  // fdrp.rs:97-107
+                        if (ov >= prm.min_overlap && ov > 0) {  // fdrp.rs:133-136 (without overlap: ham = 0, adds nothing)
+                            const unsigned long long b0 = sh.cm[ri][0] & sh.cm[rj][0], b1 = sh.cm[ri][1] & sh.cm[rj][1];
                             unsigned long long v0 = b0, v1 = b1;  // both called AND both covered: drop the uncovered calls
-                            if ((iu & ju[b]) != 255u) {           // rare: a reverse-strand call at start - 1 (fdrp.rs:65-72)
-                                const uint32_t uj = ju[b];
-                                if (iu < 64u) v0 &= ~(1ull << iu); else if (iu < 128u) v1 &= ~(1ull << (iu - 64u));
+                            const uint32_t ui = sh.ub[ri], uj = sh.ub[rj];
+                            if ((ui & uj) != 255u) {  // rare: a reverse-strand call at start - 1 (fdrp.rs:65-72)
+                                if (ui < 64u) v0 &= ~(1ull << ui); else if (ui < 128u) v1 &= ~(1ull << (ui - 64u));
                                 if (uj < 64u) v0 &= ~(1ull << uj); else if (uj < 128u) v1 &= ~(1ull << (uj - 64u));
                             }
-                            const uint32_t ham = (uint32_t)__popcll(v0 & (im0 ^ jm0[b])) + (uint32_t)__popcll(v1 & (im1 ^ jm1[b]));  // fdrp.rs:109-122
+                            const uint32_t ham = (uint32_t)__popcll(v0 & (sh.mm[ri][0] ^ sh.mm[rj][0])) +
+                                                 (uint32_t)__popcll(v1 & (sh.mm[ri][1] ^ sh.mm[rj][1]));  // fdrp.rs:109-122
                             if (want_q && ham) term = __fdiv_rn((float)ham, (float)(__popcll(b0) + __popcll(b1)));  // qfdrp.rs:152
                             if (want_d) disc += ham ? 1u : 0u;                                                       // fdrp.rs:138-140
                         }
-                        if (want_q) {  // sequential f32 accumulation in pair order: lanes ascending = j ascending
-                            uint32_t nz = __ballot_sync(FULL, term != 0.f);
-                            if (__popc(nz) > 10) {
-                                // dense row: fold all 32 lanes in order, branch-free (x + 0.0f == x exactly, acc >= 0)
+                        jj += 32;
+                        while (i < n && jj >= n) { jj = jj - n + i + 2; i++; }
+                    }
+                    if (want_q) {  // sequential f32 accumulation in pair order
+                        uint32_t nz = __ballot_sync(FULL, term != 0.f);
+                        if (__popc(nz) > 8) {
+                            // dense step: fold all 32 lanes in order, branch-free (x + 0.0f == x exactly, acc >= 0)
 #pragma unroll
-                                for (int src = 0; src < 32; src++) acc = __fadd_rn(acc, __shfl_sync(FULL, term, src));
-                            } else {
-                                while (nz) {
-                                    const int src = __ffs(nz) - 1;
-                                    acc = __fadd_rn(acc, __shfl_sync(FULL, term, src));
-                                    nz &= nz - 1;
-                                }
+                            for (int src = 0; src < 32; src++) acc = __fadd_rn(acc, __shfl_sync(FULL, term, src));
+                        } else {
+                            while (nz) {
+                                const int src = __ffs(nz) - 1;
+                                acc = __fadd_rn(acc, __shfl_sync(FULL, term, src));
+                                nz &= nz - 1;
                             }
                         }
                     }
@@ -292,20 +280,29 @@ int launch_fdrp_tile(const ReadsView& rv, const int32_t* site_pos, int64_t C, co
                      cudaStream_t s) {
     if (C <= 0) return 0;
     static bool attr_set = false;
+    static int force = 0;  // METHEOR_FDRP_TILE = dense | sparse32 | sparse64: kernel-variant experiments (profiles/)
     if (!attr_set) {
-        cudaFuncSetAttribute(k_fdrp_tile<FT_RCAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FtSmem<FT_RCAP>));
-        cudaFuncSetAttribute(k_fdrp_tile<FT_RCAP_SPARSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FtSmem<FT_RCAP_SPARSE>));
+        cudaFuncSetAttribute(k_fdrp_tile<64, FT_RCAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FtSmem<FT_RCAP>));
+        cudaFuncSetAttribute(k_fdrp_tile<32, FT_RCAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FtSmem<FT_RCAP>));
+        cudaFuncSetAttribute(k_fdrp_tile<64, FT_RCAP_SPARSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FtSmem<FT_RCAP_SPARSE>));
+        const char* e = getenv("METHEOR_FDRP_TILE");
+        if (e) force = !strcmp(e, "dense") ? 1 : !strcmp(e, "sparse32") ? 2 : !strcmp(e, "sparse64") ? 3 : 0;
         attr_set = true;
     }
-    int64_t tiles = (C + FT_SITES - 1) / FT_SITES;
+    // reads a tile has to stage ~ sites x reads per site gap: pick the instance whose capacity covers it with some room
+    const double per_site = (double)rv.R / (double)C;
+    int variant = force ? force : (64.0 * per_site * 1.3 <= (double)FT_RCAP ? 1 : 2);
+    const int sites = variant == 2 ? 32 : 64;
+    int64_t tiles = (C + sites - 1) / sites;
     if (tiles > 148 * 48) tiles = 148 * 48;
-    // reads a tile has to stage ~ FT_SITES x reads per site gap: pick the instance whose capacity covers it with some room
-    const double est = (double)FT_SITES * (double)rv.R / (double)C;
-    if (est * 1.3 <= (double)FT_RCAP)
-        k_fdrp_tile<FT_RCAP><<<(unsigned)tiles, FT_THREADS, sizeof(FtSmem<FT_RCAP>), s>>>(rv, site_pos, C, bitmap, n_words, word_prefix, sc, prm,
-                                                                                       quantitative, seed, ct, value, rowcnt, value_q, rowcnt_q, fallback);
+    if (variant == 1)
+        k_fdrp_tile<64, FT_RCAP><<<(unsigned)tiles, FT_THREADS, sizeof(FtSmem<FT_RCAP>), s>>>(rv, site_pos, C, bitmap, n_words, word_prefix, sc, prm,
+                                                                                           quantitative, seed, ct, value, rowcnt, value_q, rowcnt_q, fallback);
+    else if (variant == 2)
+        k_fdrp_tile<32, FT_RCAP><<<(unsigned)tiles, FT_THREADS, sizeof(FtSmem<FT_RCAP>), s>>>(rv, site_pos, C, bitmap, n_words, word_prefix, sc, prm,
+                                                                                           quantitative, seed, ct, value, rowcnt, value_q, rowcnt_q, fallback);
     else
-        k_fdrp_tile<FT_RCAP_SPARSE><<<(unsigned)tiles, FT_THREADS, sizeof(FtSmem<FT_RCAP_SPARSE>), s>>>(
+        k_fdrp_tile<64, FT_RCAP_SPARSE><<<(unsigned)tiles, FT_THREADS, sizeof(FtSmem<FT_RCAP_SPARSE>), s>>>(
             rv, site_pos, C, bitmap, n_words, word_prefix, sc, prm, quantitative, seed, ct, value, rowcnt, value_q, rowcnt_q, fallback);
     return 1;
 }

@@ -11,6 +11,9 @@
 //
 // What does not fit — tiles with more than MS_RCAP reads or MS_CCAP calls, reads with more than MS_L calls (dense CpG
 // islands), > 64 calls per read — is flagged in `fallback` and done by the warp-per-site kernel afterwards.
+#include <stdlib.h>
+#include <string.h>
+
 #include "gather.cuh"
 #include "kernels.h"
 
@@ -176,7 +179,12 @@ int launch_mhl_site(const ReadsView& rv, const int32_t* site_pos, int64_t C, con
     if (tiles > 148 * 64) tiles = 148 * 64;
     // reads a tile has to stage ~ MS_SITES x reads per site gap: pick the instance whose capacity covers it with some room
     const double est = (double)MS_SITES * (double)rv.R / (double)C;
-    if (est * 1.3 <= (double)MS_RCAP)
+    static int force = -1;  // METHEOR_MHL_TILE = dense | sparse: kernel-variant experiments (profiles/)
+    if (force < 0) {
+        const char* e = getenv("METHEOR_MHL_TILE");
+        force = e ? (!strcmp(e, "dense") ? 1 : !strcmp(e, "sparse") ? 2 : 0) : 0;
+    }
+    if (force == 1 || (force == 0 && est * 1.3 <= (double)MS_RCAP))
         k_mhl_site<MS_RCAP, MS_CCAP><<<(unsigned)tiles, MS_SITES, sizeof(Dense), s>>>(rv, site_pos, C, sc, prm, value, rowcnt, fallback);
     else
         k_mhl_site<MS_RCAP_SPARSE, MS_CCAP_SPARSE><<<(unsigned)tiles, MS_SITES, sizeof(Sparse), s>>>(rv, site_pos, C, sc, prm, value, rowcnt, fallback);

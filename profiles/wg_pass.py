@@ -20,6 +20,7 @@ ap.add_argument("--coverage", type=float, default=30.0)
 ap.add_argument("--passes", type=int, default=1)
 ap.add_argument("--warm", type=int, default=0)
 ap.add_argument("--sidecar", default="")
+ap.add_argument("--profile", action="store_true", help="per-kernel CUDA-event times (MTH_FLAG_PROFILE) of the last pass")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 contigs = G.genome(a.scale)
@@ -44,7 +45,7 @@ for name in a.sets.split(","):
         batches, rl = [c19], [X.CONTIG_LEN]
     else:
         batches, rl = wg, ref_len
-    ctx = engine.Context(engine.default_params(measures, flags=engine.FLAG_KEEP_ON_DEVICE), rl, device=0)
+    ctx = engine.Context(engine.default_params(measures, flags=engine.FLAG_KEEP_ON_DEVICE | (engine.FLAG_PROFILE if a.profile else 0)), rl, device=0)
     launches = 0
     t0 = time.perf_counter()
     for it in range(a.warm + a.passes):
@@ -57,7 +58,8 @@ for name in a.sets.split(","):
     side["sets"].append({"name": name, "measures": list(measures), "passes": a.warm + a.passes, "engine_kernel_launches": int(launches),
                          "reads": int(st["n_reads"]), "calls": int(st["n_cpg"]), "sites": int(st["n_sites"]),
                          "rows": {m: int(res[m]["n"]) for m in res if "n" in res[m]}, "pair_ops": int(st["fdrp_pair_ops"]),
-                         "seconds": time.perf_counter() - t0})
+                         "seconds": time.perf_counter() - t0, "fallback_sites": [int(st["fallback_sites_mhl"]), int(st["fallback_sites_fdrp"])],
+                         "kernels_ms": {k: round(v["ms"], 3) for k, v in st["kernels"].items()} if a.profile else None})
     ctx.close()
 print(json.dumps(side))
 if a.sidecar:
