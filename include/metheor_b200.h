@@ -232,6 +232,13 @@ int mth_submit(mth_ctx* ctx, const mth_batch* batch);
 int mth_reserve(mth_ctx* ctx, int64_t n_reads, int64_t n_cpg);
 /* Same as mth_submit for the compact wire format (host or device memory). */
 int mth_submit_compact(mth_ctx* ctx, const mth_batch_compact* batch);
+/* `--cpg-set` on the device (replaces get_target_cpgs + filter_isin, readutil.rs:347-374 and :87-95): the host hands over the BED
+ * file's (tid, pos) pairs once, before the first batch, and ships its batches UNFILTERED; the engine drops every call that is not
+ * in the set before anything else is computed from a read — exactly where the reference filters.  Entries may come in any order
+ * and may repeat.  mth_clear_cpg_set returns to unfiltered operation.  Both are only legal before the first submit / after
+ * mth_reset (MTH_ERR_STATE otherwise). */
+int mth_set_cpg_set(mth_ctx* ctx, int64_t n, const int32_t* tid, const int32_t* pos);
+int mth_clear_cpg_set(mth_ctx* ctx);
 /* Host reads that carried no CpG call were dropped before submit: only LPMD's n_read counts them (lpmd.rs:176). */
 int mth_add_skipped_reads(mth_ctx* ctx, int64_t n_reads, int64_t n_reads_mapq_ok);
 /* Closes the input, runs the measure kernels, brings the rows back (unless KEEP_ON_DEVICE) and synchronises. */

@@ -103,7 +103,7 @@ EXPORTS = ["mth_params_default", "mth_ctx_create", "mth_ctx_destroy", "mth_set_s
            "mth_reset", "mth_sync", "mth_sync_copies", "mth_get_stats", "mth_last_error", "mth_host_alloc", "mth_host_free",
            "mth_device_count", "mth_version", "mth_reservoir_draw", "mth_genome_create", "mth_genome_set_contig", "mth_tag",
            "mth_genome_destroy", "mth_genome_last_error", "mth_genome_last_kernel_ms", "mth_comm_unique_id", "mth_comm_init_rank",
-           "mth_comm_init_all", "mth_allreduce", "mth_allreduce_group", "mth_comm_destroy", "mth_comm_n_ranks"]
+           "mth_comm_init_all", "mth_allreduce", "mth_allreduce_group", "mth_comm_destroy", "mth_comm_n_ranks", "mth_set_cpg_set", "mth_clear_cpg_set"]
 
 
 def build(force=False):
@@ -148,6 +148,8 @@ def lib():
     L.mth_device_count.argtypes = []; L.mth_device_count.restype = C.c_int
     L.mth_version.argtypes = []; L.mth_version.restype = C.c_char_p
     L.mth_reservoir_draw.argtypes = [u64, i32, i32, u32]; L.mth_reservoir_draw.restype = u32
+    L.mth_set_cpg_set.argtypes = [vp, i64, vp, vp]; L.mth_set_cpg_set.restype = C.c_int
+    L.mth_clear_cpg_set.argtypes = [vp]; L.mth_clear_cpg_set.restype = C.c_int
     L.mth_comm_unique_id.argtypes = [vp]; L.mth_comm_unique_id.restype = C.c_int
     L.mth_comm_init_rank.argtypes = [vp, C.c_int, C.c_int, vp]; L.mth_comm_init_rank.restype = C.c_int
     L.mth_comm_init_all.argtypes = [P(vp), C.c_int]; L.mth_comm_init_all.restype = C.c_int

@@ -105,6 +105,13 @@ struct mth_ctx {
     int64_t lpmd_total_host[4] = {0, 0, 0, 0};
     int me_lut_max = 0;
 
+    // --cpg-set on the device (k_cpgset.cu): the set as per-contig sorted position lists, the region's set bitmap and scratch
+    bool has_set = false;
+    std::vector<int64_t> set_off;   // n_ref + 1 offsets into set_dev
+    DevBuf set_dev, set_bitmap, set_kept, set_scan, set_total, set_pos_tmp, set_rel_tmp;
+    HostBuf h_set_total;
+    size_t set_words_valid = 0;
+
     ncclComm_t comm = nullptr;  // multi-GPU: joins this context with its peers (mth_comm_init_*)
     int comm_ranks = 0;
 
@@ -262,6 +269,14 @@ static int add_contig(mth_ctx* c, int32_t tid, int32_t lin_off) {
     TRY(dev_reserve(c, c->bitmap, w1 * 8, c->bitmap_words_valid * 8));
     CUDA_TRY(c, cudaMemsetAsync((char*)c->bitmap.p + w0 * 8, 0, (w1 - w0) * 8, c->compute));
     c->bitmap_words_valid = w1;
+    if (c->has_set) {  // the contig's part of the CpG-set bitmap (same coordinate as the site bitmap)
+        TRY(dev_reserve(c, c->set_bitmap, w1 * 8, c->set_words_valid * 8));
+        CUDA_TRY(c, cudaMemsetAsync((char*)c->set_bitmap.p + w0 * 8, 0, (w1 - w0) * 8, c->compute));
+        c->set_words_valid = w1;
+        const int64_t a = c->set_off[(size_t)tid], b = c->set_off[(size_t)tid + 1];
+        c->stats.kernel_launches += launch_cpgset_mark((const int32_t*)c->set_dev.p + a, b - a, lin_off, (int32_t)c->ref_len[tid],
+                                                       (unsigned long long*)c->set_bitmap.p, c->compute);
+    }
     return MTH_OK;
 }
 
@@ -273,6 +288,7 @@ static int begin_region(mth_ctx* c, int32_t tid) {
     c->reg_lin_off.clear();
     c->reg_tid.clear();
     c->bitmap_words_valid = 0;
+    c->set_words_valid = 0;
     TRY(dev_reserve(c, c->scalars, sizeof(RegionScalars), 0));
     RegionScalars init;
     memset(&init, 0, sizeof(init));
@@ -424,8 +440,73 @@ static int run_ingest(mth_ctx* c, int32_t tid, int64_t r0, int64_t n, int64_t i0
     return MTH_OK;
 }
 
+// --cpg-set: drop the calls of reads [r0, r0 + n) (calls [i0, i0 + n_cpg) of the arena) that are not in the set, compacting the
+// batch's slice of the call arrays; *kept = calls left.  Synchronises the compute stream (the host must know where the next
+// batch goes).
+static int filter_batch(mth_ctx* c, int64_t r0, int64_t n, int64_t i0, int64_t n_cpg, int64_t* kept) {
+    *kept = n_cpg;
+    if (!c->has_set || n <= 0) return MTH_OK;
+    const bool lp = (c->prm.measures & MTH_LPMD) != 0;
+    TRY(dev_reserve(c, c->set_kept, (size_t)n * 4 + 64, 0));
+    TRY(dev_reserve(c, c->set_scan, (size_t)((n + 2047) / 2048 + 2) * 4, 0));
+    TRY(dev_reserve(c, c->set_total, 16, 0));
+    TRY(dev_reserve(c, c->set_pos_tmp, (size_t)n_cpg * 4 + 64, 0));
+    if (lp) TRY(dev_reserve(c, c->set_rel_tmp, (size_t)n_cpg * 2 + 64, 0));
+    TRY(host_reserve(c, c->h_set_total, 16));
+    cudaStream_t s = c->compute;
+    {
+        ProfScope ps(c, "k_cpgset_filter");
+        ps.add(launch_cpgset_filter(r0, n, i0, (uint32_t*)c->a_off.p, (const int32_t*)c->a_pos.p, lp ? (const uint16_t*)c->a_rel.p : nullptr,
+                                    (uint64_t*)c->a_meth.p, c->has_meth_off ? (const uint32_t*)c->a_moff.p : nullptr,
+                                    (const unsigned long long*)c->set_bitmap.p, (int64_t)c->set_words_valid, (uint32_t*)c->set_kept.p,
+                                    (uint32_t*)c->set_scan.p, (unsigned long long*)c->set_total.p, (int32_t*)c->set_pos_tmp.p,
+                                    lp ? (uint16_t*)c->set_rel_tmp.p : nullptr, s));
+    }
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_set_total.p, c->set_total.p, 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(c, cudaStreamSynchronize(s));
+    const int64_t k = (int64_t) * (unsigned long long*)c->h_set_total.p;
+    if (k > n_cpg) return fail(c, MTH_ERR_INVALID, "cpg_off inconsistent with n_cpg");
+    if (k) {
+        CUDA_TRY(c, cudaMemcpyAsync((int32_t*)c->a_pos.p + i0, c->set_pos_tmp.p, (size_t)k * 4, cudaMemcpyDeviceToDevice, s));
+        if (lp) CUDA_TRY(c, cudaMemcpyAsync((uint16_t*)c->a_rel.p + i0, c->set_rel_tmp.p, (size_t)k * 2, cudaMemcpyDeviceToDevice, s));
+    }
+    *kept = k;
+    return MTH_OK;
+}
+
 // ---- C ABI -----------------------------------------------------------------------------------------
 extern "C" {
+
+int mth_set_cpg_set(mth_ctx* c, int64_t n, const int32_t* tid, const int32_t* pos) {
+    if (!c || n < 0 || (n && (!tid || !pos))) return MTH_ERR_INVALID;
+    if (c->region_active || c->stats.n_reads) return fail(c, MTH_ERR_STATE, "mth_set_cpg_set must be called before the first batch (after mth_reset)");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const size_t n_ref = c->ref_len.size();
+    std::vector<int64_t> cnt(n_ref + 1, 0);
+    for (int64_t i = 0; i < n; i++) {
+        if (tid[i] < 0 || (size_t)tid[i] >= n_ref) return fail(c, MTH_ERR_INVALID, "CpG set entry with a tid outside the reference list");
+        cnt[(size_t)tid[i] + 1]++;
+    }
+    for (size_t t = 0; t < n_ref; t++) cnt[t + 1] += cnt[t];
+    std::vector<int32_t> sorted((size_t)n);
+    {
+        std::vector<int64_t> at(cnt.begin(), cnt.end() - 1);
+        for (int64_t i = 0; i < n; i++) sorted[(size_t)at[(size_t)tid[i]]++] = pos[i];
+    }
+    c->set_off = cnt;
+    TRY(dev_reserve(c, c->set_dev, (size_t)n * 4 + 64, 0));
+    if (n) CUDA_TRY(c, cudaMemcpy(c->set_dev.p, sorted.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+    c->has_set = true;
+    return MTH_OK;
+}
+
+int mth_clear_cpg_set(mth_ctx* c) {
+    if (!c) return MTH_ERR_INVALID;
+    if (c->region_active || c->stats.n_reads) return fail(c, MTH_ERR_STATE, "mth_clear_cpg_set must be called before the first batch (after mth_reset)");
+    c->has_set = false;
+    c->set_off.clear();
+    return MTH_OK;
+}
 
 void mth_params_default(mth_params* p) {
     memset(p, 0, sizeof(*p));
@@ -508,7 +589,8 @@ int mth_ctx_destroy(mth_ctx* c) {
     cudaDeviceSynchronize();
     DevBuf* devs[] = {&c->a_start, &c->a_end, &c->a_meta, &c->a_off, &c->a_pos, &c->a_rel, &c->a_meth, &c->a_moff, &c->a_flags, &c->bitmap,
                       &c->word_prefix, &c->block_sums, &c->site_pos, &c->scalars, &c->totals, &c->ct_lin, &c->ct_tid, &c->cnt2,
-                      &c->scan_scratch, &c->fdrp_scratch, &c->me_lut, &c->lpmd_total};
+                      &c->scan_scratch, &c->fdrp_scratch, &c->me_lut, &c->lpmd_total, &c->set_dev, &c->set_bitmap, &c->set_kept, &c->set_scan,
+                      &c->set_total, &c->set_pos_tmp, &c->set_rel_tmp};
     for (DevBuf* b : devs) dev_free(*b);
     for (auto& set : c->stage)
         for (DevBuf& b : set) dev_free(b);
@@ -536,6 +618,7 @@ int mth_ctx_destroy(mth_ctx* c) {
     }
     host_free(c->h_scalars);
     host_free(c->h_totals);
+    host_free(c->h_set_total);
     for (auto& sp : c->spans) { cudaEventDestroy(sp.e0); cudaEventDestroy(sp.e1); }
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     mth_comm_destroy(c);
@@ -617,7 +700,7 @@ int mth_submit(mth_ctx* c, const mth_batch* b) {
     const int64_t r0 = c->R, i0 = c->I, w0 = c->W;
     // borrowed arrays are read in place; the TMA bulk copies of k_ingest need 16-byte aligned bases
     auto al16 = [](const void* p) { return ((uintptr_t)p & 15u) == 0; };
-    const bool can_borrow = b->mem_kind == 1 && r0 == 0 && lin_off == 0 && al16(b->cpg_pos) && al16(b->cpg_rel);
+    const bool can_borrow = b->mem_kind == 1 && r0 == 0 && lin_off == 0 && al16(b->cpg_pos) && al16(b->cpg_rel) && !c->has_set;
     const uint16_t* rel_dev = nullptr;
     if (can_borrow) {
         c->borrowed = true;
@@ -673,8 +756,13 @@ int mth_submit(mth_ctx* c, const mth_batch* b) {
     c->R = r0 + b->n_reads;
     c->I = i0 + b->n_cpg;
     c->W = w0 + bw;
+    int64_t n_kept = b->n_cpg;
+    if (c->has_set) {  // readutil.rs:87-95: the CpG-set filter comes before everything else
+        TRY(filter_batch(c, r0, b->n_reads, i0, b->n_cpg, &n_kept));
+        c->I = i0 + n_kept;
+    }
 
-    TRY(run_ingest(c, b->tid, r0, b->n_reads, i0, b->n_cpg, rel_dev));
+    TRY(run_ingest(c, b->tid, r0, b->n_reads, i0, n_kept, rel_dev));
     return MTH_OK;
 }
 
@@ -814,7 +902,12 @@ int mth_submit_compact(mth_ctx* c, const mth_batch_compact* b) {
         c->R = r0 + (int64_t)nR;
         c->I = i0 + nI;
         c->W = w0 + (int64_t)nR;
-        TRY(run_ingest(c, b->tid, r0, (int64_t)nR, i0, nI, lp ? (const uint16_t*)c->a_rel.p : nullptr));
+        int64_t n_kept = nI;
+        if (c->has_set) {
+            TRY(filter_batch(c, r0, (int64_t)nR, i0, nI, &n_kept));
+            c->I = i0 + n_kept;
+        }
+        TRY(run_ingest(c, b->tid, r0, (int64_t)nR, i0, n_kept, lp ? (const uint16_t*)c->a_rel.p : nullptr));
         x0 += nI;
         e0 += nE;
     }

@@ -51,6 +51,15 @@ struct ExpandArgs {
 int launch_expand(const ExpandArgs& a, unsigned long long* total_scratch, cudaStream_t s);
 int launch_scan_sums(uint32_t* sums, int64_t n, unsigned long long* total, cudaStream_t s);  // single block, in place
 
+// ---- --cpg-set on the device (k_cpgset.cu) ------------------------------------------------------
+// bits (lin_off + p + 1) of `bitmap` for the set positions p of one contig
+int launch_cpgset_mark(const int32_t* pos, int64_t n, int32_t lin_off, int32_t len, unsigned long long* bitmap, cudaStream_t s);
+// Drops the calls of reads [r0, r0 + n) (calls from i0 on) that are not in the set: methylation words squeezed in place, kept
+// positions / query indices written to pos_tmp / rel_tmp (batch-relative), cpg_off rewritten, *total = kept calls (device).
+int launch_cpgset_filter(int64_t r0, int64_t n, int64_t i0, uint32_t* off, const int32_t* pos, const uint16_t* rel, uint64_t* meth,
+                         const uint32_t* meth_off, const unsigned long long* set_bitmap, int64_t set_words, uint32_t* kept, uint32_t* scan_scratch,
+                         unsigned long long* total, int32_t* pos_tmp, uint16_t* rel_tmp, cudaStream_t s);
+
 // ---- site dictionary + scans (k_sites.cu) ---------------------------------------------------
 // phase 1: popcount per 1024-word block -> block_sums, scanned in place; total -> sc->n_sites
 int launch_sites_count(const unsigned long long* bitmap, int64_t n_words, uint32_t* block_sums, RegionScalars* sc,

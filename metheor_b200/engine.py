@@ -128,6 +128,14 @@ class Context:
         mb.mem_kind = 1 if dev else 0
         self._check(self._L.mth_submit_compact(self._h, C.byref(mb)))
 
+    def set_cpg_set(self, tid, pos):
+        """`--cpg-set` on the device: (tid, pos) pairs of the BED file; batches are then submitted unfiltered."""
+        t, p = np.ascontiguousarray(tid, np.int32), np.ascontiguousarray(pos, np.int32)
+        self._check(self._L.mth_set_cpg_set(self._h, len(t), t.ctypes.data, p.ctypes.data))
+
+    def clear_cpg_set(self):
+        self._check(self._L.mth_clear_cpg_set(self._h))
+
     def add_skipped_reads(self, n_reads, n_mapq_ok):
         self._check(self._L.mth_add_skipped_reads(self._h, n_reads, n_mapq_ok))
 
@@ -250,12 +258,14 @@ def allreduce_group(contexts):
     return [c.lpmd_refresh() for c in contexts]
 
 
-def run_batches(batches, ref_len, measures, device=0, flags=0, seed=0, compact=False, **overrides):
+def run_batches(batches, ref_len, measures, device=0, flags=0, seed=0, compact=False, cpg_set=None, **overrides):
     """Convenience: one context, submit every batch, finish.  -> (results dict, stats dict)
     compact: send the batches in the compact wire format (True), or alternate between the two formats ("mix")."""
     from .batch import to_compact
     ctx = Context(default_params(measures, flags=flags, seed=seed, **overrides), ref_len, device)
     try:
+        if cpg_set is not None:
+            ctx.set_cpg_set(*cpg_set)
         for k, b in enumerate(batches):
             if compact and (compact != "mix" or k % 2 == 0) and b["n_reads"] and \
                     np.diff(np.asarray(b["cpg_off"], np.int64)).max(initial=0) <= 64:

@@ -14,6 +14,7 @@
 #include <charconv>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <future>
 #include <memory>
 
@@ -489,7 +490,20 @@ void run(const mthh_options& o) {
     }
 
     DecodeOptions dopt;
-    dopt.cpg_set = o.cpg_set ? &cpg_set : nullptr;
+    // --cpg-set (readutil.rs:87-95, 347-374): the BED positions go to the engine once and the filter runs on the device,
+    // before anything else is computed from a read; the decoder ships unfiltered calls.  METHEOR_CPGSET_HOST=1 keeps the
+    // filter in the host decoder instead (kernel-variant experiments).
+    const bool set_on_host = o.cpg_set && getenv("METHEOR_CPGSET_HOST") != nullptr;
+    if (o.cpg_set && !set_on_host) {
+        std::vector<int32_t> st, sp;
+        for (size_t t = 0; t < cpg_set.by_tid.size(); t++)
+            for (int32_t p : cpg_set.by_tid[t]) { st.push_back((int32_t)t); sp.push_back(p); }
+        for (auto& gp : gpus) {
+            int rc = mth_set_cpg_set(gp->ctx, (int64_t)st.size(), st.data(), sp.data());
+            if (rc != MTH_OK) engine_fail(gp->ctx, rc, "mth_set_cpg_set");
+        }
+    }
+    dopt.cpg_set = set_on_host ? &cpg_set : nullptr;
     dopt.min_qual = o.min_qual;
     dopt.lpmd_order = o.measure == MTHH_LPMD;
     const bool want_rel = o.measure == MTHH_LPMD;

@@ -41,12 +41,15 @@ DEFAULTS = dict(pdr=dict(min_depth=10, min_cpgs=4, min_qual=10), mhl=dict(min_de
                 lpmd=dict(min_distance=2, max_distance=16, min_qual=10))
 
 
-def check_all(batches, ref_len, measures, seed=0, flags=0, compact=False, **overrides):
-    """Engine vs oracle, bit-exact, for every requested measure.  Returns (engine results, stats)."""
+def check_all(batches, ref_len, measures, seed=0, flags=0, compact=False, cpg_set=None, **overrides):
+    """Engine vs oracle, bit-exact, for every requested measure.  Returns (engine results, stats).
+    cpg_set = (tid array, pos array): the engine filters on the device (mth_set_cpg_set), the oracle with filter_isin."""
     prm = {m: dict(DEFAULTS[m], **overrides.get(m, {})) for m in measures}
-    res, stats = engine.run_batches(batches, ref_len, measures, flags=flags, seed=seed, compact=compact,
+    res, stats = engine.run_batches(batches, ref_len, measures, flags=flags, seed=seed, compact=compact, cpg_set=cpg_set,
                                     **{k: dict(v) for k, v in prm.items()})
     orc = Oracle.from_soa(**B.to_oracle_soa(batches))
+    if cpg_set is not None:
+        orc.set_cpg_set(*cpg_set)
     if "pdr" in measures:
         w = orc.pdr(**prm["pdr"])
         assert_site_rows(res["pdr"], w, "pdr", "pdr")

@@ -354,3 +354,55 @@ def test_pdr_flush_segment_is_replayed_on_hazard_sites_only():
     got = {int(p): (int(c), int(d)) for p, c, d in zip(r["pos"], r["n_conc"], r["n_disc"])}
     assert got[105] == (0, 1) and got[110] == (0, 1), got   # only B's segment survives (A's was flushed, then overwritten)
     assert got[313] == (1, 1)                               # T (discordant) + C
+
+
+def test_cpg_set_filter_on_the_device():
+    """--cpg-set as a device bitmap (mth_set_cpg_set; readutil.rs:87-95, 347-374): the host ships unfiltered calls, the engine
+    drops the ones outside the set before anything else — SoA, compact and dense batches, several batches and contigs, reads
+    that lose all their calls, reads with more than 64 calls."""
+    lens = [150_000, 90_000]
+    rng = np.random.default_rng(77)
+    batches, st, sp = [], [], []
+    for tid, L in enumerate(lens):
+        sites = synth.make_sites(500 + tid, L)
+        b = synth.make_reads(510 + tid, sites, L, 25.0, tid=tid, del_frac=0.1)
+        keep = sites[rng.random(len(sites)) < 0.55]
+        st.append(np.full(len(keep), tid, np.int32)); sp.append(keep.astype(np.int32))
+        cuts = [0, b["n_reads"] // 2, b["n_reads"]]
+        batches += [B.slice_reads(b, lo, hi) for lo, hi in zip(cuts[:-1], cuts[1:])]
+    cs = (np.concatenate(st), np.concatenate(sp))
+    kw = dict(pdr=dict(min_depth=4, min_cpgs=2), mhl=dict(min_depth=4, min_cpgs=2), fdrp=dict(min_depth=4), qfdrp=dict(min_depth=4),
+              pm=dict(min_depth=3), me=dict(min_depth=3), lpmd=dict(want_pairs=1))
+    for compact in (False, True, "dense", "mix"):
+        res, stt = parity.check_all(batches, lens, ALL, cpg_set=cs, compact=compact, **{k: dict(v) for k, v in kw.items()})
+        assert res["pdr"]["n"] > 100 and res["pm"]["n"] > 10 and stt["n_cpg"] < sum(b["n_cpg"] for b in batches)
+    # every call filtered out; an empty set; entries in random order with duplicates and positions nobody calls
+    parity.check_all(batches, lens, ALL, cpg_set=(np.zeros(1, np.int32), np.array([7], np.int32)))
+    parity.check_all(batches, lens, ("pdr", "lpmd", "pm"), cpg_set=(np.zeros(0, np.int32), np.zeros(0, np.int32)))
+    perm = rng.permutation(len(cs[0]))
+    parity.check_all(batches, lens, ("pdr", "mhl", "lpmd"), cpg_set=(np.concatenate([cs[0][perm], cs[0][:50]]), np.concatenate([cs[1][perm], cs[1][:50]])),
+                     pdr=dict(min_depth=4, min_cpgs=2), mhl=dict(min_depth=4, min_cpgs=2))
+    # more than 64 calls per read (meth_off): methylation words squeezed across word boundaries
+    sites = np.arange(10, 20_000, 2, dtype=np.int32)
+    b = synth.make_reads(517, sites, 20_000, 10.0, nocall=0.02)
+    keep = sites[rng.random(len(sites)) < 0.9]
+    parity.check_all([b], [20_000], ALL, cpg_set=(np.zeros(len(keep), np.int32), keep), pdr=dict(min_depth=4), mhl=dict(min_depth=4),
+                     fdrp=dict(min_depth=4), qfdrp=dict(min_depth=4), pm=dict(min_depth=4), me=dict(min_depth=4))
+
+
+def test_regions_with_host_soa_batches_and_mixed_quartets():
+    """Several regions fed through mth_submit with HOST SoA batches (the copy stream writes the next region's reads at arena
+    offset 0 while the previous region's PM/ME and --pairs emit kernels may still be reading it: the copy stream must wait)."""
+    lens = [1_400_000_000, 1_300_000_000, 1_200_000_000, 900_000]
+    batches = []
+    for tid, off in ((0, 1_399_000_000), (1, 5_000), (2, 700_000_000), (3, 100)):
+        sites = synth.make_sites(600 + tid, 200_000, mean_gap=12.0)
+        b = synth.make_reads(610 + tid, sites, 200_000, 20.0, tid=tid, nocall=0.05, del_frac=0.05)
+        for k in ("start", "end", "cpg_pos"):
+            b[k] = (b[k].astype(np.int64) + off).astype(np.int32)
+        cuts = [0, b["n_reads"] // 2, b["n_reads"]]
+        batches += [B.slice_reads(b, lo, hi) for lo, hi in zip(cuts[:-1], cuts[1:])]
+    for _ in range(3):
+        res, st = parity.check_all(batches, lens, ("pm", "me", "lpmd", "pdr"), pm=dict(min_depth=3), me=dict(min_depth=3),
+                                   pdr=dict(min_depth=4), lpmd=dict(want_pairs=1))
+        assert st["n_regions"] >= 3 and res["pm"]["n"] > 1000
