@@ -76,7 +76,8 @@ void mth_params_default(mth_params* p); /* reference defaults, measures = 0 */
 /* One batch of decoded reads of ONE contig, in file order (start ascending).  Replaces the per-record
  * BismarkRead of src/readutil.rs:15-21.  Arrays are caller-owned and must stay valid until the next
  * mth_finish()/mth_sync()/mth_sync_copies() returns (copies are asynchronous).  mem_kind: 0 = host memory (pinned preferred,
- * see mth_host_alloc), 1 = device memory on the context's GPU.
+ * see mth_host_alloc), 1 = device memory on the context's GPU that stays valid until mth_finish (the engine may read it in
+ * place), 2 = device memory that is only valid until mth_sync_copies (always copied).
  *   start/end : first / last aligned reference position of the read (readutil.rs:25-33)
  *   meta      : bits 0-7 mapq (pdr.rs:150), bit 8 = forward strand (informational), bit 9 = MTH_META_HALO
  *   cpg_off   : n_reads+1 prefix offsets into cpg_pos / cpg_rel, cpg_off[0] == 0
@@ -330,6 +331,46 @@ int mth_tag(mth_genome* g, const mth_tag_batch* batch, mth_tag_result* out);
 double mth_genome_last_kernel_ms(mth_genome* g);
 int mth_genome_destroy(mth_genome* g);
 const char* mth_genome_last_error(mth_genome* g); /* g may be NULL: last create error */
+
+/* ---------------------------------------------------------------------------------------------------------------------
+ * BGZF inflate + BAM record decode on the device.  Replaces, for BAM input on one GPU, the per-record host
+ * work of the reference: htslib's bgzf inflate + bam_read1 behind bam::Reader::records() (bamutil.rs:4-11) and BismarkRead::new
+ * + get_cpgs (readutil.rs:24-53, 323-345).  The host walks the BGZF member headers (18 bytes per <= 64 KiB member) and hands the
+ * COMPRESSED bytes over window by window; the decoder returns device-resident mth_batch runs (mem_kind 2, one per contig
+ * present in the window) for mth_submit.  mem_kind 2 = device memory that is only valid until the decoder's next window: the
+ * engine copies it (never borrows it); call mth_sync_copies before the next mth_bamdec_window.
+ * ------------------------------------------------------------------------------------------------------------------- */
+typedef struct mth_bamdec mth_bamdec;
+typedef struct {
+    uint64_t offset;   /* first byte of the member's raw DEFLATE payload within the compressed window */
+    uint32_t size;     /* payload bytes (member size - header - 8) */
+    uint32_t isize;    /* uncompressed size (the member's ISIZE field) */
+} mth_bgzf_member;
+typedef struct {
+    int64_t n_records;                    /* records that END in this window (a record cut by the window's end moves to the next) */
+    int64_t n_dropped, n_dropped_mapq_ok; /* records not shipped: no retained CpG call, or (lpmd_order) mapq < min_qual; LPMD still counts them */
+    int32_t n_runs;                       /* contig runs among the kept reads */
+    int32_t max_cpgs;
+    const mth_batch* runs;                /* n_runs batches in DEVICE memory (mem_kind 2), valid until the next window / destroy */
+    int64_t max_span;
+    int64_t bad_record;                   /* -1, else the first record (index within the window) without a usable XM:Z tag (readutil.rs:45-51) */
+    int32_t bad_is_corrupt;               /* that record does not parse at all */
+    int32_t reserved;
+    uint64_t uncompressed_bytes;
+    double ms_inflate, ms_boundaries, ms_decode; /* device time per stage, cumulative since create */
+    int64_t chain_repairs;                /* windows whose speculative record chain needed the sequential repair */
+} mth_bamdec_result;
+/* lpmd_order / min_qual: lpmd.rs:176-181 tests mapq BEFORE it builds the read (low-mapq records are only counted and may lack XM). */
+int mth_bamdec_create(mth_bamdec** out, int device, int32_t n_ref, const int64_t* ref_len, uint32_t lpmd_order, uint32_t min_qual);
+/* comp: host memory (pinned preferred).  skip: bytes at the start of the FIRST window's output that are the BAM header.
+ * last != 0: no window follows — a trailing partial record is an error. */
+int mth_bamdec_window(mth_bamdec* d, const uint8_t* comp, size_t comp_bytes, const mth_bgzf_member* members, int64_t n_members,
+                      uint64_t skip, int last, mth_bamdec_result* out);
+int mth_bamdec_destroy(mth_bamdec* d);
+const char* mth_bamdec_last_error(mth_bamdec* d); /* d may be NULL: last create error */
+/* The inflate kernel alone (tests, profiles): members of `comp` -> out_host, concatenated; per-member status (0 = ok). */
+int mth_bgzf_inflate(int device, const uint8_t* comp, size_t comp_bytes, const mth_bgzf_member* members, int64_t n, uint8_t* out_host,
+                     size_t out_bytes, int32_t* status_host, double* kernel_ms);
 
 /* Seeded replacement draw used for reservoir sampling: returns j in 1..=total (documented in DESIGN.md). */
 uint32_t mth_reservoir_draw(uint64_t seed, int32_t tid, int32_t pos, uint32_t total);

@@ -98,12 +98,23 @@ class TagResult(C.Structure):
     _fields_ = [("n_reads", i64), ("n_failed", i64), ("xm_off", vp), ("xm_len", vp), ("xm", vp), ("status", vp)]
 
 
+class BgzfMember(C.Structure):
+    _fields_ = [("offset", u64), ("size", u32), ("isize", u32)]
+
+
+class BamdecResult(C.Structure):
+    _fields_ = [("n_records", i64), ("n_dropped", i64), ("n_dropped_mapq_ok", i64), ("n_runs", i32), ("max_cpgs", i32), ("runs", C.POINTER(Batch)),
+                ("max_span", i64), ("bad_record", i64), ("bad_is_corrupt", i32), ("reserved", i32), ("uncompressed_bytes", u64),
+                ("ms_inflate", C.c_double), ("ms_boundaries", C.c_double), ("ms_decode", C.c_double), ("chain_repairs", i64)]
+
+
 EXPORTS = ["mth_params_default", "mth_ctx_create", "mth_ctx_destroy", "mth_set_stream", "mth_submit", "mth_submit_compact", "mth_reserve",
            "mth_add_skipped_reads", "mth_finish", "mth_results_device", "mth_lpmd_counters_device", "mth_lpmd_refresh",
            "mth_reset", "mth_sync", "mth_sync_copies", "mth_get_stats", "mth_last_error", "mth_host_alloc", "mth_host_free",
            "mth_device_count", "mth_version", "mth_reservoir_draw", "mth_genome_create", "mth_genome_set_contig", "mth_tag",
            "mth_genome_destroy", "mth_genome_last_error", "mth_genome_last_kernel_ms", "mth_comm_unique_id", "mth_comm_init_rank",
-           "mth_comm_init_all", "mth_allreduce", "mth_allreduce_group", "mth_comm_destroy", "mth_comm_n_ranks", "mth_set_cpg_set", "mth_clear_cpg_set"]
+           "mth_comm_init_all", "mth_allreduce", "mth_allreduce_group", "mth_comm_destroy", "mth_comm_n_ranks", "mth_set_cpg_set", "mth_clear_cpg_set", "mth_bamdec_create",
+           "mth_bamdec_window", "mth_bamdec_destroy", "mth_bamdec_last_error", "mth_bgzf_inflate"]
 
 
 def build(force=False):
@@ -150,6 +161,11 @@ def lib():
     L.mth_reservoir_draw.argtypes = [u64, i32, i32, u32]; L.mth_reservoir_draw.restype = u32
     L.mth_set_cpg_set.argtypes = [vp, i64, vp, vp]; L.mth_set_cpg_set.restype = C.c_int
     L.mth_clear_cpg_set.argtypes = [vp]; L.mth_clear_cpg_set.restype = C.c_int
+    L.mth_bamdec_create.argtypes = [P(vp), C.c_int, i32, P(i64), u32, u32]; L.mth_bamdec_create.restype = C.c_int
+    L.mth_bamdec_window.argtypes = [vp, vp, C.c_size_t, P(BgzfMember), i64, u64, C.c_int, P(BamdecResult)]; L.mth_bamdec_window.restype = C.c_int
+    L.mth_bamdec_destroy.argtypes = [vp]; L.mth_bamdec_destroy.restype = C.c_int
+    L.mth_bamdec_last_error.argtypes = [vp]; L.mth_bamdec_last_error.restype = C.c_char_p
+    L.mth_bgzf_inflate.argtypes = [C.c_int, vp, C.c_size_t, P(BgzfMember), i64, vp, C.c_size_t, vp, P(C.c_double)]; L.mth_bgzf_inflate.restype = C.c_int
     L.mth_comm_unique_id.argtypes = [vp]; L.mth_comm_unique_id.restype = C.c_int
     L.mth_comm_init_rank.argtypes = [vp, C.c_int, C.c_int, vp]; L.mth_comm_init_rank.restype = C.c_int
     L.mth_comm_init_all.argtypes = [P(vp), C.c_int]; L.mth_comm_init_all.restype = C.c_int

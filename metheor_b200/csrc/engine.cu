@@ -688,7 +688,7 @@ int mth_submit(mth_ctx* c, const mth_batch* b) {
         return fail(c, MTH_ERR_INVALID, "null array in batch");
     bool lp = (c->prm.measures & MTH_LPMD) != 0;
     if (lp && b->n_cpg && !b->cpg_rel) return fail(c, MTH_ERR_INVALID, "cpg_rel is required when MTH_LPMD is requested");
-    if (b->mem_kind != 0 && b->mem_kind != 1) return fail(c, MTH_ERR_INVALID, "mem_kind must be 0 (host) or 1 (device)");
+    if (b->mem_kind != 0 && b->mem_kind != 1 && b->mem_kind != 2) return fail(c, MTH_ERR_INVALID, "mem_kind must be 0 (host), 1 or 2 (device)");
     if (b->n_reads > (int64_t)INT32_MAX - 64 || b->n_cpg > (int64_t)UINT32_MAX - 64)
         return fail(c, MTH_ERR_UNSUPPORTED, "batch too large (reads < 2^31, CpG calls < 2^32)");
     int64_t bw = batch_words(b);

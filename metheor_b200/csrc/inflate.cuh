@@ -1,0 +1,256 @@
+// inflate.cuh — raw DEFLATE (RFC 1951) on the GPU, one WARP per BGZF member.
+//
+// The reference reads BAM through htslib, which inflates one BGZF member after the other on one thread (bamutil.rs:4-11).
+// BGZF members are independent raw-DEFLATE streams of at most 64 KiB of output, so a file is thousands of independent
+// decode jobs: here each warp takes one member.  Huffman decoding is inherently serial, so all 32 lanes decode the SAME
+// bit stream redundantly (identical registers, broadcast loads: no divergence, no shuffles) and the lanes only split the
+// work that is parallel: filling the decode tables of a dynamic block and copying LZ77 matches.  Parallelism comes from
+// the number of members in flight (148 SMs x up to 48 warps), not from within a stream.
+//
+// Decode tables per warp in shared memory: a 10-bit primary look-up for literal/length codes and an 8-bit one for
+// distance codes (entry = symbol << 4 | code length); longer codes fall back to the canonical count/first-code walk
+// (the method of zlib's contrib/puff).  Output goes straight to global memory; matches read it back through L2
+// (ld.global.cg), ordered by __syncwarp().
+#pragma once
+#include "common.cuh"
+
+namespace mth {
+
+constexpr int INF_LL_BITS = 10, INF_D_BITS = 8;
+constexpr int INF_MAXBITS = 15, INF_MAXL = 288, INF_MAXD = 30;
+
+struct InflateTables {                      // per warp
+    uint16_t ll_fast[1 << INF_LL_BITS];     // (symbol << 4) | length, 0 = not a short code
+    uint16_t d_fast[1 << INF_D_BITS];
+    uint16_t ll_sym[INF_MAXL + 32], d_sym[INF_MAXD + 2];  // symbols ordered by (length, symbol): canonical order
+    uint16_t ll_cnt[INF_MAXBITS + 1], d_cnt[INF_MAXBITS + 1];
+    uint8_t len[INF_MAXL + INF_MAXD + 34];  // code lengths of the block being set up
+};
+
+enum : int { INF_OK = 0, INF_ERR_BTYPE = 1, INF_ERR_STORED = 2, INF_ERR_CODE = 3, INF_ERR_DIST = 4, INF_ERR_OVERRUN = 5,
+             INF_ERR_INPUT = 6, INF_ERR_SIZE = 7, INF_ERR_TABLE = 8 };
+
+// LSB-first bit reader over global memory; every lane of the warp holds the same state.
+struct BitReader {
+    const uint8_t* p;
+    const uint8_t* end;
+    unsigned long long buf;
+    int cnt;
+    __device__ __forceinline__ void init(const uint8_t* b, const uint8_t* e) { p = b; end = e; buf = 0; cnt = 0; }
+    __device__ __forceinline__ void refill() {  // at least 32 valid bits afterwards (zeros past the end)
+        while (cnt <= 32) {
+            unsigned long long w = 0;
+            if (p + 4 <= end && (((uintptr_t)p) & 3) == 0) {
+                w = __ldg(reinterpret_cast<const unsigned int*>(p));
+                p += 4;
+                buf |= w << cnt;
+                cnt += 32;
+            } else {
+                w = p < end ? (unsigned long long)__ldg(p) : 0ull;
+                p += 1;
+                buf |= w << cnt;
+                cnt += 8;
+            }
+        }
+    }
+    __device__ __forceinline__ uint32_t peek(int n) const { return (uint32_t)(buf & ((1ull << n) - 1ull)); }
+    __device__ __forceinline__ void drop(int n) { buf >>= n; cnt -= n; }
+    __device__ __forceinline__ uint32_t bits(int n) {  // n <= 16
+        if (cnt < n) refill();
+        uint32_t v = peek(n);
+        drop(n);
+        return v;
+    }
+    __device__ __forceinline__ bool overrun() const { return (p - end) * 8 > (long long)cnt; }  // consumed bits past the end
+};
+
+// Canonical Huffman set-up from code lengths len[0..n): counts per length, symbols in canonical order (lane 0 — a few
+// hundred steps), then the fast table in parallel (each lane fills the entries of its symbols).  Returns false for an
+// over-subscribed code.
+__device__ __forceinline__ bool build_table(const uint8_t* len, int n, uint16_t* cnt, uint16_t* sym, uint16_t* fast, int fast_bits) {
+    const int lane = lane_id();
+    __syncwarp();
+    bool ok = true;
+    if (lane == 0) {
+        uint16_t offs[INF_MAXBITS + 2];
+        for (int l = 0; l <= INF_MAXBITS; l++) cnt[l] = 0;
+        for (int s = 0; s < n; s++) cnt[len[s]]++;
+        int left = 1;
+        for (int l = 1; l <= INF_MAXBITS; l++) {
+            left <<= 1;
+            left -= cnt[l];
+            if (left < 0) ok = false;  // over-subscribed
+        }
+        offs[1] = 0;
+        for (int l = 1; l < INF_MAXBITS; l++) offs[l + 1] = offs[l] + cnt[l];
+        for (int s = 0; s < n; s++)
+            if (len[s]) sym[offs[len[s]]++] = (uint16_t)s;
+    }
+    ok = __shfl_sync(FULL, ok ? 1 : 0, 0) != 0;
+    for (int i = lane; i < (1 << fast_bits); i += 32) fast[i] = 0;
+    __syncwarp();
+    if (!ok) return false;
+    // canonical codes: symbols of length l are numbered consecutively from first[l]; entry index = bit-reversed code
+    int first = 0, index = 0;
+    for (int l = 1; l <= fast_bits; l++) {
+        const int c = cnt[l];
+        for (int k = lane; k < c; k += 32) {
+            const uint32_t code = (uint32_t)(first + k);
+            const uint32_t rev = __brev(code) >> (32 - l);
+            const uint16_t e = (uint16_t)((sym[index + k] << 4) | l);
+            for (uint32_t x = rev; x < (1u << fast_bits); x += (1u << l)) fast[x] = e;
+        }
+        index += c;
+        first = (first + c) << 1;
+    }
+    __syncwarp();
+    return true;
+}
+
+// One symbol: fast table, else the canonical walk over the lengths above the fast width.
+__device__ __forceinline__ int decode_sym(BitReader& br, const uint16_t* cnt, const uint16_t* sym, const uint16_t* fast, int fast_bits) {
+    if (br.cnt < INF_MAXBITS) br.refill();
+    const uint32_t e = fast[br.peek(fast_bits)];
+    if (e) {
+        br.drop((int)(e & 15u));
+        return (int)(e >> 4);
+    }
+    int code = 0, first = 0, index = 0;
+    unsigned long long b = br.buf;
+    for (int l = 1; l <= INF_MAXBITS; l++) {
+        code |= (int)(b & 1ull);
+        b >>= 1;
+        const int c = cnt[l];
+        if (code - c < first) {
+            br.drop(l);
+            return sym[index + (code - first)];
+        }
+        index += c;
+        first += c;
+        first <<= 1;
+        code <<= 1;
+    }
+    return -1;
+}
+
+__device__ const uint16_t INF_LBASE[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+__device__ const uint8_t INF_LEXT[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+__device__ const uint16_t INF_DBASE[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+__device__ const uint8_t INF_DEXT[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+__device__ const uint8_t INF_CLORDER[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+// Inflates one raw-DEFLATE stream in[0, in_len) into out[0, out_cap); all 32 lanes of a warp call it with the same
+// arguments.  Returns INF_OK and the number of bytes produced in *produced.
+__device__ __forceinline__ int warp_inflate(const uint8_t* __restrict__ in, uint32_t in_len, uint8_t* out, uint32_t out_cap, InflateTables& T,
+                                            uint32_t* produced) {
+    const int lane = lane_id();
+    BitReader br;
+    br.init(in, in + in_len);
+    uint32_t pos = 0;
+    int err = INF_OK;
+    bool last = false;
+    while (!last && err == INF_OK) {
+        last = br.bits(1) != 0;
+        const uint32_t type = br.bits(2);
+        if (type == 0) {  // stored
+            br.drop(br.cnt & 7);
+            // the bit buffer holds whole bytes now: give them back
+            const uint8_t* q = br.p - (br.cnt >> 3);
+            br.buf = 0; br.cnt = 0;
+            if (q + 4 > br.end) { err = INF_ERR_INPUT; break; }
+            const uint32_t len = (uint32_t)q[0] | ((uint32_t)q[1] << 8), nlen = (uint32_t)q[2] | ((uint32_t)q[3] << 8);
+            q += 4;
+            if ((len ^ 0xFFFFu) != nlen || q + len > br.end) { err = INF_ERR_STORED; break; }
+            if (pos + len > out_cap) { err = INF_ERR_SIZE; break; }
+            for (uint32_t k = lane; k < len; k += 32) out[pos + k] = __ldg(q + k);
+            __syncwarp();
+            pos += len;
+            br.p = q + len;
+            continue;
+        }
+        if (type == 3) { err = INF_ERR_BTYPE; break; }
+        if (type == 1) {  // fixed code
+            for (int s = lane; s < 288; s += 32) T.len[s] = s < 144 ? 8 : s < 256 ? 9 : s < 280 ? 7 : 8;
+            for (int s = lane; s < 30; s += 32) T.len[288 + s] = 5;
+            __syncwarp();
+            if (!build_table(T.len, 288, T.ll_cnt, T.ll_sym, T.ll_fast, INF_LL_BITS) ||
+                !build_table(T.len + 288, 30, T.d_cnt, T.d_sym, T.d_fast, INF_D_BITS)) { err = INF_ERR_TABLE; break; }
+        } else {  // dynamic code
+            const int nlen = (int)br.bits(5) + 257, ndist = (int)br.bits(5) + 1, ncode = (int)br.bits(4) + 4;
+            if (nlen > 286 || ndist > 30) { err = INF_ERR_TABLE; break; }
+            // code-length code: reuse the distance tables as scratch (7-bit codes, 19 symbols)
+            for (int s = lane; s < 19; s += 32) T.len[s] = 0;
+            __syncwarp();
+            for (int k = 0; k < ncode; k++) {
+                const uint32_t v = br.bits(3);
+                if (lane == 0) T.len[INF_CLORDER[k]] = (uint8_t)v;
+            }
+            __syncwarp();
+            if (!build_table(T.len, 19, T.d_cnt, T.d_sym, T.d_fast, 7)) { err = INF_ERR_TABLE; break; }
+            // the literal/length and distance code lengths, run-length coded with the code-length code: decode into a
+            // second area (the code-length lengths sit in T.len[0..19) while they are in use)
+            uint8_t* L = T.len + 32;
+            int idx = 0;
+            while (idx < nlen + ndist) {
+                const int s = decode_sym(br, T.d_cnt, T.d_sym, T.d_fast, 7);
+                if (s < 0) { err = INF_ERR_CODE; break; }
+                if (s < 16) {
+                    if (lane == 0) L[idx] = (uint8_t)s;
+                    idx++;
+                } else {
+                    int prev = 0, rep;
+                    if (s == 16) {
+                        if (idx == 0) { err = INF_ERR_CODE; break; }
+                        __syncwarp();
+                        prev = L[idx - 1];
+                        rep = 3 + (int)br.bits(2);
+                    } else if (s == 17) {
+                        rep = 3 + (int)br.bits(3);
+                    } else {
+                        rep = 11 + (int)br.bits(7);
+                    }
+                    if (idx + rep > nlen + ndist) { err = INF_ERR_CODE; break; }
+                    if (lane == 0)
+                        for (int k = 0; k < rep; k++) L[idx + k] = (uint8_t)prev;
+                    idx += rep;
+                    __syncwarp();
+                }
+            }
+            if (err != INF_OK) break;
+            __syncwarp();
+            if (L[256] == 0) { err = INF_ERR_CODE; break; }  // no end-of-block code
+            if (!build_table(L, nlen, T.ll_cnt, T.ll_sym, T.ll_fast, INF_LL_BITS) ||
+                !build_table(L + nlen, ndist, T.d_cnt, T.d_sym, T.d_fast, INF_D_BITS)) { err = INF_ERR_TABLE; break; }
+        }
+        // ---- the symbols of the block ----
+        while (true) {
+            const int s = decode_sym(br, T.ll_cnt, T.ll_sym, T.ll_fast, INF_LL_BITS);
+            if (s < 0) { err = INF_ERR_CODE; break; }
+            if (s < 256) {
+                if (pos >= out_cap) { err = INF_ERR_SIZE; break; }
+                if (lane == 0) out[pos] = (uint8_t)s;
+                pos++;
+                continue;
+            }
+            if (s == 256) break;
+            const int ls = s - 257;
+            if (ls >= 29) { err = INF_ERR_CODE; break; }
+            const uint32_t len = INF_LBASE[ls] + br.bits(INF_LEXT[ls]);
+            const int ds = decode_sym(br, T.d_cnt, T.d_sym, T.d_fast, INF_D_BITS);
+            if (ds < 0 || ds >= 30) { err = INF_ERR_CODE; break; }
+            const uint32_t dist = INF_DBASE[ds] + br.bits(INF_DEXT[ds]);
+            if (dist > pos) { err = INF_ERR_DIST; break; }
+            if (pos + len > out_cap) { err = INF_ERR_SIZE; break; }
+            __syncwarp();  // the bytes written so far (literals by lane 0) are visible to every lane
+            const uint8_t* src = out + pos - dist;
+            for (uint32_t k = lane; k < len; k += 32) out[pos + k] = __ldcg(src + (dist >= len ? k : k % dist));
+            __syncwarp();
+            pos += len;
+        }
+        if (br.overrun()) err = INF_ERR_OVERRUN;
+    }
+    *produced = pos;
+    return err;
+}
+
+}  // namespace mth

@@ -142,6 +142,20 @@ def read_bam(path):
     return refs, reads, text
 
 
+def read_header_len(path):
+    """-> (refs, number of uncompressed bytes in front of the first record)."""
+    d = bgzf_decompress(open(path, "rb").read())
+    o = 4
+    l_text = struct.unpack_from("<i", d, o)[0]; o += 4 + l_text
+    n_ref = struct.unpack_from("<i", d, o)[0]; o += 4
+    refs = []
+    for _ in range(n_ref):
+        ln = struct.unpack_from("<i", d, o)[0]; o += 4
+        name = d[o:o + ln - 1].decode(); o += ln
+        refs.append((name, struct.unpack_from("<i", d, o)[0])); o += 4
+    return refs, o
+
+
 def read_sam(path):
     refs, reads = [], []
     for line in open(path):
