@@ -194,7 +194,19 @@ def bam_leg(b, n_reads, length):
             r = subprocess.run([oracle_lib.CLI_PATH, m, "-i", bam, "-o", tsv + ".oracle"], capture_output=True, text=True)
             dt_o = time.perf_counter() - t0
             same = r.returncode == 0 and open(tsv, "rb").read() == open(tsv + ".oracle", "rb").read()
-            out[m] = {"reads_per_sec": info["records"] / best[0], "seconds": best[0],
+            # the same file through the host-side decoder (all cores: inflate + record decode on the CPU) for comparison
+            best_h = None
+            for _ in range(2):
+                t0 = time.perf_counter()
+                host.run(m, bam, tsv + ".hostdec", stats_json=st, decode_host=1)
+                dt = time.perf_counter() - t0
+                if best_h is None or dt < best_h[0]:
+                    best_h = (dt, json.load(open(st)))
+            same_h = open(tsv, "rb").read() == open(tsv + ".hostdec", "rb").read()
+            out[m] = {"reads_per_sec": info["records"] / best[0], "seconds": best[0], "decode": best[1].get("decode"),
+                      "device_decode": best[1].get("device_decode"),
+                      "host_decode_path": {"reads_per_sec": info["records"] / best_h[0], "seconds": best_h[0], "stage_seconds": best_h[1]["seconds"],
+                                           "tsv_identical": bool(same_h)},
                       "uncompressed_MB_per_sec": info["bytes_uncompressed"] / best[0] / 1e6, "stage_seconds": best[1]["seconds"],
                       "cpu_oracle_cli_seconds": dt_o, "cpu_oracle_cli_reads_per_sec": info["records"] / dt_o,
                       "tsv_identical_to_oracle": bool(same)}

@@ -42,6 +42,8 @@ typedef struct {
     int32_t device;         /* --device N : first GPU to use (default 0) */
     int32_t n_gpus;         /* --gpus N   : the genome is sharded over N GPUs of this node (default 1): position bins + halo */
     int32_t shard_contigs;  /* --shard contigs : shard whole contigs instead of position bins (default 0 = bins) */
+    int32_t decode_host;    /* --decode host   : inflate + decode BAM records on the host cores instead of the GPU (default 0: GPU for
+                               BAM input on one GPU; SAM text and --gpus > 1 always decode on the host) */
     int32_t threads;        /* --threads N: decode threads, 0 = all cores */
     uint64_t seed;          /* --seed     : reservoir sampling seed once a pile exceeds max_depth */
     const char* stats_json; /* --stats F  : write reads/s, per-stage seconds and kernel stats as JSON, or NULL */

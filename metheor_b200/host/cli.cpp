@@ -50,6 +50,7 @@ const ArgSpec CPGSET = {'c', "cpg-set", A_STR, false, nullptr, "(Optional) Speci
 const ArgSpec E_DEVICE = {0, "device", A_I32, false, "0", "[engine] first CUDA device to use", "DEVICE"};
 const ArgSpec E_GPUS = {0, "gpus", A_I32, false, "1", "[engine] shard the genome over this many GPUs (position bins + halo reads)", "GPUS"};
 const ArgSpec E_SHARD = {0, "shard", A_STR, false, "bins", "[engine] multi-GPU sharding: bins (equal position ranges) or contigs (whole contigs)", "SHARD"};
+const ArgSpec E_DECODE = {0, "decode", A_STR, false, "gpu", "[engine] where BAM is inflated and decoded: gpu (one GPU, BAM input) or host", "DECODE"};
 const ArgSpec E_THREADS = {0, "threads", A_I32, false, "0", "[engine] host decode threads (0 = all cores)", "THREADS"};
 const ArgSpec E_SEED = {0, "seed", A_U64, false, "0", "[engine] reservoir-sampling seed once a pile exceeds --max-depth", "SEED"};
 const ArgSpec E_STATS = {0, "stats", A_STR, false, nullptr, "[engine] write timing / throughput statistics as JSON", "STATS"};
@@ -93,7 +94,7 @@ std::vector<CmdSpec> commands() {
                   {'g', "genome", A_STR, true, nullptr, "", "GENOME"}, E_DEVICE, E_THREADS, E_STATS}});
     for (auto& cmd : c)
         if (cmd.measure >= 0) {
-            cmd.args.push_back(E_DEVICE); cmd.args.push_back(E_GPUS); cmd.args.push_back(E_SHARD); cmd.args.push_back(E_THREADS); cmd.args.push_back(E_STATS);
+            cmd.args.push_back(E_DEVICE); cmd.args.push_back(E_GPUS); cmd.args.push_back(E_SHARD); cmd.args.push_back(E_DECODE); cmd.args.push_back(E_THREADS); cmd.args.push_back(E_STATS);
             if (cmd.measure == MTHH_FDRP || cmd.measure == MTHH_QFDRP) cmd.args.push_back(E_SEED);
         }
     return c;
@@ -169,6 +170,7 @@ void mthh_options_default(mthh_options* o, int32_t measure) {
     o->max_distance = 16;
     o->n_gpus = 1;
     o->shard_contigs = 0;
+    o->decode_host = 0;
 }
 
 int mthh_run(const mthh_options* o, char* err, size_t errcap) {
@@ -317,6 +319,11 @@ int mthh_main(int argc, char** argv) {
             if (!strcmp(v, "contigs")) o.shard_contigs = 1;
             else if (!strcmp(v, "bins")) o.shard_contigs = 0;
             else return usage_error(cmd, std::string("invalid value '") + v + "' for '--shard <SHARD>': expected bins or contigs");
+        }
+        else if (n == "decode") {
+            if (!strcmp(v, "host")) o.decode_host = 1;
+            else if (!strcmp(v, "gpu")) o.decode_host = 0;
+            else return usage_error(cmd, std::string("invalid value '") + v + "' for '--decode <DECODE>': expected gpu or host");
         }
         else if (n == "threads") o.threads = (int32_t)s;
         else if (n == "seed") o.seed = u;

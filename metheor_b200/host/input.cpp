@@ -104,6 +104,12 @@ size_t bgzf_member(const uint8_t* d, size_t size, size_t o, size_t* cdata, size_
 
 }  // namespace
 
+size_t bgzf_member_info(const uint8_t* d, size_t size, size_t o, size_t* cdata, size_t* clen, uint32_t* usize, uint32_t* crc) {
+    return bgzf_member(d, size, o, cdata, clen, usize, crc);
+}
+
+size_t RecordStream::bam_header_bytes() const { return bam_header_len_; }
+
 RecordStream::RecordStream(const std::string& path, int n_threads, size_t window_bytes)
     : path_(path), pool_(n_threads), window_bytes_(window_bytes) {
     file_.open(path);
@@ -271,6 +277,7 @@ void RecordStream::parse_bam_header() {
             ok = true;
         } while (false);
         if (ok) {
+            bam_header_len_ = o;
             carry_.assign(b + o, b + n);  // the records behind the header start the first window
             return;
         }

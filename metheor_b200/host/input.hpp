@@ -37,6 +37,10 @@ private:
 
 enum class Format { BAM, SAM };
 
+// One BGZF member header at offset `o` of d[0, size): returns the member's total size (0: not a BGZF member) and where its raw
+// DEFLATE payload lies, its uncompressed size (ISIZE) and CRC-32.
+size_t bgzf_member_info(const uint8_t* d, size_t size, size_t o, size_t* cdata, size_t* clen, uint32_t* usize, uint32_t* crc);
+
 // One record of the input in a format-neutral form that points into the window buffer (no copies).
 struct RecordRef {
     const uint8_t* p;  // BAM: first byte after block_size; SAM: first byte of the line
@@ -53,6 +57,9 @@ public:
     // Fills `recs` with the records of the next window (pointers valid until the next call); false at end of file.
     bool next(std::vector<RecordRef>* recs);
     size_t file_size() const { return file_.size(); }
+    const MappedFile& file() const { return file_; }
+    // BAM: uncompressed bytes in front of the first alignment record (magic, header text, reference list)
+    size_t bam_header_bytes() const;
     size_t compressed_consumed() const { return consumed_; }  // compressed bytes behind the records handed out so far
     double seconds_inflate = 0, seconds_walk = 0;
     uint64_t bytes_compressed = 0, bytes_uncompressed = 0;
@@ -96,6 +103,7 @@ private:
     std::vector<uint8_t> carry_;      // bytes of the record that straddles into the next run (producer only)
     Window cur_;                      // the window whose records were handed out last
     size_t consumed_ = 0;
+    size_t bam_header_len_ = 0;
     bool eof_ = false;
 };
 

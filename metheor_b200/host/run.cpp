@@ -423,6 +423,148 @@ std::vector<std::vector<ShardInterval>> plan_contigs(const std::vector<int64_t>&
     return out;
 }
 
+// ---- device-side decode: the host only walks BGZF member headers and ships COMPRESSED bytes ---------------
+// Windows of whole members go through mth_bamdec_window (inflate, record boundaries, BismarkRead decode on the GPU) and come
+// back as device-resident batches for mth_submit.  Returns false when the file needs the host decoder (a read with more than
+// 64 CpG calls, ...): the caller resets the engine and runs the CPU path.
+struct DeviceFeedStats {
+    double s_stage = 0, s_window = 0, s_submit = 0;
+    double ms_inflate = 0, ms_boundaries = 0, ms_decode = 0;
+    int64_t windows = 0, chain_repairs = 0;
+    uint64_t bytes_compressed = 0, bytes_uncompressed = 0;
+};
+
+static bool feed_device(const mthh_options& o, const RecordStream& in, mth_ctx* ctx, int device, uint32_t lpmd_order, DecodeCounters* total,
+                        int64_t* n_batches, int64_t* n_reads, int64_t* n_cpg, DeviceFeedStats* fs) {
+    const Header& hdr = in.header();
+    const uint8_t* d = in.file().data();
+    const size_t fsize = in.file().size();
+    const size_t WINDOW_U = 96u << 20;  // uncompressed bytes per window
+    struct Staged {
+        void* pin = nullptr;
+        size_t cap = 0, bytes = 0;
+        std::vector<mth_bgzf_member> members;
+        uint64_t skip = 0;
+        bool last = false, ok = true;
+        std::string err;
+        double seconds = 0;
+        ~Staged() { mth_host_free(pin); }
+    };
+    Staged st[2];
+    size_t coff = 0;           // next compressed offset
+    uint64_t hdr_left = in.bam_header_bytes();  // header bytes not skipped yet
+    // stage the next window: member walk + copy of the compressed bytes into pinned memory
+    auto stage = [&](Staged& w) {
+        const double t0 = now_s();
+        w.members.clear();
+        w.bytes = 0; w.skip = 0; w.ok = true;
+        size_t c0 = coff, u = 0;
+        std::vector<std::pair<size_t, size_t>> pay;  // payload (offset, size) in the file
+        while (coff < fsize && u < WINDOW_U) {
+            size_t cdata, clen;
+            uint32_t usize, crc;
+            const size_t total = bgzf_member_info(d, fsize, coff, &cdata, &clen, &usize, &crc);
+            if (!total) { w.ok = false; w.err = std::string("Error opening BAM file. corrupt or truncated BGZF block at offset ") + std::to_string(coff) + ": " + o.input; return; }
+            coff += total;
+            if (usize == 0) continue;  // empty member (the EOF marker)
+            if (hdr_left >= usize) { hdr_left -= usize; c0 = coff; continue; }  // a member that holds only header bytes
+            pay.push_back({cdata, clen});
+            w.members.push_back(mth_bgzf_member{(uint64_t)(cdata - c0), (uint32_t)clen, usize});
+            u += usize;
+        }
+        w.skip = hdr_left;
+        hdr_left = 0;
+        w.last = coff >= fsize;
+        if (w.members.empty()) { w.seconds = now_s() - t0; return; }
+        const size_t bytes = pay.back().first + pay.back().second - c0;
+        if (bytes > w.cap) {
+            mth_host_free(w.pin);
+            w.cap = bytes + bytes / 4 + (1u << 20);
+            w.pin = mth_host_alloc(w.cap);
+            if (!w.pin) { w.ok = false; w.err = "cannot allocate pinned host memory"; w.cap = 0; return; }
+        }
+        // parallel copy out of the page cache (one memcpy runs at a few GB/s only)
+        const int nt = 8;
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; t++) {
+            const size_t a = bytes * (size_t)t / nt, b = bytes * (size_t)(t + 1) / nt;
+            th.emplace_back([=, &w] { memcpy((uint8_t*)w.pin + a, d + c0 + a, b - a); });
+        }
+        for (auto& t : th) t.join();
+        w.bytes = bytes;
+        w.seconds = now_s() - t0;
+    };
+    mth_bamdec* dec = nullptr;
+    int rc = mth_bamdec_create(&dec, device, (int32_t)hdr.lengths.size(), hdr.lengths.data(), lpmd_order, o.min_qual);
+    if (rc != MTH_OK) throw HostError{1, std::string("metheor_b200 engine: ") + mth_bamdec_last_error(nullptr)};
+    struct DecGuard { mth_bamdec* d; ~DecGuard() { mth_bamdec_destroy(d); } } guard{dec};
+    int cur = 0;
+    stage(st[cur]);
+    bool first = true;
+    for (;;) {
+        Staged& w = st[cur];
+        if (!w.ok) throw HostError{101, w.err};
+        fs->s_stage += w.seconds;
+        if (w.members.empty() && !first) break;
+        const bool last = w.last;
+        // the next window is staged by a helper thread while the GPU works on this one
+        std::future<void> nxt;
+        if (!last) nxt = std::async(std::launch::async, [&, cur] { stage(st[cur ^ 1]); });
+        double t0 = now_s();
+        rc = mth_sync_copies(ctx);  // the previous window's device batches have been copied into the arena
+        if (rc != MTH_OK) engine_fail(ctx, rc, "mth_sync_copies");
+        mth_bamdec_result res;
+        rc = mth_bamdec_window(dec, (const uint8_t*)w.pin, w.bytes, w.members.data(), (int64_t)w.members.size(), w.skip, last ? 1 : 0, &res);
+        if (rc == MTH_ERR_UNSUPPORTED) {
+            if (nxt.valid()) nxt.wait();
+            return false;
+        }
+        if (rc != MTH_OK) {
+            if (nxt.valid()) nxt.wait();
+            throw HostError{101, std::string("Error opening BAM file. ") + mth_bamdec_last_error(dec) + ": " + o.input};
+        }
+        fs->s_window += now_s() - t0;
+        if (res.bad_record >= 0) {
+            if (nxt.valid()) nxt.wait();
+            if (res.bad_is_corrupt) throw HostError{101, "Error opening BAM file. corrupt BAM record"};
+            throw HostError{101, "Error reading XM tag in BAM record. Make sure the reads are aligned using Bismark!"};  // readutil.rs:45-51
+        }
+        total->n_records += res.n_records;
+        total->n_dropped += res.n_dropped;
+        total->n_dropped_mapq_ok += res.n_dropped_mapq_ok;
+        if (res.max_cpgs > total->max_cpgs) total->max_cpgs = res.max_cpgs;
+        if (res.max_span > total->max_span) total->max_span = res.max_span;
+        fs->ms_inflate = res.ms_inflate; fs->ms_boundaries = res.ms_boundaries; fs->ms_decode = res.ms_decode;
+        fs->chain_repairs = res.chain_repairs;
+        fs->bytes_uncompressed += res.uncompressed_bytes;
+        fs->bytes_compressed += w.bytes;
+        fs->windows++;
+        t0 = now_s();
+        for (int k = 0; k < res.n_runs; k++) {
+            const mth_batch& b = res.runs[k];
+            if (b.tid < 0 || (size_t)b.tid >= hdr.lengths.size())
+                throw HostError{101, "metheor_b200: a read with CpG calls has no valid reference id (tid " + std::to_string(b.tid) + ")"};
+            rc = mth_submit(ctx, &b);
+            if (rc != MTH_OK) engine_fail(ctx, rc, "mth_submit");
+            (*n_batches)++;
+            *n_reads += b.n_reads;
+            *n_cpg += b.n_cpg;
+        }
+        fs->s_submit += now_s() - t0;
+        if (first && !last && w.bytes) {  // size the arena once from the first window: reads per compressed byte x file size (+15 %)
+            const double scale = 1.15 * (double)fsize / (double)w.bytes;
+            if (scale > 1.5) mth_reserve(ctx, (int64_t)((double)*n_reads * scale) + 4096, (int64_t)((double)*n_cpg * scale) + 4096);
+        }
+        first = false;
+        if (nxt.valid()) nxt.wait();
+        if (last) break;
+        cur ^= 1;
+    }
+    rc = mth_sync_copies(ctx);
+    if (rc != MTH_OK) engine_fail(ctx, rc, "mth_sync_copies");
+    return true;
+}
+
 void run(const mthh_options& o) {
     const double t_begin = now_s();
     if (!o.input || !o.output) throw HostError{2, "error: the following required arguments were not provided:\n  --input <INPUT>\n  --output <OUTPUT>"};
@@ -517,7 +659,20 @@ void run(const mthh_options& o) {
     bool reserved = false;
     const Format fmt = in.format();
 
-    while (in.next(&recs)) {
+    // BAM on one GPU: inflate + record decode on the device (the host ships compressed bytes); everything else — SAM text,
+    // several GPUs, a file beyond the device decoder's limits, --decode host — goes through the CPU decoder below.
+    bool used_device = false;
+    DeviceFeedStats dfs;
+    if (fmt == Format::BAM && n_gpus == 1 && !o.decode_host && !set_on_host && !getenv("METHEOR_DECODE_HOST")) {
+        used_device = feed_device(o, in, gpus[0]->ctx, o.device, dopt.lpmd_order ? 1u : 0u, &total, &n_batches, &n_shipped_reads, &n_shipped_cpg, &dfs);
+        if (!used_device) {  // start over on the host decoder
+            int rc = mth_reset(gpus[0]->ctx);
+            if (rc != MTH_OK) engine_fail(gpus[0]->ctx, rc, "mth_reset");
+            total = DecodeCounters();
+            n_batches = n_shipped_reads = n_shipped_cpg = 0;
+        }
+    }
+    while (!used_device && in.next(&recs)) {
         // cut the window at contig changes (a batch carries one tid)
         size_t seg0 = 0;
         while (seg0 < recs.size()) {
@@ -744,11 +899,16 @@ void run(const mthh_options& o) {
             fprintf(f, "\", \"format\": \"%s\", \"threads\": %d, \"gpus\": %d, \"records\": %lld, \"reads_shipped\": %lld, "
                        "\"cpg_calls_shipped\": %lld, \"batches\": %lld, \"rows\": %lld, \"bytes_uncompressed\": %llu, \"zlib_fallbacks\": %lld, "
                        "\"seconds\": {\"total\": %.6f, \"stream\": %.6f, \"inflate\": %.6f, \"walk\": %.6f, \"decode\": %.6f, "
-                       "\"assemble\": %.6f, \"submit\": %.6f, \"finish\": %.6f, \"write\": %.6f}, \"reads_per_sec\": %.1f, \"gpu\": [",
+                       "\"assemble\": %.6f, \"submit\": %.6f, \"finish\": %.6f, \"write\": %.6f}, \"reads_per_sec\": %.1f, \"decode\": \"%s\", "
+                       "\"device_decode\": {\"windows\": %lld, \"stage_s\": %.6f, \"window_s\": %.6f, \"submit_s\": %.6f, \"inflate_ms\": %.3f, "
+                       "\"boundaries_ms\": %.3f, \"decode_ms\": %.3f, \"chain_repairs\": %lld, \"bytes_compressed\": %llu, \"bytes_uncompressed\": %llu}, \"gpu\": [",
                     fmt == Format::BAM ? "bam" : "sam", n_threads, n_gpus, (long long)total.n_records, (long long)n_shipped_reads,
-                    (long long)n_shipped_cpg, (long long)n_batches, (long long)n_rows_total, (unsigned long long)in.bytes_uncompressed,
+                    (long long)n_shipped_cpg, (long long)n_batches, (long long)n_rows_total,
+                    (unsigned long long)(used_device ? dfs.bytes_uncompressed : in.bytes_uncompressed),
                     (long long)g_zlib_fallbacks.load(), wall, t_decoded - t_begin, in.seconds_inflate, in.seconds_walk, s_decode, s_assemble, s_submit,
-                    t_finished - t_decoded, t_end - t_finished, (double)total.n_records / wall);
+                    t_finished - t_decoded, t_end - t_finished, (double)total.n_records / wall, used_device ? "device" : "host",
+                    (long long)dfs.windows, dfs.s_stage, dfs.s_window, dfs.s_submit, dfs.ms_inflate, dfs.ms_boundaries, dfs.ms_decode,
+                    (long long)dfs.chain_repairs, (unsigned long long)dfs.bytes_compressed, (unsigned long long)dfs.bytes_uncompressed);
             for (size_t g = 0; g < gpus.size(); g++) {
                 const mth_stats& st = gpus[g]->stats;
                 fprintf(f, "%s{\"reads\": %lld, \"cpg_calls\": %lld, \"sites\": %lld, \"regions\": %lld, \"kernel_launches\": %lld, "
