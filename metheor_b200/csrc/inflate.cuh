@@ -20,6 +20,7 @@ constexpr int INF_LL_BITS = 10, INF_D_BITS = 8;
 constexpr int INF_MAXBITS = 15, INF_MAXL = 288, INF_MAXD = 30;
 
 struct InflateTables {                      // per warp
+    unsigned int ring[64];                  // compressed input staging (BitReader)
     uint16_t ll_fast[1 << INF_LL_BITS];     // (symbol << 4) | length, 0 = not a short code
     uint16_t d_fast[1 << INF_D_BITS];
     uint16_t ll_sym[INF_MAXL + 32], d_sym[INF_MAXD + 2];  // symbols ordered by (length, symbol): canonical order
@@ -30,27 +31,48 @@ struct InflateTables {                      // per warp
 enum : int { INF_OK = 0, INF_ERR_BTYPE = 1, INF_ERR_STORED = 2, INF_ERR_CODE = 3, INF_ERR_DIST = 4, INF_ERR_OVERRUN = 5,
              INF_ERR_INPUT = 6, INF_ERR_SIZE = 7, INF_ERR_TABLE = 8 };
 
-// LSB-first bit reader over global memory; every lane of the warp holds the same state.
+// LSB-first bit reader; every lane of the warp holds the same state.  The compressed bytes come through a 256-byte ring in
+// shared memory that the warp refills with one coalesced load (2 words per lane) every 64 words, so the serial decode loop
+// waits on shared memory (~30 cycles), not on global memory (~500), for its input.
+constexpr int INF_RING_WORDS = 64;
 struct BitReader {
-    const uint8_t* p;
-    const uint8_t* end;
+    const unsigned int* g;      // the stream as 32-bit words from the 4-byte aligned address at or below its first byte
+    unsigned int* ring;         // shared memory, INF_RING_WORDS words, this warp's
+    uint32_t n_words;           // words that contain stream bytes
+    uint32_t n_bytes;           // stream length from the aligned base (skip + in_len)
+    uint32_t rw;                // next word to move into the bit buffer
+    uint32_t filled;            // words [0, filled) have been staged (multiple of INF_RING_WORDS)
     unsigned long long buf;
     int cnt;
-    __device__ __forceinline__ void init(const uint8_t* b, const uint8_t* e) { p = b; end = e; buf = 0; cnt = 0; }
+    __device__ __forceinline__ void fill() {  // stage words [filled, filled + 64): every earlier word has been consumed
+        const int lane = lane_id();
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < INF_RING_WORDS / 32; k++) {
+            const uint32_t w = filled + lane + 32 * k;
+            ring[lane + 32 * k] = w < n_words ? __ldg(g + w) : 0u;
+        }
+        filled += INF_RING_WORDS;
+        __syncwarp();
+    }
+    __device__ __forceinline__ void init(const uint8_t* b, uint32_t len, unsigned int* ring_) {
+        const uint32_t skip = (uint32_t)((uintptr_t)b & 3u);
+        g = reinterpret_cast<const unsigned int*>(b - skip);
+        ring = ring_;
+        n_bytes = skip + len;
+        n_words = (n_bytes + 3) >> 2;
+        rw = 0; filled = 0; buf = 0; cnt = 0;
+        // bytes of the first / last word outside the stream are never interpreted: `skip` bytes are dropped here and the decoder
+        // stops at the end-of-block code (consumption past n_bytes is detected by overrun())
+        refill();
+        drop((int)skip * 8);
+    }
     __device__ __forceinline__ void refill() {  // at least 32 valid bits afterwards (zeros past the end)
         while (cnt <= 32) {
-            unsigned long long w = 0;
-            if (p + 4 <= end && (((uintptr_t)p) & 3) == 0) {
-                w = __ldg(reinterpret_cast<const unsigned int*>(p));
-                p += 4;
-                buf |= w << cnt;
-                cnt += 32;
-            } else {
-                w = p < end ? (unsigned long long)__ldg(p) : 0ull;
-                p += 1;
-                buf |= w << cnt;
-                cnt += 8;
-            }
+            if (rw >= filled) fill();
+            buf |= (unsigned long long)ring[rw & (INF_RING_WORDS - 1)] << cnt;
+            rw++;
+            cnt += 32;
         }
     }
     __device__ __forceinline__ uint32_t peek(int n) const { return (uint32_t)(buf & ((1ull << n) - 1ull)); }
@@ -61,7 +83,17 @@ struct BitReader {
         drop(n);
         return v;
     }
-    __device__ __forceinline__ bool overrun() const { return (p - end) * 8 > (long long)cnt; }  // consumed bits past the end
+    // byte position (from the aligned base) of the next unread bit, which must be byte aligned
+    __device__ __forceinline__ uint32_t byte_pos() const { return rw * 4u - (uint32_t)(cnt >> 3); }
+    __device__ __forceinline__ void seek(uint32_t pos) {  // continue at byte `pos`
+        rw = pos >> 2;
+        filled = rw & ~(uint32_t)(INF_RING_WORDS - 1);
+        buf = 0; cnt = 0;
+        fill();
+        refill();
+        drop((int)(pos & 3u) * 8);
+    }
+    __device__ __forceinline__ bool overrun() const { return (long long)rw * 32 - cnt > (long long)n_bytes * 8; }  // consumed bits past the end
 };
 
 // Canonical Huffman set-up from code lengths len[0..n): counts per length, symbols in canonical order (lane 0 — a few
@@ -145,7 +177,7 @@ __device__ __forceinline__ int warp_inflate(const uint8_t* __restrict__ in, uint
                                             uint32_t* produced) {
     const int lane = lane_id();
     BitReader br;
-    br.init(in, in + in_len);
+    br.init(in, in_len, T.ring);
     uint32_t pos = 0;
     int err = INF_OK;
     bool last = false;
@@ -154,18 +186,17 @@ __device__ __forceinline__ int warp_inflate(const uint8_t* __restrict__ in, uint
         const uint32_t type = br.bits(2);
         if (type == 0) {  // stored
             br.drop(br.cnt & 7);
-            // the bit buffer holds whole bytes now: give them back
-            const uint8_t* q = br.p - (br.cnt >> 3);
-            br.buf = 0; br.cnt = 0;
-            if (q + 4 > br.end) { err = INF_ERR_INPUT; break; }
-            const uint32_t len = (uint32_t)q[0] | ((uint32_t)q[1] << 8), nlen = (uint32_t)q[2] | ((uint32_t)q[3] << 8);
+            const uint32_t q0 = br.byte_pos();  // LEN NLEN data, byte aligned
+            if (q0 + 4 > br.n_bytes) { err = INF_ERR_INPUT; break; }
+            const uint8_t* q = reinterpret_cast<const uint8_t*>(br.g) + q0;
+            const uint32_t len = (uint32_t)__ldg(q) | ((uint32_t)__ldg(q + 1) << 8), nlen = (uint32_t)__ldg(q + 2) | ((uint32_t)__ldg(q + 3) << 8);
             q += 4;
-            if ((len ^ 0xFFFFu) != nlen || q + len > br.end) { err = INF_ERR_STORED; break; }
+            if ((len ^ 0xFFFFu) != nlen || q0 + 4 + len > br.n_bytes) { err = INF_ERR_STORED; break; }
             if (pos + len > out_cap) { err = INF_ERR_SIZE; break; }
             for (uint32_t k = lane; k < len; k += 32) out[pos + k] = __ldg(q + k);
             __syncwarp();
             pos += len;
-            br.p = q + len;
+            br.seek(q0 + 4 + len);
             continue;
         }
         if (type == 3) { err = INF_ERR_BTYPE; break; }

@@ -439,7 +439,10 @@ static bool feed_device(const mthh_options& o, const RecordStream& in, mth_ctx* 
     const Header& hdr = in.header();
     const uint8_t* d = in.file().data();
     const size_t fsize = in.file().size();
-    const size_t WINDOW_U = 96u << 20;  // uncompressed bytes per window
+    // uncompressed bytes per window: one warp inflates one <= 64 KiB member, so a window has to hold several thousand members to
+    // fill the GPU (148 SMs x ~50 warps); the first window is small so that the pipeline starts early
+    size_t WINDOW_U = 96u << 20;
+    const size_t WINDOW_U_NEXT = 448u << 20;
     struct Staged {
         void* pin = nullptr;
         size_t cap = 0, bytes = 0;
@@ -475,6 +478,7 @@ static bool feed_device(const mthh_options& o, const RecordStream& in, mth_ctx* 
         w.skip = hdr_left;
         hdr_left = 0;
         w.last = coff >= fsize;
+        WINDOW_U = WINDOW_U_NEXT;
         if (w.members.empty()) { w.seconds = now_s() - t0; return; }
         const size_t bytes = pay.back().first + pay.back().second - c0;
         if (bytes > w.cap) {
