@@ -362,7 +362,11 @@ typedef struct {
 } mth_bamdec_result;
 /* lpmd_order / min_qual: lpmd.rs:176-181 tests mapq BEFORE it builds the read (low-mapq records are only counted and may lack XM). */
 int mth_bamdec_create(mth_bamdec** out, int device, int32_t n_ref, const int64_t* ref_len, uint32_t lpmd_order, uint32_t min_qual);
-/* comp: host memory (pinned preferred).  skip: bytes at the start of the FIRST window's output that are the BAM header.
+/* Uploads the compressed bytes of an upcoming window into staging slot 0 or 1 (blocking; any host memory, e.g. the memory-mapped
+ * file).  May be called from a second thread while mth_bamdec_window works on the other slot. */
+int mth_bamdec_stage(mth_bamdec* d, int slot, const uint8_t* comp, size_t comp_bytes);
+/* comp: host memory holding the window's compressed bytes, or NULL: then comp_bytes is the staging slot (0 / 1) filled by
+ * mth_bamdec_stage.  skip: bytes at the start of the FIRST window's output that are the BAM header.
  * last != 0: no window follows — a trailing partial record is an error. */
 int mth_bamdec_window(mth_bamdec* d, const uint8_t* comp, size_t comp_bytes, const mth_bgzf_member* members, int64_t n_members,
                       uint64_t skip, int last, mth_bamdec_result* out);

@@ -114,7 +114,7 @@ EXPORTS = ["mth_params_default", "mth_ctx_create", "mth_ctx_destroy", "mth_set_s
            "mth_device_count", "mth_version", "mth_reservoir_draw", "mth_genome_create", "mth_genome_set_contig", "mth_tag",
            "mth_genome_destroy", "mth_genome_last_error", "mth_genome_last_kernel_ms", "mth_comm_unique_id", "mth_comm_init_rank",
            "mth_comm_init_all", "mth_allreduce", "mth_allreduce_group", "mth_comm_destroy", "mth_comm_n_ranks", "mth_set_cpg_set", "mth_clear_cpg_set", "mth_bamdec_create",
-           "mth_bamdec_window", "mth_bamdec_destroy", "mth_bamdec_last_error", "mth_bgzf_inflate"]
+           "mth_bamdec_window", "mth_bamdec_stage", "mth_bamdec_destroy", "mth_bamdec_last_error", "mth_bgzf_inflate"]
 
 
 def build(force=False):
@@ -163,6 +163,7 @@ def lib():
     L.mth_clear_cpg_set.argtypes = [vp]; L.mth_clear_cpg_set.restype = C.c_int
     L.mth_bamdec_create.argtypes = [P(vp), C.c_int, i32, P(i64), u32, u32]; L.mth_bamdec_create.restype = C.c_int
     L.mth_bamdec_window.argtypes = [vp, vp, C.c_size_t, P(BgzfMember), i64, u64, C.c_int, P(BamdecResult)]; L.mth_bamdec_window.restype = C.c_int
+    L.mth_bamdec_stage.argtypes = [vp, C.c_int, vp, C.c_size_t]; L.mth_bamdec_stage.restype = C.c_int
     L.mth_bamdec_destroy.argtypes = [vp]; L.mth_bamdec_destroy.restype = C.c_int
     L.mth_bamdec_last_error.argtypes = [vp]; L.mth_bamdec_last_error.restype = C.c_char_p
     L.mth_bgzf_inflate.argtypes = [C.c_int, vp, C.c_size_t, P(BgzfMember), i64, vp, C.c_size_t, vp, P(C.c_double)]; L.mth_bgzf_inflate.restype = C.c_int

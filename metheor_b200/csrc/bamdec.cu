@@ -374,11 +374,12 @@ struct DBuf {
 
 struct mth_bamdec {
     int device = 0;
-    cudaStream_t s = nullptr;
+    cudaStream_t s = nullptr, s_stage[2] = {nullptr, nullptr};
+    size_t staged_bytes[2] = {0, 0};
     std::string err;
     int32_t n_ref = 0;
     uint32_t lpmd_order = 0, min_qual = 0;
-    DBuf ref_len, comp, members, status, u, entry, n_rec, landing, base, rec_off, keep, ncpg, scan_scratch, small;
+    DBuf ref_len, comp_slot[2], comp, members, status, u, entry, n_rec, landing, base, rec_off, keep, ncpg, scan_scratch, small;
     DBuf o_start, o_end, o_meta, o_off, o_pos, o_rel, o_meth;
     void* h_small = nullptr;  // pinned mirror of `small`
     size_t carry = 0;         // bytes at the front of `u` carried over from the previous window (a partial record)
@@ -441,6 +442,7 @@ int mth_bamdec_create(mth_bamdec** out, int device, int32_t n_ref, const int64_t
         return dfail(nullptr, MTH_ERR_CUDA, "CUDA initialisation failed");
     }
     for (auto& e : d->ev) cudaEventCreate(&e);
+    for (auto& st : d->s_stage) cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
     if (reserve(d, d->ref_len, (size_t)std::max(1, n_ref) * 8) != MTH_OK || reserve(d, d->small, SM_WORDS * 8) != MTH_OK ||
         cudaHostAlloc(&d->h_small, SM_WORDS * 8, cudaHostAllocDefault) != cudaSuccess) {
         g_dec_err = d->err;
@@ -461,7 +463,9 @@ int mth_bamdec_destroy(mth_bamdec* d) {
     if (!d) return MTH_OK;
     cudaSetDevice(d->device);
     if (d->s) cudaStreamSynchronize(d->s);
-    for (DBuf* b : {&d->ref_len, &d->comp, &d->members, &d->status, &d->u, &d->entry, &d->n_rec, &d->landing, &d->base, &d->rec_off, &d->keep,
+    for (auto& st : d->s_stage)
+        if (st) cudaStreamDestroy(st);
+    for (DBuf* b : {&d->ref_len, &d->comp_slot[0], &d->comp_slot[1], &d->comp, &d->members, &d->status, &d->u, &d->entry, &d->n_rec, &d->landing, &d->base, &d->rec_off, &d->keep,
                     &d->ncpg, &d->scan_scratch, &d->small, &d->o_start, &d->o_end, &d->o_meta, &d->o_off, &d->o_pos, &d->o_rel, &d->o_meth})
         if (b->p) cudaFree(b->p);
     if (d->h_small) cudaFreeHost(d->h_small);
@@ -513,9 +517,37 @@ int mth_bgzf_inflate(int device, const uint8_t* comp, size_t comp_bytes, const m
     return rc;
 }
 
+// Upload the compressed bytes of the NEXT window into staging slot 0 / 1.  Blocking (the source is ordinary pageable memory,
+// typically the memory-mapped file), on its own stream: meant to be called from a helper thread while mth_bamdec_window works on
+// the other slot.
+int mth_bamdec_stage(mth_bamdec* d, int slot, const uint8_t* comp, size_t comp_bytes) {
+    if (!d || slot < 0 || slot > 1 || (comp_bytes && !comp)) return MTH_ERR_INVALID;
+    DTRY(d, cudaSetDevice(d->device));
+    DBuf& b = d->comp_slot[slot];
+    if (comp_bytes + 64 > b.cap) {  // (not reserve(): that synchronises the decode stream, which another thread may be using)
+        if (b.p) DTRY(d, cudaFree(b.p));
+        b.p = nullptr;
+        b.cap = 0;
+        const size_t ncap = comp_bytes + comp_bytes / 4 + (1u << 20);
+        DTRY(d, cudaMalloc(&b.p, ncap));
+        b.cap = ncap;
+    }
+    if (comp_bytes) DTRY(d, cudaMemcpyAsync(b.p, comp, comp_bytes, cudaMemcpyHostToDevice, d->s_stage[slot]));
+    DTRY(d, cudaStreamSynchronize(d->s_stage[slot]));
+    d->staged_bytes[slot] = comp_bytes;
+    return MTH_OK;
+}
+
+// comp == nullptr: the window's compressed bytes are the ones staged in slot `comp_bytes` (0 / 1) by mth_bamdec_stage.
 int mth_bamdec_window(mth_bamdec* d, const uint8_t* comp, size_t comp_bytes, const mth_bgzf_member* members, int64_t n_members, uint64_t skip,
                       int last, mth_bamdec_result* out) {
-    if (!d || !out || (n_members && (!comp || !members)) || n_members < 0) return MTH_ERR_INVALID;
+    if (!d || !out || (n_members && !members) || n_members < 0) return MTH_ERR_INVALID;
+    const uint8_t* comp_dev = nullptr;
+    if (!comp) {
+        if (comp_bytes > 1) return MTH_ERR_INVALID;
+        comp_dev = (const uint8_t*)d->comp_slot[comp_bytes].p;
+        comp_bytes = d->staged_bytes[comp_bytes];
+    }
     memset(out, 0, sizeof(*out));
     out->bad_record = -1;
     DTRY(d, cudaSetDevice(d->device));
@@ -531,17 +563,22 @@ int mth_bamdec_window(mth_bamdec* d, const uint8_t* comp, size_t comp_bytes, con
     const size_t u_end = uo;
     if (u_end >= 0xfffffff0ull) return dfail(d, MTH_ERR_UNSUPPORTED, "window larger than 4 GiB of uncompressed BAM");
     if (skip > u_end - d->carry || (skip && d->carry)) return dfail(d, MTH_ERR_INVALID, "skip outside the first window");
-    if (reserve(d, d->comp, comp_bytes + 64) || reserve(d, d->members, (size_t)n_members * sizeof(MemberDesc) + 64) ||
+    if ((!comp_dev && reserve(d, d->comp, comp_bytes + 64)) || reserve(d, d->members, (size_t)n_members * sizeof(MemberDesc) + 64) ||
         reserve(d, d->status, (size_t)n_members * 4 + 64) || reserve(d, d->u, u_end + 64, d->carry))
         return MTH_ERR_CUDA;
     DTRY(d, cudaMemsetAsync(d->small.p, 0, SM_WORDS * 8, s));
-    DTRY(d, cudaEventRecord(d->ev[0], s));
     if (n_members) {
-        DTRY(d, cudaMemcpyAsync(d->comp.p, comp, comp_bytes, cudaMemcpyHostToDevice, s));
+        if (!comp_dev) {
+            DTRY(d, cudaMemcpyAsync(d->comp.p, comp, comp_bytes, cudaMemcpyHostToDevice, s));
+            comp_dev = (const uint8_t*)d->comp.p;
+        }
         DTRY(d, cudaMemcpyAsync(d->members.p, md.data(), (size_t)n_members * sizeof(MemberDesc), cudaMemcpyHostToDevice, s));
+        DTRY(d, cudaEventRecord(d->ev[0], s));
         k_bgzf_inflate<<<(unsigned)((n_members + INF_WARPS - 1) / INF_WARPS), INF_WARPS * 32, INF_WARPS * sizeof(InflateTables), s>>>(
-            (const uint8_t*)d->comp.p, (const MemberDesc*)d->members.p, n_members, (uint8_t*)d->u.p, (int*)d->status.p,
+            comp_dev, (const MemberDesc*)d->members.p, n_members, (uint8_t*)d->u.p, (int*)d->status.p,
             (int*)((unsigned long long*)d->small.p + SM_ANYBAD));
+    } else {
+        DTRY(d, cudaEventRecord(d->ev[0], s));
     }
     DTRY(d, cudaEventRecord(d->ev[1], s));
     // ---- record boundaries: speculate, verify, (repair) ----

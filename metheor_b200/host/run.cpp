@@ -441,28 +441,25 @@ static bool feed_device(const mthh_options& o, const RecordStream& in, mth_ctx* 
     const size_t fsize = in.file().size();
     // uncompressed bytes per window: one warp inflates one <= 64 KiB member, so a window has to hold several thousand members to
     // fill the GPU (148 SMs x ~50 warps); the first window is small so that the pipeline starts early
-    size_t WINDOW_U = 96u << 20;
-    const size_t WINDOW_U_NEXT = 448u << 20;
+    const size_t WINDOW_U = 256u << 20;
     struct Staged {
-        void* pin = nullptr;
-        size_t cap = 0, bytes = 0;
+        size_t bytes = 0;
         std::vector<mth_bgzf_member> members;
         uint64_t skip = 0;
         bool last = false, ok = true;
         std::string err;
         double seconds = 0;
-        ~Staged() { mth_host_free(pin); }
     };
     Staged st[2];
     size_t coff = 0;           // next compressed offset
     uint64_t hdr_left = in.bam_header_bytes();  // header bytes not skipped yet
-    // stage the next window: member walk + copy of the compressed bytes into pinned memory
-    auto stage = [&](Staged& w) {
+    mth_bamdec* dec = nullptr;
+    // stage the next window: member walk + upload of its compressed bytes (straight from the page cache) into a device slot
+    auto stage = [&](Staged& w, int slot) {
         const double t0 = now_s();
         w.members.clear();
         w.bytes = 0; w.skip = 0; w.ok = true;
-        size_t c0 = coff, u = 0;
-        std::vector<std::pair<size_t, size_t>> pay;  // payload (offset, size) in the file
+        size_t c0 = coff, u = 0, c1 = coff;
         while (coff < fsize && u < WINDOW_U) {
             size_t cdata, clen;
             uint32_t usize, crc;
@@ -471,39 +468,25 @@ static bool feed_device(const mthh_options& o, const RecordStream& in, mth_ctx* 
             coff += total;
             if (usize == 0) continue;  // empty member (the EOF marker)
             if (hdr_left >= usize) { hdr_left -= usize; c0 = coff; continue; }  // a member that holds only header bytes
-            pay.push_back({cdata, clen});
             w.members.push_back(mth_bgzf_member{(uint64_t)(cdata - c0), (uint32_t)clen, usize});
+            c1 = cdata + clen;
             u += usize;
         }
         w.skip = hdr_left;
         hdr_left = 0;
         w.last = coff >= fsize;
-        WINDOW_U = WINDOW_U_NEXT;
-        if (w.members.empty()) { w.seconds = now_s() - t0; return; }
-        const size_t bytes = pay.back().first + pay.back().second - c0;
-        if (bytes > w.cap) {
-            mth_host_free(w.pin);
-            w.cap = bytes + bytes / 4 + (1u << 20);
-            w.pin = mth_host_alloc(w.cap);
-            if (!w.pin) { w.ok = false; w.err = "cannot allocate pinned host memory"; w.cap = 0; return; }
+        if (!w.members.empty()) {
+            w.bytes = c1 - c0;
+            const int rc = mth_bamdec_stage(dec, slot, d + c0, w.bytes);
+            if (rc != MTH_OK) { w.ok = false; w.err = std::string("metheor_b200 engine: ") + mth_bamdec_last_error(dec); }
         }
-        // parallel copy out of the page cache (one memcpy runs at a few GB/s only)
-        const int nt = 8;
-        std::vector<std::thread> th;
-        for (int t = 0; t < nt; t++) {
-            const size_t a = bytes * (size_t)t / nt, b = bytes * (size_t)(t + 1) / nt;
-            th.emplace_back([=, &w] { memcpy((uint8_t*)w.pin + a, d + c0 + a, b - a); });
-        }
-        for (auto& t : th) t.join();
-        w.bytes = bytes;
         w.seconds = now_s() - t0;
     };
-    mth_bamdec* dec = nullptr;
     int rc = mth_bamdec_create(&dec, device, (int32_t)hdr.lengths.size(), hdr.lengths.data(), lpmd_order, o.min_qual);
     if (rc != MTH_OK) throw HostError{1, std::string("metheor_b200 engine: ") + mth_bamdec_last_error(nullptr)};
     struct DecGuard { mth_bamdec* d; ~DecGuard() { mth_bamdec_destroy(d); } } guard{dec};
     int cur = 0;
-    stage(st[cur]);
+    stage(st[cur], cur);
     bool first = true;
     for (;;) {
         Staged& w = st[cur];
@@ -513,12 +496,12 @@ static bool feed_device(const mthh_options& o, const RecordStream& in, mth_ctx* 
         const bool last = w.last;
         // the next window is staged by a helper thread while the GPU works on this one
         std::future<void> nxt;
-        if (!last) nxt = std::async(std::launch::async, [&, cur] { stage(st[cur ^ 1]); });
+        if (!last) nxt = std::async(std::launch::async, [&, cur] { stage(st[cur ^ 1], cur ^ 1); });
         double t0 = now_s();
         rc = mth_sync_copies(ctx);  // the previous window's device batches have been copied into the arena
         if (rc != MTH_OK) engine_fail(ctx, rc, "mth_sync_copies");
         mth_bamdec_result res;
-        rc = mth_bamdec_window(dec, (const uint8_t*)w.pin, w.bytes, w.members.data(), (int64_t)w.members.size(), w.skip, last ? 1 : 0, &res);
+        rc = mth_bamdec_window(dec, nullptr, (size_t)cur, w.members.data(), (int64_t)w.members.size(), w.skip, last ? 1 : 0, &res);
         if (rc == MTH_ERR_UNSUPPORTED) {
             if (nxt.valid()) nxt.wait();
             return false;
