@@ -165,10 +165,20 @@ __device__ __forceinline__ int decode_sym(BitReader& br, const uint16_t* cnt, co
     return -1;
 }
 
-__device__ const uint16_t INF_LBASE[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
-__device__ const uint8_t INF_LEXT[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
-__device__ const uint16_t INF_DBASE[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
-__device__ const uint8_t INF_DEXT[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+// length / distance codes -> base value and number of extra bits (RFC 1951 3.2.5), computed instead of looked up
+__device__ __forceinline__ void len_code(int ls, uint32_t* base, int* ext) {   // ls = symbol - 257, 0..28
+    if (ls < 8) { *base = 3u + (uint32_t)ls; *ext = 0; return; }
+    if (ls == 28) { *base = 258u; *ext = 0; return; }
+    const int e = (ls - 4) >> 2;
+    *ext = e;
+    *base = 3u + ((4u + ((uint32_t)ls & 3u)) << e);
+}
+__device__ __forceinline__ void dist_code(int ds, uint32_t* base, int* ext) {  // 0..29
+    if (ds < 4) { *base = 1u + (uint32_t)ds; *ext = 0; return; }
+    const int e = (ds - 2) >> 1;
+    *ext = e;
+    *base = 1u + ((2u + ((uint32_t)ds & 1u)) << e);
+}
 __device__ const uint8_t INF_CLORDER[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
 // Inflates one raw-DEFLATE stream in[0, in_len) into out[0, out_cap); all 32 lanes of a warp call it with the same
@@ -254,6 +264,26 @@ __device__ __forceinline__ int warp_inflate(const uint8_t* __restrict__ in, uint
                 !build_table(L + nlen, ndist, T.d_cnt, T.d_sym, T.d_fast, INF_D_BITS)) { err = INF_ERR_TABLE; break; }
         }
         // ---- the symbols of the block ----
+        // A match is a copy out[pos + k] = out[pos - dist + k % dist]: its loads come back from L2 after a few hundred cycles.
+        // They are issued at once but the dependent stores are DEFERRED until the next match (or the end of the block) needs the
+        // bytes, so the warp goes on decoding the following symbols while the loads are in flight (the warp issues in order:
+        // storing immediately would stall it on every match).  Up to 9 bytes per lane (258 / 32) are pending at any time.
+        uint32_t pend_pos = 0, pend_len = 0;
+        uint32_t pv0 = 0, pv1 = 0, pv2 = 0;  // pending bytes k = lane + 32 j, packed 4 per register
+        auto flush = [&]() {
+            if (pend_len) {
+#pragma unroll
+                for (int j = 0; j < 9; j++) {
+                    const uint32_t k = (uint32_t)lane + 32u * j;
+                    if (k < pend_len) {
+                        const uint32_t w = j < 4 ? pv0 : j < 8 ? pv1 : pv2;
+                        out[pend_pos + k] = (uint8_t)(w >> (8 * (j & 3)));
+                    }
+                }
+                pend_len = 0;
+            }
+            __syncwarp();  // everything written so far (literals by lane 0, the flushed match) is visible to every lane
+        };
         while (true) {
             const int s = decode_sym(br, T.ll_cnt, T.ll_sym, T.ll_fast, INF_LL_BITS);
             if (s < 0) { err = INF_ERR_CODE; break; }
@@ -266,18 +296,32 @@ __device__ __forceinline__ int warp_inflate(const uint8_t* __restrict__ in, uint
             if (s == 256) break;
             const int ls = s - 257;
             if (ls >= 29) { err = INF_ERR_CODE; break; }
-            const uint32_t len = INF_LBASE[ls] + br.bits(INF_LEXT[ls]);
+            uint32_t lbase, dbase;
+            int lext, dext;
+            len_code(ls, &lbase, &lext);
+            const uint32_t len = lbase + br.bits(lext);
             const int ds = decode_sym(br, T.d_cnt, T.d_sym, T.d_fast, INF_D_BITS);
             if (ds < 0 || ds >= 30) { err = INF_ERR_CODE; break; }
-            const uint32_t dist = INF_DBASE[ds] + br.bits(INF_DEXT[ds]);
+            dist_code(ds, &dbase, &dext);
+            const uint32_t dist = dbase + br.bits(dext);
             if (dist > pos) { err = INF_ERR_DIST; break; }
             if (pos + len > out_cap) { err = INF_ERR_SIZE; break; }
-            __syncwarp();  // the bytes written so far (literals by lane 0) are visible to every lane
+            flush();
             const uint8_t* src = out + pos - dist;
-            for (uint32_t k = lane; k < len; k += 32) out[pos + k] = __ldcg(src + (dist >= len ? k : k % dist));
-            __syncwarp();
+            pv0 = pv1 = pv2 = 0;
+#pragma unroll
+            for (int j = 0; j < 9; j++) {
+                const uint32_t k = (uint32_t)lane + 32u * j;
+                if (k < len) {
+                    const uint32_t v = (uint32_t)__ldcg(src + (dist >= len ? k : k % dist));
+                    if (j < 4) pv0 |= v << (8 * (j & 3)); else if (j < 8) pv1 |= v << (8 * (j & 3)); else pv2 |= v << (8 * (j & 3));
+                }
+            }
+            pend_pos = pos;
+            pend_len = len;
             pos += len;
         }
+        flush();
         if (br.overrun()) err = INF_ERR_OVERRUN;
     }
     *produced = pos;

@@ -428,7 +428,7 @@ std::vector<std::vector<ShardInterval>> plan_contigs(const std::vector<int64_t>&
 // back as device-resident batches for mth_submit.  Returns false when the file needs the host decoder (a read with more than
 // 64 CpG calls, ...): the caller resets the engine and runs the CPU path.
 struct DeviceFeedStats {
-    double s_stage = 0, s_window = 0, s_submit = 0;
+    double s_stage = 0, s_window = 0, s_submit = 0, s_create = 0, s_reserve = 0, s_wait_stage = 0, s_tail = 0;
     double ms_inflate = 0, ms_boundaries = 0, ms_decode = 0;
     int64_t windows = 0, chain_repairs = 0;
     uint64_t bytes_compressed = 0, bytes_uncompressed = 0;
@@ -441,7 +441,7 @@ static bool feed_device(const mthh_options& o, const RecordStream& in, mth_ctx* 
     const size_t fsize = in.file().size();
     // uncompressed bytes per window: one warp inflates one <= 64 KiB member, so a window has to hold several thousand members to
     // fill the GPU (148 SMs x ~50 warps); the first window is small so that the pipeline starts early
-    const size_t WINDOW_U = 256u << 20;
+    const size_t WINDOW_U = 384u << 20;
     struct Staged {
         size_t bytes = 0;
         std::vector<mth_bgzf_member> members;
@@ -482,8 +482,10 @@ static bool feed_device(const mthh_options& o, const RecordStream& in, mth_ctx* 
         }
         w.seconds = now_s() - t0;
     };
+    double tc0 = now_s();
     int rc = mth_bamdec_create(&dec, device, (int32_t)hdr.lengths.size(), hdr.lengths.data(), lpmd_order, o.min_qual);
     if (rc != MTH_OK) throw HostError{1, std::string("metheor_b200 engine: ") + mth_bamdec_last_error(nullptr)};
+    fs->s_create = now_s() - tc0;
     struct DecGuard { mth_bamdec* d; ~DecGuard() { mth_bamdec_destroy(d); } } guard{dec};
     int cur = 0;
     stage(st[cur], cur);
@@ -540,15 +542,21 @@ static bool feed_device(const mthh_options& o, const RecordStream& in, mth_ctx* 
         fs->s_submit += now_s() - t0;
         if (first && !last && w.bytes) {  // size the arena once from the first window: reads per compressed byte x file size (+15 %)
             const double scale = 1.15 * (double)fsize / (double)w.bytes;
+            const double tr0 = now_s();
             if (scale > 1.5) mth_reserve(ctx, (int64_t)((double)*n_reads * scale) + 4096, (int64_t)((double)*n_cpg * scale) + 4096);
+            fs->s_reserve += now_s() - tr0;
         }
         first = false;
+        const double tw0 = now_s();
         if (nxt.valid()) nxt.wait();
+        fs->s_wait_stage += now_s() - tw0;
         if (last) break;
         cur ^= 1;
     }
+    const double tt0 = now_s();
     rc = mth_sync_copies(ctx);
     if (rc != MTH_OK) engine_fail(ctx, rc, "mth_sync_copies");
+    fs->s_tail = now_s() - tt0;
     return true;
 }
 
@@ -887,14 +895,14 @@ void run(const mthh_options& o) {
                        "\"cpg_calls_shipped\": %lld, \"batches\": %lld, \"rows\": %lld, \"bytes_uncompressed\": %llu, \"zlib_fallbacks\": %lld, "
                        "\"seconds\": {\"total\": %.6f, \"stream\": %.6f, \"inflate\": %.6f, \"walk\": %.6f, \"decode\": %.6f, "
                        "\"assemble\": %.6f, \"submit\": %.6f, \"finish\": %.6f, \"write\": %.6f}, \"reads_per_sec\": %.1f, \"decode\": \"%s\", "
-                       "\"device_decode\": {\"windows\": %lld, \"stage_s\": %.6f, \"window_s\": %.6f, \"submit_s\": %.6f, \"inflate_ms\": %.3f, "
+                       "\"device_decode\": {\"windows\": %lld, \"create_s\": %.6f, \"reserve_s\": %.6f, \"wait_stage_s\": %.6f, \"tail_s\": %.6f, \"stage_s\": %.6f, \"window_s\": %.6f, \"submit_s\": %.6f, \"inflate_ms\": %.3f, "
                        "\"boundaries_ms\": %.3f, \"decode_ms\": %.3f, \"chain_repairs\": %lld, \"bytes_compressed\": %llu, \"bytes_uncompressed\": %llu}, \"gpu\": [",
                     fmt == Format::BAM ? "bam" : "sam", n_threads, n_gpus, (long long)total.n_records, (long long)n_shipped_reads,
                     (long long)n_shipped_cpg, (long long)n_batches, (long long)n_rows_total,
                     (unsigned long long)(used_device ? dfs.bytes_uncompressed : in.bytes_uncompressed),
                     (long long)g_zlib_fallbacks.load(), wall, t_decoded - t_begin, in.seconds_inflate, in.seconds_walk, s_decode, s_assemble, s_submit,
                     t_finished - t_decoded, t_end - t_finished, (double)total.n_records / wall, used_device ? "device" : "host",
-                    (long long)dfs.windows, dfs.s_stage, dfs.s_window, dfs.s_submit, dfs.ms_inflate, dfs.ms_boundaries, dfs.ms_decode,
+                    (long long)dfs.windows, dfs.s_create, dfs.s_reserve, dfs.s_wait_stage, dfs.s_tail, dfs.s_stage, dfs.s_window, dfs.s_submit, dfs.ms_inflate, dfs.ms_boundaries, dfs.ms_decode,
                     (long long)dfs.chain_repairs, (unsigned long long)dfs.bytes_compressed, (unsigned long long)dfs.bytes_uncompressed);
             for (size_t g = 0; g < gpus.size(); g++) {
                 const mth_stats& st = gpus[g]->stats;
