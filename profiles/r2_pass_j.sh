@@ -1,6 +1,6 @@
 #!/bin/bash
 O=gpurun_out/${1:-r2j}; mkdir -p $O
-timeout 600 python -m pytest tests/test_gpu_bamdec.py tests/test_cli_gpu.py -m gpu -x -q > $O/pytest.log 2>&1; echo "pytest rc=$?" >> $O/pytest.log
+timeout 600 python -m pytest tests/test_gpu_bamdec.py -m gpu -x -q > $O/pytest.log 2>&1; echo "pytest rc=$?" >> $O/pytest.log
 tail -5 $O/pytest.log
 timeout 900 python - > $O/bam_leg.json 2> $O/bam_leg.err <<'PY'
 import json, sys, time, tempfile, os
