@@ -16,7 +16,7 @@ ls -la $O
 ncu -i $O/prof_chr1.ncu-rep --page raw --csv > $O/prof_chr1_raw.csv 2>/dev/null
 SZ=$(stat -c %s $O/prof_chr1.ncu-rep 2>/dev/null || echo 0)
 if [ "$SZ" -gt 45000000 ]; then
-  for k in k_ingest k_fdrp_tile k_mhl_site k_quartet_scatter k_quartet_canon k_pdr_scatter k_mhl k_fdrp; do
+  for k in k_ingest k_fdrp_tile k_mhl_site k_quartet_scatter k_quartet_hist k_quartet_canon_emit k_pdr_scatter k_mhl k_fdrp k_quartet; do
     ncu -i $O/prof_chr1.ncu-rep --page source --csv --print-source cuda,sass --kernel-name regex:"$k\b" > $O/src_$k.csv 2>/dev/null
   done
   gzip -9 $O/src_*.csv
