@@ -350,6 +350,7 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary legs (chr19 configs[1], 60x, BAM, tag)")
     ap.add_argument("--chr19-coverage", type=float, default=30.0)
     ap.add_argument("--wg60", type=float, default=60.0, help="coverage of the configs[3] leg (fdrp + qfdrp); 0 disables")
+    ap.add_argument("--wg100", type=float, default=100.0, help="coverage of the configs[4] leg (all seven measures); 0 disables")
     ap.add_argument("--tag-reads", type=int, default=2_000_000)
     ap.add_argument("--bam-reads", type=int, default=2_000_000)
     args = ap.parse_args()
@@ -671,27 +672,40 @@ def main():
         del wg
     torch.cuda.empty_cache()
 
-    # ---------------- secondary legs (N = 1 only) ----------------
+    # ---------------- the larger BASELINE configs, sharded over the ranks like the headline ----------------
     extra = {}
-    if world == 1 and not args.no_extra:
+
+    def coverage_leg(key, cov, measures, what, steps=2):
+        """One measure set at another coverage of the same genome (every rank generates its own position bin)."""
+        nonlocal R_loc, I_loc
+        try:
+            t0 = time.perf_counter()
+            wc, r_own, i_own = gen_shard(torch, dev, contigs, cov, intervals, world)
+            torch.cuda.synchronize()
+            gsec = time.perf_counter() - t0
+            tt = torch.tensor([r_own, i_own], device=dev, dtype=torch.int64)
+            if world > 1:
+                dist.all_reduce(tt)
+            R_save, I_save = R_loc, I_loc
+            R_loc, I_loc = sum(b["n_reads"] for b in wc), sum(b["n_cpg"] for b in wc)
+            blk = measure_block(measures, steps, batches=wc, n_reads=int(tt[0]), n_calls=int(tt[1]))
+            add_roofline(blk, {})
+            R_loc, I_loc = R_save, I_save
+            blk.update(workload=f"{what}: {' + '.join(measures)}, {workload_name(cov, args.scale)}", reads=int(tt[0]), cpg_calls=int(tt[1]),
+                       n_gpus=world, generate_seconds=gsec)
+            del wc
+            torch.cuda.empty_cache()
+            return blk
+        except Exception as e:  # a secondary leg must never cost the bench line
+            torch.cuda.empty_cache()
+            return {"error": repr(e)}
+
+    if not args.no_extra:
         if args.wg60 > 0:
-            try:
-                t0 = time.perf_counter()
-                w60, r60, i60 = gen_shard(torch, dev, contigs, args.wg60, [(t, 0, l) for t, l in enumerate(ref_len)], 1)
-                torch.cuda.synchronize()
-                g60 = time.perf_counter() - t0
-                R_save, I_save = R_loc, I_loc
-                R_loc, I_loc = r60, i60
-                b60 = measure_block(("fdrp", "qfdrp"), 2, batches=w60, n_reads=r60, n_calls=i60)
-                add_roofline(b60, {})
-                R_loc, I_loc = R_save, I_save
-                b60.update(workload=f"BASELINE.json configs[3] on one GPU: fdrp + qfdrp, {workload_name(args.wg60, args.scale)}", reads=r60,
-                           cpg_calls=i60, generate_seconds=g60)
-                extra["config3_wg60x_fdrp_qfdrp"] = b60
-                del w60
-                torch.cuda.empty_cache()
-            except Exception as e:
-                extra["config3_wg60x_fdrp_qfdrp"] = {"error": repr(e)}
+            extra["config3_wg60x_fdrp_qfdrp"] = coverage_leg("config3", args.wg60, ("fdrp", "qfdrp"), f"BASELINE.json configs[3] on {world} GPU(s)")
+        if args.wg100 > 0:
+            extra["config4_wg100x_all_seven"] = coverage_leg("config4", args.wg100, ALL7, f"BASELINE.json configs[4] on {world} GPU(s)")
+    if world == 1 and not args.no_extra:
         try:
             c19, b19 = X.chr19_leg(args, torch, dev, stream, max(3, min(args.steps, 10)))
             extra["config1_chr19_pdr_lpmd"] = c19

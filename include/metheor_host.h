@@ -44,6 +44,11 @@ typedef struct {
     int32_t shard_contigs;  /* --shard contigs : shard whole contigs instead of position bins (default 0 = bins) */
     int32_t decode_host;    /* --decode host   : inflate + decode BAM records on the host cores instead of the GPU (default 0: GPU for
                                BAM input on one GPU; SAM text and --gpus > 1 always decode on the host) */
+    int32_t out_format;     /* --format tsv | tsv.gz | bedgraph | bedgraph.gz : bit 0 = BGZF-compressed output, bit 1 = bedGraph
+                               (chrom start end value; per-CpG measures only).  Default 0: the reference's plain TSV */
+    const char* region;     /* --region chr[:beg-end] (1-based, inclusive like samtools) or NULL: only the rows of sites inside the
+                               region are computed and written — identical to the same rows of a whole-file run; with a .bai next
+                               to the BAM the decoder seeks to the region through the linear index */
     int32_t threads;        /* --threads N: decode threads, 0 = all cores */
     uint64_t seed;          /* --seed     : reservoir sampling seed once a pile exceeds max_depth */
     const char* stats_json; /* --stats F  : write reads/s, per-stage seconds and kernel stats as JSON, or NULL */

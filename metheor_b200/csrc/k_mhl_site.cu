@@ -22,12 +22,12 @@ namespace mth {
 constexpr int MS_SITES = 128;    // sites (= threads) per CTA
 constexpr int MS_RCAP = 2048;    // reads staged per tile (dense instance: chr19-like density, ~1400 reads per 128 sites at 30x)
 constexpr int MS_CCAP = 6144;    // calls staged per tile
-constexpr int MS_RCAP_SPARSE = 4608;  // sparse instance: whole-genome density (a 128-site tile spans ~14 kb: ~3000 reads at 30x)
+constexpr int MS_RCAP_SPARSE = 4096;  // sparse instance: whole-genome density (a 128-site tile spans ~14 kb: ~3300 reads at 30x)
 constexpr int MS_CCAP_SPARSE = 8192;
 constexpr int MS_L = 16;         // longest read (in calls) the per-thread accumulators hold
 constexpr int MS_SPAN = 60000;   // positions a tile may span (calls are staged as 16-bit offsets)
 
-// Shared-memory footprint decides how many sites are in flight per SM, so everything is packed: 10 bytes per read,
+// Shared-memory footprint decides how many sites are in flight per SM, so everything is packed: 12 bytes per read,
 // 2 bytes per call, 16-bit accumulators (a segment deeper than 65 535 reads goes to the per-site kernel).
 template <int RCAP, int CCAP>
 struct MsSmem {
@@ -35,6 +35,7 @@ struct MsSmem {
     uint16_t meta[RCAP];      // mapq | n << 8   (n <= MS_L)
     uint16_t o0[RCAP];        // first call of the read, tile-relative
     uint16_t first[RCAP];     // first call, as offset from the tile base (0xFFFF: no call)
+    uint16_t mbits[RCAP];     // methylation bits of the read's calls (n <= MS_L = 16 calls in this kernel)
     uint16_t pos[CCAP];       // calls, as offsets from the tile base
     uint16_t S[MS_L + 1][MS_SITES];   // [l][thread]: bank-conflict-free
     uint16_t N[MS_L + 1][MS_SITES];
@@ -87,6 +88,7 @@ __global__ void __launch_bounds__(MS_SITES) k_mhl_site(ReadsView rv, const int32
             sh.start[r] = rv.start[j];
             sh.meta[r] = (uint16_t)((rv.meta[j] & 0xFFu) | (min(n, 255u) << 8));
             sh.o0[r] = (uint16_t)(o0 - c0);
+            sh.mbits[r] = (uint16_t)rv.meth[j];  // staged once (coalesced) instead of one global load per (site, read)
             if (n > (uint32_t)MS_L) toolong = 1;
         }
         for (int y = tid; y < ncalls; y += MS_SITES) sh.pos[y] = (uint16_t)(rv.cpg_pos[c0 + y] - base);
@@ -151,7 +153,7 @@ __global__ void __launch_bounds__(MS_SITES) k_mhl_site(ReadsView rv, const int32
             if (++depth >= 4000u) deep = true;  // 16 calls x 4000 reads still fit the 16-bit accumulators
             maxn = max(maxn, n);
             sh.N[n][tid]++;  // mhl.rs:75-80
-            unsigned long long x = rv.meth[ra + r] & low_mask64(n);
+            unsigned long long x = (unsigned long long)sh.mbits[r] & low_mask64(n);
             for (uint32_t l = 1; x; l++) {  // stretch_info[l] = popc(x_l), readutil.rs:147-164
                 sh.S[l][tid] += (uint32_t)__popcll(x);
                 x &= x >> 1;

@@ -17,7 +17,7 @@ class Options(C.Structure):
     _fields_ = [("measure", C.c_int32), ("input", C.c_char_p), ("output", C.c_char_p), ("cpg_set", C.c_char_p),
                 ("pairs", C.c_char_p), ("min_depth", C.c_uint32), ("min_cpgs", C.c_uint32), ("min_qual", C.c_uint32),
                 ("max_depth", C.c_uint32), ("min_overlap", C.c_int32), ("min_distance", C.c_int32),
-                ("max_distance", C.c_int32), ("device", C.c_int32), ("n_gpus", C.c_int32), ("shard_contigs", C.c_int32), ("decode_host", C.c_int32), ("threads", C.c_int32),
+                ("max_distance", C.c_int32), ("device", C.c_int32), ("n_gpus", C.c_int32), ("shard_contigs", C.c_int32), ("decode_host", C.c_int32), ("out_format", C.c_int32), ("region", C.c_char_p), ("threads", C.c_int32),
                 ("seed", C.c_uint64), ("stats_json", C.c_char_p)]
 
 

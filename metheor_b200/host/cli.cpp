@@ -51,6 +51,8 @@ const ArgSpec E_DEVICE = {0, "device", A_I32, false, "0", "[engine] first CUDA d
 const ArgSpec E_GPUS = {0, "gpus", A_I32, false, "1", "[engine] shard the genome over this many GPUs (position bins + halo reads)", "GPUS"};
 const ArgSpec E_SHARD = {0, "shard", A_STR, false, "bins", "[engine] multi-GPU sharding: bins (equal position ranges) or contigs (whole contigs)", "SHARD"};
 const ArgSpec E_DECODE = {0, "decode", A_STR, false, "gpu", "[engine] where BAM is inflated and decoded: gpu (one GPU, BAM input) or host", "DECODE"};
+const ArgSpec E_FORMAT = {0, "format", A_STR, false, "tsv", "[engine] output format: tsv (the reference's), tsv.gz (BGZF), bedgraph, bedgraph.gz", "FORMAT"};
+const ArgSpec E_REGION = {0, "region", A_STR, false, nullptr, "[engine] only the sites of chr[:beg-end] (1-based, inclusive); uses <input>.bai when present", "REGION"};
 const ArgSpec E_THREADS = {0, "threads", A_I32, false, "0", "[engine] host decode threads (0 = all cores)", "THREADS"};
 const ArgSpec E_SEED = {0, "seed", A_U64, false, "0", "[engine] reservoir-sampling seed once a pile exceeds --max-depth", "SEED"};
 const ArgSpec E_STATS = {0, "stats", A_STR, false, nullptr, "[engine] write timing / throughput statistics as JSON", "STATS"};
@@ -94,7 +96,7 @@ std::vector<CmdSpec> commands() {
                   {'g', "genome", A_STR, true, nullptr, "", "GENOME"}, E_DEVICE, E_THREADS, E_STATS}});
     for (auto& cmd : c)
         if (cmd.measure >= 0) {
-            cmd.args.push_back(E_DEVICE); cmd.args.push_back(E_GPUS); cmd.args.push_back(E_SHARD); cmd.args.push_back(E_DECODE); cmd.args.push_back(E_THREADS); cmd.args.push_back(E_STATS);
+            cmd.args.push_back(E_DEVICE); cmd.args.push_back(E_GPUS); cmd.args.push_back(E_SHARD); cmd.args.push_back(E_DECODE); cmd.args.push_back(E_FORMAT); cmd.args.push_back(E_REGION); cmd.args.push_back(E_THREADS); cmd.args.push_back(E_STATS);
             if (cmd.measure == MTHH_FDRP || cmd.measure == MTHH_QFDRP) cmd.args.push_back(E_SEED);
         }
     return c;
@@ -171,6 +173,8 @@ void mthh_options_default(mthh_options* o, int32_t measure) {
     o->n_gpus = 1;
     o->shard_contigs = 0;
     o->decode_host = 0;
+    o->out_format = 0;
+    o->region = nullptr;
 }
 
 int mthh_run(const mthh_options* o, char* err, size_t errcap) {
@@ -325,6 +329,14 @@ int mthh_main(int argc, char** argv) {
             else if (!strcmp(v, "gpu")) o.decode_host = 0;
             else return usage_error(cmd, std::string("invalid value '") + v + "' for '--decode <DECODE>': expected gpu or host");
         }
+        else if (n == "format") {
+            if (!strcmp(v, "tsv")) o.out_format = 0;
+            else if (!strcmp(v, "tsv.gz")) o.out_format = 1;
+            else if (!strcmp(v, "bedgraph")) o.out_format = 2;
+            else if (!strcmp(v, "bedgraph.gz")) o.out_format = 3;
+            else return usage_error(cmd, std::string("invalid value '") + v + "' for '--format <FORMAT>': expected tsv, tsv.gz, bedgraph or bedgraph.gz");
+        }
+        else if (n == "region") o.region = v;
         else if (n == "threads") o.threads = (int32_t)s;
         else if (n == "seed") o.seed = u;
         else if (n == "stats") o.stats_json = v;

@@ -110,6 +110,15 @@ size_t bgzf_member_info(const uint8_t* d, size_t size, size_t o, size_t* cdata, 
 
 size_t RecordStream::bam_header_bytes() const { return bam_header_len_; }
 
+void RecordStream::seek_virtual(uint64_t voffset) {
+    if (format_ != Format::BAM || prefetching_ || inflating_) throw HostError{1, "metheor_b200: seek on a stream that is already being read"};
+    coff_ = (size_t)(voffset >> 16);
+    skip_first_ = (size_t)(voffset & 0xffffu);
+    carry_.clear();
+    consumed_ = coff_;
+    if (coff_ > file_.size()) throw HostError{101, "Error opening BAM file. index offset beyond the end of the file: " + path_};
+}
+
 RecordStream::RecordStream(const std::string& path, int n_threads, size_t window_bytes)
     : path_(path), pool_(n_threads), window_bytes_(window_bytes) {
     file_.open(path);
@@ -214,6 +223,11 @@ RecordStream::Window RecordStream::produce() {
         const size_t n = carry + in.len;
         double t0 = now_s();
         size_t o = 0;
+        if (skip_first_) {  // seek_virtual: the first record starts this far into the first inflated member
+            if (skip_first_ > n) { w.ok = false; w.err = "index points past the end of a BGZF block: " + path_; return w; }
+            o = skip_first_;
+            skip_first_ = 0;
+        }
         w.recs.reserve(n / 256);
         while (o + 4 <= n) {
             int32_t bs = le32(b + o);

@@ -60,6 +60,9 @@ public:
     const MappedFile& file() const { return file_; }
     // BAM: uncompressed bytes in front of the first alignment record (magic, header text, reference list)
     size_t bam_header_bytes() const;
+    // BAM only, before the first next(): continue at a BGZF virtual offset (compressed offset << 16 | offset within the member's
+    // output) that points at a record boundary, e.g. from the linear index of a .bai
+    void seek_virtual(uint64_t voffset);
     size_t compressed_consumed() const { return consumed_; }  // compressed bytes behind the records handed out so far
     double seconds_inflate = 0, seconds_walk = 0;
     uint64_t bytes_compressed = 0, bytes_uncompressed = 0;
@@ -104,6 +107,7 @@ private:
     Window cur_;                      // the window whose records were handed out last
     size_t consumed_ = 0;
     size_t bam_header_len_ = 0;
+    size_t skip_first_ = 0;
     bool eof_ = false;
 };
 

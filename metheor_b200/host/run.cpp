@@ -18,6 +18,8 @@
 #include <future>
 #include <memory>
 
+#include <zlib.h>
+
 #include "../../include/metheor_b200.h"
 #include "../../include/metheor_host.h"
 #include "decode.hpp"
@@ -298,19 +300,61 @@ void assemble_compact(ThreadPool& pool, std::vector<SoaChunk>& all_chunks, size_
 }
 
 // ---- TSV ----------------------------------------------------------------------------------------------------
+// Output table: plain text like the reference (pdr.rs:95-101), or — engine extension --format *.gz — the same bytes as BGZF
+// (concatenated <= 64 KiB gzip members + the 28-byte EOF marker: readable by gzip, indexable by tabix).
 struct OutFile {
     FILE* f = nullptr;
-    explicit OutFile(const char* path) {
+    bool bgzf = false;
+    std::string pend;  // bytes not yet compressed
+    OutFile(const char* path, bool compress = false) : bgzf(compress) {
         // pdr.rs:95-101: create + truncate; .unwrap() panics when the path cannot be opened
         f = fopen(path, "w");
         if (!f) throw HostError{101, std::string("called `Result::unwrap()` on an `Err` value: cannot open output file ") + path + ": " + strerror(errno)};
         setvbuf(f, nullptr, _IOFBF, 1 << 20);
     }
     ~OutFile() {
-        if (f) fclose(f);
+        if (f) {
+            try { close(); } catch (...) {}
+        }
+    }
+    void raw(const void* p, size_t n) {
+        if (fwrite(p, 1, n, f) != n) throw HostError{101, "Error writing to output file."};
+    }
+    void member(const char* p, size_t n) {  // one BGZF member holding p[0, n), n <= 0xff00
+        uint8_t hdr[18] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 'B', 'C', 2, 0, 0, 0};
+        std::vector<uint8_t> buf(compressBound((uLong)n) + 64);
+        z_stream zs;
+        memset(&zs, 0, sizeof(zs));
+        if (deflateInit2(&zs, 6, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) throw HostError{101, "Error writing to output file."};
+        zs.next_in = (Bytef*)p; zs.avail_in = (uInt)n; zs.next_out = buf.data(); zs.avail_out = (uInt)buf.size();
+        const int rc = deflate(&zs, Z_FINISH);
+        const size_t clen = buf.size() - zs.avail_out;
+        deflateEnd(&zs);
+        if (rc != Z_STREAM_END || clen + 26 > 65536) throw HostError{101, "Error writing to output file."};
+        const uint32_t bsize = (uint32_t)(clen + 25), crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), (const Bytef*)p, (uInt)n), isize = (uint32_t)n;
+        hdr[16] = (uint8_t)bsize; hdr[17] = (uint8_t)(bsize >> 8);
+        uint8_t tail[8];
+        for (int k = 0; k < 4; k++) { tail[k] = (uint8_t)(crc >> (8 * k)); tail[4 + k] = (uint8_t)(isize >> (8 * k)); }
+        raw(hdr, 18); raw(buf.data(), clen); raw(tail, 8);
     }
     void write(const std::string& s) {
-        if (fwrite(s.data(), 1, s.size(), f) != s.size()) throw HostError{101, "Error writing to output file."};
+        if (!bgzf) { raw(s.data(), s.size()); return; }
+        pend += s;
+        size_t o = 0;
+        while (pend.size() - o >= 0xff00) { member(pend.data() + o, 0xff00); o += 0xff00; }
+        pend.erase(0, o);
+    }
+    void close() {
+        if (!f) return;
+        FILE* g = f;
+        if (bgzf) {
+            if (!pend.empty()) member(pend.data(), pend.size());
+            pend.clear();
+            static const uint8_t eof[28] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0, 27, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+            raw(eof, 28);
+        }
+        f = nullptr;
+        if (fclose(g) != 0) throw HostError{101, "Error writing to output file."};
     }
 };
 
@@ -654,11 +698,87 @@ void run(const mthh_options& o) {
     bool reserved = false;
     const Format fmt = in.format();
 
+    // --region chr[:beg-end] (engine extension): the region is ONE ownership interval — exactly the multi-GPU
+    // machinery with a single shard: reads starting up to SHARD_HALO before it are decoded as halo copies so that every site
+    // inside has all its contributors and flush triggers, rows outside are dropped, LPMD counts the reads that start inside.
+    bool has_region = false;
+    Interval region{0, 0, 0};
+    bool region_empty = false;
+    if (o.region) {
+        if (n_gpus != 1) throw HostError{2, "error: --region cannot be combined with --gpus > 1"};
+        std::string r = o.region, name = r;
+        int64_t beg = 1, end = INT64_MAX;
+        if (hdr.tid_of(name) < 0) {
+            const size_t c = r.rfind(':');
+            if (c == std::string::npos) throw HostError{101, "unknown chromosome '" + r + "' in --region"};
+            name = r.substr(0, c);
+            std::string span = r.substr(c + 1);
+            span.erase(std::remove(span.begin(), span.end(), ','), span.end());
+            const size_t dsh = span.find('-');
+            char* ep = nullptr;
+            beg = strtoll(span.c_str(), &ep, 10);
+            if (ep == span.c_str() || beg < 1) throw HostError{2, "error: invalid --region '" + r + "' (expected chr[:beg-end], 1-based)"};
+            if (dsh != std::string::npos) {
+                const char* e0 = span.c_str() + dsh + 1;
+                end = strtoll(e0, &ep, 10);
+                if (ep == e0 || end < beg) throw HostError{2, "error: invalid --region '" + r + "' (expected chr[:beg-end], 1-based)"};
+            }
+            if (hdr.tid_of(name) < 0) throw HostError{101, "unknown chromosome '" + name + "' in --region"};
+        }
+        region.tid = hdr.tid_of(name);
+        region.lo = beg - 1;
+        region.hi = std::min<int64_t>(end, ref_len[(size_t)region.tid]);
+        has_region = true;
+        gpus[0]->own.assign(1, region);
+        // the .bai's linear index (one virtual offset per 16 kb window) says where to start reading
+        if (fmt == Format::BAM) {
+            std::string p1 = std::string(o.input) + ".bai", p2 = o.input;
+            if (p2.size() > 4 && p2.compare(p2.size() - 4, 4, ".bam") == 0) p2 = p2.substr(0, p2.size() - 4) + ".bai";
+            MappedFile bai;
+            bool have = false;
+            for (const std::string& p : {p1, p2}) {
+                try { bai.open(p); have = true; break; } catch (const HostError&) {}
+            }
+            if (have) {
+                const uint8_t* b = bai.data();
+                const size_t n = bai.size();
+                size_t q = 8;
+                bool ok = n >= 8 && memcmp(b, "BAI\1", 4) == 0 && le32(b + 4) == (int32_t)ref_len.size();
+                for (int32_t t = 0; ok && t <= region.tid; t++) {
+                    if (q + 4 > n) { ok = false; break; }
+                    const int32_t n_bin = le32(b + q);
+                    q += 4;
+                    for (int32_t k = 0; ok && k < n_bin; k++) {
+                        if (q + 8 > n) { ok = false; break; }
+                        const int32_t n_chunk = le32(b + q + 4);
+                        q += 8 + (size_t)n_chunk * 16;
+                    }
+                    if (!ok || q + 4 > n) { ok = false; break; }
+                    const int32_t n_intv = le32(b + q);
+                    q += 4;
+                    if (q + (size_t)n_intv * 8 > n) { ok = false; break; }
+                    if (t == region.tid) {
+                        auto iv = [&](int32_t w) { uint64_t v; memcpy(&v, b + q + (size_t)w * 8, 8); return v; };
+                        if (n_intv == 0) { region_empty = true; break; }
+                        int32_t w = (int32_t)std::min<int64_t>(std::max<int64_t>(0, region.lo - SHARD_HALO) >> 14, n_intv - 1);
+                        uint64_t v = 0;
+                        for (int32_t x = w; x >= 0 && !v; x--) v = iv(x);   // the last window at or before the start that holds a read
+                        for (int32_t x = w + 1; x < n_intv && !v; x++) v = iv(x);  // nothing before: the contig's reads start later
+                        if (v) in.seek_virtual(v); else region_empty = true;
+                    }
+                    q += (size_t)n_intv * 8;
+                }
+                if (!ok) fprintf(stderr, "metheor_b200: ignoring a malformed index next to %s (reading from the start)\n", o.input);
+            }
+        }
+    }
+    const bool sharded = n_gpus > 1 || has_region;
+
     // BAM on one GPU: inflate + record decode on the device (the host ships compressed bytes); everything else — SAM text,
     // several GPUs, a file beyond the device decoder's limits, --decode host — goes through the CPU decoder below.
     bool used_device = false;
     DeviceFeedStats dfs;
-    if (fmt == Format::BAM && n_gpus == 1 && !o.decode_host && !set_on_host && !getenv("METHEOR_DECODE_HOST")) {
+    if (fmt == Format::BAM && n_gpus == 1 && !o.decode_host && !set_on_host && !has_region && !getenv("METHEOR_DECODE_HOST")) {
         used_device = feed_device(o, in, gpus[0]->ctx, o.device, dopt.lpmd_order ? 1u : 0u, &total, &n_batches, &n_shipped_reads, &n_shipped_cpg, &dfs);
         if (!used_device) {  // start over on the host decoder
             int rc = mth_reset(gpus[0]->ctx);
@@ -667,7 +787,8 @@ void run(const mthh_options& o) {
             n_batches = n_shipped_reads = n_shipped_cpg = 0;
         }
     }
-    while (!used_device && in.next(&recs)) {
+    bool past_region = region_empty;
+    while (!used_device && !past_region && in.next(&recs)) {
         // cut the window at contig changes (a batch carries one tid)
         size_t seg0 = 0;
         while (seg0 < recs.size()) {
@@ -738,7 +859,7 @@ void run(const mthh_options& o) {
                     if (iv.tid != tid) continue;
                     // chunks (ascending starts) that hold a read starting in [lo - halo, hi]
                     size_t c0 = n_tasks, c1 = 0;
-                    const int64_t need_lo = n_gpus > 1 ? iv.lo - SHARD_HALO : INT64_MIN, need_hi = n_gpus > 1 ? iv.hi : INT64_MAX;
+                    const int64_t need_lo = sharded ? iv.lo - SHARD_HALO : INT64_MIN, need_hi = sharded ? iv.hi : INT64_MAX;
                     for (size_t k = 0; k < n_tasks; k++) {
                         const auto& st = chunks[k].start;
                         if (st.empty() || (int64_t)st.back() < need_lo || (int64_t)st.front() > need_hi) continue;
@@ -746,7 +867,7 @@ void run(const mthh_options& o) {
                         c1 = std::max(c1, k + 1);
                     }
                     if (c0 >= c1) continue;
-                    const int64_t own_lo = n_gpus > 1 ? iv.lo : INT64_MIN, own_hi = n_gpus > 1 ? iv.hi : INT64_MAX;
+                    const int64_t own_lo = sharded ? iv.lo : INT64_MIN, own_hi = sharded ? iv.hi : INT64_MAX;
                     t0 = now_s();
                     // the slot was last used RING submits ago: its copy has long been issued, wait for it to have completed
                     if (G.submitted >= RING) {
@@ -780,6 +901,9 @@ void run(const mthh_options& o) {
                     n_shipped_cpg += nc_b;
                 }
             }
+            if (has_region && (tid > region.tid || (tid == region.tid && !chunks.empty() && n_tasks && !chunks[0].start.empty() &&
+                                                    (int64_t)chunks[0].start.front() > region.hi)))
+                past_region = true;  // coordinate-sorted input: nothing further can matter
             seg0 = seg1;
         }
     }
@@ -804,7 +928,11 @@ void run(const mthh_options& o) {
     const double t_finished = now_s();
 
     // ---- output ----
-    OutFile out(o.output);
+    // engine extensions: --format tsv | tsv.gz | bedgraph | bedgraph.gz  (on-disk formats behind the path)
+    const bool bedgraph = (o.out_format & 2) != 0, out_gz = (o.out_format & 1) != 0;
+    if (bedgraph && (o.measure == MTHH_LPMD || o.measure == MTHH_PM || o.measure == MTHH_ME))
+        throw HostError{2, "error: --format bedgraph needs a per-CpG measure (pdr, mhl, fdrp, qfdrp)"};
+    OutFile out(o.output, out_gz);
     auto chrom = [&](int32_t tid) -> const std::string& { return hdr.names[(size_t)tid]; };
     int64_t n_rows_total = 0;
     if (o.measure == MTHH_LPMD) {
@@ -867,7 +995,7 @@ void run(const mthh_options& o) {
                 default: return G.res.qfdrp;
             }
         };
-        const bool counts = o.measure == MTHH_PDR;
+        const bool counts = o.measure == MTHH_PDR && !bedgraph;  // bedGraph: chrom, start, end, value
         std::vector<int64_t> nr;
         for (auto& gp : gpus) nr.push_back(rows_of(*gp).n);
         auto runs = owned_runs(gpus, nr, [&](int g, int64_t i) { return rows_of(*gpus[(size_t)g]).tid[i]; },

@@ -74,7 +74,9 @@ def write_bam(path, refs, reads, header_text=None, with_seq=False, block=0xFF00)
     for n, l in refs:
         nb = n.encode() + b"\0"
         buf += struct.pack("<i", len(nb)) + nb + struct.pack("<i", l)
+    rec_off = []  # uncompressed offset of every record
     for i, r in enumerate(reads):
+        rec_off.append(len(buf))
         name = (r.get("name") or f"read_{i}").encode() + b"\0"
         ops = parse_cigar(r["cigar"])
         qlen = sum(n for n, o in ops if o in (0, 1, 4, 7, 8))
@@ -92,6 +94,42 @@ def write_bam(path, refs, reads, header_text=None, with_seq=False, block=0xFF00)
         buf += struct.pack("<i", len(body)) + body
     with open(path, "wb") as f:
         f.write(bgzf_compress(bytes(buf), block))
+    return rec_off
+
+
+def write_bai(bam_path, refs, reads, rec_off, block=0xFF00, bai_path=None):
+    """A .bai for a BAM written by write_bam(..., block): no bins, only the linear index (smallest virtual offset of the reads
+    overlapping each 16 kb window; empty windows stay 0, as in indexes that were not back-filled)."""
+    raw = open(bam_path, "rb").read()
+    coffs, off = [], 0  # compressed offset of every BGZF member
+    while off < len(raw):
+        coffs.append(off)
+        xlen = struct.unpack_from("<H", raw, off + 10)[0]
+        x, bsize = off + 12, None
+        while x < off + 12 + xlen:
+            slen = struct.unpack_from("<H", raw, x + 2)[0]
+            if raw[x] == 66 and raw[x + 1] == 67:
+                bsize = struct.unpack_from("<H", raw, x + 4)[0]
+            x += 4 + slen
+        off += bsize + 1
+    lin = [dict() for _ in refs]
+    for r, uo in zip(reads, rec_off):
+        if r["tid"] < 0:
+            continue
+        voff = (coffs[uo // block] << 16) | (uo % block)
+        ops = parse_cigar(r["cigar"])
+        rlen = max(1, sum(n for n, o in ops if o in (0, 2, 3, 7, 8)))
+        for w in range(r["pos"] >> 14, ((r["pos"] + rlen - 1) >> 14) + 1):
+            d = lin[r["tid"]]
+            d[w] = min(d.get(w, voff), voff)
+    out = bytearray(b"BAI\x01" + struct.pack("<i", len(refs)))
+    for d in lin:
+        out += struct.pack("<i", 0)  # n_bin
+        n_intv = (max(d) + 1) if d else 0
+        out += struct.pack("<i", n_intv)
+        for w in range(n_intv):
+            out += struct.pack("<Q", d.get(w, 0))
+    open(bai_path or bam_path + ".bai", "wb").write(bytes(out))
 
 
 def read_bam(path):

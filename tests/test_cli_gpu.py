@@ -198,3 +198,56 @@ def test_multi_gpu_position_bins_and_contigs(tmp_path):
     assert host.cli("lpmd", "-i", bam, "-o", str(tmp_path / "l.tsv"), "-p", pa, "--gpus", n).returncode == 0
     assert _oracle_cli("lpmd", "-i", bam, "-o", str(tmp_path / "l2.tsv"), "-p", pb).returncode == 0
     assert open(pa).read() == open(pb).read()
+
+
+def test_output_formats_and_region(tmp_path):
+    """Engine extensions behind the path: --format tsv.gz / bedgraph[.gz] and --region through the .bai's linear
+    index.  A region run must give exactly the rows of the whole-file run whose site lies inside the region."""
+    import gzip
+    refs = [("chrA", 300_000), ("chrB", 120_000), ("chrC", 50_000)]
+    recs = []
+    for tid, (_, length) in enumerate(refs):
+        if tid == 2:
+            continue  # a contig without reads
+        sites = synth.make_sites(700 + tid, length)
+        recs += recgen.batch_to_records(synth.make_reads(710 + tid, sites, length, 20.0, tid=tid, del_frac=0.05))
+    bam = str(tmp_path / "r.bam")
+    block = 20_000
+    rec_off = bamio.write_bam(bam, refs, recs, block=block)
+    bamio.write_bai(bam, refs, recs, rec_off, block=block)
+    whole = {}
+    for m in ("pdr", "mhl", "fdrp", "pm"):
+        whole[m] = str(tmp_path / f"{m}.tsv")
+        assert host.cli(m, "-i", bam, "-o", whole[m]).returncode == 0
+    # formats
+    gz, bg, bgz = str(tmp_path / "p.tsv.gz"), str(tmp_path / "p.bedgraph"), str(tmp_path / "p.bedgraph.gz")
+    assert host.cli("pdr", "-i", bam, "-o", gz, "--format", "tsv.gz").returncode == 0
+    assert host.cli("pdr", "-i", bam, "-o", bg, "--format", "bedgraph").returncode == 0
+    assert host.cli("mhl", "-i", bam, "-o", bgz, "--format", "bedgraph.gz").returncode == 0
+    assert gzip.open(gz, "rb").read() == open(whole["pdr"], "rb").read()
+    assert open(gz, "rb").read()[-28:] == bamio.BGZF_EOF and len(bamio.bgzf_decompress(open(gz, "rb").read())) == os.path.getsize(whole["pdr"])
+    assert open(bg).read() == "".join("\t".join(l.split("\t")[:4]) + "\n" for l in open(whole["pdr"]).read().splitlines())
+    assert gzip.open(bgz, "rt").read() == open(whole["mhl"]).read()
+    r = host.cli("pm", "-i", bam, "-o", bg, "--format", "bedgraph")
+    assert r.returncode == 2 and "per-CpG measure" in r.stderr
+    # regions: inside a contig, across BGZF blocks, at the contig ends, a whole contig, an empty contig, 1-based inclusive ends
+    for reg, (tid, lo, hi) in (("chrA:100001-150000", (0, 100_000, 150_000)), ("chrA:1-20000", (0, 0, 20_000)), ("chrB", (1, 0, 120_000)),
+                               ("chrA:250,000-300,000", (0, 249_999, 300_000)), ("chrC", (2, 0, 50_000)), ("chrB:60000", (1, 59_999, 120_000))):
+        for m in ("pdr", "mhl", "fdrp", "pm"):
+            out = str(tmp_path / "reg.tsv")
+            r = host.cli(m, "-i", bam, "-o", out, "--region", reg)
+            assert r.returncode == 0, r.stderr
+            name = refs[tid][0]
+            want = [l for l in open(whole[m]).read().splitlines() if l.split("\t")[0] == name and lo <= int(l.split("\t")[1]) < hi]
+            assert open(out).read().splitlines() == want, (reg, m)
+        if tid != 2:
+            assert len(want) > 10
+    # LPMD over a region = LPMD over the reads that start inside it
+    sub = [r for r in recs if r["tid"] == 0 and 100_000 <= r["pos"] < 150_000]
+    bam2 = str(tmp_path / "sub.bam")
+    bamio.write_bam(bam2, refs, sub)
+    a, b_ = str(tmp_path / "l1.tsv"), str(tmp_path / "l2.tsv")
+    assert host.cli("lpmd", "-i", bam, "-o", a, "--region", "chrA:100001-150000").returncode == 0
+    assert _oracle_cli("lpmd", "-i", bam2, "-o", b_).returncode == 0
+    assert open(a).read().splitlines()[1].split("\t")[1] == open(b_).read().splitlines()[1].split("\t")[1]
+    assert host.cli("pdr", "-i", bam, "-o", a, "--region", "chrZ:1-5").returncode == 101
