@@ -16,6 +16,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -783,8 +784,15 @@ int mth_reserve(mth_ctx* c, int64_t n_reads, int64_t n_cpg) {
     n_reads = std::min<int64_t>(n_reads, (int64_t)INT32_MAX - 128);
     n_cpg = std::min<int64_t>(n_cpg, (int64_t)UINT32_MAX - 128);
     if (n_reads <= c->R && n_cpg <= c->I) return MTH_OK;
+    const bool dbg = getenv("METHEOR_DEBUG_TIMING") != nullptr;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
+    CUDA_TRY(c, cudaStreamSynchronize(c->copy));
+    CUDA_TRY(c, cudaStreamSynchronize(c->compute));
+    const double t1 = now();
     TRY(ensure_arena(c, std::max(n_reads, c->R), std::max(n_cpg, c->I), std::max(n_reads, c->W), lp, c->has_meth_off));
     TRY(dev_reserve(c, c->a_flags, (size_t)std::max(n_cpg, c->I) + 64, (size_t)c->I));
+    if (dbg) fprintf(stderr, "mth_reserve: %lld reads %lld calls: wait for streams %.4f s, reallocation %.4f s\n", (long long)n_reads, (long long)n_cpg, t1 - t0, now() - t1);
     return MTH_OK;
 }
 

@@ -572,6 +572,14 @@ static bool feed_device(const mthh_options& o, const RecordStream& in, mth_ctx* 
         fs->bytes_uncompressed += res.uncompressed_bytes;
         fs->bytes_compressed += w.bytes;
         fs->windows++;
+        if (first && !last && w.bytes) {  // size the (still empty) arena once: reads per compressed byte of the first window x file size (+15 %)
+            int64_t r1 = 0, c1 = 0;
+            for (int k = 0; k < res.n_runs; k++) { r1 += res.runs[k].n_reads; c1 += res.runs[k].n_cpg; }
+            const double scale = 1.15 * (double)fsize / (double)w.bytes;
+            const double tr0 = now_s();
+            if (scale > 1.5) mth_reserve(ctx, (int64_t)((double)r1 * scale) + 4096, (int64_t)((double)c1 * scale) + 4096);
+            fs->s_reserve += now_s() - tr0;
+        }
         t0 = now_s();
         for (int k = 0; k < res.n_runs; k++) {
             const mth_batch& b = res.runs[k];
@@ -584,12 +592,6 @@ static bool feed_device(const mthh_options& o, const RecordStream& in, mth_ctx* 
             *n_cpg += b.n_cpg;
         }
         fs->s_submit += now_s() - t0;
-        if (first && !last && w.bytes) {  // size the arena once from the first window: reads per compressed byte x file size (+15 %)
-            const double scale = 1.15 * (double)fsize / (double)w.bytes;
-            const double tr0 = now_s();
-            if (scale > 1.5) mth_reserve(ctx, (int64_t)((double)*n_reads * scale) + 4096, (int64_t)((double)*n_cpg * scale) + 4096);
-            fs->s_reserve += now_s() - tr0;
-        }
         first = false;
         const double tw0 = now_s();
         if (nxt.valid()) nxt.wait();
