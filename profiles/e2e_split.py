@@ -4,7 +4,7 @@ import os, sys, time, json
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import bench
+import bench_chr19 as bench
 from metheor_b200 import engine, batch as B
 b, _ = bench.make_workload(0)
 hostc = B.to_compact(b)

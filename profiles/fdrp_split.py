@@ -1,7 +1,7 @@
 import json, os, sys
 import numpy as np, torch
 sys.path.insert(0, '.')
-import bench
+import bench_chr19 as bench
 from metheor_b200 import engine
 b, _ = bench.make_workload(0, 30.0, 20_000_000)
 view = {np.dtype("uint32"): np.int32, np.dtype("uint16"): np.int16, np.dtype("uint64"): np.int64}

@@ -4,7 +4,7 @@ import os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import bench
+import bench_chr19 as bench
 from metheor_b200 import engine
 cov = float(sys.argv[1]) if len(sys.argv) > 1 else 30.0
 length = int(sys.argv[2]) if len(sys.argv) > 2 else bench.CONTIG_LEN

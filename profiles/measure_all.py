@@ -6,7 +6,7 @@ import numpy as np
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import bench
+import bench_chr19 as bench
 from metheor_b200 import engine
 
 cov = float(sys.argv[1]) if len(sys.argv) > 1 else 30.0

@@ -6,7 +6,7 @@ import json, os, sys, time
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import bench
+import bench_chr19 as bench
 from metheor_b200 import engine
 
 K = int(sys.argv[1]) if len(sys.argv) > 1 else 24
