@@ -17,7 +17,7 @@ KEYS = ("start", "end", "meta", "cpg_off", "cpg_pos", "cpg_rel", "meth")
 
 def child(lib):
     import torch
-    import bench
+    import bench_chr19 as bench
     from metheor_b200 import engine
     z = np.load(PARK)
     b = {k: z[k] for k in KEYS}
@@ -65,7 +65,7 @@ def child(lib):
 def main():
     if sys.argv[1] == "--child":
         return child(sys.argv[2])
-    import bench
+    import bench_chr19 as bench
     made = not os.path.exists(PARK)
     if made:
         b, _ = bench.make_workload(0, bench.COVERAGE, bench.CONTIG_LEN)
