@@ -27,14 +27,14 @@ constexpr int MS_CCAP_SPARSE = 8192;
 constexpr int MS_L = 16;         // longest read (in calls) the per-thread accumulators hold
 constexpr int MS_SPAN = 60000;   // positions a tile may span (calls are staged as 16-bit offsets)
 
-// Shared-memory footprint decides how many sites are in flight per SM, so everything is packed: 12 bytes per read,
+// Shared-memory footprint decides how many sites are in flight per SM, so everything is packed: 10 bytes per read,
 // 2 bytes per call, 16-bit accumulators (a segment deeper than 65 535 reads goes to the per-site kernel).
 template <int RCAP, int CCAP>
 struct MsSmem {
-    int32_t start[RCAP];
-    uint16_t meta[RCAP];      // mapq | n << 8   (n <= MS_L)
-    uint16_t o0[RCAP];        // first call of the read, tile-relative
-    uint16_t first[RCAP];     // first call, as offset from the tile base (0xFFFF: no call)
+    // one 64-bit word per read, fetched with ONE shared-memory load in the per-site loop:
+    //   bits 0-15 start (offset from the tile base) | 16-31 first call (offset; 0xFFFF: no call) | 32-47 index of its first call
+    //   in pos[] | 48-55 mapq | 56-63 number of calls (<= MS_L)
+    unsigned long long rec[RCAP];
     uint16_t mbits[RCAP];     // methylation bits of the read's calls (n <= MS_L = 16 calls in this kernel)
     uint16_t pos[CCAP];       // calls, as offsets from the tile base
     uint16_t S[MS_L + 1][MS_SITES];   // [l][thread]: bank-conflict-free
@@ -85,9 +85,8 @@ __global__ void __launch_bounds__(MS_SITES) k_mhl_site(ReadsView rv, const int32
         for (int r = tid; r < nreads; r += MS_SITES) {
             const int64_t j = ra + r;
             const uint32_t o0 = rv.cpg_off[j], n = rv.cpg_off[j + 1] - o0;
-            sh.start[r] = rv.start[j];
-            sh.meta[r] = (uint16_t)((rv.meta[j] & 0xFFu) | (min(n, 255u) << 8));
-            sh.o0[r] = (uint16_t)(o0 - c0);
+            sh.rec[r] = (unsigned long long)(uint16_t)(rv.start[j] - base) | 0xFFFF0000ull | ((unsigned long long)(uint16_t)(o0 - c0) << 32) |
+                        ((unsigned long long)(rv.meta[j] & 0xFFu) << 48) | ((unsigned long long)min(n, 255u) << 56);
             sh.mbits[r] = (uint16_t)rv.meth[j];  // staged once (coalesced) instead of one global load per (site, read)
             if (n > (uint32_t)MS_L) toolong = 1;
         }
@@ -96,7 +95,10 @@ __global__ void __launch_bounds__(MS_SITES) k_mhl_site(ReadsView rv, const int32
             if (tid < ns) fallback[s0 + tid] = 1;
             continue;
         }
-        for (int r = tid; r < nreads; r += MS_SITES) sh.first[r] = (sh.meta[r] >> 8) ? sh.pos[sh.o0[r]] : (uint16_t)0xFFFF;
+        for (int r = tid; r < nreads; r += MS_SITES) {
+            const unsigned long long w = sh.rec[r];
+            if (w >> 56) sh.rec[r] = (w & ~0xFFFF0000ull) | ((unsigned long long)sh.pos[(uint32_t)(w >> 32) & 0xFFFFu] << 16);
+        }
         __syncthreads();
         if (tid >= ns) continue;
 
@@ -104,8 +106,9 @@ __global__ void __launch_bounds__(MS_SITES) k_mhl_site(ReadsView rv, const int32
         const int32_t p = site_pos[s0 + tid];
         const uint32_t pq = (uint32_t)(p - base);  // the site in tile offsets
         bool deep = false;
+        const uint32_t key_lo = pq - (uint32_t)lmax + 1u, key_hi = pq + 1u;  // reads with start in [p - lmax + 1, p + 1], as tile offsets
         int lo = 0, hi = nreads;  // first read with start >= p - lmax + 1
-        while (lo < hi) { int m = (lo + hi) >> 1; if (sh.start[m] < p - lmax + 1) lo = m + 1; else hi = m; }
+        while (lo < hi) { int m = (lo + hi) >> 1; if (((uint32_t)sh.rec[m] & 0xFFFFu) < key_lo) lo = m + 1; else hi = m; }
 #pragma unroll
         for (int l = 0; l <= MS_L; l++) { sh.S[l][tid] = 0; sh.N[l][tid] = 0; }
         uint32_t depth = 0, maxn = 0;
@@ -137,12 +140,14 @@ __global__ void __launch_bounds__(MS_SITES) k_mhl_site(ReadsView rv, const int32
             for (int l = 1; l <= MS_L; l++) { sh.S[l][tid] = 0; sh.N[l][tid] = 0; }
             depth = maxn = 0;
         };
-        for (int r = lo; r < nreads && sh.start[r] <= p + 1; r++) {
-            const uint32_t m = sh.meta[r], n = m >> 8;
+        for (int r = lo; r < nreads; r++) {
+            const unsigned long long w = sh.rec[r];
+            if (((uint32_t)w & 0xFFFFu) > key_hi) break;
+            const uint32_t m = (uint32_t)(w >> 48), n = m >> 8;
             if (n == 0) continue;
-            if ((uint32_t)sh.first[r] > pq) { close(); continue; }  // mhl.rs:162-173: ANY read with >= 1 CpG flushes what lies before its first CpG
+            if (((uint32_t)(w >> 16) & 0xFFFFu) > pq) { close(); continue; }  // mhl.rs:162-173: ANY read with >= 1 CpG flushes what lies before its first CpG
             // does the read call p?  (its calls are sorted; n <= MS_L)
-            const uint16_t* cp = sh.pos + sh.o0[r];
+            const uint16_t* cp = sh.pos + ((uint32_t)(w >> 32) & 0xFFFFu);
             bool calls = false;
             for (uint32_t k = 0; k < n; k++) {
                 const uint32_t x = cp[k];
