@@ -127,3 +127,22 @@ def test_device_decode_synthetic_wgbs_and_missing_xm(tmp_path):
     res, _ = dec.window(data, bamdec.bgzf_members(data), skip=hdr_len, last=True)
     assert res.bad_record < 0
     dec.close()
+
+
+def test_records_longer_than_a_chain_chunk(tmp_path):
+    """Records far larger than the 32 KiB chunks of the speculative boundary search (CIGARs with 12 000 operations: ~48 KB each):
+    chunks without any record start, chains that jump over chunks, tiny windows that end inside such a record."""
+    rng = np.random.default_rng(9)
+    reads = recgen.random_records(55, REFS, 600, max_len=60)
+    big = []
+    for k in range(6):
+        ops = "".join(f"{int(rng.integers(1, 3))}M1I" for _ in range(6000))
+        qlen = sum(int(x) for x in ops.replace("M", " ").replace("I", " ").split())
+        xm = "".join(rng.choice(list("zZ.h"), min(qlen, 900)))
+        big.append(dict(tid=0, pos=int(1000 + 20_000 * k), flag=0, mapq=40, cigar=ops, xm=xm))
+    allr = sorted([r for r in reads if r["tid"] >= 0] + big, key=lambda r: (r["tid"], r["pos"]))
+    path = str(tmp_path / "big.bam")
+    bamio.write_bam(path, REFS, allr, block=40_000)
+    for window in (1, 2, 1000):
+        batches, tot = _decode_all(path, window)
+        _compare_with_host(path, batches, tot)
