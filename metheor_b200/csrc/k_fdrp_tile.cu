@@ -30,6 +30,29 @@ constexpr int FT_WIN = 256;        // 64-bit words of the site bitmap staged for
 constexpr int FT_MAXD = 64;        // pile slots per warp
 constexpr int FT_MAX_READ_LEN = 201;  // fdrp.rs:10
 
+// Pair t (lexicographic order over i < j, itertools combinations(2): fdrp.rs:128) of a pile of depth n, as i | j << 8, for every
+// n <= FT_MAXD: the table of depth n starts at C(n, 3).  Replaces the per-lane index arithmetic of the pair loop (12 % of the
+// kernel's instructions, profiles/R2c_lines_k_fdrp_tile.txt) by one cached load.  Filled once per device by k_fdrp_tables.
+constexpr int FT_PAIR_TAB = (FT_MAXD + 1) * FT_MAXD * (FT_MAXD - 1) / 6;
+__device__ uint16_t g_pair_tab[FT_PAIR_TAB];
+// ham / shared for the small operands of qfdrp.rs:152, the very same f32 division done once
+constexpr int FT_DIV_LUT = 32;
+__device__ float g_div_lut[(FT_DIV_LUT + 1) * (FT_DIV_LUT + 1)];
+
+__global__ void k_fdrp_tables() {
+    const uint32_t n = blockIdx.x + 2;  // one CTA per depth 2..FT_MAXD
+    uint16_t* tab = g_pair_tab + (size_t)n * (n - 1) * (n - 2) / 6;
+    for (uint32_t i = threadIdx.x; i + 1 < n; i += blockDim.x) {
+        const uint32_t t0 = i * (n - 1) - i * (i - 1) / 2;  // pairs before row i: sum_{r<i} (n - 1 - r)
+        for (uint32_t j = i + 1; j < n; j++) tab[t0 + (j - i - 1)] = (uint16_t)(i | (j << 8));
+    }
+    if (blockIdx.x == 0)
+        for (int k = threadIdx.x; k < (FT_DIV_LUT + 1) * (FT_DIV_LUT + 1); k += blockDim.x) {
+            const int sh = k / (FT_DIV_LUT + 1), h = k % (FT_DIV_LUT + 1);
+            g_div_lut[k] = sh ? __fdiv_rn((float)h, (float)sh) : 0.f;
+        }
+}
+
 template <int RCAP>
 struct FtSmem {
     unsigned long long cm[RCAP][2], mm[RCAP][2];
@@ -154,14 +177,14 @@ __global__ void __launch_bounds__(FT_THREADS, RCAP <= 1024 ? 3 : 2) k_fdrp_tile(
             auto evaluate = [&](uint32_t n) {
                 const uint64_t P = (uint64_t)n * (n - 1) / 2;
                 pair_ops += P;
-                uint32_t i = 0, jj = 1 + lane;  // this lane's pair (i, jj): pair index = lane, then += 32
-                while (i < n && jj >= n) { jj = jj - n + i + 2; i++; }
+                const uint16_t* __restrict__ tab = g_pair_tab + (size_t)n * (n - 1) * (n - 2) / 6;
                 float acc = 0.f;
                 uint32_t disc = 0;
                 for (uint64_t t0 = 0; t0 < P; t0 += 32) {
                     float term = 0.f;
                     if (t0 + lane < P) {
-                        const int ri = pile[i], rj = pile[jj];
+                        const uint32_t e = __ldg(tab + t0 + lane);  // this lane's pair (i, j) of the step
+                        const int ri = pile[e & 0xFFu], rj = pile[e >> 8];
                         const int32_t ov = min(sh.end[ri], sh.end[rj]) - max(sh.start[ri], sh.start[rj]) + 1;  // fdrp.rs:97-107
                         if (ov >= prm.min_overlap && ov > 0) {  // fdrp.rs:133-136 (without overlap: ham = 0, adds nothing)
                             const unsigned long long b0 = sh.cm[ri][0] & sh.cm[rj][0], b1 = sh.cm[ri][1] & sh.cm[rj][1];
@@ -173,11 +196,12 @@ __global__ void __launch_bounds__(FT_THREADS, RCAP <= 1024 ? 3 : 2) k_fdrp_tile(
                             }
                             const uint32_t ham = (uint32_t)__popcll(v0 & (sh.mm[ri][0] ^ sh.mm[rj][0])) +
                                                  (uint32_t)__popcll(v1 & (sh.mm[ri][1] ^ sh.mm[rj][1]));  // fdrp.rs:109-122
-                            if (want_q && ham) term = __fdiv_rn((float)ham, (float)(__popcll(b0) + __popcll(b1)));  // qfdrp.rs:152
-                            if (want_d) disc += ham ? 1u : 0u;                                                       // fdrp.rs:138-140
+                            if (want_q && ham) {  // qfdrp.rs:152
+                                const uint32_t shr = (uint32_t)(__popcll(b0) + __popcll(b1));
+                                term = shr <= (uint32_t)FT_DIV_LUT ? __ldg(&g_div_lut[shr * (FT_DIV_LUT + 1) + ham]) : __fdiv_rn((float)ham, (float)shr);
+                            }
+                            if (want_d) disc += ham ? 1u : 0u;  // fdrp.rs:138-140
                         }
-                        jj += 32;
-                        while (i < n && jj >= n) { jj = jj - n + i + 2; i++; }
                     }
                     if (want_q) {  // sequential f32 accumulation in pair order
                         uint32_t nz = __ballot_sync(FULL, term != 0.f);
@@ -279,6 +303,16 @@ int launch_fdrp_tile(const ReadsView& rv, const int32_t* site_pos, int64_t C, co
                      ContigTable ct, float* value, uint32_t* rowcnt, float* value_q, uint32_t* rowcnt_q, uint8_t* fallback,
                      cudaStream_t s) {
     if (C <= 0) return 0;
+    static bool tables_ready[64] = {false};
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev >= 0 && dev < 64 && !tables_ready[dev]) {  // the pair-index table and the division table, once per device
+            k_fdrp_tables<<<FT_MAXD - 1, 64, 0, s>>>();
+            cudaStreamSynchronize(s);  // once per device: other streams of this process may use the tables next
+            tables_ready[dev] = true;
+        }
+    }
     static bool attr_set = false;
     static int force = 0;  // METHEOR_FDRP_TILE = dense | sparse32 | sparse64: kernel-variant experiments (profiles/)
     if (!attr_set) {
