@@ -345,6 +345,8 @@ typedef struct {
     uint64_t offset;   /* first byte of the member's raw DEFLATE payload within the compressed window */
     uint32_t size;     /* payload bytes (member size - header - 8) */
     uint32_t isize;    /* uncompressed size (the member's ISIZE field) */
+    uint32_t crc;      /* CRC-32 of the uncompressed bytes (the member's CRC32 field) */
+    uint32_t flags;    /* bit 0: verify `crc` on the device after inflating (what htslib does for every block) */
 } mth_bgzf_member;
 typedef struct {
     int64_t n_records;                    /* records that END in this window (a record cut by the window's end moves to the next) */

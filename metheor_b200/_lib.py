@@ -99,7 +99,7 @@ class TagResult(C.Structure):
 
 
 class BgzfMember(C.Structure):
-    _fields_ = [("offset", u64), ("size", u32), ("isize", u32)]
+    _fields_ = [("offset", u64), ("size", u32), ("isize", u32), ("crc", u32), ("flags", u32)]
 
 
 class BamdecResult(C.Structure):

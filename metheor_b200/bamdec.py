@@ -11,7 +11,7 @@ from ._lib import BamdecResult, BgzfMember
 
 
 def bgzf_members(data, offset=0):
-    """Walk the BGZF member headers of `data` (bytes) from `offset` -> list of (payload offset, payload size, isize, member end)."""
+    """Walk the BGZF member headers of `data` (bytes) from `offset` -> list of (payload offset, payload size, isize, member end, crc)."""
     out = []
     n = len(data)
     o = offset
@@ -29,8 +29,8 @@ def bgzf_members(data, offset=0):
             raise ValueError(f"gzip member without the BGZF extra field at {o}")
         total = bsize + 1
         pay = o + 12 + xlen
-        isize = struct.unpack_from("<I", data, o + total - 4)[0]
-        out.append((pay, total - (12 + xlen) - 8, isize, o + total))
+        crc, isize = struct.unpack_from("<II", data, o + total - 8)
+        out.append((pay, total - (12 + xlen) - 8, isize, o + total, crc))
         o += total
     return out
 
@@ -41,8 +41,11 @@ def inflate_members(data, members, device=0):
     n = len(members)
     arr = (BgzfMember * max(n, 1))()
     tot = 0
-    for i, (off, size, isize, _) in enumerate(members):
+    for i, mb in enumerate(members):
+        off, size, isize = mb[0], mb[1], mb[2]
         arr[i].offset, arr[i].size, arr[i].isize = off, size, isize
+        if len(mb) > 4:
+            arr[i].crc, arr[i].flags = mb[4], 1
         tot += isize
     out = np.zeros(max(tot, 1), np.uint8)
     status = np.zeros(max(n, 1), np.int32)
@@ -80,8 +83,10 @@ class Decoder:
         """-> (result struct, list of numpy batches).  `members` as from bgzf_members (absolute offsets into data)."""
         n = len(members)
         arr = (BgzfMember * max(n, 1))()
-        for i, (off, size, isize, _) in enumerate(members):
-            arr[i].offset, arr[i].size, arr[i].isize = off, size, isize
+        for i, mb in enumerate(members):
+            arr[i].offset, arr[i].size, arr[i].isize = mb[0], mb[1], mb[2]
+            if len(mb) > 4:
+                arr[i].crc, arr[i].flags = mb[4], 1
         buf = np.frombuffer(data, np.uint8)
         res = BamdecResult()
         rc = self._L.mth_bamdec_window(self._h, buf.ctypes.data, len(data), arr, n, int(skip), int(last), C.byref(res))

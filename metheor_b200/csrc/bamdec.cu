@@ -45,18 +45,26 @@ struct MemberDesc {
     unsigned long long in_off;   // raw DEFLATE payload within the compressed window
     uint32_t in_len, isize;
     unsigned long long out_off;  // where its output goes in the uncompressed stream
+    uint32_t crc, check_crc;     // CRC-32 of the output (gzip trailer); check_crc 0: not given
 };
 
 __global__ void __launch_bounds__(INF_WARPS * 32) k_bgzf_inflate(const uint8_t* __restrict__ comp, const MemberDesc* __restrict__ m, int64_t n,
                                                                  uint8_t* out, int* __restrict__ status, int* __restrict__ any_bad) {
     extern __shared__ __align__(16) unsigned char inf_raw[];
+    __shared__ uint32_t s_crc_tab[256];
     InflateTables* T = reinterpret_cast<InflateTables*>(inf_raw) + (threadIdx.x >> 5);
+    crc_table_init(s_crc_tab);
+    __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * INF_WARPS + (threadIdx.x >> 5);
     if (i >= n) return;
     const MemberDesc d = m[i];
     uint32_t produced = 0;
     int err = warp_inflate(comp + d.in_off, d.in_len, out + d.out_off, d.isize, *T, &produced);
     if (err == INF_OK && produced != d.isize) err = INF_ERR_SIZE;
+    if (err == INF_OK && d.check_crc) {  // what htslib's bgzf reader verifies for every block
+        __syncwarp();
+        if (warp_crc32(out + d.out_off, d.isize, s_crc_tab) != d.crc) err = INF_ERR_CRC;
+    }
     if (lane_id() == 0) {
         status[i] = err;
         if (err) atomicOr(any_bad, 1);
@@ -494,7 +502,7 @@ int mth_bgzf_inflate(int device, const uint8_t* comp, size_t comp_bytes, const m
     size_t uo = 0;
     for (int64_t i = 0; i < n; i++) {
         if (members[i].offset + members[i].size > comp_bytes) { mth_bamdec_destroy(d); return dfail(nullptr, MTH_ERR_INVALID, "member outside the buffer"); }
-        md[(size_t)i] = MemberDesc{members[i].offset, members[i].size, members[i].isize, uo};
+        md[(size_t)i] = MemberDesc{members[i].offset, members[i].size, members[i].isize, uo, members[i].crc, members[i].flags & 1u};
         uo += members[i].isize;
     }
     if (uo > out_bytes) { mth_bamdec_destroy(d); return dfail(nullptr, MTH_ERR_INVALID, "output buffer too small"); }
@@ -580,7 +588,7 @@ int mth_bamdec_window(mth_bamdec* d, const uint8_t* comp, size_t comp_bytes, con
     size_t uo = d->carry;
     for (int64_t i = 0; i < n_members; i++) {
         if (members[i].offset + members[i].size > comp_bytes) return dfail(d, MTH_ERR_INVALID, "BGZF member outside the compressed window");
-        md[(size_t)i] = MemberDesc{members[i].offset, members[i].size, members[i].isize, uo};
+        md[(size_t)i] = MemberDesc{members[i].offset, members[i].size, members[i].isize, uo, members[i].crc, members[i].flags & 1u};
         uo += members[i].isize;
     }
     const size_t u_end = uo;
@@ -621,7 +629,7 @@ int mth_bamdec_window(mth_bamdec* d, const uint8_t* comp, size_t comp_bytes, con
         DTRY(d, cudaMemcpyAsync(d->h_small, d->small.p, 64, cudaMemcpyDeviceToHost, s));
         DTRY(d, cudaStreamSynchronize(s));
         const unsigned long long* hs = (const unsigned long long*)d->h_small;
-        if ((int)hs[SM_ANYBAD]) return dfail(d, MTH_ERR_INVALID, "BGZF inflate failed on the device (corrupt member)");
+        if ((int)hs[SM_ANYBAD]) return dfail(d, MTH_ERR_INVALID, "BGZF inflate / CRC check failed on the device (corrupt member)");
         if ((int)hs[SM_MISMATCH]) {
             d->repairs++;
             k_rec_repair<<<1, 32, 0, s>>>(u, u_end, n_chunks, (uint32_t*)d->entry.p, (uint32_t*)d->n_rec.p, (uint32_t*)d->landing.p);

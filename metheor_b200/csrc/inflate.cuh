@@ -29,7 +29,7 @@ struct InflateTables {                      // per warp
 };
 
 enum : int { INF_OK = 0, INF_ERR_BTYPE = 1, INF_ERR_STORED = 2, INF_ERR_CODE = 3, INF_ERR_DIST = 4, INF_ERR_OVERRUN = 5,
-             INF_ERR_INPUT = 6, INF_ERR_SIZE = 7, INF_ERR_TABLE = 8 };
+             INF_ERR_INPUT = 6, INF_ERR_SIZE = 7, INF_ERR_TABLE = 8, INF_ERR_CRC = 9 };
 
 // LSB-first bit reader; every lane of the warp holds the same state.  The compressed bytes come through a 256-byte ring in
 // shared memory that the warp refills with one coalesced load (2 words per lane) every 64 words, so the serial decode loop
@@ -298,6 +298,63 @@ __device__ __forceinline__ int warp_inflate(const uint8_t* __restrict__ in, uint
     }
     *produced = pos;
     return err;
+}
+
+// ---- CRC-32 of a member's output (the gzip trailer of every BGZF member carries it; htslib checks it) -------------------------
+// Each lane takes one contiguous 1/32 of the bytes with the classic byte-wise table (in shared memory), then the 32 partial
+// values are joined with crc(A || B) = crc(A) * x^(8 |B|) mod P  xor  crc(B) (zlib's crc32_combine, polynomial arithmetic on the
+// bit-reflected representation).  ~1 % of the instructions the inflate itself needs.
+constexpr uint32_t CRC_POLY = 0xedb88320u;
+
+__device__ __forceinline__ uint32_t crc_multmodp(uint32_t a, uint32_t b) {  // a(x) * b(x) mod p(x), reflected
+    uint32_t m = 1u << 31, p = 0;
+    for (;;) {
+        if (a & m) {
+            p ^= b;
+            if ((a & (m - 1)) == 0) break;
+        }
+        m >>= 1;
+        b = (b & 1u) ? (b >> 1) ^ CRC_POLY : b >> 1;
+    }
+    return p;
+}
+__device__ __forceinline__ uint32_t crc_x2nmodp(uint32_t n, uint32_t k) {  // x^(n * 2^k) mod p(x)
+    uint32_t p = 1u << 31, q = 1u << 30;  // q = x^(2^0)
+    for (uint32_t i = 0; i < k; i++) q = crc_multmodp(q, q);
+    while (n) {
+        if (n & 1u) p = crc_multmodp(q, p);
+        n >>= 1;
+        if (n) q = crc_multmodp(q, q);
+    }
+    return p;
+}
+__device__ __forceinline__ void crc_table_init(uint32_t* tab256) {  // by the whole CTA
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
+        uint32_t c = i;
+#pragma unroll
+        for (int k = 0; k < 8; k++) c = (c & 1u) ? (c >> 1) ^ CRC_POLY : c >> 1;
+        tab256[i] = c;
+    }
+}
+// all 32 lanes of a warp; returns the CRC-32 of data[0, n) (same value on every lane)
+__device__ __forceinline__ uint32_t warp_crc32(const uint8_t* data, uint32_t n, const uint32_t* __restrict__ tab256) {
+    const int lane = lane_id();
+    const uint32_t chunk = (n + 31u) >> 5;
+    const uint32_t a = min(n, chunk * (uint32_t)lane), b = min(n, a + chunk);
+    uint32_t c = 0xffffffffu;
+    for (uint32_t k = a; k < b; k++) c = tab256[(c ^ __ldcg(data + k)) & 0xffu] ^ (c >> 8);
+    c ^= 0xffffffffu;             // the CRC of this lane's bytes (0 for an empty range)
+    uint32_t len = b - a;         // bytes it covers
+    // join neighbours pairwise: after round r lane l (l % 2^(r+1) == 0) holds the CRC of 2^(r+1) chunks
+#pragma unroll
+    for (int r = 0; r < 5; r++) {
+        const uint32_t oc = __shfl_down_sync(FULL, c, 1u << r), ol = __shfl_down_sync(FULL, len, 1u << r);
+        if ((lane & ((2 << r) - 1)) == 0) {
+            if (ol) c = crc_multmodp(crc_x2nmodp(ol, 3), c) ^ oc;
+            len += ol;
+        }
+    }
+    return __shfl_sync(FULL, c, 0);
 }
 
 }  // namespace mth

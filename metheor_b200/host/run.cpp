@@ -512,7 +512,7 @@ static bool feed_device(const mthh_options& o, const RecordStream& in, mth_ctx* 
             coff += total;
             if (usize == 0) continue;  // empty member (the EOF marker)
             if (hdr_left >= usize) { hdr_left -= usize; c0 = coff; continue; }  // a member that holds only header bytes
-            w.members.push_back(mth_bgzf_member{(uint64_t)(cdata - c0), (uint32_t)clen, usize});
+            w.members.push_back(mth_bgzf_member{(uint64_t)(cdata - c0), (uint32_t)clen, usize, crc, 1u});
             c1 = cdata + clen;
             u += usize;
         }

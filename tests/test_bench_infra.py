@@ -68,4 +68,5 @@ def test_bgzf_member_walk():
     raw = bamio.bgzf_compress(data, block=30_000)
     mem = bamdec.bgzf_members(raw)
     assert len(mem) == 8 and mem[-1][2] == 0 and sum(m[2] for m in mem) == len(data) and mem[-1][3] == len(raw)
-    assert b"".join(zlib.decompress(raw[o:o + s], -15) for o, s, _, _ in mem) == data
+    assert b"".join(zlib.decompress(raw[o:o + s], -15) for o, s, _, _, _ in mem) == data
+    assert all(zlib.crc32(zlib.decompress(raw[o:o + s], -15)) == c for o, s, _, _, c in mem)

@@ -31,7 +31,7 @@ def test_inflate_kernel_matches_zlib():
         for level, strat in ((1, zlib.Z_DEFAULT_STRATEGY), (6, zlib.Z_DEFAULT_STRATEGY), (9, zlib.Z_DEFAULT_STRATEGY), (6, zlib.Z_FIXED),
                              (0, zlib.Z_DEFAULT_STRATEGY), (6, zlib.Z_HUFFMAN_ONLY), (6, zlib.Z_RLE)):
             raw = _raw(data, level, strat)
-            members.append((len(blob), len(raw), len(data), 0))
+            members.append((len(blob), len(raw), len(data), 0, zlib.crc32(data)))
             blob += raw
             want.append(data)
             blob += b"\0" * int(rng.integers(0, 5))  # unaligned payload starts
@@ -44,6 +44,11 @@ def test_inflate_kernel_matches_zlib():
         bad[k] ^= 0x5A
     _, status, _ = bamdec.inflate_members(bytes(bad), members)
     assert status.any()
+    # a wrong CRC-32 in the trailer is reported for exactly that member (status 9), the others stay clean
+    wrong = list(members)
+    wrong[5] = wrong[5][:4] + (wrong[5][4] ^ 0x1,)
+    got2, status, _ = bamdec.inflate_members(bytes(blob), wrong)
+    assert status[5] == 9 and not np.delete(status, 5).any() and got2 == got
 
 
 def _decode_all(path, window_members, **kw):
