@@ -179,12 +179,14 @@ def bam_leg(b, n_reads, length):
     with tempfile.TemporaryDirectory() as d:
         bam = os.path.join(d, "synthetic.bam")
         info = synth_bam.write_bam(bam, [("chr19", length)], [sub], threads=os.cpu_count() or 8)
+        os.sync()          # the file was just written: let the write-back finish before anything is timed
+        time.sleep(1.0)
         out.update(records=info["records"], bam_bytes=info["bytes_compressed"], uncompressed_bytes=info["bytes_uncompressed"],
                    host_threads=os.cpu_count())
         for m in MEASURES:
             tsv, st = os.path.join(d, f"{m}.tsv"), os.path.join(d, f"{m}.json")
             best = None
-            for _ in range(5):  # (the host side of these boxes is shared: single runs vary a lot)
+            for _ in range(7):  # (the host side of these boxes is shared: single runs vary a lot)
                 t0 = time.perf_counter()
                 host.run(m, bam, tsv, stats_json=st)
                 dt = time.perf_counter() - t0
