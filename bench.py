@@ -421,6 +421,9 @@ def main():
         wall = time.perf_counter() - t0
         ms = torch.tensor([e0.elapsed_time(e1), wall * 1e3], device=dev, dtype=torch.float64)
         if world > 1:
+            per = [torch.zeros_like(ms) for _ in range(world)]
+            dist.all_gather(per, ms)
+            timed.per_rank_ms = [float(x[0]) / steps for x in per]  # device time per pass of every rank: the max is what counts
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         barrier()
         return float(ms[0]), float(ms[1])
@@ -456,7 +459,14 @@ def main():
         st = ctx.stats()
         dig = rows_digest(torch, dev, ctx, measures, owned=None if world == 1 else intervals)
         ms_step = ms_dev / steps
-        blk = {"measures": list(measures), "steps": steps, "ms_per_step": ms_step, "wall_ms_per_step": ms_wall / steps,
+        per_rank = None
+        if world > 1:
+            info = torch.tensor([st["n_regions"], st["kernel_launches"], sum(b["n_reads"] for b in batches)], device=dev, dtype=torch.int64)
+            allinfo = [torch.zeros_like(info) for _ in range(world)]
+            dist.all_gather(allinfo, info)
+            per_rank = [{"ms_per_step": round(m, 4), "regions": int(x[0]), "launches": int(x[1]), "reads_incl_halo": int(x[2])}
+                        for m, x in zip(timed.per_rank_ms, allinfo)]
+        blk = {"measures": list(measures), "steps": steps, "ms_per_step": ms_step, "wall_ms_per_step": ms_wall / steps, "per_rank": per_rank,
                "value": n_reads / (ms_step * 1e-3), "unit": "reads/s", "launches_per_step": int(st["kernel_launches"]),
                "regions_per_step": int(st["n_regions"]), "digest": dig}
         counts = torch.tensor([st["n_sites"]] + [dig[m][0] if m in dig else 0 for m in ALL7] + [st["fdrp_pair_ops"]], device=dev, dtype=torch.int64)
