@@ -594,7 +594,9 @@ def main():
             Re = R
         e2e = {"value": Re / (e_wall / e_steps * 1e-3), "unit": "reads/s", "ms_per_step": e_wall / e_steps,
                "h2d_bytes_per_step": int(est["h2d_bytes"]), "d2h_bytes_per_step": int(est["d2h_bytes"]), "steps": e_steps,
-               "measures": list(HEADLINE), "contigs": len(e_batches),
+               "measures": list(HEADLINE), "contigs": len(e_batches), "aggregate_h2d_GBps": int(est["h2d_bytes"]) * world / (e_wall / e_steps * 1e-3) / 1e9,
+               "limiter": "PCIe: every pass moves the whole SoA host -> device (53-54 GB/s on one GPU; GPUs that share a PCIe switch uplink share "
+                          "that bandwidth, so the aggregate stops near 180-210 GB/s on an 8-GPU box)",
                "wire_format": "SoA (mth_submit): pinned host arrays in the layout north_star names, one batch per contig; no host-side "
                               "encoding inside or outside the timed region; rows come back into the context's pinned buffers",
                "rows": {m: int(eres[m]["n"]) for m in HEADLINE}}
