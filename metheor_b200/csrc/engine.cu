@@ -70,7 +70,8 @@ struct mth_ctx {
     mth_params prm;
     std::vector<int64_t> ref_len;
     cudaStream_t own_compute = nullptr, copy = nullptr, compute = nullptr;
-    cudaEvent_t ev_copy = nullptr, ev_compute = nullptr;
+    cudaStream_t aux = nullptr;  // side stream of process_region: the latency-bound mixed-site gather of PM / ME beside the streaming kernels
+    cudaEvent_t ev_copy = nullptr, ev_compute = nullptr, ev_fork = nullptr, ev_join = nullptr;
     std::string err;
     int finished = 0;
 
@@ -110,7 +111,7 @@ struct mth_ctx {
     bool has_set = false;
     std::vector<int64_t> set_off;   // n_ref + 1 offsets into set_dev
     DevBuf set_dev, set_bitmap, set_kept, set_scan, set_total, set_pos_tmp, set_rel_tmp;
-    HostBuf h_set_total;
+    HostBuf h_set_total, h_ct;
     size_t set_words_valid = 0;
 
     ncclComm_t comm = nullptr;  // multi-GPU: joins this context with its peers (mth_comm_init_*)
@@ -571,6 +572,9 @@ int mth_ctx_create(mth_ctx** out, int device, const mth_params* params, int32_t 
     memset(&c->stats, 0, sizeof(c->stats));
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->own_compute, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_compute, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_stage_free[0], cudaEventDisableTiming) != cudaSuccess ||
@@ -620,13 +624,17 @@ int mth_ctx_destroy(mth_ctx* c) {
     host_free(c->h_scalars);
     host_free(c->h_totals);
     host_free(c->h_set_total);
+    host_free(c->h_ct);
     for (auto& sp : c->spans) { cudaEventDestroy(sp.e0); cudaEventDestroy(sp.e1); }
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     mth_comm_destroy(c);
     if (c->ev_copy) cudaEventDestroy(c->ev_copy);
     if (c->ev_compute) cudaEventDestroy(c->ev_compute);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->own_compute) cudaStreamDestroy(c->own_compute);
     if (c->copy) cudaStreamDestroy(c->copy);
+    if (c->aux) cudaStreamDestroy(c->aux);
     delete c;
     return MTH_OK;
 }
@@ -968,6 +976,21 @@ static int build_me_lut(mth_ctx* c) {
     return MTH_OK;
 }
 
+// Fork / join of the side stream: work queued on the returned stream starts after everything queued on `s` so far and `s`
+// continues after side_stream_end only when it is done.  Under MTH_FLAG_PROFILE the side stream IS `s` (serial, so that the
+// per-kernel event times mean what they say).
+static cudaStream_t side_stream_begin(mth_ctx* c, cudaStream_t s) {
+    if (c->prm.flags & MTH_FLAG_PROFILE) return s;
+    if (cudaEventRecord(c->ev_fork, s) != cudaSuccess || cudaStreamWaitEvent(c->aux, c->ev_fork, 0) != cudaSuccess) return s;
+    return c->aux;
+}
+static int side_stream_end(mth_ctx* c, cudaStream_t s, cudaStream_t side) {
+    if (side == s) return MTH_OK;
+    CUDA_TRY(c, cudaEventRecord(c->ev_join, side));
+    CUDA_TRY(c, cudaStreamWaitEvent(s, c->ev_join, 0));
+    return MTH_OK;
+}
+
 static int process_region(mth_ctx* c) {
     if (!c->region_active) return MTH_OK;
     cudaStream_t s = c->compute;
@@ -1004,11 +1027,13 @@ static int process_region(mth_ctx* c) {
         }
         // contig table
         size_t nct = c->reg_tid.size();
-        TRY(dev_reserve(c, c->ct_lin, nct * 4, 0));
-        TRY(dev_reserve(c, c->ct_tid, nct * 4, 0));
-        CUDA_TRY(c, cudaMemcpyAsync(c->ct_lin.p, c->reg_lin_off.data(), nct * 4, cudaMemcpyHostToDevice, s));
-        CUDA_TRY(c, cudaMemcpyAsync(c->ct_tid.p, c->reg_tid.data(), nct * 4, cudaMemcpyHostToDevice, s));
-        ContigTable ct{(int32_t)nct, (const int32_t*)c->ct_lin.p, (const int32_t*)c->ct_tid.p};
+        // one copy from pinned memory ([lin_off | tid]); the buffer is free again: the previous region's copy ran before its syncs
+        TRY(dev_reserve(c, c->ct_lin, nct * 8, 0));
+        TRY(host_reserve(c, c->h_ct, nct * 8));
+        memcpy(c->h_ct.p, c->reg_lin_off.data(), nct * 4);
+        memcpy((char*)c->h_ct.p + nct * 4, c->reg_tid.data(), nct * 4);
+        CUDA_TRY(c, cudaMemcpyAsync(c->ct_lin.p, c->h_ct.p, nct * 8, cudaMemcpyHostToDevice, s));
+        ContigTable ct{(int32_t)nct, (const int32_t*)c->ct_lin.p, (const int32_t*)c->ct_lin.p + nct};
         const int32_t* site_pos = (const int32_t*)c->site_pos.p;
 
         TRY(dev_reserve(c, c->gfallback, (size_t)C + 64, 0));
@@ -1147,10 +1172,15 @@ static int process_region(mth_ctx* c) {
                                               (unsigned long long*)c->qobs_n.p + q, s));
             }
             {
+                // The gather over the mixed sites is a handful of sites, each a chain of dependent loads: a launch lasts as long as
+                // one site takes.  It writes rowcnt[] of the mixed sites only, the canonical count those of the others: the two run
+                // side by side (not under MTH_FLAG_PROFILE, whose per-kernel times want them one after the other).
                 ProfScope ps(c, q ? "k_me_count" : "k_pm_count");
+                cudaStream_t gs = side_stream_begin(c, s);
                 ps.add(launch_quartet_canon_count((const uint32_t*)c->qcnt[q].p, (const uint8_t*)c->qmixed[q].p, C, qp.min_depth,
                                                   (uint32_t*)c->rowcnt[m].p, s));
-                ps.add(launch_quartet_count(rv, site_pos, C, d_sc, qp, (const uint8_t*)c->qmixed[q].p, (uint32_t*)c->rowcnt[m].p, s));
+                ps.add(launch_quartet_count(rv, site_pos, C, d_sc, qp, (const uint8_t*)c->qmixed[q].p, (uint32_t*)c->rowcnt[m].p, gs));
+                TRY(side_stream_end(c, s, gs));
             }
             ProfScope ps(c, q ? "me_rows_count" : "pm_rows_count");
             ps.add(launch_exclusive_scan_u32((uint32_t*)c->rowcnt[m].p, C, scratch, d_tot + m, s));
@@ -1214,7 +1244,10 @@ static int process_region(mth_ctx* c) {
                 const mth_quartet_params qp = q ? c->prm.me : c->prm.pm;
                 const int qs = q_set[q];
                 const uint8_t* qm = (const uint8_t*)c->qmixed[qs].p;
-                if (!(shared && q == 1)) {  // row histograms from the observation list (once per histogram set)
+                if (shared && q == 1) continue;  // histogram and rows were written together with PM's
+                // rows of the mixed sites (gather, latency-bound) beside the histogram + canonical rows (streaming): disjoint rows
+                cudaStream_t gs = side_stream_begin(c, s);
+                {  // row histograms from the observation list (once per histogram set)
                     ProfScope ps(c, q ? "k_me_hist" : "k_pm_hist");
                     TRY(dev_reserve(c, c->qhrows[qs], (size_t)(tot[m] + 1) * 64, 0));
                     CUDA_TRY(c, cudaMemsetAsync(c->qhrows[qs].p, 0, (size_t)(tot[m] + 1) * 64, s));
@@ -1222,7 +1255,6 @@ static int process_region(mth_ctx* c) {
                                                (const unsigned long long*)c->qobs_n.p + qs, rv.I, (const uint32_t*)c->qcnt[qs].p, qm,
                                                (const uint32_t*)c->rowcnt[m].p, qp.min_depth, (uint32_t*)c->qhrows[qs].p, s));
                 }
-                if (shared && q == 1) continue;  // written together with the PM rows
                 ProfScope ps(c, shared ? "k_pm_me_emit" : (q ? "k_me_emit" : "k_pm_emit"));
                 if (shared) {  // PM and ME rows from one read of the histograms / one gather pass over the mixed sites
                     QuartetRowsDev rd2 = quartet_rows_dev(c->rows_me);
@@ -1231,13 +1263,14 @@ static int process_region(mth_ctx* c) {
                                                      (const uint32_t*)c->rowcnt[m].p, (const float*)c->me_lut.p, c->me_lut_max, ct, rd, r.n, rd2,
                                                      c->rows_me.n, s));
                     ps.add(launch_quartet_emit(rv, site_pos, C, d_sc, qp, 2, qm, (const uint32_t*)c->rowcnt[m].p, (const float*)c->me_lut.p,
-                                               c->me_lut_max, ct, rd, r.n, rd2, c->rows_me.n, s));
+                                               c->me_lut_max, ct, rd, r.n, rd2, c->rows_me.n, gs));
                 } else {
                     ps.add(launch_quartet_canon_emit((const uint32_t*)c->qcnt[qs].p, qm, (const uint32_t*)c->qhrows[qs].p, site_pos, C, qp.min_depth, q,
                                                      (const uint32_t*)c->rowcnt[m].p, (const float*)c->me_lut.p, c->me_lut_max, ct, rd, r.n, rd, r.n, s));
                     ps.add(launch_quartet_emit(rv, site_pos, C, d_sc, qp, q, qm, (const uint32_t*)c->rowcnt[m].p, (const float*)c->me_lut.p,
-                                               c->me_lut_max, ct, rd, r.n, rd, r.n, s));
+                                               c->me_lut_max, ct, rd, r.n, rd, r.n, gs));
                 }
+                TRY(side_stream_end(c, s, gs));
             }
             if (M & MTH_PM) c->rows_pm.n += (int64_t)tot[M_PM];
             if (M & MTH_ME) c->rows_me.n += (int64_t)tot[M_ME];

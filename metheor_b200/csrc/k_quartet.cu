@@ -119,6 +119,8 @@ struct QuartetArgs {
     int64_t row_base_b;
 };
 
+constexpr int QCACHE = 4;  // chunks of 32 reads of a site's window whose quartets stay in registers between the passes
+
 template <bool EMIT>
 __global__ void __launch_bounds__(GATHER_BLOCK) k_quartet(QuartetArgs a) {
     __shared__ uint32_t s_cnt[GATHER_BLOCK / 32][16];
@@ -191,12 +193,25 @@ __global__ void __launch_bounds__(GATHER_BLOCK) k_quartet(QuartetArgs a) {
         __syncwarp();
 
         // ---- pass 0: optimistic single-key pass ----
+        // The lanes keep what they saw (key, pattern, valid) for the first QCACHE chunks of the window in registers: a site with
+        // several keys is then resolved without touching memory again.  (Each pass over the window is a chain of dependent
+        // loads — start, offsets, positions, bits — of several microseconds; mixed sites are rare, so a launch lasts as long
+        // as ONE site takes and that latency, not throughput, is what the passes cost.)
         bool have_guess = false, mixed = false;
         QKey guess{0, 0, 0};
+        QKey ck[QCACHE];
+        uint32_t cpv[QCACHE];  // pattern | 16 when the lane's read of that chunk starts a quartet at p
+#pragma unroll
+        for (int c = 0; c < QCACHE; c++) { ck[c] = QKey{0, 0, 0}; cpv[c] = 0u; }
+        int n_chunks = 0;
         scan_window(rv, lo, p, target, [&](const LaneRead& lr) {
             QKey key{0, 0, 0};
             uint32_t pat = 0;
             bool valid = lane_quartet(lr, &key, &pat);
+#pragma unroll
+            for (int c = 0; c < QCACHE; c++)
+                if (c == n_chunks) { ck[c] = key; cpv[c] = valid ? (pat | 16u) : 0u; }
+            n_chunks++;
             uint32_t vm = __ballot_sync(FULL, valid);
             if (!vm) return;
             if (!have_guess) {
@@ -218,30 +233,51 @@ __global__ void __launch_bounds__(GATHER_BLOCK) k_quartet(QuartetArgs a) {
             __syncwarp();
             QKey last{INT32_MIN, INT32_MIN, INT32_MIN};
             bool first_round = true;
-            while (true) {
-                bool found = false;
-                QKey best{INT32_MAX, INT32_MAX, INT32_MAX};
-                scan_window(rv, lo, p, target, [&](const LaneRead& lr) {
-                    QKey key{0, 0, 0};
-                    uint32_t pat = 0;
-                    bool valid = lane_quartet(lr, &key, &pat);
-                    bool cand = valid && (first_round || key_less(last, key));
-                    uint32_t cmask = __ballot_sync(FULL, cand);
-                    if (!cmask) return;
-                    QKey m = warp_min_key(cmask, key);
-                    if (!found || key_less(m, best)) best = m;
-                    found = true;
-                });
-                if (!found) break;
-                scan_window(rv, lo, p, target, [&](const LaneRead& lr) {
-                    QKey key{0, 0, 0};
-                    uint32_t pat = 0;
-                    bool valid = lane_quartet(lr, &key, &pat);
-                    count_chunk(valid && key_eq(key, best), pat);
-                });
-                finish_key(best);
-                last = best;
-                first_round = false;
+            if (n_chunks <= QCACHE) {  // from the registers
+                while (true) {
+                    bool cand = false;
+                    QKey mine{INT32_MAX, INT32_MAX, INT32_MAX};
+#pragma unroll
+                    for (int c = 0; c < QCACHE; c++) {
+                        const bool v = (cpv[c] & 16u) && (first_round || key_less(last, ck[c]));
+                        if (v && (!cand || key_less(ck[c], mine))) { mine = ck[c]; cand = true; }
+                    }
+                    const uint32_t cmask = __ballot_sync(FULL, cand);
+                    if (!cmask) break;
+                    const QKey best = warp_min_key(cmask, mine);
+#pragma unroll
+                    for (int c = 0; c < QCACHE; c++)
+                        if (c < n_chunks) count_chunk((cpv[c] & 16u) && key_eq(ck[c], best), cpv[c] & 15u);
+                    finish_key(best);
+                    last = best;
+                    first_round = false;
+                }
+            } else {  // a window of more than 32 * QCACHE reads: one pass over the window per step
+                while (true) {
+                    bool found = false;
+                    QKey best{INT32_MAX, INT32_MAX, INT32_MAX};
+                    scan_window(rv, lo, p, target, [&](const LaneRead& lr) {
+                        QKey key{0, 0, 0};
+                        uint32_t pat = 0;
+                        bool valid = lane_quartet(lr, &key, &pat);
+                        bool cand = valid && (first_round || key_less(last, key));
+                        uint32_t cmask = __ballot_sync(FULL, cand);
+                        if (!cmask) return;
+                        QKey m = warp_min_key(cmask, key);
+                        if (!found || key_less(m, best)) best = m;
+                        found = true;
+                    });
+                    if (!found) break;
+                    scan_window(rv, lo, p, target, [&](const LaneRead& lr) {
+                        QKey key{0, 0, 0};
+                        uint32_t pat = 0;
+                        bool valid = lane_quartet(lr, &key, &pat);
+                        count_chunk(valid && key_eq(key, best), pat);
+                    });
+                    finish_key(best);
+                    last = best;
+                    first_round = false;
+                }
             }
         }
         if (!EMIT && lane == 0) a.rowcnt[s] = n_rows;

@@ -53,23 +53,43 @@ __global__ void __launch_bounds__(SCAN_BLOCK) k_sites_count(const unsigned long 
     if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
 }
 
-// single block: in-place exclusive scan of sums[0..n), grand total -> *total
-__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_sums(uint32_t* sums, int64_t n, unsigned long long* total) {
-    __shared__ unsigned long long carry_s;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    for (int64_t base = 0; base < n; base += SCAN_BLOCK) {
-        int64_t i = base + threadIdx.x;
-        uint32_t v = i < n ? sums[i] : 0;
-        uint32_t tot;
-        uint32_t ex = block_exclusive_scan(v, &tot);
-        unsigned long long carry = carry_s;
-        if (i < n) sums[i] = (uint32_t)(carry + ex);
-        __syncthreads();
-        if (threadIdx.x == 0) carry_s = carry + tot;
-        __syncthreads();
+// single block: in-place exclusive scan of sums[0..n), grand total -> *total.
+// n is small (one entry per 65 536 positions / 2 048 sites) and this kernel sits on every region's critical path three or
+// more times, so it is built for latency: 1024 threads, each owning a run of ceil(n / 1024) consecutive entries, ONE block-wide
+// scan of the per-thread totals (two barriers) instead of a loop of 256-entry scans with a carry.
+constexpr int SUMS_BLOCK = 1024;
+__global__ void __launch_bounds__(SUMS_BLOCK) k_scan_sums(uint32_t* sums, int64_t n, unsigned long long* total) {
+    __shared__ unsigned long long warp_tot[SUMS_BLOCK / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t per = (n + SUMS_BLOCK - 1) / SUMS_BLOCK;
+    const int64_t i0 = (int64_t)threadIdx.x * per, i1 = min(n, i0 + per);
+    unsigned long long mine = 0;
+    for (int64_t i = i0; i < i1; i++) mine += sums[i];
+    unsigned long long inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long t = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o) inc += t;
     }
-    if (threadIdx.x == 0) *total = carry_s;
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long w = warp_tot[lane], winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long t = __shfl_up_sync(FULL, winc, o);
+            if (lane >= o) winc += t;
+        }
+        warp_tot[lane] = winc - w;
+        if (lane == 31) *total = winc;
+    }
+    __syncthreads();
+    unsigned long long run = warp_tot[warp] + inc - mine;
+    for (int64_t i = i0; i < i1; i++) {
+        const uint32_t v = sums[i];
+        sums[i] = (uint32_t)run;
+        run += v;
+    }
 }
 
 __global__ void __launch_bounds__(SCAN_BLOCK) k_sites_emit(const unsigned long long* __restrict__ bitmap, int64_t n_words,
@@ -99,7 +119,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK) k_sites_emit(const unsigned long l
 }
 
 int launch_scan_sums(uint32_t* sums, int64_t n, unsigned long long* total, cudaStream_t s) {
-    k_scan_sums<<<1, SCAN_BLOCK, 0, s>>>(sums, n, total);
+    k_scan_sums<<<1, SUMS_BLOCK, 0, s>>>(sums, n, total);
     return 1;
 }
 
@@ -108,7 +128,7 @@ int launch_sites_count(const unsigned long long* bitmap, int64_t n_words, uint32
     int64_t nb = (n_words + WORDS_PER_BLOCK - 1) / WORDS_PER_BLOCK;
     if (nb <= 0) nb = 1;
     k_sites_count<<<(unsigned)nb, SCAN_BLOCK, 0, s>>>(bitmap, n_words, block_sums);
-    k_scan_sums<<<1, SCAN_BLOCK, 0, s>>>(block_sums, nb, &sc->n_sites);
+    k_scan_sums<<<1, SUMS_BLOCK, 0, s>>>(block_sums, nb, &sc->n_sites);
     return 2;
 }
 
@@ -159,7 +179,7 @@ int launch_exclusive_scan_u32(uint32_t* a, int64_t n, uint32_t* scratch, unsigne
     int64_t nb = (n + ITEMS_PER_BLOCK - 1) / ITEMS_PER_BLOCK;
     if (nb <= 0) nb = 1;
     k_scan_partial<<<(unsigned)nb, SCAN_BLOCK, 0, s>>>(a, n, scratch);
-    k_scan_sums<<<1, SCAN_BLOCK, 0, s>>>(scratch, nb, total);
+    k_scan_sums<<<1, SUMS_BLOCK, 0, s>>>(scratch, nb, total);
     k_scan_final<<<(unsigned)nb, SCAN_BLOCK, 0, s>>>(a, n, scratch);
     return 3;
 }

@@ -483,9 +483,10 @@ static bool feed_device(const mthh_options& o, const RecordStream& in, mth_ctx* 
     const Header& hdr = in.header();
     const uint8_t* d = in.file().data();
     const size_t fsize = in.file().size();
-    // uncompressed bytes per window: one warp inflates one <= 64 KiB member, so a window has to hold several thousand members to
-    // fill the GPU (148 SMs x ~50 warps); the first window is small so that the pipeline starts early
-    const size_t WINDOW_U = 384u << 20;
+    // uncompressed bytes per window: one warp inflates one <= 64 KiB member and 148 SMs x 16 warps of k_bgzf_inflate are
+    // resident at a time, so a window of 148 x 16 full members is exactly one wave of that kernel — the smallest window that
+    // fills the GPU.  Small windows keep the pipeline short: the upload of the first one is the only stage nothing overlaps.
+    const size_t WINDOW_U = (size_t)148 * 16 * 64000;
     struct Staged {
         size_t bytes = 0;
         std::vector<mth_bgzf_member> members;

@@ -406,3 +406,14 @@ def test_regions_with_host_soa_batches_and_mixed_quartets():
         res, st = parity.check_all(batches, lens, ("pm", "me", "lpmd", "pdr"), pm=dict(min_depth=3), me=dict(min_depth=3),
                                    pdr=dict(min_depth=4), lpmd=dict(want_pairs=1))
         assert st["n_regions"] >= 3 and res["pm"]["n"] > 1000
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("coverage", [40.0, 400.0])
+def test_mixed_quartet_sites_shallow_and_deep_windows(coverage):
+    """PM / ME sites with several quartet keys (no-calls and deletions): at 40x the window of a site fits the lanes' register
+    cache of k_quartet (<= 128 reads), at 400x it does not and the keys are enumerated by passes over the window."""
+    sites = synth.make_sites(910, 60_000, mean_gap=9.0)
+    b = synth.make_reads(911, sites, 60_000, coverage, tid=0, nocall=0.08, del_frac=0.08)
+    res, _ = parity.check_all([b], [60_000], ("pm", "me"), pm=dict(min_depth=2), me=dict(min_depth=2))
+    assert res["pm"]["n"] > 1000 and res["me"]["n"] == res["pm"]["n"]
