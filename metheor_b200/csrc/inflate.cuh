@@ -34,19 +34,16 @@ enum : int { INF_OK = 0, INF_ERR_BTYPE = 1, INF_ERR_STORED = 2, INF_ERR_CODE = 3
 // LSB-first bit reader; every lane of the warp holds the same state.  The compressed bytes come through a 256-byte ring in
 // shared memory that the warp refills with one coalesced load (2 words per lane) every 64 words, so the serial decode loop
 // waits on shared memory (~30 cycles), not on global memory (~500), for its input.
-// The window on the stream is two 32-bit words (lo, hi) and the number of bits of `lo` already consumed (off < 32): at least 33
-// unread bits are always in the window, so a look-ahead of up to 32 bits is ONE funnel shift with no "enough bits?" test, and
-// consuming bits is one add plus — every 32 bits — a word moving up from the ring.  (The decode loop is bound by issued
-// instructions: a 64-bit buffer with a bit count cost three times the instructions per symbol.)
 constexpr int INF_RING_WORDS = 64;
 struct BitReader {
     const unsigned int* g;      // the stream as 32-bit words from the 4-byte aligned address at or below its first byte
     unsigned int* ring;         // shared memory, INF_RING_WORDS words, this warp's
     uint32_t n_words;           // words that contain stream bytes
     uint32_t n_bytes;           // stream length from the aligned base (skip + in_len)
-    uint32_t rw;                // next word to move into the window (lo = word rw - 2, hi = word rw - 1)
+    uint32_t rw;                // next word to move into the bit buffer
     uint32_t filled;            // words [0, filled) have been staged (multiple of INF_RING_WORDS)
-    uint32_t lo, hi, off;
+    unsigned long long buf;
+    int cnt;
     __device__ __forceinline__ void fill() {  // stage words [filled, filled + 64): every earlier word has been consumed
         const int lane = lane_id();
         __syncwarp();
@@ -58,50 +55,45 @@ struct BitReader {
         filled += INF_RING_WORDS;
         __syncwarp();
     }
-    __device__ __forceinline__ uint32_t next_word() {  // zeros past the end
-        if (rw >= filled) fill();
-        return ring[rw++ & (INF_RING_WORDS - 1)];
-    }
     __device__ __forceinline__ void init(const uint8_t* b, uint32_t len, unsigned int* ring_) {
         const uint32_t skip = (uint32_t)((uintptr_t)b & 3u);
         g = reinterpret_cast<const unsigned int*>(b - skip);
         ring = ring_;
         n_bytes = skip + len;
         n_words = (n_bytes + 3) >> 2;
-        rw = 0; filled = 0;
-        // bytes of the first / last word outside the stream are never interpreted: `skip` bytes are skipped here and the decoder
+        rw = 0; filled = 0; buf = 0; cnt = 0;
+        // bytes of the first / last word outside the stream are never interpreted: `skip` bytes are dropped here and the decoder
         // stops at the end-of-block code (consumption past n_bytes is detected by overrun())
-        lo = next_word();
-        hi = next_word();
-        off = skip * 8u;
+        refill();
+        drop((int)skip * 8);
     }
-    __device__ __forceinline__ uint32_t peek32() const { return __funnelshift_r(lo, hi, off); }  // the next 32 bits
-    __device__ __forceinline__ uint32_t peek(int n) const { return peek32() & ((1u << n) - 1u); }  // n <= 31
-    __device__ __forceinline__ void drop(int n) {  // n <= 32
-        off += (uint32_t)n;
-        if (off >= 32u) {
-            lo = hi;
-            hi = next_word();
-            off -= 32u;
+    __device__ __forceinline__ void refill() {  // at least 32 valid bits afterwards (zeros past the end)
+        while (cnt <= 32) {
+            if (rw >= filled) fill();
+            buf |= (unsigned long long)ring[rw & (INF_RING_WORDS - 1)] << cnt;
+            rw++;
+            cnt += 32;
         }
     }
+    __device__ __forceinline__ uint32_t peek(int n) const { return (uint32_t)(buf & ((1ull << n) - 1ull)); }
+    __device__ __forceinline__ void drop(int n) { buf >>= n; cnt -= n; }
     __device__ __forceinline__ uint32_t bits(int n) {  // n <= 16
-        const uint32_t v = peek(n);
+        if (cnt < n) refill();
+        uint32_t v = peek(n);
         drop(n);
         return v;
     }
-    __device__ __forceinline__ void align_byte() { drop((int)((8u - (off & 7u)) & 7u)); }
     // byte position (from the aligned base) of the next unread bit, which must be byte aligned
-    __device__ __forceinline__ uint32_t byte_pos() const { return ((rw - 2u) * 32u + off) >> 3; }
+    __device__ __forceinline__ uint32_t byte_pos() const { return rw * 4u - (uint32_t)(cnt >> 3); }
     __device__ __forceinline__ void seek(uint32_t pos) {  // continue at byte `pos`
         rw = pos >> 2;
         filled = rw & ~(uint32_t)(INF_RING_WORDS - 1);
-        lo = next_word();
-        hi = next_word();
-        off = (pos & 3u) * 8u;
+        buf = 0; cnt = 0;
+        fill();
+        refill();
+        drop((int)(pos & 3u) * 8);
     }
-    // consumed bits past the end
-    __device__ __forceinline__ bool overrun() const { return (unsigned long long)(rw - 2u) * 32ull + off > (unsigned long long)n_bytes * 8ull; }
+    __device__ __forceinline__ bool overrun() const { return (long long)rw * 32 - cnt > (long long)n_bytes * 8; }  // consumed bits past the end
 };
 
 // Canonical Huffman set-up from code lengths len[0..n): counts per length, symbols in canonical order (lane 0 — a few
@@ -149,15 +141,16 @@ __device__ __forceinline__ bool build_table(const uint8_t* len, int n, uint16_t*
 
 // One symbol: fast table, else the canonical walk over the lengths above the fast width.
 __device__ __forceinline__ int decode_sym(BitReader& br, const uint16_t* cnt, const uint16_t* sym, const uint16_t* fast, int fast_bits) {
-    uint32_t b = br.peek32();
-    const uint32_t e = fast[b & ((1u << fast_bits) - 1u)];
+    if (br.cnt < INF_MAXBITS) br.refill();
+    const uint32_t e = fast[br.peek(fast_bits)];
     if (e) {
         br.drop((int)(e & 15u));
         return (int)(e >> 4);
     }
     int code = 0, first = 0, index = 0;
+    unsigned long long b = br.buf;
     for (int l = 1; l <= INF_MAXBITS; l++) {
-        code |= (int)(b & 1u);
+        code |= (int)(b & 1ull);
         b >>= 1;
         const int c = cnt[l];
         if (code - c < first) {
@@ -202,7 +195,7 @@ __device__ __forceinline__ int warp_inflate(const uint8_t* __restrict__ in, uint
         last = br.bits(1) != 0;
         const uint32_t type = br.bits(2);
         if (type == 0) {  // stored
-            br.align_byte();
+            br.drop(br.cnt & 7);
             const uint32_t q0 = br.byte_pos();  // LEN NLEN data, byte aligned
             if (q0 + 4 > br.n_bytes) { err = INF_ERR_INPUT; break; }
             const uint8_t* q = reinterpret_cast<const uint8_t*>(br.g) + q0;
@@ -297,11 +290,7 @@ __device__ __forceinline__ int warp_inflate(const uint8_t* __restrict__ in, uint
             if (pos + len > out_cap) { err = INF_ERR_SIZE; break; }
             __syncwarp();  // the bytes written so far (literals by lane 0) are visible to every lane
             const uint8_t* src = out + pos - dist;
-            if (dist >= len) {  // source and destination do not overlap
-                for (uint32_t k = lane; k < len; k += 32) out[pos + k] = __ldcg(src + k);
-            } else {            // a run: the last `dist` bytes repeated
-                for (uint32_t k = lane; k < len; k += 32) out[pos + k] = __ldcg(src + k % dist);
-            }
+            for (uint32_t k = lane; k < len; k += 32) out[pos + k] = __ldcg(src + (dist >= len ? k : k % dist));
             __syncwarp();
             pos += len;
         }

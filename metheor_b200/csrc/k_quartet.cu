@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(256) k_quartet_canon_count(const uint32_t* __r
                                                              uint32_t min_depth, uint32_t* __restrict__ rowcnt) {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= C) return;
-    if (mixed[s]) { rowcnt[s] = 0; return; }  // overwritten by the gather pass
+    if (mixed[s]) return;  // rowcnt[s] of a mixed site belongs to the gather pass, which may be running beside this kernel
     const uint4 q = reinterpret_cast<const uint4*>(qcnt)[s];
     const uint32_t md = max(min_depth, 1u);
     rowcnt[s] = (q.x >= md) + (q.y >= md) + (q.z >= md) + (q.w >= md);

@@ -483,10 +483,11 @@ static bool feed_device(const mthh_options& o, const RecordStream& in, mth_ctx* 
     const Header& hdr = in.header();
     const uint8_t* d = in.file().data();
     const size_t fsize = in.file().size();
-    // uncompressed bytes per window: one warp inflates one <= 64 KiB member and 148 SMs x 16 warps of k_bgzf_inflate are
-    // resident at a time, so a window of 148 x 16 full members is exactly one wave of that kernel — the smallest window that
-    // fills the GPU.  Small windows keep the pipeline short: the upload of the first one is the only stage nothing overlaps.
-    const size_t WINDOW_U = (size_t)148 * 16 * 64000;
+    // uncompressed bytes per window: one warp inflates one <= 64 KiB member and 148 SMs x 32 warps of k_bgzf_inflate are
+    // resident at a time, so 148 x 32 full members are one wave of that kernel.  A member takes a warp ~11 ms however few
+    // are in flight (Huffman decoding is a serial dependency chain), so smaller windows cost the same 11 ms each (measured:
+    // 7 windows of half a wave 76 ms, 3 windows of 1.24 waves 47 ms, one launch of 3 waves 35 ms for a 918 MB BAM).
+    const size_t WINDOW_U = (size_t)148 * 32 * 65280;
     struct Staged {
         size_t bytes = 0;
         std::vector<mth_bgzf_member> members;
