@@ -63,6 +63,36 @@ constexpr int64_t BORROWED_REGION_MIN_READS = 1 << 20;  // see place_batch
 
 enum { M_PDR = 0, M_MHL, M_FDRP, M_QFDRP, M_PM, M_ME, M_PAIRS, M_COUNT };
 
+// What belongs to ONE region: its reads (view), its contigs and everything the ingest pass writes.  The context holds the
+// region being filled; a region whose processing is deferred behind the next region's ingest pass (see mth_submit) is
+// parked in a RegionJob, and swap_slot() puts it back into the context for the calls that work on it.
+struct RegionSlot {
+    bool region_active = false;
+    int32_t cur_lin_off = 0;
+    int64_t R = 0, I = 0, W = 0;
+    bool borrowed = false;
+    mth_batch bview;
+    bool has_meth_off = false;
+    std::vector<int32_t> reg_lin_off, reg_tid;
+    DevBuf bitmap, scalars, a_flags;
+    size_t bitmap_words_valid = 0;
+    HostBuf h_scalars, h_totals;
+};
+// Host-side values the three steps of a region hand to each other: close (site count queued) -> phase A (measure kernels,
+// row counts, scans) -> phase B (row emission).
+struct RegionCarry {
+    int64_t C = 0;
+    int q_set[2] = {0, 1};
+    unsigned long long tot[M_COUNT] = {0, 0, 0, 0, 0, 0, 0};
+    size_t nct = 0;
+    bool done = false;                            // nothing left to do (a region without sites ends in phase A)
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;   // deferred regions wait on events; nullptr = synchronise the stream
+};
+struct RegionJob {
+    RegionSlot st;
+    RegionCarry k;
+};
+
 }  // namespace
 
 struct mth_ctx {
@@ -74,6 +104,13 @@ struct mth_ctx {
     cudaEvent_t ev_copy = nullptr, ev_compute = nullptr, ev_fork = nullptr, ev_join = nullptr;
     std::string err;
     int finished = 0;
+
+    // Regions in flight behind the one being filled (borrowed device contigs only, see mth_submit): `pend` has its phase A
+    // queued and waits for phase B; `next` is the parking place of the region that was just closed (and, between uses, the
+    // owner of the spare buffer set).
+    RegionJob pend, next;
+    bool has_pend = false;
+    bool pipeline = true;
 
     // region state
     bool region_active = false;
@@ -339,6 +376,10 @@ static int materialize(mth_ctx* c) {
 }
 
 static int process_region(mth_ctx* c);
+static void swap_slot(mth_ctx* c, RegionSlot& o);
+static int region_close(mth_ctx* c, RegionCarry& k);
+static int region_phase_a(mth_ctx* c, RegionCarry& k);
+static int finish_pending(mth_ctx* c);
 
 static int check_scalars_err(mth_ctx* c, uint32_t e) {
     if (!e) return MTH_OK;
@@ -584,6 +625,7 @@ int mth_ctx_create(mth_ctx** out, int device, const mth_params* params, int32_t 
         return MTH_ERR_CUDA;
     }
     c->compute = c->own_compute;
+    c->pipeline = getenv("METHEOR_NO_PIPELINE") == nullptr;  // A/B switch: regions strictly one after the other
     *out = c;
     return MTH_OK;
 }
@@ -630,6 +672,12 @@ int mth_ctx_destroy(mth_ctx* c) {
     mth_comm_destroy(c);
     if (c->ev_copy) cudaEventDestroy(c->ev_copy);
     if (c->ev_compute) cudaEventDestroy(c->ev_compute);
+    for (RegionJob* j : {&c->pend, &c->next}) {
+        dev_free(j->st.bitmap); dev_free(j->st.scalars); dev_free(j->st.a_flags);
+        host_free(j->st.h_scalars); host_free(j->st.h_totals);
+        if (j->k.ev_a) cudaEventDestroy(j->k.ev_a);
+        if (j->k.ev_b) cudaEventDestroy(j->k.ev_b);
+    }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->own_compute) cudaStreamDestroy(c->own_compute);
@@ -669,6 +717,12 @@ int mth_reset(mth_ctx* c) {
     c->R = c->I = c->W = 0;
     c->borrowed = false;
     c->last_tid = -1;
+    c->has_pend = false;
+    for (RegionJob* j : {&c->pend, &c->next}) {
+        j->st.region_active = false;
+        j->st.borrowed = false;
+        j->st.R = j->st.I = j->st.W = 0;
+    }
     c->rows_pdr.n = c->rows_mhl.n = c->rows_fdrp.n = c->rows_qfdrp.n = 0;
     c->rows_pm.n = c->rows_me.n = 0;
     c->rows_pairs.n = 0;
@@ -703,13 +757,32 @@ int mth_submit(mth_ctx* c, const mth_batch* b) {
     int64_t bw = batch_words(b);
     if (bw < b->n_reads && b->meth_off == nullptr) return fail(c, MTH_ERR_INVALID, "n_meth_words inconsistent");
 
+    // borrowed arrays are read in place; the TMA bulk copies of k_ingest need 16-byte aligned bases
+    auto al16 = [](const void* p) { return ((uintptr_t)p & 15u) == 0; };
+    const bool borrowable = b->mem_kind == 1 && al16(b->cpg_pos) && al16(b->cpg_rel) && !c->has_set;
+
+    // A chain of large device-resident contigs (each is a region of its own, see place_batch): the region that ends here is
+    // only CLOSED now (its site count is queued); its phase A is queued behind THIS batch's ingest pass and its phase B
+    // behind the next one's, so that the host's two waits per region fall while the GPU has an ingest pass to run.
+    bool deferred = false;
+    if (c->pipeline && c->region_active && c->borrowed && c->R >= BORROWED_REGION_MIN_READS && b->tid > c->last_tid && borrowable) {
+        RegionCarry& k = c->next.k;
+        if (!k.ev_a && (cudaEventCreateWithFlags(&k.ev_a, cudaEventDisableTiming) != cudaSuccess ||
+                        cudaEventCreateWithFlags(&k.ev_b, cudaEventDisableTiming) != cudaSuccess))
+            return fail(c, MTH_ERR_CUDA, "cudaEventCreate failed");
+        TRY(region_close(c, k));
+        swap_slot(c, c->next.st);  // the closed region is parked; the context continues with the spare buffer set
+        c->region_active = false;
+        c->borrowed = false;
+        c->R = c->I = c->W = 0;
+        deferred = true;
+    }
+
     TRY(place_batch(c, b->tid, b->n_reads, b->n_cpg, bw));
 
     const int32_t lin_off = c->cur_lin_off;
     const int64_t r0 = c->R, i0 = c->I, w0 = c->W;
-    // borrowed arrays are read in place; the TMA bulk copies of k_ingest need 16-byte aligned bases
-    auto al16 = [](const void* p) { return ((uintptr_t)p & 15u) == 0; };
-    const bool can_borrow = b->mem_kind == 1 && r0 == 0 && lin_off == 0 && al16(b->cpg_pos) && al16(b->cpg_rel) && !c->has_set;
+    const bool can_borrow = borrowable && r0 == 0 && lin_off == 0;
     const uint16_t* rel_dev = nullptr;
     if (can_borrow) {
         c->borrowed = true;
@@ -772,6 +845,17 @@ int mth_submit(mth_ctx* c, const mth_batch* b) {
     }
 
     TRY(run_ingest(c, b->tid, r0, b->n_reads, i0, n_kept, rel_dev));
+    if (deferred) {
+        TRY(finish_pending(c));  // phase B of the region before the parked one
+        swap_slot(c, c->next.st);
+        const int rc = region_phase_a(c, c->next.k);
+        swap_slot(c, c->next.st);
+        TRY(rc);
+        if (!c->next.k.done) {  // `next` becomes the region waiting for phase B; the finished one's buffers are the spare set
+            std::swap(c->pend, c->next);
+            c->has_pend = true;
+        }
+    }
     return MTH_OK;
 }
 
@@ -991,25 +1075,72 @@ static int side_stream_end(mth_ctx* c, cudaStream_t s, cudaStream_t side) {
     return MTH_OK;
 }
 
-static int process_region(mth_ctx* c) {
-    if (!c->region_active) return MTH_OK;
-    cudaStream_t s = c->compute;
-    const uint32_t M = c->prm.measures;
-    ReadsView rv = make_view(c);
-    RegionScalars* d_sc = (RegionScalars*)c->scalars.p;
-    const bool want_pairs = (M & MTH_LPMD) && c->prm.lpmd.want_pairs;
-    const bool need_sites = (M & (MTH_PDR | MTH_MHL | MTH_PM | MTH_ME | MTH_FDRP | MTH_QFDRP)) != 0 || want_pairs;
+static void swap_slot(mth_ctx* c, RegionSlot& o) {
+    std::swap(c->region_active, o.region_active);
+    std::swap(c->cur_lin_off, o.cur_lin_off);
+    std::swap(c->R, o.R); std::swap(c->I, o.I); std::swap(c->W, o.W);
+    std::swap(c->borrowed, o.borrowed);
+    std::swap(c->bview, o.bview);
+    std::swap(c->has_meth_off, o.has_meth_off);
+    c->reg_lin_off.swap(o.reg_lin_off);
+    c->reg_tid.swap(o.reg_tid);
+    std::swap(c->bitmap, o.bitmap); std::swap(c->scalars, o.scalars); std::swap(c->a_flags, o.a_flags);
+    std::swap(c->bitmap_words_valid, o.bitmap_words_valid);
+    std::swap(c->h_scalars, o.h_scalars); std::swap(c->h_totals, o.h_totals);
+}
 
-    int64_t n_words = (int64_t)c->bitmap_words_valid;
-    int64_t nb = (n_words + 1023) / 1024 + 1;
-    if (need_sites) {
+// The processing of a region is three steps with a host round trip between them (the host sizes the per-site buffers from the
+// number of sites, and the row buffers from the row totals):
+//   region_close   : site count of the region's bitmap + its scalars on their way to the host
+//   region_phase_a : [wait] site dictionary, the measure kernels, row counts and their scans; totals on their way to the host
+//   region_phase_b : [wait] row emission
+// process_region runs them back to back.  For a chain of large device-resident contigs mth_submit interleaves them with the
+// NEXT regions' ingest passes, so that the GPU has work queued while the host waits (the waits are on events then).
+static bool region_needs_sites(const mth_ctx* c) {
+    const uint32_t M = c->prm.measures;
+    return (M & (MTH_PDR | MTH_MHL | MTH_PM | MTH_ME | MTH_FDRP | MTH_QFDRP)) != 0 || ((M & MTH_LPMD) && c->prm.lpmd.want_pairs);
+}
+
+static int region_close(mth_ctx* c, RegionCarry& k) {
+    cudaStream_t s = c->compute;
+    RegionScalars* d_sc = (RegionScalars*)c->scalars.p;
+    k.C = 0; k.done = false; k.q_set[0] = 0; k.q_set[1] = 1; k.nct = 0;
+    const int64_t n_words = (int64_t)c->bitmap_words_valid;
+    const int64_t nb = (n_words + 1023) / 1024 + 1;
+    if (region_needs_sites(c)) {
         TRY(dev_reserve(c, c->block_sums, (size_t)nb * 4, 0));
         TRY(dev_reserve(c, c->word_prefix, (size_t)n_words * 4 + 4, 0));
         ProfScope ps(c, "k_sites_count");
         ps.add(launch_sites_count((const unsigned long long*)c->bitmap.p, n_words, (uint32_t*)c->block_sums.p, d_sc, s));
     }
     CUDA_TRY(c, cudaMemcpyAsync(c->h_scalars.p, d_sc, sizeof(RegionScalars), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(c, cudaStreamSynchronize(s));
+    if (k.ev_a) CUDA_TRY(c, cudaEventRecord(k.ev_a, s));
+    return MTH_OK;
+}
+
+static int region_end(mth_ctx* c, RegionCarry& k) {
+    cudaStream_t s = c->compute;
+    k.done = true;
+    c->region_active = false;
+    c->borrowed = false;
+    c->R = c->I = c->W = 0;
+    // The emit kernels queued above still read the arena; the next region's host->device copies (copy stream) overwrite it
+    // from offset 0: order them behind this point.
+    CUDA_TRY(c, cudaEventRecord(c->ev_compute, s));
+    CUDA_TRY(c, cudaStreamWaitEvent(c->copy, c->ev_compute, 0));
+    return MTH_OK;
+}
+
+static int region_phase_a(mth_ctx* c, RegionCarry& k) {
+    cudaStream_t s = c->compute;
+    const uint32_t M = c->prm.measures;
+    ReadsView rv = make_view(c);
+    RegionScalars* d_sc = (RegionScalars*)c->scalars.p;
+    const bool want_pairs = (M & MTH_LPMD) && c->prm.lpmd.want_pairs;
+    const bool need_sites = region_needs_sites(c);
+    const int64_t n_words = (int64_t)c->bitmap_words_valid;
+    if (k.ev_a) CUDA_TRY(c, cudaEventSynchronize(k.ev_a));
+    else CUDA_TRY(c, cudaStreamSynchronize(s));
     RegionScalars sc = *(RegionScalars*)c->h_scalars.p;
     TRY(check_scalars_err(c, sc.err));
     for (int k = 0; k < 4; k++) c->lpmd_total_host[k] += (int64_t)sc.lpmd[k];
@@ -1017,8 +1148,10 @@ static int process_region(mth_ctx* c) {
     const int64_t C = need_sites ? (int64_t)sc.n_sites : 0;
     c->stats.n_sites += C;
     c->stats.n_regions += 1;
+    k.C = C;
+    if (C <= 0) return region_end(c, k);
 
-    if (C > 0) {
+    {
         TRY(dev_reserve(c, c->site_pos, (size_t)C * 4, 0));
         {
             ProfScope ps(c, "k_sites_emit");
@@ -1034,6 +1167,7 @@ static int process_region(mth_ctx* c) {
         memcpy((char*)c->h_ct.p + nct * 4, c->reg_tid.data(), nct * 4);
         CUDA_TRY(c, cudaMemcpyAsync(c->ct_lin.p, c->h_ct.p, nct * 8, cudaMemcpyHostToDevice, s));
         ContigTable ct{(int32_t)nct, (const int32_t*)c->ct_lin.p, (const int32_t*)c->ct_lin.p + nct};
+        k.nct = nct;
         const int32_t* site_pos = (const int32_t*)c->site_pos.p;
 
         TRY(dev_reserve(c, c->gfallback, (size_t)C + 64, 0));
@@ -1142,7 +1276,7 @@ static int process_region(mth_ctx* c) {
                 ps.add(launch_exclusive_scan_u32((uint32_t*)c->rowcnt[m].p, C, scratch, d_tot + m, s));
             }
         }
-        int q_set[2] = {0, 1};  // which histogram / mixed-site set PM and ME use
+        int* const q_set = k.q_set;  // which histogram / mixed-site set PM and ME use
         for (int q = 0; q < 2; q++) {
             uint32_t bit = q ? MTH_ME : MTH_PM;
             int m = q ? M_ME : M_PM;
@@ -1198,7 +1332,27 @@ static int process_region(mth_ctx* c) {
 
         CUDA_TRY(c, cudaMemcpyAsync(c->h_totals.p, d_tot, 8 * M_COUNT, cudaMemcpyDeviceToHost, s));
         CUDA_TRY(c, cudaMemcpyAsync(c->h_scalars.p, d_sc, sizeof(RegionScalars), cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(c, cudaStreamSynchronize(s));
+        if (k.ev_b) CUDA_TRY(c, cudaEventRecord(k.ev_b, s));
+        CUDA_TRY(c, cudaGetLastError());
+    }
+    return MTH_OK;
+}
+
+static int region_phase_b(mth_ctx* c, RegionCarry& k) {
+    if (k.done) return MTH_OK;
+    cudaStream_t s = c->compute;
+    const uint32_t M = c->prm.measures;
+    ReadsView rv = make_view(c);
+    RegionScalars* d_sc = (RegionScalars*)c->scalars.p;
+    const bool want_pairs = (M & MTH_LPMD) && c->prm.lpmd.want_pairs;
+    const int64_t C = k.C;
+    const int* const q_set = k.q_set;
+    const int32_t* site_pos = (const int32_t*)c->site_pos.p;
+    ContigTable ct{(int32_t)k.nct, (const int32_t*)c->ct_lin.p, (const int32_t*)c->ct_lin.p + k.nct};
+    const uint16_t* rel_all = c->borrowed ? c->bview.cpg_rel : (const uint16_t*)c->a_rel.p;
+    {
+        if (k.ev_b) CUDA_TRY(c, cudaEventSynchronize(k.ev_b));
+        else CUDA_TRY(c, cudaStreamSynchronize(s));
         TRY(check_scalars_err(c, ((RegionScalars*)c->h_scalars.p)->err));
         c->stats.fdrp_pair_ops += (int64_t)((RegionScalars*)c->h_scalars.p)->fdrp_pairs;
         c->stats.fallback_sites_mhl += (int64_t)((RegionScalars*)c->h_scalars.p)->fallback_sites[0];
@@ -1287,14 +1441,26 @@ static int process_region(mth_ctx* c) {
         }
         CUDA_TRY(c, cudaGetLastError());
     }
-    c->region_active = false;
-    c->borrowed = false;
-    c->R = c->I = c->W = 0;
-    // The emit kernels queued above still read the arena; the next region's host->device copies (copy stream) overwrite it
-    // from offset 0: order them behind this point.
-    CUDA_TRY(c, cudaEventRecord(c->ev_compute, s));
-    CUDA_TRY(c, cudaStreamWaitEvent(c->copy, c->ev_compute, 0));
-    return MTH_OK;
+    return region_end(c, k);
+}
+
+// phase B of the parked region (rows are appended in region order: it goes first)
+static int finish_pending(mth_ctx* c) {
+    if (!c->has_pend) return MTH_OK;
+    swap_slot(c, c->pend.st);
+    const int rc = region_phase_b(c, c->pend.k);
+    swap_slot(c, c->pend.st);
+    c->has_pend = false;
+    return rc;
+}
+
+static int process_region(mth_ctx* c) {
+    TRY(finish_pending(c));
+    if (!c->region_active) return MTH_OK;
+    RegionCarry k;
+    TRY(region_close(c, k));
+    TRY(region_phase_a(c, k));
+    return region_phase_b(c, k);
 }
 
 static int fetch_site_rows(mth_ctx* c, SiteRowsBuf& r, bool counts, bool to_host, mth_site_rows* out) {

@@ -417,3 +417,30 @@ def test_mixed_quartet_sites_shallow_and_deep_windows(coverage):
     b = synth.make_reads(911, sites, 60_000, coverage, tid=0, nocall=0.08, del_frac=0.08)
     res, _ = parity.check_all([b], [60_000], ("pm", "me"), pm=dict(min_depth=2), me=dict(min_depth=2))
     assert res["pm"]["n"] > 1000 and res["me"]["n"] == res["pm"]["n"]
+
+
+@pytest.mark.gpu
+def test_chain_of_large_device_contigs_is_processed_behind_the_next_ingest(monkeypatch):
+    """Four device-resident contigs of > 2^20 reads each: every one is a region of its own, read in place, and its site
+    dictionary / measure kernels / row emission are queued behind the NEXT contigs' ingest passes (engine.cu mth_submit).
+    Rows and LPMD counters must equal (a) the same regions processed strictly one after the other (METHEOR_NO_PIPELINE) and
+    (b) the same reads fed as host batches, which are checked against the oracle."""
+    torch = pytest.importorskip("torch")
+    from metheor_b200 import synth_gpu as G
+    lens = [22_000_000, 21_000_000, 23_000_000, 400_000, 20_500_000, 21_500_000]
+    dev_batches = [G.make_contig("cuda:0", 77, tid, lens[tid], 8.0 if tid != 3 else 6.0, nocall=0.04) for tid in range(6)]
+    # contig 3 is a small one: it ends the chain (0, 1, 2 are parked in turn) and is packed with 4 and 5 into one arena region
+    assert sum(b["n_reads"] >= (1 << 20) for b in dev_batches) == 5
+    host_batches = [G.to_numpy_batch(b) for b in dev_batches]
+    want, _ = parity.check_all(host_batches, lens, ALL, pm=dict(min_depth=3), me=dict(min_depth=3))
+    over = dict(pm=dict(min_depth=3), me=dict(min_depth=3))
+    got, st = engine.run_batches(dev_batches, lens, ALL, **over)
+    monkeypatch.setenv("METHEOR_NO_PIPELINE", "1")
+    serial, st2 = engine.run_batches(dev_batches, lens, ALL, **over)
+    assert st["h2d_bytes"] == 0 and st2["h2d_bytes"] == 0 and st["n_regions"] == st2["n_regions"] >= 4
+    for other in (serial, want):
+        for m in got:
+            for k in got[m]:
+                if isinstance(got[m][k], dict):
+                    continue
+                assert np.array_equal(np.asarray(got[m][k]), np.asarray(other[m][k]), equal_nan=True), (m, k)
