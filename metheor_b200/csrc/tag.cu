@@ -216,9 +216,156 @@ __device__ __forceinline__ ReadHdr load_hdr(const TagArgs& a, int64_t r) {
     return h;
 }
 
-// One warp per read.  Reads of up to TAG_CAP - 2 body columns (all short-read data) stay in shared memory: phase A writes
+// Tables and per-warp lines in shared memory, handed to the per-read routines.
+struct TagShared {
+    const uint8_t *comp, *nt, *ctx, *cls, *rdc, *clsr;
+    const int64_t *t_off, *t_len, *t_loaded;
+    uint8_t *tr, *tf, *to;  // this warp's target columns (read / reference) and character line
+};
+
+// One read by a whole warp, any CIGAR.  Reads of up to TAG_CAP - 2 body columns stay in shared memory: phase A writes
 // the TARGET columns (already reverse-complemented for reverse-strand reads, tag.rs:244-257), phase B classifies them
 // into a shared character line and counts, phase C writes the tag (reversed for reverse-strand reads, tag.rs:380-383).
+__device__ __noinline__ void tag_read_warp(const TagArgs& a, const TagShared& T, const int64_t r, const int lane) {
+    uint8_t* const tr = T.tr;
+    uint8_t* const tf = T.tf;
+    uint8_t* const to = T.to;
+    {
+    const ReadHdr h = load_hdr(a, r);
+    const int64_t B64 = (int64_t)(h.col_hi - h.col_lo);
+    if (B64 + 2 > TAG_CAP) {
+        tag_read_generic(a, r, lane);
+        __syncwarp();
+        return;
+    }
+    const int B = (int)B64;
+    const int32_t tid = h.tid;
+    const int64_t start = h.pos;
+    const bool rc = h.rc;
+    const int32_t l_seq = h.l_seq;
+    const uint32_t c_lo = h.c_lo, c_hi = h.c_hi;
+    if (tid < 0 || tid >= a.n_ref || T.t_loaded[tid] < 0 || start < 0) {
+        if (lane == 0) { a.status[r] = MTH_TAG_BAD_CONTIG; a.xm_len[r] = 0; }
+        return;
+    }
+    const int64_t chrom = T.t_len[tid], loaded = T.t_loaded[tid];
+    const int64_t lim = chrom < loaded ? chrom : loaded;
+    const uint8_t* const g = a.genome + T.t_off[tid];
+    const uint8_t* const sq = a.seq4 + h.seq_off;
+
+    // ---- phase A: target columns ----
+    int c0 = 0;
+    int64_t ur = 0, uf = 0, ref_span = 0;
+    bool unmappable = false;
+    for (uint32_t k = c_lo; k < c_hi; k++) {
+        const uint32_t v = k == c_lo ? h.first_op : a.cigar[k];
+        const int len = (int)(v >> 4);
+        const uint32_t op = v & 15u;
+        if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) ref_span += v >> 4;
+        if (op > 2) continue;
+        if (c0 + len > B) break;
+        for (int j = lane; j < len; j += 32) {
+            uint8_t rd = '-', rf = '-';
+            if (op != 2) {
+                const int64_t i = ur + j;
+                rd = i < l_seq ? T.nt[(sq[i >> 1] >> ((~i & 1) << 2)) & 15u] : (uint8_t)'N';
+            }
+            if (op != 1) {
+                const int64_t p = start + uf + j;
+                rf = p < lim ? g[p] : (uint8_t)'N';
+            }
+            int t = c0 + j;
+            if (rc) {
+                rd = T.comp[rd];
+                rf = T.comp[rf];
+                unmappable |= !rd || !rf;
+                t = B - 1 - t;
+            }
+            tr[t] = rd;
+            tf[t] = rf;
+        }
+        c0 += len;
+        if (op != 2) ur += len;
+        if (op != 1) uf += len;
+    }
+    const int64_t end = start + (ref_span ? ref_span : 1);
+    if (lane < 2) {  // the two context columns behind the body
+        int64_t p = rc ? start - 1 - lane : end + lane;
+        uint8_t c = (p >= 0 && p < lim) ? g[p] : (uint8_t)'N';
+        if (rc) {
+            c = T.comp[c];
+            unmappable |= !c;
+        }
+        tr[B + lane] = '-';
+        tf[B + lane] = c;
+    }
+    uint8_t st = MTH_TAG_OK;
+    if (end > chrom || (end + 2 < chrom ? end + 2 : chrom) > loaded) st = MTH_TAG_PAST_END;
+    else if (ur > l_seq) st = MTH_TAG_SHORT_SEQ;
+    else if (__any_sync(FULL, unmappable)) st = MTH_TAG_NO_COMPLEMENT;
+    __syncwarp();
+    if (st) {
+        if (lane == 0) { a.status[r] = st; a.xm_len[r] = 0; }
+        __syncwarp();
+        return;
+    }
+
+    // ---- phase B: classify ----
+    const int L = B + 2;
+    int n_out = 0;
+    bool no_context = false;
+    for (int base = 0; base < B; base += 32) {
+        const int i = base + lane;
+        uint8_t ch = 0;
+        if (i < B) {
+            const uint8_t rd = tr[i];
+            if (rd == '-') {
+                ch = 0;
+            } else if (rd == 'N') {
+                ch = '.';
+            } else if (tf[i] == 'C') {
+                if ((tr[i + 1] == '-' || tr[i + 2] == '-') && i != L - 3 && i != L - 4) {  // tag.rs:268-299
+                    uint8_t ctx[2] = {0, 0};
+                    int found = 0;
+                    for (int k = 1; found != 2 && i + k <= L - 1; k++)
+                        if (tr[i + k] != '-') ctx[found++] = tf[i + k];
+                    if (found == 0) no_context = true;
+                    else ch = classify(ctx[0], ctx[1], found, rd);
+                } else {
+                    ch = T.ctx[T.cls[tf[i + 1]] * 12 + T.cls[tf[i + 2]] * 3 + T.rdc[rd]];
+                }
+            } else {
+                ch = '.';
+            }
+        }
+        const uint32_t m = __ballot_sync(FULL, ch != 0);
+        if (ch) to[n_out + __popc(m & ((1u << lane) - 1u))] = ch;
+        n_out += __popc(m);
+    }
+    if (__any_sync(FULL, no_context)) {
+        if (lane == 0) { a.status[r] = MTH_TAG_NO_CONTEXT; a.xm_len[r] = 0; }
+        __syncwarp();
+        return;
+    }
+    __syncwarp();
+    // ---- phase C: the tag, in read orientation ----
+    uint8_t* const xm = a.xm + h.xm_off;
+    for (int k = lane; k < n_out; k += 32) xm[k] = to[rc ? n_out - 1 - k : k];
+    if (lane == 0) { a.status[r] = MTH_TAG_OK; a.xm_len[r] = (uint32_t)n_out; }
+    __syncwarp();
+    }
+}
+
+// The common read — CIGAR `<l_seq>M`, at least two bases away from both contig ends — has no gap columns: column k is read
+// base k over reference base start + k, its context is the next two reference bases (forward) or the complements of the two
+// BEFORE it (reverse strand: reverse-complementing the columns, classifying and reversing the tag back puts the character of
+// column B-1-k at position k again), and every column emits one character.  Eight lanes share a read (4 reads per warp); a
+// lane takes 8 consecutive bases per step: one 32-bit word of packed SEQ, 12 reference bytes from three funnel-shifted words,
+// one 8-byte store.  A read that turns out to need the general machinery — a context that emits nothing, a base without a
+// complement on the reverse strand (tag.rs:78-99 panics; status NO_COMPLEMENT) — is redone by tag_read_warp.
+constexpr int TAG_GROUP = 8;               // lanes per read
+constexpr int TAG_RPW = 32 / TAG_GROUP;    // reads per warp and step
+
 __global__ void __launch_bounds__(TAG_BLOCK, TAG_MINB) k_tag(const __grid_constant__ TagArgs a) {
     __shared__ uint8_t s_comp[256];
     __shared__ uint8_t s_read[TAG_BLOCK / 32][TAG_CAP + 4];
@@ -226,11 +373,14 @@ __global__ void __launch_bounds__(TAG_BLOCK, TAG_MINB) k_tag(const __grid_consta
     __shared__ uint8_t s_out[TAG_BLOCK / 32][TAG_CAP];
     __shared__ int64_t s_tab[3][TAG_MAXREF];
     // classify() as three byte look-ups: context class of each of the two bases behind the C (0 'G', 1 A/T/C, 2 '-'/'N',
-    // 3 anything else), class of the read base (0 'C', 1 'T', 2 other), and the 4 x 4 x 3 table of tag characters
-    __shared__ uint8_t s_cls[256], s_rdc[256], s_ctx[48], s_nt[16];
+    // 3 anything else), class of the read base (0 'C', 1 'T', 2 other), and the 4 x 4 x 3 table of tag characters.
+    // s_clsr: the context class of the COMPLEMENT of a reference base (reverse strand), 4 = the base has no complement.
+    __shared__ uint8_t s_cls[256], s_rdc[256], s_clsr[256], s_ctx[48], s_nt[16];
     for (int c = threadIdx.x; c < 256; c += blockDim.x) {
-        s_comp[c] = complement((uint8_t)c);
+        const uint8_t cc = complement((uint8_t)c);
+        s_comp[c] = cc;
         s_cls[c] = c == 'G' ? 0 : is_h((uint8_t)c) ? 1 : is_unknown((uint8_t)c) ? 2 : 3;
+        s_clsr[c] = !cc ? 4 : cc == 'G' ? 0 : is_h(cc) ? 1 : is_unknown(cc) ? 2 : 3;
         s_rdc[c] = c == 'C' ? 0 : c == 'T' ? 1 : 2;
     }
     if (threadIdx.x < 48) {
@@ -247,138 +397,94 @@ __global__ void __launch_bounds__(TAG_BLOCK, TAG_MINB) k_tag(const __grid_consta
             s_tab[2][c] = a.loaded_len[c];
         }
     __syncthreads();
-    const int64_t* const t_off = tab_smem ? s_tab[0] : a.contig_off;
-    const int64_t* const t_len = tab_smem ? s_tab[1] : a.contig_len;
-    const int64_t* const t_loaded = tab_smem ? s_tab[2] : a.loaded_len;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    TagShared T;
+    T.comp = s_comp; T.nt = s_nt; T.ctx = s_ctx; T.cls = s_cls; T.rdc = s_rdc; T.clsr = s_clsr;
+    T.t_off = tab_smem ? s_tab[0] : a.contig_off;
+    T.t_len = tab_smem ? s_tab[1] : a.contig_len;
+    T.t_loaded = tab_smem ? s_tab[2] : a.loaded_len;
+    T.tr = s_read[wib]; T.tf = s_ref[wib]; T.to = s_out[wib];
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    uint8_t* const tr = s_read[wib];
-    uint8_t* const tf = s_ref[wib];
-    uint8_t* const to = s_out[wib];
-    for (int64_t r = warp; r < a.n_reads; r += n_warps) {
-        const ReadHdr h = load_hdr(a, r);
-        const int64_t B64 = (int64_t)(h.col_hi - h.col_lo);
-        if (B64 + 2 > TAG_CAP) {
-            tag_read_generic(a, r, lane);
-            __syncwarp();
-            continue;
-        }
-        const int B = (int)B64;
-        const int32_t tid = h.tid;
-        const int64_t start = h.pos;
-        const bool rc = h.rc;
-        const int32_t l_seq = h.l_seq;
-        const uint32_t c_lo = h.c_lo, c_hi = h.c_hi;
-        if (tid < 0 || tid >= a.n_ref || t_loaded[tid] < 0 || start < 0) {
-            if (lane == 0) { a.status[r] = MTH_TAG_BAD_CONTIG; a.xm_len[r] = 0; }
-            continue;
-        }
-        const int64_t chrom = t_len[tid], loaded = t_loaded[tid];
-        const int64_t lim = chrom < loaded ? chrom : loaded;
-        const uint8_t* const g = a.genome + t_off[tid];
-        const uint8_t* const sq = a.seq4 + h.seq_off;
-
-        // ---- phase A: target columns ----
-        int c0 = 0;
-        int64_t ur = 0, uf = 0, ref_span = 0;
-        bool unmappable = false;
-        for (uint32_t k = c_lo; k < c_hi; k++) {
-            const uint32_t v = k == c_lo ? h.first_op : a.cigar[k];
-            const int len = (int)(v >> 4);
-            const uint32_t op = v & 15u;
-            if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) ref_span += v >> 4;
-            if (op > 2) continue;
-            if (c0 + len > B) break;
-            for (int j = lane; j < len; j += 32) {
-                uint8_t rd = '-', rf = '-';
-                if (op != 2) {
-                    const int64_t i = ur + j;
-                    rd = i < l_seq ? s_nt[(sq[i >> 1] >> ((~i & 1) << 2)) & 15u] : (uint8_t)'N';
-                }
-                if (op != 1) {
-                    const int64_t p = start + uf + j;
-                    rf = p < lim ? g[p] : (uint8_t)'N';
-                }
-                int t = c0 + j;
-                if (rc) {
-                    rd = s_comp[rd];
-                    rf = s_comp[rf];
-                    unmappable |= !rd || !rf;
-                    t = B - 1 - t;
-                }
-                tr[t] = rd;
-                tf[t] = rf;
-            }
-            c0 += len;
-            if (op != 2) ur += len;
-            if (op != 1) uf += len;
-        }
-        const int64_t end = start + (ref_span ? ref_span : 1);
-        if (lane < 2) {  // the two context columns behind the body
-            int64_t p = rc ? start - 1 - lane : end + lane;
-            uint8_t c = (p >= 0 && p < lim) ? g[p] : (uint8_t)'N';
-            if (rc) {
-                c = s_comp[c];
-                unmappable |= !c;
-            }
-            tr[B + lane] = '-';
-            tf[B + lane] = c;
-        }
-        uint8_t st = MTH_TAG_OK;
-        if (end > chrom || (end + 2 < chrom ? end + 2 : chrom) > loaded) st = MTH_TAG_PAST_END;
-        else if (ur > l_seq) st = MTH_TAG_SHORT_SEQ;
-        else if (__any_sync(FULL, unmappable)) st = MTH_TAG_NO_COMPLEMENT;
-        __syncwarp();
-        if (st) {
-            if (lane == 0) { a.status[r] = st; a.xm_len[r] = 0; }
-            __syncwarp();
-            continue;
-        }
-
-        // ---- phase B: classify ----
-        const int L = B + 2;
-        int n_out = 0;
-        bool no_context = false;
-        for (int base = 0; base < B; base += 32) {
-            const int i = base + lane;
-            uint8_t ch = 0;
-            if (i < B) {
-                const uint8_t rd = tr[i];
-                if (rd == '-') {
-                    ch = 0;
-                } else if (rd == 'N') {
-                    ch = '.';
-                } else if (tf[i] == 'C') {
-                    if ((tr[i + 1] == '-' || tr[i + 2] == '-') && i != L - 3 && i != L - 4) {  // tag.rs:268-299
-                        uint8_t ctx[2] = {0, 0};
-                        int found = 0;
-                        for (int k = 1; found != 2 && i + k <= L - 1; k++)
-                            if (tr[i + k] != '-') ctx[found++] = tf[i + k];
-                        if (found == 0) no_context = true;
-                        else ch = classify(ctx[0], ctx[1], found, rd);
-                    } else {
-                        ch = s_ctx[s_cls[tf[i + 1]] * 12 + s_cls[tf[i + 2]] * 3 + s_rdc[rd]];
+    const int sub = lane / TAG_GROUP, gl = lane % TAG_GROUP;
+    for (int64_t r0 = warp * TAG_RPW; r0 < a.n_reads; r0 += n_warps * TAG_RPW) {
+        const int64_t r = r0 + sub;
+        const bool have = r < a.n_reads;
+        bool fast = false, bad = false;
+        if (have) {
+            const uint32_t c_lo = a.cigar_off[r], c_hi = a.cigar_off[r + 1];
+            const int32_t tid = a.tid[r], l_seq = a.l_seq[r];
+            const int64_t start = a.pos[r];
+            const bool rc = a.rc[r] != 0;
+            if (c_hi == c_lo + 1 && l_seq > 0 && tid >= 0 && tid < a.n_ref && start >= 2) {
+                const uint32_t op = a.cigar[c_lo];
+                const int64_t chrom = T.t_len[tid], loaded = T.t_loaded[tid];
+                const int64_t lim = chrom < loaded ? chrom : loaded;  // loaded < 0: contig missing, never fast
+                fast = op == ((uint32_t)l_seq << 4) && start + l_seq + 2 <= lim;
+                if (fast) {
+                    const uint8_t* const sq = a.seq4 + a.seq_off[r];
+                    const uint8_t* const g = a.genome + T.t_off[tid] + start;
+                    uint8_t* const xm = a.xm + a.xm_off[r];  // 8-byte aligned, capacity a multiple of 8 (mth_tag)
+                    const int U = (l_seq + 7) >> 3;
+                    for (int u = gl; u < U; u += TAG_GROUP) {
+                        const int k0 = u << 3;
+                        const int nb = l_seq - k0 < 8 ? l_seq - k0 : 8;
+                        // 8 read bases: 4 bytes of packed SEQ at any alignment
+                        const uintptr_t sa = (uintptr_t)(sq + 4 * u);
+                        const uint32_t* const sw = reinterpret_cast<const uint32_t*>(sa & ~(uintptr_t)3);
+                        const uint32_t seqw = __funnelshift_r(__ldg(sw), __ldg(sw + 1), (uint32_t)(sa & 3u) * 8u);
+                        // reference bytes k0 - 2 .. k0 + 9
+                        const uintptr_t ga = (uintptr_t)(g + k0 - 2);
+                        const uint32_t* const gw = reinterpret_cast<const uint32_t*>(ga & ~(uintptr_t)3);
+                        const uint32_t gs = (uint32_t)(ga & 3u) * 8u;
+                        const uint32_t x0 = __ldg(gw), x1 = __ldg(gw + 1), x2 = __ldg(gw + 2), x3 = __ldg(gw + 3);
+                        const uint32_t y[3] = {__funnelshift_r(x0, x1, gs), __funnelshift_r(x1, x2, gs), __funnelshift_r(x2, x3, gs)};
+                        uint8_t rf[12], cl[12];
+#pragma unroll
+                        for (int j = 0; j < 12; j++) {
+                            rf[j] = (uint8_t)(y[j >> 2] >> (8 * (j & 3)));
+                            cl[j] = rc ? s_clsr[rf[j]] : s_cls[rf[j]];
+                        }
+                        uint32_t out[2] = {0u, 0u};
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            const uint32_t rdn = (seqw >> (8 * (j >> 1) + ((j & 1) ? 0 : 4))) & 15u;
+                            const uint8_t f = rf[j + 2];
+                            uint32_t k1, k2, kr;
+                            bool is_c;
+                            if (rc) {  // complement: a reference G is the C of the target strand, its context the two bases before
+                                is_c = f == 'G';
+                                k1 = cl[j + 1]; k2 = cl[j];
+                                kr = rdn == 4u ? 0u : rdn == 1u ? 1u : 2u;
+                                if (j < nb && (rdn == 0u || cl[j + 2] == 4u)) bad = true;
+                                if (u == 0 && j == 0 && (k1 == 4u || k2 == 4u)) bad = true;  // the two context columns behind the body
+                            } else {
+                                is_c = f == 'C';
+                                k1 = cl[j + 3]; k2 = cl[j + 4];
+                                kr = rdn == 2u ? 0u : rdn == 8u ? 1u : 2u;
+                            }
+                            uint32_t ch = '.';
+                            if (is_c && rdn != 15u) {
+                                ch = (k1 | k2) & 4u ? 0u : s_ctx[k1 * 12u + k2 * 3u + kr];
+                                if (ch == 0u && j < nb) bad = true;  // a context that emits nothing (or has no complement): general path
+                            }
+                            out[j >> 2] |= ch << (8 * (j & 3));
+                        }
+                        *reinterpret_cast<uint2*>(xm + k0) = make_uint2(out[0], out[1]);
                     }
-                } else {
-                    ch = '.';
                 }
             }
-            const uint32_t m = __ballot_sync(FULL, ch != 0);
-            if (ch) to[n_out + __popc(m & ((1u << lane) - 1u))] = ch;
-            n_out += __popc(m);
         }
-        if (__any_sync(FULL, no_context)) {
-            if (lane == 0) { a.status[r] = MTH_TAG_NO_CONTEXT; a.xm_len[r] = 0; }
+        const uint32_t badm = __ballot_sync(FULL, bad);
+        const bool group_bad = ((badm >> (sub * TAG_GROUP)) & ((1u << TAG_GROUP) - 1u)) != 0u;
+        if (have && fast && !group_bad && gl == 0) { a.status[r] = MTH_TAG_OK; a.xm_len[r] = (uint32_t)a.l_seq[r]; }
+        uint32_t slow = __ballot_sync(FULL, have && gl == 0 && (!fast || group_bad));
+        while (slow) {  // the reads that need the general machinery, one after the other by the whole warp
+            const int l = __ffs(slow) - 1;
+            slow &= slow - 1;
+            tag_read_warp(a, T, r0 + l / TAG_GROUP, lane);
             __syncwarp();
-            continue;
         }
-        __syncwarp();
-        // ---- phase C: the tag, in read orientation ----
-        uint8_t* const xm = a.xm + h.xm_off;
-        for (int k = lane; k < n_out; k += 32) xm[k] = to[rc ? n_out - 1 - k : k];
-        if (lane == 0) { a.status[r] = MTH_TAG_OK; a.xm_len[r] = (uint32_t)n_out; }
-        __syncwarp();
     }
 }
 
@@ -484,7 +590,7 @@ int mth_genome_create(mth_genome** out, int device, int32_t n_ref, const int64_t
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) g->sm_count = prop.multiProcessorCount;
     if ((e = cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
-    if ((e = cudaMalloc((void**)&g->d_genome, (size_t)(off ? off : 1))) != cudaSuccess) return fail("cudaMalloc(genome)", e);
+    if ((e = cudaMalloc((void**)&g->d_genome, (size_t)off + 64)) != cudaSuccess) return fail("cudaMalloc(genome)", e);
     const size_t tb = sizeof(int64_t) * (size_t)(n_ref ? n_ref : 1);
     if ((e = cudaMalloc((void**)&g->d_contig_off, tb)) != cudaSuccess) return fail("cudaMalloc", e);
     if ((e = cudaMalloc((void**)&g->d_contig_len, tb)) != cudaSuccess) return fail("cudaMalloc", e);
@@ -543,6 +649,7 @@ int mth_tag(mth_genome* g, const mth_tag_batch* b, mth_tag_result* out) {
             if (op <= 2) cols += v >> 4;
             if (op <= 1) xms += v >> 4;
         }
+        xms = (xms + 7) & ~(uint64_t)7;  // every tag starts 8-byte aligned and owns whole 8-byte words (k_tag stores 8 characters at a time)
     }
     g->h_col_off.p[n] = cols;
     g->h_xm_off.p[n] = xms;
@@ -560,7 +667,7 @@ int mth_tag(mth_genome* g, const mth_tag_batch* b, mth_tag_result* out) {
     const size_t N = (size_t)n;
     G_CUDA(g->d_tid.ensure(N)); G_CUDA(g->d_pos.ensure(N)); G_CUDA(g->d_lseq.ensure(N)); G_CUDA(g->d_rc.ensure(N));
     G_CUDA(g->d_cigar_off.ensure(N + 1)); G_CUDA(g->d_cigar.ensure(n_cigar ? n_cigar : 1));
-    G_CUDA(g->d_seq_off.ensure(N + 1)); G_CUDA(g->d_seq4.ensure(n_seq ? n_seq : 1));
+    G_CUDA(g->d_seq_off.ensure(N + 1)); G_CUDA(g->d_seq4.ensure(n_seq + 16));  // k_tag reads whole words: up to 7 bytes past a read's SEQ
     G_CUDA(g->d_col_off.ensure(N + 1)); G_CUDA(g->d_xm_off.ensure(N + 1));
     G_CUDA(g->d_colr.ensure(cols ? cols : 1)); G_CUDA(g->d_colf.ensure(cols ? cols : 1));
     G_CUDA(g->d_xm.ensure(xms ? xms : 1)); G_CUDA(g->d_xm_len.ensure(N)); G_CUDA(g->d_status.ensure(N));
@@ -586,7 +693,8 @@ int mth_tag(mth_genome* g, const mth_tag_batch* b, mth_tag_result* out) {
     a.genome = g->d_genome; a.contig_off = g->d_contig_off; a.contig_len = g->d_contig_len; a.loaded_len = g->d_loaded;
     a.n_ref = g->n_ref;
     a.col_read = g->d_colr.p; a.col_ref = g->d_colf.p; a.xm = g->d_xm.p; a.xm_len = g->d_xm_len.p; a.status = g->d_status.p;
-    int64_t blocks = (n + (TAG_BLOCK / 32) - 1) / (TAG_BLOCK / 32);
+    const int64_t reads_per_block = (TAG_BLOCK / 32) * TAG_RPW;
+    int64_t blocks = (n + reads_per_block - 1) / reads_per_block;
     const int64_t cap = (int64_t)g->sm_count * TAG_MINB;  // resident CTAs of 256 threads per SM (launch bounds)
     if (blocks > cap) blocks = cap;
     if (!g->ev0) { G_CUDA(cudaEventCreate(&g->ev0)); G_CUDA(cudaEventCreate(&g->ev1)); }
