@@ -426,6 +426,10 @@ __global__ void __launch_bounds__(TAG_BLOCK, TAG_MINB) k_tag(const __grid_consta
                     const uint8_t* const g = a.genome + T.t_off[tid] + start;
                     uint8_t* const xm = a.xm + a.xm_off[r];  // 8-byte aligned, capacity a multiple of 8 (mth_tag)
                     const int U = (l_seq + 7) >> 3;
+                    const uint8_t* const cls2 = rc ? s_clsr : s_cls;
+                    const uint32_t c_char = rc ? 'G' : 'C';
+                    // class of the read base per 4-bit code, 2 bits each: forward C(2)->0 T(8)->1; reverse G(4)->0 A(1)->1 '='(0)->3
+                    const uint32_t kr_lut = rc ? 0xAAAAA8A7u : 0xAAA9AA8Au;
                     for (int u = gl; u < U; u += TAG_GROUP) {
                         const int k0 = u << 3;
                         const int nb = l_seq - k0 < 8 ? l_seq - k0 : 8;
@@ -439,37 +443,33 @@ __global__ void __launch_bounds__(TAG_BLOCK, TAG_MINB) k_tag(const __grid_consta
                         const uint32_t gs = (uint32_t)(ga & 3u) * 8u;
                         const uint32_t x0 = __ldg(gw), x1 = __ldg(gw + 1), x2 = __ldg(gw + 2), x3 = __ldg(gw + 3);
                         const uint32_t y[3] = {__funnelshift_r(x0, x1, gs), __funnelshift_r(x1, x2, gs), __funnelshift_r(x2, x3, gs)};
-                        uint8_t rf[12], cl[12];
+                        // Everything below is the same instruction stream for both strands (the four reads of a warp differ in
+                        // strand: a branch on it would run both sides): the strand selects a table half, a constant and offsets.
+                        uint32_t cl[12];
+                        bool no_comp = false;
 #pragma unroll
                         for (int j = 0; j < 12; j++) {
-                            rf[j] = (uint8_t)(y[j >> 2] >> (8 * (j & 3)));
-                            cl[j] = rc ? s_clsr[rf[j]] : s_cls[rf[j]];
+                            cl[j] = cls2[(y[j >> 2] >> (8 * (j & 3))) & 0xffu];
+                            if (j >= 2 && j < nb + 2) no_comp |= cl[j] == 4u;  // a body base without a complement (reverse strand only)
                         }
+                        if (u == 0) no_comp |= rc && ((cl[0] | cl[1]) & 4u);  // the two context columns behind the body
                         uint32_t out[2] = {0u, 0u};
 #pragma unroll
                         for (int j = 0; j < 8; j++) {
                             const uint32_t rdn = (seqw >> (8 * (j >> 1) + ((j & 1) ? 0 : 4))) & 15u;
-                            const uint8_t f = rf[j + 2];
-                            uint32_t k1, k2, kr;
-                            bool is_c;
-                            if (rc) {  // complement: a reference G is the C of the target strand, its context the two bases before
-                                is_c = f == 'G';
-                                k1 = cl[j + 1]; k2 = cl[j];
-                                kr = rdn == 4u ? 0u : rdn == 1u ? 1u : 2u;
-                                if (j < nb && (rdn == 0u || cl[j + 2] == 4u)) bad = true;
-                                if (u == 0 && j == 0 && (k1 == 4u || k2 == 4u)) bad = true;  // the two context columns behind the body
-                            } else {
-                                is_c = f == 'C';
-                                k1 = cl[j + 3]; k2 = cl[j + 4];
-                                kr = rdn == 2u ? 0u : rdn == 8u ? 1u : 2u;
-                            }
+                            const uint32_t f = (y[(j + 2) >> 2] >> (8 * ((j + 2) & 3))) & 0xffu;
+                            // context classes: the next two reference bases, or (reverse strand) the complements of the two before
+                            const uint32_t k1 = rc ? cl[j + 1] : cl[j + 3], k2 = rc ? cl[j] : cl[j + 4];
+                            const uint32_t kr = (kr_lut >> (2u * rdn)) & 3u;  // 0: the read shows the C, 1: the T, 2: anything else, 3: '=' on the reverse strand
                             uint32_t ch = '.';
-                            if (is_c && rdn != 15u) {
-                                ch = (k1 | k2) & 4u ? 0u : s_ctx[k1 * 12u + k2 * 3u + kr];
-                                if (ch == 0u && j < nb) bad = true;  // a context that emits nothing (or has no complement): general path
+                            if (f == c_char && rdn != 15u) {
+                                ch = ((k1 | k2) & 4u) ? 0u : s_ctx[k1 * 12u + k2 * 3u + (kr & 2u ? 2u : kr)];
+                                if (ch == 0u && j < nb) bad = true;  // a context that emits nothing: general path
                             }
+                            if (kr == 3u && j < nb) bad = true;      // no complement for '='
                             out[j >> 2] |= ch << (8 * (j & 3));
                         }
+                        bad |= no_comp;
                         *reinterpret_cast<uint2*>(xm + k0) = make_uint2(out[0], out[1]);
                     }
                 }
