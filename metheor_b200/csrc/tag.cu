@@ -359,11 +359,11 @@ __device__ __noinline__ void tag_read_warp(const TagArgs& a, const TagShared& T,
 // The common read — CIGAR `<l_seq>M`, at least two bases away from both contig ends — has no gap columns: column k is read
 // base k over reference base start + k, its context is the next two reference bases (forward) or the complements of the two
 // BEFORE it (reverse strand: reverse-complementing the columns, classifying and reversing the tag back puts the character of
-// column B-1-k at position k again), and every column emits one character.  Eight lanes share a read (4 reads per warp); a
+// column B-1-k at position k again), and every column emits one character.  Four lanes share a read (8 reads per warp); a
 // lane takes 8 consecutive bases per step: one 32-bit word of packed SEQ, 12 reference bytes from three funnel-shifted words,
 // one 8-byte store.  A read that turns out to need the general machinery — a context that emits nothing, a base without a
 // complement on the reverse strand (tag.rs:78-99 panics; status NO_COMPLEMENT) — is redone by tag_read_warp.
-constexpr int TAG_GROUP = 8;               // lanes per read
+constexpr int TAG_GROUP = 4;               // lanes per read: 4 x 8 bases = one 32-byte sector of tag per step; 19 steps-of-8 of a 150-base read fill 5 x 4 slots
 constexpr int TAG_RPW = 32 / TAG_GROUP;    // reads per warp and step
 
 __global__ void __launch_bounds__(TAG_BLOCK, TAG_MINB) k_tag(const __grid_constant__ TagArgs a) {
@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(TAG_BLOCK, TAG_MINB) k_tag(const __grid_consta
     // classify() as three byte look-ups: context class of each of the two bases behind the C (0 'G', 1 A/T/C, 2 '-'/'N',
     // 3 anything else), class of the read base (0 'C', 1 'T', 2 other), and the 4 x 4 x 3 table of tag characters.
     // s_clsr: the context class of the COMPLEMENT of a reference base (reverse strand), 4 = the base has no complement.
-    __shared__ uint8_t s_cls[256], s_rdc[256], s_clsr[256], s_ctx[48], s_nt[16];
+    __shared__ uint8_t s_cls[256], s_rdc[256], s_clsr[256], s_ctx[64], s_nt[16];
     for (int c = threadIdx.x; c < 256; c += blockDim.x) {
         const uint8_t cc = complement((uint8_t)c);
         s_comp[c] = cc;
@@ -387,6 +387,8 @@ __global__ void __launch_bounds__(TAG_BLOCK, TAG_MINB) k_tag(const __grid_consta
         static const char probe[4] = {'G', 'A', 'N', 'R'};  // one representative per context class
         const int k1 = threadIdx.x / 12, k2 = (threadIdx.x / 3) & 3, kr = threadIdx.x % 3;
         s_ctx[threadIdx.x] = classify((uint8_t)probe[k1], (uint8_t)probe[k2], 2, kr == 0 ? (uint8_t)'C' : kr == 1 ? (uint8_t)'T' : (uint8_t)'A');
+    } else if (threadIdx.x < 64) {
+        s_ctx[threadIdx.x] = 0;
     }
     if (threadIdx.x < 16) s_nt[threadIdx.x] = (uint8_t)"=ACMGRSVTWYHKDBN"[threadIdx.x];
     const bool tab_smem = a.n_ref <= TAG_MAXREF;
@@ -445,15 +447,17 @@ __global__ void __launch_bounds__(TAG_BLOCK, TAG_MINB) k_tag(const __grid_consta
                         const uint32_t y[3] = {__funnelshift_r(x0, x1, gs), __funnelshift_r(x1, x2, gs), __funnelshift_r(x2, x3, gs)};
                         // Everything below is the same instruction stream for both strands (the four reads of a warp differ in
                         // strand: a branch on it would run both sides): the strand selects a table half, a constant and offsets.
+                        // ... and no branch inside: per base one table look-up and selects; what would need the general path
+                        // is collected as one bit per base and masked with the bases that exist.
                         uint32_t cl[12];
-                        bool no_comp = false;
+                        uint32_t nc_bits = 0u;  // bit j: reference byte j (position k0 - 2 + j) has no complement (reverse strand only)
 #pragma unroll
                         for (int j = 0; j < 12; j++) {
                             cl[j] = cls2[(y[j >> 2] >> (8 * (j & 3))) & 0xffu];
-                            if (j >= 2 && j < nb + 2) no_comp |= cl[j] == 4u;  // a body base without a complement (reverse strand only)
+                            nc_bits |= (cl[j] >> 2) << j;
                         }
-                        if (u == 0) no_comp |= rc && ((cl[0] | cl[1]) & 4u);  // the two context columns behind the body
                         uint32_t out[2] = {0u, 0u};
+                        uint32_t bad_bits = 0u;
 #pragma unroll
                         for (int j = 0; j < 8; j++) {
                             const uint32_t rdn = (seqw >> (8 * (j >> 1) + ((j & 1) ? 0 : 4))) & 15u;
@@ -461,15 +465,15 @@ __global__ void __launch_bounds__(TAG_BLOCK, TAG_MINB) k_tag(const __grid_consta
                             // context classes: the next two reference bases, or (reverse strand) the complements of the two before
                             const uint32_t k1 = rc ? cl[j + 1] : cl[j + 3], k2 = rc ? cl[j] : cl[j + 4];
                             const uint32_t kr = (kr_lut >> (2u * rdn)) & 3u;  // 0: the read shows the C, 1: the T, 2: anything else, 3: '=' on the reverse strand
-                            uint32_t ch = '.';
-                            if (f == c_char && rdn != 15u) {
-                                ch = ((k1 | k2) & 4u) ? 0u : s_ctx[k1 * 12u + k2 * 3u + (kr & 2u ? 2u : kr)];
-                                if (ch == 0u && j < nb) bad = true;  // a context that emits nothing: general path
-                            }
-                            if (kr == 3u && j < nb) bad = true;      // no complement for '='
+                            const uint32_t t = s_ctx[k1 * 12u + k2 * 3u + kr];  // 64 entries: classes 4 / 3 index zeros, and are flagged below
+                            const bool is_c = f == c_char && rdn != 15u;
+                            const uint32_t ch = is_c ? t : (uint32_t)'.';
+                            bad_bits |= (uint32_t)((is_c && t == 0u) || kr == 3u) << j;  // a context that emits nothing / '=' has no complement
                             out[j >> 2] |= ch << (8 * (j & 3));
                         }
-                        bad |= no_comp;
+                        const uint32_t vm = (1u << nb) - 1u;  // the bases of this step that exist
+                        // bases without a complement: the body bases (bytes 2 ..) and, in the first step, the two context columns behind the body
+                        bad |= ((bad_bits | (nc_bits >> 2)) & vm) != 0u || (u == 0 && (nc_bits & 3u) != 0u);
                         *reinterpret_cast<uint2*>(xm + k0) = make_uint2(out[0], out[1]);
                     }
                 }
