@@ -25,7 +25,7 @@ namespace {
 constexpr uint32_t FULL = 0xffffffffu;
 constexpr int TAG_BLOCK = 256;
 #ifndef TAG_MINB
-#define TAG_MINB 4  // resident CTAs per SM the register budget is capped for
+#define TAG_MINB 4  // resident CTAs per SM the register budget is capped for (5 and 6 measured: spills, no gain)
 #endif
 
 struct TagArgs {
@@ -365,6 +365,9 @@ __device__ __noinline__ void tag_read_warp(const TagArgs& a, const TagShared& T,
 // complement on the reverse strand (tag.rs:78-99 panics; status NO_COMPLEMENT) — is redone by tag_read_warp.
 constexpr int TAG_GROUP = 4;               // lanes per read: 4 x 8 bases = one 32-byte sector of tag per step; 19 steps-of-8 of a 150-base read fill 5 x 4 slots
 constexpr int TAG_RPW = 32 / TAG_GROUP;    // reads per warp and step
+// nibbles of a 32-bit word of packed SEQ (little endian, base j = high nibble of byte j / 2 for even j) that hold bases 0 .. nb - 1
+__constant__ uint32_t c_valid[9] = {0x00000000u, 0x000000F0u, 0x000000FFu, 0x0000F0FFu, 0x0000FFFFu,
+                                    0x00F0FFFFu, 0x00FFFFFFu, 0xF0FFFFFFu, 0xFFFFFFFFu};
 
 __global__ void __launch_bounds__(TAG_BLOCK, TAG_MINB) k_tag(const __grid_constant__ TagArgs a) {
     __shared__ uint8_t s_comp[256];
@@ -447,33 +450,36 @@ __global__ void __launch_bounds__(TAG_BLOCK, TAG_MINB) k_tag(const __grid_consta
                         const uint32_t y[3] = {__funnelshift_r(x0, x1, gs), __funnelshift_r(x1, x2, gs), __funnelshift_r(x2, x3, gs)};
                         // Everything below is the same instruction stream for both strands (the four reads of a warp differ in
                         // strand: a branch on it would run both sides): the strand selects a table half, a constant and offsets.
-                        // ... and no branch inside: per base one table look-up and selects; what would need the general path
-                        // is collected as one bit per base and masked with the bases that exist.
+                        // ... and no branch inside: per base one table look-up and selects.  What needs the general path is
+                        // only DETECTED here, generously (a false alarm just sends the read through tag_read_warp).
                         uint32_t cl[12];
-                        uint32_t nc_bits = 0u;  // bit j: reference byte j (position k0 - 2 + j) has no complement (reverse strand only)
+                        uint32_t any_cl = 0u;  // class 4 = no complement (reverse-strand table only)
 #pragma unroll
                         for (int j = 0; j < 12; j++) {
                             cl[j] = cls2[(y[j >> 2] >> (8 * (j & 3))) & 0xffu];
-                            nc_bits |= (cl[j] >> 2) << j;
+                            any_cl |= cl[j];
                         }
                         uint32_t out[2] = {0u, 0u};
-                        uint32_t bad_bits = 0u;
+                        bool odd = (any_cl & 4u) != 0u;
 #pragma unroll
                         for (int j = 0; j < 8; j++) {
-                            const uint32_t rdn = (seqw >> (8 * (j >> 1) + ((j & 1) ? 0 : 4))) & 15u;
+                            // twice the 4-bit code of base j (high nibble of byte j / 2 for even j): the bit offset into kr_lut
+                            const int sh = 8 * (j >> 1) + ((j & 1) ? 0 : 4) - 1;
+                            const uint32_t rdn2 = (sh >= 0 ? seqw >> sh : seqw << 1) & 30u;
                             const uint32_t f = (y[(j + 2) >> 2] >> (8 * ((j + 2) & 3))) & 0xffu;
                             // context classes: the next two reference bases, or (reverse strand) the complements of the two before
                             const uint32_t k1 = rc ? cl[j + 1] : cl[j + 3], k2 = rc ? cl[j] : cl[j + 4];
-                            const uint32_t kr = (kr_lut >> (2u * rdn)) & 3u;  // 0: the read shows the C, 1: the T, 2: anything else, 3: '=' on the reverse strand
-                            const uint32_t t = s_ctx[k1 * 12u + k2 * 3u + kr];  // 64 entries: classes 4 / 3 index zeros, and are flagged below
-                            const bool is_c = f == c_char && rdn != 15u;
-                            const uint32_t ch = is_c ? t : (uint32_t)'.';
-                            bad_bits |= (uint32_t)((is_c && t == 0u) || kr == 3u) << j;  // a context that emits nothing / '=' has no complement
-                            out[j >> 2] |= ch << (8 * (j & 3));
+                            const uint32_t kr = (kr_lut >> rdn2) & 3u;  // 0: the read shows the C, 1: the T, 2: anything else, 3: '=' on the reverse strand
+                            const uint32_t t = s_ctx[k1 * 12u + k2 * 3u + kr];  // 64 entries: classes 4 / 3 index zeros or neighbours, and are flagged
+                            const bool is_c = f == c_char && rdn2 != 30u;
+                            odd |= is_c && t == 0u;  // a context that emits nothing
+                            out[j >> 2] |= (is_c ? t : (uint32_t)'.') << (8 * (j & 3));
                         }
-                        const uint32_t vm = (1u << nb) - 1u;  // the bases of this step that exist
-                        // bases without a complement: the body bases (bytes 2 ..) and, in the first step, the two context columns behind the body
-                        bad |= ((bad_bits | (nc_bits >> 2)) & vm) != 0u || (u == 0 && (nc_bits & 3u) != 0u);
+                        if (rc) {  // '=' (code 0) has no complement: any zero nibble among the bases that exist (borrows can only raise false alarms)
+                            const uint32_t sv = seqw | ~c_valid[nb];
+                            odd |= ((sv - 0x11111111u) & ~sv & 0x88888888u) != 0u;
+                        }
+                        bad |= odd;
                         *reinterpret_cast<uint2*>(xm + k0) = make_uint2(out[0], out[1]);
                     }
                 }
