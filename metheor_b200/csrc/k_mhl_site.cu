@@ -9,8 +9,9 @@
 // x_l = x_{l-1} & (x_{l-1} >> 1) popcount chain, and the per-site S[l] / N[n] accumulators are two small
 // shared-memory arrays per thread.  32 sites advance per warp instruction instead of one.
 //
-// What does not fit — tiles with more than MS_RCAP reads or MS_CCAP calls, reads with more than MS_L calls (dense CpG
-// islands), > 64 calls per read — is flagged in `fallback` and done by the warp-per-site kernel afterwards.
+// What does not fit — tiles with more than MS_RCAP reads or MS_CCAP calls or > 64 calls per read (whole tile), sites with a
+// contributing read of more than MS_L calls (dense CpG islands; only those sites) or a segment deeper than the 16-bit
+// accumulators — is flagged in `fallback` and done by the warp-per-site kernel afterwards.
 #include <stdlib.h>
 #include <string.h>
 
@@ -22,8 +23,11 @@ namespace mth {
 constexpr int MS_SITES = 128;    // sites (= threads) per CTA
 constexpr int MS_RCAP = 2048;    // reads staged per tile (dense instance: chr19-like density, ~1400 reads per 128 sites at 30x)
 constexpr int MS_CCAP = 6144;    // calls staged per tile
-constexpr int MS_RCAP_SPARSE = 4096;  // sparse instance: whole-genome density (a 128-site tile spans ~14 kb: ~3300 reads at 30x)
-constexpr int MS_CCAP_SPARSE = 8192;
+// sparse instance: whole-genome density (a 128-site tile spans ~14 kb: ~2900 reads, ~3800 calls at 30x, sd ~9 %).  54 KB of shared
+// memory: FOUR resident CTAs per SM instead of the three a 4096 / 8192 instance allows — the kernel is latency-bound, warps in
+// flight are what it lacks; the few tiles over capacity go to the per-site kernel.
+constexpr int MS_RCAP_SPARSE = 3584;
+constexpr int MS_CCAP_SPARSE = 5120;
 constexpr int MS_L = 16;         // longest read (in calls) the per-thread accumulators hold
 constexpr int MS_SPAN = 60000;   // positions a tile may span (calls are staged as 16-bit offsets)
 
@@ -81,20 +85,15 @@ __global__ void __launch_bounds__(MS_SITES) k_mhl_site(ReadsView rv, const int32
             continue;
         }
         const int32_t base = site_pos[s0] - lmax - 1;  // every call of a tile read is >= base
-        int toolong = 0;
         for (int r = tid; r < nreads; r += MS_SITES) {
             const int64_t j = ra + r;
             const uint32_t o0 = rv.cpg_off[j], n = rv.cpg_off[j + 1] - o0;
             sh.rec[r] = (unsigned long long)(uint16_t)(rv.start[j] - base) | 0xFFFF0000ull | ((unsigned long long)(uint16_t)(o0 - c0) << 32) |
                         ((unsigned long long)(rv.meta[j] & 0xFFu) << 48) | ((unsigned long long)min(n, 255u) << 56);
             sh.mbits[r] = (uint16_t)rv.meth[j];  // staged once (coalesced) instead of one global load per (site, read)
-            if (n > (uint32_t)MS_L) toolong = 1;
         }
         for (int y = tid; y < ncalls; y += MS_SITES) sh.pos[y] = (uint16_t)(rv.cpg_pos[c0 + y] - base);
-        if (__syncthreads_or(toolong)) {  // a read too long for the accumulators: this tile goes to the per-site kernel
-            if (tid < ns) fallback[s0 + tid] = 1;
-            continue;
-        }
+        __syncthreads();
         for (int r = tid; r < nreads; r += MS_SITES) {
             const unsigned long long w = sh.rec[r];
             if (w >> 56) sh.rec[r] = (w & ~0xFFFF0000ull) | ((unsigned long long)sh.pos[(uint32_t)(w >> 32) & 0xFFFFu] << 16);
@@ -155,6 +154,9 @@ __global__ void __launch_bounds__(MS_SITES) k_mhl_site(ReadsView rv, const int32
             }
             if (!calls) continue;
             if ((m & 0xFFu) < prm.min_qual || n < prm.min_cpgs) continue;  // mhl.rs:176, :181
+            // a contributing read with more calls than the accumulators hold (a CpG island): THIS site goes to the per-site kernel
+            // — not the whole tile, whose other sites mostly lie outside the island
+            if (n > (uint32_t)MS_L) { deep = true; break; }
             if (++depth >= 4000u) deep = true;  // 16 calls x 4000 reads still fit the 16-bit accumulators
             maxn = max(maxn, n);
             sh.N[n][tid]++;  // mhl.rs:75-80
