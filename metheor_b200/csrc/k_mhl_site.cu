@@ -145,8 +145,15 @@ __global__ void __launch_bounds__(MS_SITES) k_mhl_site(ReadsView rv, const int32
             const uint32_t m = (uint32_t)(w >> 48), n = m >> 8;
             if (n == 0) continue;
             if (((uint32_t)(w >> 16) & 0xFFFFu) > pq) { close(); continue; }  // mhl.rs:162-173: ANY read with >= 1 CpG flushes what lies before its first CpG
-            // does the read call p?  (its calls are sorted; n <= MS_L)
             const uint16_t* cp = sh.pos + ((uint32_t)(w >> 32) & 0xFFFFu);
+            // A read with more calls than the accumulators hold (a CpG island) whose calls reach p: THIS site goes to the per-site
+            // kernel — not the whole tile, whose other sites mostly lie outside the island.  (Decided from the read's last call,
+            // without walking its calls: an island read would cost every site of its window a scan of up to 255 calls.)
+            if (n > (uint32_t)MS_L) {
+                if ((uint32_t)cp[n - 1] >= pq) { deep = true; break; }
+                continue;
+            }
+            // does the read call p?  (its calls are sorted; n <= MS_L)
             bool calls = false;
             for (uint32_t k = 0; k < n; k++) {
                 const uint32_t x = cp[k];
@@ -154,9 +161,6 @@ __global__ void __launch_bounds__(MS_SITES) k_mhl_site(ReadsView rv, const int32
             }
             if (!calls) continue;
             if ((m & 0xFFu) < prm.min_qual || n < prm.min_cpgs) continue;  // mhl.rs:176, :181
-            // a contributing read with more calls than the accumulators hold (a CpG island): THIS site goes to the per-site kernel
-            // — not the whole tile, whose other sites mostly lie outside the island
-            if (n > (uint32_t)MS_L) { deep = true; break; }
             if (++depth >= 4000u) deep = true;  // 16 calls x 4000 reads still fit the 16-bit accumulators
             maxn = max(maxn, n);
             sh.N[n][tid]++;  // mhl.rs:75-80
