@@ -129,7 +129,7 @@ struct mth_ctx {
     DevBuf gfallback;            // sites the thread-per-site gather kernels hand to the warp-per-site form
     // PM / ME: per-(site, slot) observation counts, mixed-site flags, the observation list (site / slot+pattern / length) and
     // the 16-bin histograms of the output rows (k_quartet.cu)
-    DevBuf qcnt[2], qmixed[2], qobs_site[2], qobs_vp[2], qobs_n, qhrows[2];
+    DevBuf qcnt[2], qmixed[2], qobs_site[2], qobs_vp[2], qobs_n, qhrows[2], qmix_list[2], qmix_n;
     DevBuf stage[2][13], exp_blocks, exp_tot;  // compact wire format: two staging sets + scan scratch
     cudaEvent_t ev_stage_free[2] = {nullptr, nullptr};
     bool stage_busy[2] = {false, false};
@@ -643,8 +643,9 @@ int mth_ctx_destroy(mth_ctx* c) {
         for (DevBuf& b : set) dev_free(b);
     dev_free(c->exp_blocks);
     dev_free(c->exp_tot);
-    for (int q = 0; q < 2; q++) { dev_free(c->qcnt[q]); dev_free(c->qmixed[q]); dev_free(c->qobs_site[q]); dev_free(c->qobs_vp[q]); dev_free(c->qhrows[q]); }
+    for (int q = 0; q < 2; q++) { dev_free(c->qcnt[q]); dev_free(c->qmixed[q]); dev_free(c->qobs_site[q]); dev_free(c->qobs_vp[q]); dev_free(c->qhrows[q]); dev_free(c->qmix_list[q]); }
     dev_free(c->qobs_n);
+    dev_free(c->qmix_n);
     dev_free(c->gfallback);
     for (cudaEvent_t e : c->ev_stage_free)
         if (e) cudaEventDestroy(e);
@@ -1295,6 +1296,8 @@ static int region_phase_a(mth_ctx* c, RegionCarry& k) {
             TRY(dev_reserve(c, c->qobs_site[q], (size_t)rv.I * 4 + 64, 0));  // at most one observation per call
             TRY(dev_reserve(c, c->qobs_vp[q], (size_t)rv.I + 64, 0));
             TRY(dev_reserve(c, c->qobs_n, 16, 0));
+            TRY(dev_reserve(c, c->qmix_list[q], (size_t)C * 4 + 64, 0));
+            TRY(dev_reserve(c, c->qmix_n, 16, 0));
             CUDA_TRY(c, cudaMemsetAsync(c->qcnt[q].p, 0, (size_t)(C + 4) * 16, s));
             CUDA_TRY(c, cudaMemsetAsync(c->qmixed[q].p, 0, (size_t)C + 64, s));
             CUDA_TRY(c, cudaMemsetAsync((unsigned long long*)c->qobs_n.p + q, 0, 8, s));
@@ -1313,7 +1316,10 @@ static int region_phase_a(mth_ctx* c, RegionCarry& k) {
                 cudaStream_t gs = side_stream_begin(c, s);
                 ps.add(launch_quartet_canon_count((const uint32_t*)c->qcnt[q].p, (const uint8_t*)c->qmixed[q].p, C, qp.min_depth,
                                                   (uint32_t*)c->rowcnt[m].p, s));
-                ps.add(launch_quartet_count(rv, site_pos, C, d_sc, qp, (const uint8_t*)c->qmixed[q].p, (uint32_t*)c->rowcnt[m].p, gs));
+                CUDA_TRY(c, cudaMemsetAsync((unsigned long long*)c->qmix_n.p + q, 0, 8, gs));
+                ps.add(launch_quartet_mixed_list((const uint8_t*)c->qmixed[q].p, C, (uint32_t*)c->qmix_list[q].p, (unsigned long long*)c->qmix_n.p + q, gs));
+                ps.add(launch_quartet_count(rv, site_pos, C, d_sc, qp, (const uint8_t*)c->qmixed[q].p, (const uint32_t*)c->qmix_list[q].p,
+                                            (const unsigned long long*)c->qmix_n.p + q, (uint32_t*)c->rowcnt[m].p, gs));
                 TRY(side_stream_end(c, s, gs));
             }
             ProfScope ps(c, q ? "me_rows_count" : "pm_rows_count");
@@ -1416,12 +1422,14 @@ static int region_phase_b(mth_ctx* c, RegionCarry& k) {
                     ps.add(launch_quartet_canon_emit((const uint32_t*)c->qcnt[qs].p, qm, (const uint32_t*)c->qhrows[qs].p, site_pos, C, qp.min_depth, 2,
                                                      (const uint32_t*)c->rowcnt[m].p, (const float*)c->me_lut.p, c->me_lut_max, ct, rd, r.n, rd2,
                                                      c->rows_me.n, s));
-                    ps.add(launch_quartet_emit(rv, site_pos, C, d_sc, qp, 2, qm, (const uint32_t*)c->rowcnt[m].p, (const float*)c->me_lut.p,
+                    ps.add(launch_quartet_emit(rv, site_pos, C, d_sc, qp, 2, qm, (const uint32_t*)c->qmix_list[qs].p,
+                                               (const unsigned long long*)c->qmix_n.p + qs, (const uint32_t*)c->rowcnt[m].p, (const float*)c->me_lut.p,
                                                c->me_lut_max, ct, rd, r.n, rd2, c->rows_me.n, gs));
                 } else {
                     ps.add(launch_quartet_canon_emit((const uint32_t*)c->qcnt[qs].p, qm, (const uint32_t*)c->qhrows[qs].p, site_pos, C, qp.min_depth, q,
                                                      (const uint32_t*)c->rowcnt[m].p, (const float*)c->me_lut.p, c->me_lut_max, ct, rd, r.n, rd, r.n, s));
-                    ps.add(launch_quartet_emit(rv, site_pos, C, d_sc, qp, q, qm, (const uint32_t*)c->rowcnt[m].p, (const float*)c->me_lut.p,
+                    ps.add(launch_quartet_emit(rv, site_pos, C, d_sc, qp, q, qm, (const uint32_t*)c->qmix_list[qs].p,
+                                               (const unsigned long long*)c->qmix_n.p + qs, (const uint32_t*)c->rowcnt[m].p, (const float*)c->me_lut.p,
                                                c->me_lut_max, ct, rd, r.n, rd, r.n, gs));
                 }
                 TRY(side_stream_end(c, s, gs));

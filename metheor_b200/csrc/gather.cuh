@@ -94,6 +94,22 @@ __device__ __forceinline__ void for_each_site(const ReadsView& rv, const int32_t
     }
 }
 
+// The sites of a compact list (built from per-site flags when the flagged sites are few: the walk over all the flags — and a grid
+// sized for it — costs more than the sites themselves), dealt to the warps one by one.
+template <class Body>
+__device__ __forceinline__ void for_each_listed_site(const ReadsView& rv, const int32_t* __restrict__ site_pos, int32_t lmax,
+                                                     const uint32_t* __restrict__ list, unsigned long long n_list, Body&& body) {
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (unsigned long long i = (unsigned long long)warp_global; i < n_list; i += (unsigned long long)n_warps) {
+        const int64_t s = (int64_t)list[i];
+        const int32_t p = site_pos[s];
+        const int32_t target = p - lmax + 1;
+        const int64_t lo = warp_lower_bound(rv.start, rv.R, target);
+        body(s, p, lo, target);
+    }
+}
+
 // Policy interface:
 //   static constexpr int SLACK;
 //   bool contrib_ok(mapq, n) / trigger_ok(mapq, n)

@@ -108,6 +108,8 @@ struct QuartetArgs {
     mth_quartet_params prm;
     int kind;                 // 0 PM, 1 ME, 2 PM into rows and ME into rows_b (EMIT only)
     const uint8_t* mixed;     // nullptr: every site; else only the sites flagged by k_quartet_scatter
+    const uint32_t* mixed_list;           // the flagged sites as a list (k_quartet_mixed_list), or nullptr: walk the flags
+    const unsigned long long* mixed_n;    // its length (device)
     uint32_t* rowcnt;         // COUNT: out
     const uint32_t* rowoff;   // EMIT: in
     const float* me_lut;
@@ -129,7 +131,7 @@ __global__ void __launch_bounds__(GATHER_BLOCK) k_quartet(QuartetArgs a) {
     const int lane = lane_id();
     const uint32_t min_qual = a.prm.min_qual, min_depth = a.prm.min_depth;
 
-    for_each_site(rv, a.site_pos, a.C, a.sc->lmax, [&](int64_t s, int32_t p, int64_t lo, int32_t target) {
+    auto site_body = [&](int64_t s, int32_t p, int64_t lo, int32_t target) {
         uint32_t n_rows = 0;
         const int64_t out0 = EMIT ? (a.row_base + a.rowoff[s]) : 0;
         const int64_t out0b = EMIT ? (a.row_base_b + a.rowoff[s]) : 0;
@@ -281,7 +283,9 @@ __global__ void __launch_bounds__(GATHER_BLOCK) k_quartet(QuartetArgs a) {
             }
         }
         if (!EMIT && lane == 0) a.rowcnt[s] = n_rows;
-    }, a.mixed);
+    };
+    if (a.mixed_list) for_each_listed_site(rv, a.site_pos, a.sc->lmax, a.mixed_list, *a.mixed_n, site_body);
+    else for_each_site(rv, a.site_pos, a.C, a.sc->lmax, site_body, a.mixed);
 }
 
 // ---- streaming path: canonical quartets --------------------------------------------------------------------
@@ -527,26 +531,52 @@ int launch_quartet_canon_emit(const uint32_t* qcnt, const uint8_t* mixed, const 
     return 1;
 }
 
+// the flagged sites as a list: 16 flags per thread, the (few) hits appended with one atomic each; order does not matter
+__global__ void __launch_bounds__(256) k_quartet_mixed_list(const uint8_t* __restrict__ mixed, int64_t C, uint32_t* __restrict__ list,
+                                                            unsigned long long* __restrict__ n_list) {
+    const int64_t s0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (s0 >= C) return;
+    if (s0 + 16 <= C) {  // `mixed` has 64 bytes of slack and is 16-byte aligned (cudaMalloc)
+        const uint4 v = *reinterpret_cast<const uint4*>(mixed + s0);
+        if (!(v.x | v.y | v.z | v.w)) return;
+    }
+    for (int64_t s = s0; s < min(C, s0 + 16); s++)
+        if (mixed[s]) list[atomicAdd(n_list, 1ull)] = (uint32_t)s;
+}
+
+int launch_quartet_mixed_list(const uint8_t* mixed, int64_t C, uint32_t* list, unsigned long long* n_list, cudaStream_t s) {
+    if (C <= 0) return 0;
+    k_quartet_mixed_list<<<(unsigned)((C + 4095) / 4096), 256, 0, s>>>(mixed, C, list, n_list);
+    return 1;
+}
+
+// grid of the gather kernels over a list of flagged sites: they are few (one warp each, a few per SM)
+static int listed_grid(int64_t C) { return min(gather_grid(C), 148 * 8); }
+
 int launch_quartet_count(const ReadsView& rv, const int32_t* site_pos, int64_t C, const RegionScalars* sc,
-                         mth_quartet_params prm, const uint8_t* mixed, uint32_t* rowcnt, cudaStream_t s) {
+                         mth_quartet_params prm, const uint8_t* mixed, const uint32_t* mixed_list, const unsigned long long* mixed_n,
+                         uint32_t* rowcnt, cudaStream_t s) {
     if (C <= 0) return 0;
     QuartetArgs a;
     memset(&a, 0, sizeof(a));
     a.rv = rv; a.site_pos = site_pos; a.C = C; a.sc = sc; a.prm = prm; a.rowcnt = rowcnt; a.mixed = mixed;
-    k_quartet<false><<<gather_grid(C), GATHER_BLOCK, 0, s>>>(a);
+    a.mixed_list = mixed_list; a.mixed_n = mixed_n;
+    k_quartet<false><<<mixed_list ? listed_grid(C) : gather_grid(C), GATHER_BLOCK, 0, s>>>(a);
     return 1;
 }
 
 int launch_quartet_emit(const ReadsView& rv, const int32_t* site_pos, int64_t C, const RegionScalars* sc,
-                        mth_quartet_params prm, int kind, const uint8_t* mixed, const uint32_t* rowoff, const float* me_lut,
+                        mth_quartet_params prm, int kind, const uint8_t* mixed, const uint32_t* mixed_list, const unsigned long long* mixed_n,
+                        const uint32_t* rowoff, const float* me_lut,
                         int me_lut_max, ContigTable ct, QuartetRowsDev rows, int64_t row_base, QuartetRowsDev rows_b, int64_t row_base_b,
                         cudaStream_t s) {
     if (C <= 0) return 0;
     QuartetArgs a;
     memset(&a, 0, sizeof(a));
     a.rv = rv; a.site_pos = site_pos; a.C = C; a.sc = sc; a.prm = prm; a.kind = kind; a.rowoff = rowoff; a.mixed = mixed;
+    a.mixed_list = mixed_list; a.mixed_n = mixed_n;
     a.me_lut = me_lut; a.me_lut_max = me_lut_max; a.ct = ct; a.rows = rows; a.row_base = row_base; a.rows_b = rows_b; a.row_base_b = row_base_b;
-    k_quartet<true><<<gather_grid(C), GATHER_BLOCK, 0, s>>>(a);
+    k_quartet<true><<<mixed_list ? listed_grid(C) : gather_grid(C), GATHER_BLOCK, 0, s>>>(a);
     return 1;
 }
 

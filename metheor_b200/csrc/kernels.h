@@ -120,11 +120,15 @@ int launch_quartet_canon_emit(const uint32_t* qcnt, const uint8_t* mixed, const 
                               QuartetRowsDev rows_a, int64_t base_a, QuartetRowsDev rows_b, int64_t base_b, cudaStream_t s);
 // gather pass 1: rowcnt[s] = number of quartets starting at site s whose depth >= min_depth.  `mixed` != nullptr restricts
 // both gather passes to the sites it flags (the others keep what the canonical kernels wrote).
+// the sites flagged in mixed[] as a list (any order) + its length, for the two gather passes below
+int launch_quartet_mixed_list(const uint8_t* mixed, int64_t C, uint32_t* list, unsigned long long* n_list, cudaStream_t s);
 int launch_quartet_count(const ReadsView& rv, const int32_t* site_pos, int64_t C, const RegionScalars* sc,
-                         mth_quartet_params prm, const uint8_t* mixed, uint32_t* rowcnt, cudaStream_t s);
+                         mth_quartet_params prm, const uint8_t* mixed, const uint32_t* mixed_list, const unsigned long long* mixed_n,
+                         uint32_t* rowcnt, cudaStream_t s);
 // pass 2: write the rows (sorted by key within a site) at rowoff[s]; kind 0 = PM, 1 = ME, 2 = PM into rows AND ME into rows_b
 int launch_quartet_emit(const ReadsView& rv, const int32_t* site_pos, int64_t C, const RegionScalars* sc,
-                        mth_quartet_params prm, int kind, const uint8_t* mixed, const uint32_t* rowoff, const float* me_lut,
+                        mth_quartet_params prm, int kind, const uint8_t* mixed, const uint32_t* mixed_list, const unsigned long long* mixed_n,
+                        const uint32_t* rowoff, const float* me_lut,
                         int me_lut_max, ContigTable ct, QuartetRowsDev rows, int64_t row_base, QuartetRowsDev rows_b, int64_t row_base_b,
                         cudaStream_t s);
 
