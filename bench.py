@@ -87,9 +87,16 @@ def ensure_built():
 # ---------------------------------------------------------------------------------------------------------------------
 # workload
 # ---------------------------------------------------------------------------------------------------------------------
-def plan_bins_by_length(ref_len, world):
+# A region (one contig part on one GPU) costs the light passes ~0.12 ms next to their cost per base (~25 launches of small kernels,
+# measured at N = 8: DESIGN.md 7) — as much as ~30 Mb of genome in the pm + me pass at 30x.  The position bins of the resident
+# workload are balanced on bases + REGION_COST_BP x contigs (shard.plan_bins region_cost), scaled with 30 / coverage; the heavier
+# 60x / 100x legs (a region boundary is worth ~2 Mb there) are balanced on length alone.
+REGION_COST_BP = 30_000_000
+
+
+def plan_bins_by_length(ref_len, world, region_cost=0):
     from metheor_b200 import shard
-    return shard.plan_bins(ref_len, world)
+    return shard.plan_bins(ref_len, world, region_cost=region_cost)
 
 
 def gen_shard(torch, dev, contigs, coverage, intervals, world):
@@ -345,6 +352,7 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--coverage", type=float, default=COVERAGE)
     ap.add_argument("--scale", type=float, default=1.0, help="shrink every contig (quick runs); 1.0 = the BASELINE workload")
+    ap.add_argument("--region-cost", type=float, default=REGION_COST_BP, help="N > 1: bases one contig boundary is worth when the bins are balanced (at 30x; 0 = length alone)")
     ap.add_argument("--measure-steps", type=int, default=5, help="timed passes of every non-headline measure set")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip every CPU oracle leg (cpu_baseline, parity)")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary legs (chr19 configs[1], 60x, BAM, tag)")
@@ -382,7 +390,9 @@ def main():
 
     contigs = G.genome(args.scale)
     ref_len = [l for _, l in contigs]
-    intervals = plan_bins_by_length(ref_len, world)[rank]
+    region_cost = int(args.region_cost * args.scale * 30.0 / max(args.coverage, 1e-9)) if world > 1 else 0
+    intervals = plan_bins_by_length(ref_len, world, region_cost)[rank]
+    intervals_len = plan_bins_by_length(ref_len, world)[rank]  # the 60x / 100x legs: length alone
     t0 = time.perf_counter()
     wg, owned_R, owned_I = gen_shard(torch, dev, contigs, args.coverage, intervals, world)
     torch.cuda.synchronize()
@@ -446,7 +456,7 @@ def main():
             res["lpmd_all_ranks"] = ctx.allreduce()  # the path's one exchange: NCCL sum of 4 int64 inside the library
         return res
 
-    def measure_block(measures, steps, batches=wg, n_reads=R, n_calls=I, profile=True):
+    def measure_block(measures, steps, batches=wg, n_reads=R, n_calls=I, profile=True, owned_iv=None):
         """Resident timing + per-kernel profile of one measure set -> dict"""
         lp = "lpmd" in measures
         ctx = make_ctx(measures, engine.FLAG_KEEP_ON_DEVICE, comm=lp)
@@ -457,7 +467,7 @@ def main():
             step()
         ms_dev, ms_wall = timed(step, steps)
         st = ctx.stats()
-        dig = rows_digest(torch, dev, ctx, measures, owned=None if world == 1 else intervals)
+        dig = rows_digest(torch, dev, ctx, measures, owned=None if world == 1 else (owned_iv if owned_iv is not None else intervals))
         ms_step = ms_dev / steps
         per_rank = None
         if world > 1:
@@ -704,7 +714,7 @@ def main():
         nonlocal R_loc, I_loc
         try:
             t0 = time.perf_counter()
-            wc, r_own, i_own = gen_shard(torch, dev, contigs, cov, intervals, world)
+            wc, r_own, i_own = gen_shard(torch, dev, contigs, cov, intervals_len, world)
             torch.cuda.synchronize()
             gsec = time.perf_counter() - t0
             tt = torch.tensor([r_own, i_own], device=dev, dtype=torch.int64)
@@ -712,7 +722,7 @@ def main():
                 dist.all_reduce(tt)
             R_save, I_save = R_loc, I_loc
             R_loc, I_loc = sum(b["n_reads"] for b in wc), sum(b["n_cpg"] for b in wc)
-            blk = measure_block(measures, steps, batches=wc, n_reads=int(tt[0]), n_calls=int(tt[1]))
+            blk = measure_block(measures, steps, batches=wc, n_reads=int(tt[0]), n_calls=int(tt[1]), owned_iv=intervals_len)
             add_roofline(blk, {})
             R_loc, I_loc = R_save, I_save
             blk.update(workload=f"{what}: {' + '.join(measures)}, {workload_name(cov, args.scale)}", reads=int(tt[0]), cpg_calls=int(tt[1]),
@@ -758,8 +768,9 @@ def main():
                 "config": {"workload": workload_name(args.coverage, args.scale), "measures": list(HEADLINE), "reads": R, "cpg_calls": I,
                            "cpg_sites": head["cpg_sites"], "rows": head["rows"], "seed": SEED, "contigs": len(contigs),
                            "l2": "inputs (%.1f GB per step) larger than L2" % ((16 * R + 4 * I + 8 * R) / 1e9),
-                           "parallelism": (f"one genome cut into {world} position bins (+{HALO}-bp halo), one bin per GPU; NCCL all-reduce of LPMD's 4 counters "
-                                           f"inside the library (mth_allreduce), once per pass") if world > 1 else "single GPU",
+                           "parallelism": (f"one genome cut into {world} position bins (+{HALO}-bp halo), one bin per GPU, balanced on bases + {region_cost} x contigs "
+                                           f"(a contig part is a region with a fixed cost; the 60x / 100x legs: on length alone); NCCL all-reduce of LPMD's 4 "
+                                           f"counters inside the library (mth_allreduce), once per pass") if world > 1 else "single GPU",
                            "generate_seconds": gen_s},
                 "cpgs_per_sec": head["cpgs_per_sec"], "wall_ms_per_step": head["wall_ms_per_step"],
                 "e2e": e2e, "gpu_launches": int(head["launches_per_step"] * args.steps), "launches_per_step": head["launches_per_step"],

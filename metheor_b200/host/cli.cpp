@@ -210,7 +210,7 @@ int mthh_format_f32(float v, char* buf, int cap) { return mthh::format_f32(v, bu
 int mthh_plan_shards(int32_t n_ref, const int64_t* ref_len, int32_t world, int32_t by_contig, mthh_interval* out, int32_t cap) {
     if (n_ref < 0 || world < 1 || (n_ref && !ref_len)) return -1;
     std::vector<int64_t> rl(ref_len, ref_len + n_ref);
-    auto plan = by_contig ? mthh::plan_contigs(rl, world) : mthh::plan_bins(rl, world);
+    auto plan = by_contig ? mthh::plan_contigs(rl, world) : mthh::plan_bins(rl, world, mthh::shard_region_cost_env());
     int32_t n = 0;
     for (int r = 0; r < world; r++)
         for (const auto& iv : plan[(size_t)r]) {

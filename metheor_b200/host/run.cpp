@@ -426,22 +426,30 @@ void json_escape(FILE* f, const char* s) {
 
 // ---- multi-GPU sharding plans (mirrors metheor_b200/shard.py) ------------------------------------------
 // bins: the linearised genome is cut into `world` contiguous ranges of equal length; rank r owns the sites in its range.
-std::vector<std::vector<ShardInterval>> plan_bins(const std::vector<int64_t>& ref_len, int world) {
+// region_cost (bases): every contig a rank touches is a region of its own on the GPU, with a fixed cost next to the cost per
+// base; each contig gets that many bases of padding in front and the PADDED coordinate is cut evenly (a cut inside the padding
+// moves to the contig's first base).  0 = length alone.  `metheor --gpus N` takes it from METHEOR_SHARD_REGION_COST.
+std::vector<std::vector<ShardInterval>> plan_bins(const std::vector<int64_t>& ref_len, int world, int64_t region_cost) {
     std::vector<std::vector<ShardInterval>> out((size_t)world);
     const int n_ref = (int)ref_len.size();
     if (n_ref == 0) return out;
-    std::vector<int64_t> base((size_t)n_ref + 1, 0);
-    for (int t = 0; t < n_ref; t++) base[(size_t)t + 1] = base[(size_t)t] + ref_len[(size_t)t];
-    const int64_t total = base[(size_t)n_ref];
+    const int64_t P = region_cost > 0 ? region_cost : 0;
+    std::vector<int64_t> base((size_t)n_ref + 1, 0), first((size_t)n_ref + 1, 0);  // base: first base of contig t (padded); first: start of its padding
+    base[0] = P;
+    for (int t = 0; t < n_ref; t++) base[(size_t)t + 1] = base[(size_t)t] + ref_len[(size_t)t] + P;
+    for (int t = 0; t <= n_ref; t++) first[(size_t)t] = base[(size_t)t] - P;
+    const int64_t total = base[(size_t)n_ref] - P;
     std::vector<std::pair<int, int64_t>> cuts;  // rank r covers [cuts[r], cuts[r+1]) in (tid, pos) order
     cuts.push_back({0, 0});
     for (int r = 1; r < world; r++) {
         const int64_t x = (int64_t)((__int128)total * r / world);
-        int tid = (int)(std::upper_bound(base.begin(), base.end(), x) - base.begin()) - 1;
+        int tid = (int)(std::upper_bound(first.begin(), first.end(), x) - first.begin()) - 1;
         if (tid > n_ref - 1) tid = n_ref - 1;
-        cuts.push_back({tid, x - base[(size_t)tid]});
+        cuts.push_back({tid, std::max<int64_t>(0, x - base[(size_t)tid])});
     }
     cuts.push_back({n_ref - 1, ref_len[(size_t)n_ref - 1]});
+    for (size_t r = 1; r < cuts.size(); r++)  // keep the cut list monotone
+        if (cuts[r] < cuts[r - 1]) cuts[r] = cuts[r - 1];
     for (int r = 0; r < world; r++) {
         const auto a = cuts[(size_t)r], b = cuts[(size_t)r + 1];
         for (int tid = a.first; tid <= b.first; tid++) {
@@ -450,6 +458,10 @@ std::vector<std::vector<ShardInterval>> plan_bins(const std::vector<int64_t>& re
         }
     }
     return out;
+}
+int64_t shard_region_cost_env() {
+    const char* e = getenv("METHEOR_SHARD_REGION_COST");
+    return e ? std::max<long long>(0, atoll(e)) : 0;
 }
 // contigs: whole contigs, longest first onto the least loaded rank
 std::vector<std::vector<ShardInterval>> plan_contigs(const std::vector<int64_t>& ref_len, int world) {
@@ -664,7 +676,7 @@ void run(const mthh_options& o) {
     // sites inside the interval: every contributor and every flush trigger of an owned site is among its reads, so the rows
     // it reports for them are final.  Halo copies carry MTH_META_HALO so that LPMD counts each read once.
     {
-        auto plan = (n_gpus > 1 && o.shard_contigs) ? plan_contigs(ref_len, n_gpus) : plan_bins(ref_len, n_gpus);
+        auto plan = (n_gpus > 1 && o.shard_contigs) ? plan_contigs(ref_len, n_gpus) : plan_bins(ref_len, n_gpus, shard_region_cost_env());
         for (int g = 0; g < n_gpus; g++) gpus[(size_t)g]->own = plan[(size_t)g];
         if (n_gpus > 1) {  // the contexts are joined by one NCCL communicator: LPMD's counters are summed at the end
             std::vector<mth_ctx*> cs;

@@ -25,7 +25,8 @@ struct ShardInterval {
     int32_t tid;
     int64_t lo, hi;
 };
-std::vector<std::vector<ShardInterval>> plan_bins(const std::vector<int64_t>& ref_len, int world);
+std::vector<std::vector<ShardInterval>> plan_bins(const std::vector<int64_t>& ref_len, int world, int64_t region_cost = 0);
+int64_t shard_region_cost_env();  // METHEOR_SHARD_REGION_COST (bases), 0 if unset
 std::vector<std::vector<ShardInterval>> plan_contigs(const std::vector<int64_t>& ref_len, int world);
 
 inline double now_s() {

@@ -32,20 +32,25 @@ def plan_contigs(ref_len, world):
     return [sorted(x) for x in out]
 
 
-def plan_bins(ref_len, world, weights=None):
+def plan_bins(ref_len, world, weights=None, region_cost=0):
     """Split the linearised genome into `world` contiguous ranges of equal length, or of equal read count when
-    `weights` is a per-contig list of sorted read starts.  -> list (per rank) of (tid, lo, hi) intervals, hi exclusive."""
+    `weights` is a per-contig list of sorted read starts.  -> list (per rank) of (tid, lo, hi) intervals, hi exclusive.
+    region_cost (bases, length mode): every contig a rank touches is a region of its own on the GPU and a region has a fixed
+    cost (launches of ~25 small kernels, two host waits) next to the cost per base; the ranges are balanced on
+    bases + region_cost x contigs by giving every contig `region_cost` bases of padding in front (a cut that falls into the
+    padding moves to the contig's first base).  0 = balance on length alone."""
     n_ref = len(ref_len)
     cuts = [(0, 0)]  # rank r covers [cuts[r], cuts[r+1]) in (tid, pos) order
     if weights is None:
-        base = [0]
+        P = int(region_cost)
+        base = [P]  # first base of contig t in the padded coordinate
         for l in ref_len:
-            base.append(base[-1] + int(l))
-        total = base[-1]
+            base.append(base[-1] + int(l) + P)
+        total = base[-1] - P
         for r in range(1, world):  # integer arithmetic: host/run.cpp plan_bins computes the same cuts
             x = total * r // world
-            tid = min(int(np.searchsorted(np.asarray(base, np.int64), x, "right")) - 1, n_ref - 1)
-            cuts.append((tid, x - base[tid]))
+            tid = min(int(np.searchsorted(np.asarray(base, np.int64) - P, x, "right")) - 1, n_ref - 1)
+            cuts.append((tid, max(0, x - base[tid])))
     else:
         counts = np.array([len(w) for w in weights], np.int64)
         base = np.concatenate([[0], np.cumsum(counts)])

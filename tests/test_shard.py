@@ -141,3 +141,16 @@ def test_cpp_host_plans_equal_the_python_planner():
                 assert iv[0][0] == 0 and iv[-1][1] == l and all(iv[k][1] == iv[k + 1][0] for k in range(len(iv) - 1)), (rl, w, t)
             c = host.plan_shards(rl, w, True)
             assert [[t for t, _, _ in r] for r in c] == shard.plan_contigs([int(x) for x in rl], w)
+            # bins balanced on bases + region_cost x contigs (METHEOR_SHARD_REGION_COST in the C++ host)
+            for cost in (1, 5_000, 30_000_000):
+                os.environ["METHEOR_SHARD_REGION_COST"] = str(cost)
+                try:
+                    a = host.plan_shards(rl, w)
+                finally:
+                    del os.environ["METHEOR_SHARD_REGION_COST"]
+                b = shard.plan_bins([int(x) for x in rl], w, region_cost=cost)
+                assert [[tuple(int(v) for v in x) for x in r] for r in a] == [[tuple(int(v) for v in x) for x in r] for r in b], (rl, w, cost)
+                cover = sorted(x for r in a for x in r)
+                for t, l in enumerate(rl):
+                    iv = [(lo, hi) for tt, lo, hi in cover if tt == t]
+                    assert iv[0][0] == 0 and iv[-1][1] == l and all(iv[k][1] == iv[k + 1][0] for k in range(len(iv) - 1)), (rl, w, t, cost)
