@@ -314,30 +314,39 @@ int launch_fdrp_tile(const ReadsView& rv, const int32_t* site_pos, int64_t C, co
         }
     }
     static bool attr_set = false;
-    static int force = 0;  // METHEOR_FDRP_TILE = dense | sparse32 | sparse64: kernel-variant experiments (profiles/)
+    static int force = 0;  // METHEOR_FDRP_TILE = dense | sparse32 | sparse64 | sparse16 | sparse8: kernel-variant experiments (profiles/)
     if (!attr_set) {
         cudaFuncSetAttribute(k_fdrp_tile<64, FT_RCAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FtSmem<FT_RCAP>));
         cudaFuncSetAttribute(k_fdrp_tile<32, FT_RCAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FtSmem<FT_RCAP>));
+        cudaFuncSetAttribute(k_fdrp_tile<16, FT_RCAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FtSmem<FT_RCAP>));
+        cudaFuncSetAttribute(k_fdrp_tile<8, FT_RCAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FtSmem<FT_RCAP>));
         cudaFuncSetAttribute(k_fdrp_tile<64, FT_RCAP_SPARSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FtSmem<FT_RCAP_SPARSE>));
         const char* e = getenv("METHEOR_FDRP_TILE");
-        if (e) force = !strcmp(e, "dense") ? 1 : !strcmp(e, "sparse32") ? 2 : !strcmp(e, "sparse64") ? 3 : 0;
+        if (e) force = !strcmp(e, "dense") ? 1 : !strcmp(e, "sparse32") ? 2 : !strcmp(e, "sparse64") ? 3 : !strcmp(e, "sparse16") ? 4 : !strcmp(e, "sparse8") ? 5 : 0;
         attr_set = true;
     }
-    // reads a tile has to stage ~ sites x reads per site gap: pick the instance whose capacity covers it with some room
+    // Reads a tile has to stage ~ sites x reads per site gap (coverage / CpG density): the instance with the most sites per
+    // tile whose 1024-read capacity covers that with some room — 64 sites at chr19-like density and 30x, 32 at whole-genome
+    // density and 30x, 16 at 60x, 8 (one site per warp) at 100x.  Without the small instances every tile of a 60x / 100x genome
+    // overflowed and ALL sites went through the per-site kernel (245 of 290 ms, 340 of 471 ms of those passes).
     const double per_site = (double)rv.R / (double)C;
-    int variant = force ? force : (64.0 * per_site * 1.3 <= (double)FT_RCAP ? 1 : 2);
-    const int sites = variant == 2 ? 32 : 64;
+    int variant = force;
+    if (!variant) {
+        const double need = per_site * 1.3;
+        variant = 64.0 * need <= (double)FT_RCAP ? 1 : 32.0 * need <= (double)FT_RCAP ? 2 : 16.0 * need <= (double)FT_RCAP ? 4 : 5;
+    }
+    const int sites = variant == 2 ? 32 : variant == 4 ? 16 : variant == 5 ? 8 : 64;
     int64_t tiles = (C + sites - 1) / sites;
     if (tiles > 148 * 48) tiles = 148 * 48;
-    if (variant == 1)
-        k_fdrp_tile<64, FT_RCAP><<<(unsigned)tiles, FT_THREADS, sizeof(FtSmem<FT_RCAP>), s>>>(rv, site_pos, C, bitmap, n_words, word_prefix, sc, prm,
-                                                                                           quantitative, seed, ct, value, rowcnt, value_q, rowcnt_q, fallback);
-    else if (variant == 2)
-        k_fdrp_tile<32, FT_RCAP><<<(unsigned)tiles, FT_THREADS, sizeof(FtSmem<FT_RCAP>), s>>>(rv, site_pos, C, bitmap, n_words, word_prefix, sc, prm,
-                                                                                           quantitative, seed, ct, value, rowcnt, value_q, rowcnt_q, fallback);
-    else
-        k_fdrp_tile<64, FT_RCAP_SPARSE><<<(unsigned)tiles, FT_THREADS, sizeof(FtSmem<FT_RCAP_SPARSE>), s>>>(
-            rv, site_pos, C, bitmap, n_words, word_prefix, sc, prm, quantitative, seed, ct, value, rowcnt, value_q, rowcnt_q, fallback);
+#define MTH_FT_LAUNCH(S, R)                                                                                                              \
+    k_fdrp_tile<S, R><<<(unsigned)tiles, FT_THREADS, sizeof(FtSmem<R>), s>>>(rv, site_pos, C, bitmap, n_words, word_prefix, sc, prm, quantitative, \
+                                                                            seed, ct, value, rowcnt, value_q, rowcnt_q, fallback)
+    if (variant == 1) MTH_FT_LAUNCH(64, FT_RCAP);
+    else if (variant == 2) MTH_FT_LAUNCH(32, FT_RCAP);
+    else if (variant == 4) MTH_FT_LAUNCH(16, FT_RCAP);
+    else if (variant == 5) MTH_FT_LAUNCH(8, FT_RCAP);
+    else MTH_FT_LAUNCH(64, FT_RCAP_SPARSE);
+#undef MTH_FT_LAUNCH
     return 1;
 }
 
