@@ -56,8 +56,10 @@ def _worker(rank, world, port, mode, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         data = _data()
-        if mode == "bins":
-            plan = shard.plan_bins(LENS, world, weights=[b["start"] for b in data])
+        if mode in ("bins", "bins_region_cost"):
+            # read-count balanced cuts, or length + a cost per contig boundary (what bench.py --gpus N uses)
+            plan = shard.plan_bins(LENS, world, weights=[b["start"] for b in data]) if mode == "bins" else \
+                shard.plan_bins(LENS, world, region_cost=max(1, min(LENS) // 3))
             mine, owned = [], []
             for b in data:
                 sub, n_own = shard.select_shard(b, plan[rank], halo=400)
@@ -95,7 +97,7 @@ def _worker(rank, world, port, mode, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["bins", "contigs"])
+@pytest.mark.parametrize("mode", ["bins", "bins_region_cost", "contigs"])
 def test_world_size_2_gloo(mode):
     import torch.multiprocessing as mp
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
@@ -112,7 +114,8 @@ def test_world_size_2_gloo(mode):
 
 def test_plans_cover_the_genome_exactly():
     for world in (1, 2, 3, 8):
-        for plan in (shard.plan_bins(LENS, world), shard.plan_bins(LENS, world, weights=[b["start"] for b in _data()])):
+        for plan in (shard.plan_bins(LENS, world), shard.plan_bins(LENS, world, weights=[b["start"] for b in _data()]),
+                     shard.plan_bins(LENS, world, region_cost=min(LENS) // 3), shard.plan_bins(LENS, world, region_cost=10 * max(LENS))):
             cover = np.zeros(sum(LENS), np.int32)
             base = np.concatenate([[0], np.cumsum(LENS)])
             for r in plan:
